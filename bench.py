@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the all-vs-all affine-gap DP (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path over the whole pair list of BASELINE config 2:
+1,000 synthetic 300-residue proteins (seed 2 family), all 499,500 unordered
+pairs, BLOSUM62, gaps [-11, -1], global mode, score per pair (what GuideTreeBuilder needs).
+With N > 1 the pair list is sharded by DP cells over the ranks and the condensed score vector
+is assembled with one NCCL all-gather per step.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python bench.py --impl reference ...    # the reference's own C path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from praline_b200 import matrices, synth  # noqa: E402
+
+WORKLOAD = dict(n_seqs=1000, length=300, seed=2, gaps=[-11.0, -1.0], mode="global")
+W_FLOPS_PER_CELL = 11.0   # 7 add + 4 max of the reference recurrence
+
+
+def n_seqs_for(world):
+    """Weak scaling: the pair count (the per-GPU work) stays that of configs[1] per rank, so the
+    sequence count grows with sqrt(world): 1000, 1414, 2000, 2828 at 1, 2, 4, 8 GPUs."""
+    return int(round(WORKLOAD["n_seqs"] * np.sqrt(world)))
+
+
+def workload(world=1):
+    seqs = synth.family(WORKLOAD["seed"], n_seqs_for(world), WORKLOAD["length"])
+    return seqs, matrices.blosum62()
+
+
+def config_dict(extra=None, world=1):
+    n = n_seqs_for(world)
+    c = {"workload": "all-vs-all pairwise scoring, %d synthetic 300-aa proteins (%d pairs), "
+                     "BLOSUM62 affine [-11,-1], global, score per pair (BASELINE configs[1]%s)"
+                     % (n, n * (n - 1) // 2, "" if world == 1 else ", pair count scaled x%d" % world),
+         "n_seqs": n, "seq_len": WORKLOAD["length"], "pairs": n * (n - 1) // 2,
+         "l2": "256 MiB buffer written between timed steps (inputs are smaller than L2)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---- clocks sampling -------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.stop = False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.samples.append([v.strip() for v in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) < 6:
+                continue
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU baselines ---------------------------------------------------------------------------
+def _ref_worker(args):
+    """One worker of the reference arm: cext_build_scores + cext_align_global per pair, i.e. the
+    reference's own compiled C path (oracle/_ref), exactly the arrays PairwiseAligner builds."""
+    import oracle
+    seqs, S, pairs, gaps = args
+    cx = oracle.ref_cext()
+    cells = 0
+    scores = []
+    onehot = {}
+    for i, j in pairs:
+        for k in (i, j):
+            if k not in onehot:
+                p = np.zeros((len(seqs[k]), S.shape[0]), np.float32)
+                p[np.arange(len(seqs[k])), seqs[k]] = 1.0
+                nz = np.full(p.shape, -1, np.intp)
+                nz[:, 0] = seqs[k]
+                onehot[k] = (p, nz)
+        (p1, nz1), (p2, nz2) = onehot[i], onehot[j]
+        L1, L2 = p1.shape[0], p2.shape[0]
+        m = np.zeros((L1, L2), np.float32)
+        cx.cext_build_scores([p1], [p2], [nz1], [nz2], [S], m)
+        g1, g2 = oracle.gap_arrays(L1, L2, gaps)
+        o, t = oracle.ref_init_borders("global", g1, g2, L1, L2)
+        z = np.zeros((L1 + 1, L2 + 1), np.uint8)
+        cx.cext_align_global(m, g1, g2, o, t, z)
+        scores.append(float(o[L1, L2].max()))
+        cells += L1 * L2
+    return cells, scores
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on all host cores."""
+    import multiprocessing as mp
+    import oracle
+    seqs, S = workload(max(args.gpus, 1))
+    pi, pj = synth.all_pairs(len(seqs))
+    cores = os.cpu_count() or 1
+    kind = "reference" if oracle.ref_cext() is not None else "port"
+    rng = np.random.default_rng(0)
+    per_step = 250 * cores                      # bounded sample: ~3 s of work per core and step
+    flat, offs = synth.pack(seqs)
+
+    def one_step(pool, k):
+        pick = rng.choice(len(pi), per_step, replace=False)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            chunks = np.array_split(pick, cores)
+            res = pool.map(_ref_worker, [(seqs, S, list(zip(pi[c], pj[c])), WORKLOAD["gaps"]) for c in chunks])
+            cells = sum(r[0] for r in res)
+        else:
+            oracle.align_batch("global", flat, offs, pi[pick], pj[pick], S, WORKLOAD["gaps"])
+            cells = int((offs[1:] - offs[:-1])[pi[pick]] @ (offs[1:] - offs[:-1])[pj[pick]])
+        return cells, time.perf_counter() - t0
+
+    with mp.get_context("fork").Pool(cores) as pool:
+        for k in range(args.warmup):
+            one_step(pool, k)
+        tot_c, tot_t = 0, 0.0
+        for k in range(args.steps):
+            c, t = one_step(pool, k)
+            tot_c += c
+            tot_t += t
+    gcups = tot_c / tot_t / 1e9
+    used = cores if kind == "reference" else 1
+    line = {"impl": "reference", "metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict({"sample": "%d random pairs of the workload per step" % per_step},
+                                  max(args.gpus, 1)),
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": kind,
+                             "sample": "%d random pairs per step x %d steps, cext_build_scores + cext_align_global"
+                                       % (per_step, args.steps)},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_port(seqs, S, seconds=12.0):
+    """The oracle's scalar C loop on one core over a bounded sample of the same pairs."""
+    import oracle
+    flat, offs = synth.pack(seqs)
+    pi, pj = synth.all_pairs(len(seqs))
+    rng = np.random.default_rng(1)
+    pick = rng.choice(len(pi), 400, replace=False)
+    t0 = time.perf_counter()
+    oracle.align_batch("global", flat, offs, pi[pick], pj[pick], S, WORKLOAD["gaps"])
+    dt = time.perf_counter() - t0
+    n = int(min(len(pi), max(400, 400 * seconds / max(dt, 1e-3))))
+    pick = rng.choice(len(pi), n, replace=False)
+    lens = offs[1:] - offs[:-1]
+    t0 = time.perf_counter()
+    oracle.align_batch("global", flat, offs, pi[pick], pj[pick], S, WORKLOAD["gaps"])
+    dt = time.perf_counter() - t0
+    cells = int((lens[pi[pick]] * lens[pj[pick]]).sum())
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
+            "sample": "%d random pairs of the workload (%.1f s), oracle/praline_oracle.c scalar loop incl. traceback"
+                      % (n, dt)}
+
+
+# ---- our arm ---------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from praline_b200 import get_engine, parallel
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = get_engine(local_rank)
+    dev = eng.device
+    seqs, S = workload(world)
+    gaps, mode = WORKLOAD["gaps"], WORKLOAD["mode"]
+    n = len(seqs)
+    n_pairs = n * (n - 1) // 2
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- resident-input arm: sequences, matrix and tile plan already in HBM ------------------
+    batch = eng.batch(seqs)
+    S_dev = eng.dev(S)
+    plan = eng.allpairs_tiles(batch, (rank, world))
+    slot_cuts = plan[3]
+    my_cells = plan[2]
+    out = torch.empty(n_pairs, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total_cells = int(sum(len(seqs[i]) for i in range(n)) ** 2 - sum(len(s) ** 2 for s in seqs)) // 2
+
+    def step_resident():
+        eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan)
+        if world > 1:
+            parallel.allgather_condensed(out, slot_cuts)
+
+    for _ in range(max(args.warmup, 0)):
+        step_resident()
+    sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launches
+    with ClockSampler(local_rank) as clk:
+        sync()
+        for k in range(args.steps):
+            flush.fill_(k & 0xff)            # L2 flush, outside the timed events
+            torch.cuda.synchronize(dev)
+            ev[k][0].record()
+            step_resident()
+            ev[k][1].record()
+        sync()
+    launches = eng.launches - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / max(args.steps, 1)
+    gcups = total_cells / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end-to-end arm: host buffers in, host scores out, every step --------------------------
+    host_out = torch.empty(n_pairs, dtype=torch.float32).pin_memory()
+    h2d = d2h = 0
+
+    def step_e2e():
+        nonlocal h2d, d2h
+        b = eng.batch(seqs)                                  # pinned host -> device
+        sd = eng.dev(S)
+        pl = eng.allpairs_tiles(b, (rank, world))
+        o, (lo, hi), _ = eng.allpairs_scores(b, sd, S.shape[0], gaps, mode=mode, shard=(rank, world), plan=pl)
+        if world > 1:
+            parallel.allgather_condensed(o, pl[3])
+            lo, hi = 0, n_pairs
+        host_out[lo:hi].copy_(o[lo:hi], non_blocking=True)   # device -> pinned host
+        torch.cuda.synchronize(dev)
+        h2d = b.h2d_bytes + S.nbytes + sum(t.nbytes for t in pl[0].values())
+        d2h = (hi - lo) * 4
+
+    for _ in range(max(args.warmup, 1)):
+        step_e2e()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    sync()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_gcups = total_cells * args.steps / float(te.item()) / 1e9
+
+    # ---- roofline of the dominant kernel (k_stream), timed live with CUDA events ----------------
+    roof = None
+    cpu = None
+    if rank == 0:
+        mb = eng.microbench()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk_sum = clk.summary()
+        mhz = clk_sum["sm_mhz"] or mb["sm_mhz"]
+        # peak f32 add/max lane-ops per second on this box: measured issue rate of the 4 add : 3 max
+        # cell mix (warp-instructions / clk / SM) x 32 lanes x SMs x SM clock under load
+        peak = mb["cell_mix"] * 32 * sms * mhz * 1e6
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a, b in kev:
+            a.record()
+            eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan)
+            b.record()
+        torch.cuda.synchronize(dev)
+        kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+        achieved = my_cells * W_FLOPS_PER_CELL / (kms * 1e-3)
+        roof = {"bound": "cuda_core_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
+                "frac": achieved / peak, "traffic": None,
+                "note": "DP-cell roofline (SURVEY 8d): 11 f32 add/max per cell; peak = measured issue rate of the "
+                        "recurrence's add:max mix x 32 lanes x %d SMs x %.0f MHz (of measured); HBM is not the bound: "
+                        "4 B/pair out" % (sms, mhz),
+                "kernel": "k_stream<10,global,score-only>", "kernel_ms": kms,
+                "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_port(seqs, S)
+
+    if rank == 0:
+        line = {"metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict({"parallelism": "pairs sharded by DP cells over %d rank(s)%s"
+                                       % (world, ", NCCL all-gather of scores" if world > 1 else "")}, world),
+                "clocks": clk_sum,
+                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/*
+ * praline_b200.h -- C ABI of libpraline_b200.so: the B200 (sm_100a) drop-in for PRALINE's
+ * pairwise dynamic-programming alignment core.
+ *
+ * What it replaces (paths relative to the reference tree, ibivu/PRALINE):
+ *   praline/util/cext.c:506-520      the six functions of the `praline.util.cext` CPython module
+ *   praline/component/align.py:357-431  RawPairwiseAligner's border init and end-cell choice
+ *   praline/util/align.py:144-185, 268-297  get_paths and extend_path_semiglobal
+ * The reference binds its native code through the CPython API; this library is bound with
+ * ctypes (see INTEGRATION.md for the stub a PRALINE maintainer adds).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pgpu_last_error() then holds
+ *     a message (thread local).  1 = bad argument, 2 = CUDA runtime error, 3 = no usable GPU.
+ *   - pointers named *_dev are DEVICE pointers owned by the caller (PyTorch tensors'
+ *     data_ptr() in the Python host layer); nothing is allocated behind the caller's back
+ *     except in pgpu_fill_debug, which takes HOST buffers like the reference's functions do.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously and the
+ *     caller synchronises.
+ *   - modes are numbered as in praline/util/cext.c:27-31.
+ *   - sequences are uint8 symbol indices (PRALINE alphabets have <= 27 symbols,
+ *     praline/container/alphabet.py:96-109), concatenated, with int64 offsets [n+1].
+ */
+#ifndef PRALINE_B200_H
+#define PRALINE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGPU_ABI_VERSION 1
+
+#define PGPU_MODE_GLOBAL 0
+#define PGPU_MODE_LOCAL 1
+#define PGPU_MODE_SEMIGLOBAL_BOTH 2
+#define PGPU_MODE_SEMIGLOBAL_ONE 3
+#define PGPU_MODE_SEMIGLOBAL_TWO 4
+
+/* One unit of work of the inter-task kernel: a resident sequence against a run of streamed
+ * sequences; results go to consecutive output slots starting at out_base. */
+typedef struct pgpu_tile {
+    int32_t resident;
+    int32_t stream_begin;
+    int32_t stream_end;
+    int32_t reserved;
+    int64_t out_base;
+} pgpu_tile;
+
+int pgpu_abi_version(void);
+int pgpu_init(int device);
+void pgpu_shutdown(void);
+const char* pgpu_last_error(void);
+
+/* Columns-per-lane values the inter-task kernel is instantiated for (a resident sequence of
+ * length L needs K >= ceil(L/32)), and the number of warps that share one tile. */
+int pgpu_supported_k(int k);
+int pgpu_warps_per_tile(void);
+
+/*
+ * Inter-task batch (K2): sequence-sequence alignments with constant gap penalties.
+ * Replaces, per pair, cext_build_scores + cext_align_<mode> + the end-cell choice
+ * (cext.c:308-455, :99-306; component/align.py:401-431), i.e. one PairwiseAligner.execute
+ * (component/align.py:88-251) for PlainTrack inputs.
+ *
+ *   transposed   0: resident sequences are `sequence_two` (DP columns, as in the reference)
+ *                1: resident sequences are `sequence_one`
+ *   stream_ids   sequence id per stream element, or NULL when element s is sequence s
+ *   topD/leftD   DP border values max(M,U,L) along row 0 / column 0 in the KERNEL orientation
+ *                (component/align.py:367-385), border_len >= 32*K+1 and > every stream length
+ *   scores       [n_slots] f32
+ *   keys         [2*n_slots] u64 scratch, local and semiglobal modes (running maxima); only
+ *                slots produced by this call have their score written
+ *   tb .. pair_tb  NULL for score-only runs; else packed traceback words, per-(tile,warp) word
+ *                offsets, and per-slot outputs consumed by pgpu_traceback_tiles
+ */
+int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
+                     const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, int64_t n_slots,
+                     const float* S_dev, int A, float gap_open, float gap_extend, const float* topD_dev,
+                     const float* leftD_dev, int border_len, float* scores_dev, uint64_t* keys_dev,
+                     uint32_t* tb_dev, const int64_t* tb_base_dev, int32_t* emit_t_dev,
+                     int64_t* pair_tb_dev, void* stream);
+
+/*
+ * Traceback of an inter-task batch (K4).  Replaces get_paths (util/align.py:144-185), the
+ * semiglobal end-cell scan (component/align.py:405-426) and extend_path_semiglobal
+ * (util/align.py:268-297).  Paths are (y, x) rows in the reference orientation, written
+ * right-aligned into each slot's region of capacity len(resident)+len(stream)+2 rows:
+ * rows [path_off[s] + path_start[s], +path_len[s]).
+ */
+int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs_dev,
+                         const int32_t* slot_resident_dev, const int32_t* slot_stream_dev, int64_t n_slots,
+                         const uint64_t* keys_dev, const uint32_t* tb_dev, const int32_t* emit_t_dev,
+                         const int64_t* pair_tb_dev, int code00, int top_ramp, int left_ramp,
+                         const int64_t* path_off_dev, int32_t* path_buf_dev, int32_t* path_start_dev,
+                         int32_t* path_len_dev, void* stream);
+
+/*
+ * Match-score matrix (K1).  Replaces cext_build_scores (cext.c:308-455): m[y][x] = sum over
+ * track sets of P1[y] . S . P2[x]^T, evaluated in the reference's order.  P1/P2/S are HOST
+ * arrays of DEVICE pointers (one per set), A the alphabet size per set.
+ */
+int pgpu_build_scores(int n_sets, const float* const* P1_dev, const float* const* P2_dev,
+                      const float* const* S_dev, const int* A, int L1, int L2, float* m_dev, int m_pitch,
+                      void* stream);
+int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
+                          int L2, float* m_dev, int m_pitch, void* stream);
+
+/*
+ * General single alignment (K3 wavefront + traceback).  Replaces RawPairwiseAligner.execute
+ * (component/align.py:302-447): arbitrary match scores m [L1][m_pitch], per-position gap
+ * arrays g1 [L1][2], g2 [L2][2], optional mask z [(L1+1)][z_pitch] (zero_idxs), any mode.
+ * Outputs: *score_out, cell_out[3] = end cell (y, x, state), path rows right-aligned in
+ * path_buf (capacity L1+L2+2 rows) at [path_start[0], +path_len[0]).  path_buf may be NULL
+ * (score only).  o_full / t_full, when non-NULL, receive the reference's complete o and t
+ * arrays [(L1+1)][(L2+1)][3] (debug level > 1, component/align.py:390-399).
+ */
+int64_t pgpu_general_workspace_bytes(int L1, int L2);
+int pgpu_align_general(int mode, int L1, int L2, const float* m_dev, int m_pitch, const float* g1_dev,
+                       const float* g2_dev, const uint8_t* z_dev, int z_pitch, void* workspace_dev,
+                       float* score_out_dev, int32_t* cell_out_dev, int32_t* path_buf_dev,
+                       int32_t* path_start_dev, int32_t* path_len_dev, float* o_full_dev,
+                       uint8_t* t_full_dev, void* stream);
+
+/*
+ * Parity shim with the exact shape of the reference's cext_align_<mode>(m, g1, g2, o, t, z)
+ * (cext.c:103-107): HOST buffers, dense row-major, o [(L1+1)][(L2+1)][3] f32 and t u8 are
+ * overwritten completely (borders included), z may be NULL.  Synchronous.
+ */
+int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, float* o, uint8_t* t,
+                    const uint8_t* z, int L1, int L2);
+
+/*
+ * Pipe-rate micro-benchmarks used for the DP roofline denominator: returns in out[0..n) the
+ * measured warp-instructions per clock per SM for (0) FADD, (1) FMNMX, (2) FMNMX3,
+ * (3) the 4 FADD : 3 FMNMX mix of the score-only recurrence, (4) VIADDMNMX.S32,
+ * (5) VIADDMNMX.S16x2, (6) SHFL, (7) LDS.128, and out[8] = SM clock in MHz seen by the run.
+ */
+int pgpu_microbench(double* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

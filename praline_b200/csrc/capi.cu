@@ -1,0 +1,205 @@
+// capi.cu -- the C ABI of libpraline_b200.so (declared in include/praline_b200.h).
+// Plain pointers and sizes only; every entry returns 0 on success or a non-zero code with the
+// text available from pgpu_last_error().  Nothing here throws across the boundary.
+#include "common.cuh"
+#include "../../include/praline_b200.h"
+
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+void pg_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+const char* pgpu_last_error(void) { return g_err; }
+int pgpu_abi_version(void) { return PGPU_ABI_VERSION; }
+
+int pgpu_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        pg_set_error("no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return 3;
+    }
+    if (device < 0 || device >= n) { pg_set_error("device %d out of range (0..%d)", device, n - 1); return 1; }
+    PG_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp p;
+    PG_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) { pg_set_error("built for sm_100a, device is sm_%d%d", p.major, p.minor); return 3; }
+    PG_CUDA_OK(cudaFree(0));
+    return 0;
+}
+
+void pgpu_shutdown(void) {}
+
+int pgpu_supported_k(int k) { return pg_stream_supported_k(k); }
+int pgpu_warps_per_tile(void) { return 8; }
+
+int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs, const int64_t* offs,
+                     const int32_t* stream_ids, const void* tiles, int n_tiles, int64_t n_slots,
+                     const float* S, int A, float gap_open, float gap_extend, const float* topD,
+                     const float* leftD, int border_len, float* scores, uint64_t* keys, uint32_t* tb,
+                     const int64_t* tb_base, int32_t* emit_t, int64_t* pair_tb, void* stream)
+{
+    if (mode < 0 || mode > 4) { pg_set_error("unknown alignment mode %d", mode); return 1; }
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    if (border_len < 32 * K + 1) { pg_set_error("border arrays too short for K=%d", K); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool semi = mode != PG_GLOBAL;   // local and semiglobal results are reduced through keys
+    if (semi && !keys) { pg_set_error("local / semiglobal modes need the keys scratch buffer"); return 1; }
+    StreamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seqs = seqs; a.offs = offs; a.stream_ids = stream_ids; a.tiles = (const PgTile*)tiles;
+    a.S = S; a.A = A; a.transposed = transposed; a.go = gap_open; a.ge = gap_extend;
+    a.topD = topD; a.leftD = leftD; a.border_len = border_len;
+    a.scores = scores;
+    a.rowkey = (unsigned long long*)keys;
+    a.colkey = keys ? (unsigned long long*)keys + n_slots : nullptr;
+    a.tb = tb; a.tb_base = tb_base; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    // kernel-orientation mode: a transposed launch swaps the roles of sequence one and two
+    int kmode = mode;
+    if (transposed && (mode == PG_SG_ONE || mode == PG_SG_TWO)) kmode = (mode == PG_SG_ONE) ? PG_SG_TWO : PG_SG_ONE;
+    (void)kmode;  // borders arrive pre-oriented in topD / leftD; only the score rule needs `mode`
+    if (semi) PG_CUDA_OK(cudaMemsetAsync(keys, 0, sizeof(uint64_t) * 2 * (size_t)n_slots, st));
+    int rc = pg_launch_stream(a, n_tiles, K, mode, tb != nullptr, st);
+    if (rc) return rc;
+    if (semi) rc = pg_launch_semi_scores(n_slots, a.rowkey, a.colkey, mode, transposed, scores, st);
+    return rc;
+}
+
+int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, const int32_t* slot_resident,
+                         const int32_t* slot_stream, int64_t n_slots, const uint64_t* keys,
+                         const uint32_t* tb, const int32_t* emit_t, const int64_t* pair_tb, int code00,
+                         int top_ramp, int left_ramp, const int64_t* path_off, int32_t* path_buf,
+                         int32_t* path_start, int32_t* path_len, void* stream)
+{
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_slots = n_slots; a.mode = mode; a.K = K; a.transposed = transposed; a.offs = offs;
+    a.slot_resident = slot_resident; a.slot_stream = slot_stream; a.tb = tb; a.emit_t = emit_t;
+    a.pair_tb = pair_tb;
+    a.rowkey = (const unsigned long long*)keys;
+    a.colkey = keys ? (const unsigned long long*)keys + n_slots : nullptr;
+    a.code00 = code00; a.top_ramp = top_ramp; a.left_ramp = left_ramp;
+    a.path_off = path_off; a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
+    return pg_launch_traceback(a, (cudaStream_t)stream);
+}
+
+int pgpu_build_scores(int n_sets, const float* const* P1, const float* const* P2, const float* const* S,
+                      const int* A, int L1, int L2, float* m, int m_pitch, void* stream)
+{
+    if (n_sets < 1 || n_sets > 16) { pg_set_error("n_sets %d outside 1..16", n_sets); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ScoreSet h[16];
+    for (int i = 0; i < n_sets; i++) { h[i].P1 = P1[i]; h[i].P2 = P2[i]; h[i].S = S[i]; h[i].A = A[i]; }
+    ScoreSet* d = nullptr;
+    PG_CUDA_OK(cudaMallocAsync((void**)&d, sizeof(ScoreSet) * n_sets, st));
+    PG_CUDA_OK(cudaMemcpyAsync(d, h, sizeof(ScoreSet) * n_sets, cudaMemcpyHostToDevice, st));
+    PG_CUDA_OK(cudaStreamSynchronize(st));  // h is on this stack frame
+    int rc = pg_launch_build_scores(n_sets, d, L1, L2, m, m_pitch, st);
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
+int pgpu_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,
+                          float* m, int m_pitch, void* stream)
+{
+    return pg_launch_build_scores_seq(a, b, S, A, L1, L2, m, m_pitch, (cudaStream_t)stream);
+}
+
+static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int general_kg(int L2) { return L2 <= 2048 ? 2 : 8; }
+
+int64_t pgpu_general_workspace_bytes(int L1, int L2)
+{
+    const int kg = general_kg(L2);
+    int ns = (L2 + 32 * kg - 1) / (32 * kg);
+    if (ns < 1) ns = 1;
+    const size_t fp = up256((size_t)L2 + 1);
+    size_t b = 0;
+    b += up256((size_t)(L1 + 1) * fp);                              // flags
+    b += up256(sizeof(float) * 3 * (size_t)(ns + 1) * (L1 + 1));    // edge
+    b += up256(sizeof(int) * (size_t)(ns + 1));                     // progress
+    b += 2 * up256(sizeof(float) * 3 * (size_t)(L2 + 1));           // top, lastrow
+    b += up256(sizeof(float) * 3 * (size_t)(L1 + 1));               // lastcol
+    b += 256;                                                       // best
+    return (int64_t)b;
+}
+
+int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, const float* g1,
+                       const float* g2, const uint8_t* z, int z_pitch, void* workspace, float* score_out,
+                       int32_t* cell_out, int32_t* path_buf, int32_t* path_start, int32_t* path_len,
+                       float* o_full, uint8_t* t_full, void* stream)
+{
+    if (mode < 0 || mode > 4) { pg_set_error("unknown alignment mode %d", mode); return 1; }
+    if (L1 < 1 || L2 < 1) { pg_set_error("empty sequence (L1=%d, L2=%d)", L1, L2); return 1; }
+    const int kg = general_kg(L2);
+    int ns = (L2 + 32 * kg - 1) / (32 * kg);
+    GenArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = mode; a.L1 = L1; a.L2 = L2; a.m = m; a.m_pitch = m_pitch; a.g1 = g1; a.g2 = g2;
+    a.z = z; a.z_pitch = z_pitch; a.o_full = o_full; a.t_full = t_full;
+    unsigned char* w = (unsigned char*)workspace;
+    const size_t fp = up256((size_t)L2 + 1);
+    a.flags = w; a.f_pitch = (int)fp; w += up256((size_t)(L1 + 1) * fp);
+    a.edge = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(ns + 1) * (L1 + 1));
+    a.progress = (int*)w; w += up256(sizeof(int) * (size_t)(ns + 1));
+    a.top = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));
+    a.lastrow = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));
+    a.lastcol = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L1 + 1));
+    a.best = (unsigned long long*)w;
+    a.score_out = score_out; a.cell_out = cell_out;
+    a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
+    return pg_launch_general(a, kg, (cudaStream_t)stream);
+}
+
+// B3 parity shim: the reference's cext_align_<mode>(m, g1, g2, o, t, z) with host buffers
+// (praline/util/cext.c:103-107).  o and t are fully overwritten (borders included).
+int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, float* o, uint8_t* t,
+                    const uint8_t* z, int L1, int L2)
+{
+    if (L1 < 1 || L2 < 1) { pg_set_error("empty sequence (L1=%d, L2=%d)", L1, L2); return 1; }
+    const size_t cells = (size_t)(L1 + 1) * (L2 + 1);
+    const int64_t wsb = pgpu_general_workspace_bytes(L1, L2);
+    unsigned char* d = nullptr;
+    const size_t off_m = 0, off_g1 = up256(sizeof(float) * (size_t)L1 * L2), off_g2 = off_g1 + up256(sizeof(float) * 2 * L1),
+                 off_z = off_g2 + up256(sizeof(float) * 2 * L2), off_o = off_z + up256(cells),
+                 off_t = off_o + up256(sizeof(float) * 3 * cells), off_ws = off_t + up256(3 * cells),
+                 off_out = off_ws + (size_t)wsb, total = off_out + 256;
+    PG_CUDA_OK(cudaMalloc((void**)&d, total));
+    int rc = 0;
+    do {
+        cudaError_t e;
+#define CK(x) if ((e = (x)) != cudaSuccess) { pg_set_error("%s: %s", #x, cudaGetErrorString(e)); rc = 2; break; }
+        CK(cudaMemcpy(d + off_m, m, sizeof(float) * (size_t)L1 * L2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d + off_g1, g1, sizeof(float) * 2 * L1, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d + off_g2, g2, sizeof(float) * 2 * L2, cudaMemcpyHostToDevice));
+        if (z) CK(cudaMemcpy(d + off_z, z, cells, cudaMemcpyHostToDevice));
+        CK(cudaMemset(d + off_o, 0, sizeof(float) * 3 * cells));
+        CK(cudaMemset(d + off_t, 0, 3 * cells));
+        rc = pgpu_align_general(mode, L1, L2, (const float*)(d + off_m), L2, (const float*)(d + off_g1),
+                                (const float*)(d + off_g2), z ? d + off_z : nullptr, L2 + 1, d + off_ws,
+                                (float*)(d + off_out), (int32_t*)(d + off_out + 16), nullptr, nullptr, nullptr,
+                                (float*)(d + off_o), d + off_t, nullptr);
+        if (rc) break;
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(o, d + off_o, sizeof(float) * 3 * cells, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(t, d + off_t, 3 * cells, cudaMemcpyDeviceToHost));
+#undef CK
+    } while (0);
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

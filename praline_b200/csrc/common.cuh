@@ -1,0 +1,119 @@
+// common.cuh -- shared declarations of the sm_100a alignment kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+// Alignment modes, numbered as in the reference (praline/util/cext.c:27-31).
+enum { PG_GLOBAL = 0, PG_LOCAL = 1, PG_SG_BOTH = 2, PG_SG_ONE = 3, PG_SG_TWO = 4 };
+
+// Tie flags of the reference traceback (praline/util/cext.c:9-15).  All seven fit one byte,
+// so the debug fill keeps one byte per cell instead of the reference's three.
+enum { TB_MM = 1 << 1, TB_MU = 1 << 2, TB_ML = 1 << 3, TB_UO = 1 << 4, TB_UE = 1 << 5,
+       TB_LO = 1 << 6, TB_LE = 1 << 7 };
+
+// One unit of work of the inter-task kernel: a resident sequence (laid across the lanes of
+// every warp of the CTA) against a contiguous run of streamed sequences.
+struct PgTile {
+    int32_t resident;       // sequence id of the resident sequence
+    int32_t stream_begin;   // [begin, end) into stream_ids (or sequence ids when stream_ids == NULL)
+    int32_t stream_end;
+    int32_t _pad;
+    int64_t out_base;       // output slot of the first streamed sequence; slots are consecutive
+};
+
+struct PgBorder {
+    // Values of the DP borders in the kernel's orientation (columns = resident sequence,
+    // rows = streamed sequence), see reference component/align.py:367-385.
+    float d00;              // max3 of the three states at (0,0)
+    float top0, top1;       // D(0,x) = top0 + x*top1  (x >= 1): the state-L ramp, or 0
+    float left0, left1;     // D(y,0) = left0 + y*left1 (y >= 1): the state-U ramp, or 0
+};
+
+// Arguments of the inter-task streaming kernel (gotoh_stream.cu).
+struct StreamArgs {
+    const uint8_t* seqs;
+    const int64_t* offs;
+    const int32_t* stream_ids;   // NULL: stream element s is sequence id s
+    const PgTile* tiles;
+    const float* S;
+    int A;
+    int transposed;              // resident is the reference's sequence one
+    float go, ge;
+    const float* topD;           // D(0, x), x = 0 .. border_len-1 (kernel orientation)
+    const float* leftD;          // D(y, 0)
+    int border_len;
+    float* scores;               // global / local: one per output slot
+    unsigned long long* rowkey;  // semiglobal: (ordered f32 << 32 | x) of the last row
+    unsigned long long* colkey;  //             (ordered f32 << 32 | y) of the last column
+    uint32_t* tb;                // packed traceback words
+    const int64_t* tb_base;      // word offset per (tile, warp)
+    int32_t* emit_t;             // per slot: step at which the owning lane saw the last row
+    int64_t* pair_tb;            // per slot: word offset of its warp's traceback region
+};
+
+// Arguments of the per-pair traceback walk (traceback.cu).
+struct TraceArgs {
+    int64_t n_slots;
+    int mode, K, transposed;
+    const int64_t* offs;
+    const int32_t* slot_resident;   // sequence id laid across the lanes
+    const int32_t* slot_stream;     // sequence id streamed through
+    const uint32_t* tb;
+    const int32_t* emit_t;
+    const int64_t* pair_tb;
+    const unsigned long long* rowkey;
+    const unsigned long long* colkey;
+    int code00, top_ramp, left_ramp;
+    const int64_t* path_off;        // per slot: first row of its region in path_buf (capacity Lr+Ls+2 rows)
+    int32_t* path_buf;              // [rows][2] = (y, x) in the REFERENCE orientation
+    int32_t* path_start;            // per slot: first used row within its region
+    int32_t* path_len;              // per slot: rows used
+};
+
+// Arguments of the general single-alignment path (general.cu).
+struct GenArgs {
+    int mode, L1, L2;
+    const float* m;  int m_pitch;        // [L1][m_pitch]
+    const float* g1; const float* g2;    // [L1][2], [L2][2]
+    const uint8_t* z; int z_pitch;       // [(L1+1)][z_pitch] or NULL
+    uint8_t* flags;  int f_pitch;        // [(L1+1)][f_pitch], one byte per cell
+    float* o_full;   uint8_t* t_full;    // optional [(L1+1)][(L2+1)][3] (debug / B3 shim)
+    float* edge;                         // [n_strips+1][L1+1][3]
+    int* progress;                       // [n_strips+1]
+    float* top;                          // [3][L2+1]  border row 0
+    float* lastrow;                      // [3][L2+1]
+    float* lastcol;                      // [3][L1+1]
+    unsigned long long* best;            // local mode: (ordered value << 32 | ~linear index)
+    int n_strips;
+    // finalize / traceback outputs
+    float* score_out;                    // [1]
+    int32_t* cell_out;                   // [3] y, x, state
+    int32_t* path_buf;                   // [L1+L2+2][2]
+    int32_t* path_start;                 // [1]
+    int32_t* path_len;                   // [1]
+};
+
+struct ScoreSet { const float* P1; const float* P2; const float* S; int A; };
+
+void pg_set_error(const char* fmt, ...);
+int pg_launch_general(GenArgs a, int kg, cudaStream_t st);
+int pg_launch_build_scores(int n_sets, const ScoreSet* sets_dev, int L1, int L2, float* m, int m_pitch, cudaStream_t st);
+int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,
+                               float* m, int m_pitch, cudaStream_t st);
+int pg_stream_supported_k(int k);
+int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb, cudaStream_t st);
+int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,
+                          int mode, int transposed, float* scores, cudaStream_t st);
+int pg_launch_traceback(const TraceArgs& a, cudaStream_t st);
+
+#define PG_CUDA_OK(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            pg_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                       \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)

@@ -1,0 +1,123 @@
+// microbench.cu -- issue-rate micro-benchmarks behind the DP roofline denominator.
+//
+// the DP fill is bound by CUDA-core instruction issue, and
+// MEASURED_PEAKS.json has no such figure, so the box is probed directly.  Each kernel runs
+// 32 warps per SM, every thread carrying 8 independent dependency chains of one instruction
+// kind, and reports warp-instructions per clock per SM from clock64 deltas on the SM itself.
+#include "common.cuh"
+#include "../../include/praline_b200.h"
+
+#include <vector>
+
+#define CH 8
+#define ITERS 2048
+
+template <int OP>
+__global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin, float* fout, long long* cyc)
+{
+    float f[CH];
+    int v[CH];
+    const float c1 = fin[0], c2 = fin[1];
+    const int i1 = iin[0], i2 = iin[1];
+#pragma unroll
+    for (int i = 0; i < CH; i++) { f[i] = fin[2 + i] + threadIdx.x; v[i] = iin[2 + i] + threadIdx.x; }
+    __shared__ float4 sh[1024];
+    sh[threadIdx.x] = make_float4(c1, c2, c1, c2);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            if (OP == 0) asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+            if (OP == 1) asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+            if (OP == 2) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(c1), "f"(c2));
+            if (OP == 3) {  // the score-only cell: 4 FADD, 2 FMNMX, 1 FMNMX3
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2));
+                asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+                asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2));
+                asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(c1), "f"(c2));
+                asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2));
+            }
+            if (OP == 4) v[i] = __viaddmax_s32(v[i], i1, i2);
+            if (OP == 5) v[i] = (int)__viaddmax_s16x2((unsigned)v[i], (unsigned)i1, (unsigned)i2);
+            if (OP == 6) f[i] = __shfl_up_sync(0xffffffffu, f[i], 1);
+            if (OP == 7) {
+                const float4 q = sh[(threadIdx.x + i + it) & 1023];
+                f[i] += q.x;
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; i++) acc += f[i] + (float)v[i];
+    fout[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+static int run_rate(int sms, const float* fin, const int* iin, float* fout, long long* cyc, double* rate)
+{
+    k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc);   // warm-up
+    k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc);
+    PG_CUDA_OK(cudaGetLastError());
+    PG_CUDA_OK(cudaDeviceSynchronize());
+    std::vector<long long> h(sms);
+    PG_CUDA_OK(cudaMemcpy(h.data(), cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    double mean = 0;
+    for (int i = 0; i < sms; i++) mean += (double)h[i];
+    mean /= sms;
+    const double per_it = (OP == 3) ? 7.0 : 1.0;
+    double extra = (OP == 7) ? 2.0 : 1.0;   // the LDS kernel issues LDS + FADD
+    (void)extra;
+    *rate = 32.0 * CH * ITERS * per_it / mean;   // warp-instructions of the probed kind per clock per SM
+    return 0;
+}
+
+extern "C" int pgpu_microbench(double* out, int n)
+{
+    if (n < 9) { pg_set_error("pgpu_microbench needs room for 9 doubles"); return 1; }
+    int dev = 0, sms = 0, khz = 0;
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    PG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PG_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    float hf[2 + CH] = {0.25f, -0.5f, 1, 2, 3, 4, 5, 6, 7, 8};
+    int hi[2 + CH] = {3, -7, 1, 2, 3, 4, 5, 6, 7, 8};
+    float *fin, *fout;
+    int* iin;
+    long long* cyc;
+    PG_CUDA_OK(cudaMalloc((void**)&fin, sizeof(hf)));
+    PG_CUDA_OK(cudaMalloc((void**)&iin, sizeof(hi)));
+    PG_CUDA_OK(cudaMalloc((void**)&fout, sizeof(float) * sms * 1024));
+    PG_CUDA_OK(cudaMalloc((void**)&cyc, sizeof(long long) * sms));
+    PG_CUDA_OK(cudaMemcpy(fin, hf, sizeof(hf), cudaMemcpyHostToDevice));
+    PG_CUDA_OK(cudaMemcpy(iin, hi, sizeof(hi), cudaMemcpyHostToDevice));
+    int rc = 0;
+    rc |= run_rate<0>(sms, fin, iin, fout, cyc, &out[0]);
+    rc |= run_rate<1>(sms, fin, iin, fout, cyc, &out[1]);
+    rc |= run_rate<2>(sms, fin, iin, fout, cyc, &out[2]);
+    rc |= run_rate<3>(sms, fin, iin, fout, cyc, &out[3]);
+    rc |= run_rate<4>(sms, fin, iin, fout, cyc, &out[4]);
+    rc |= run_rate<5>(sms, fin, iin, fout, cyc, &out[5]);
+    rc |= run_rate<6>(sms, fin, iin, fout, cyc, &out[6]);
+    rc |= run_rate<7>(sms, fin, iin, fout, cyc, &out[7]);
+    // SM clock actually held during a timed burst: cycles (clock64) over wall time (events)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k_rate<3><<<sms, 1024>>>(fin, iin, fout, cyc);
+    cudaEventRecord(e1);
+    PG_CUDA_OK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long c0 = 0;
+    PG_CUDA_OK(cudaMemcpy(&c0, cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+    out[8] = (ms > 0) ? (double)c0 / (ms * 1e3) : (double)khz / 1e3;   // MHz
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(fin); cudaFree(iin); cudaFree(fout); cudaFree(cyc);
+    return rc;
+}

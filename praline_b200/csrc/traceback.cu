@@ -1,0 +1,121 @@
+// traceback.cu -- K4, per-pair traceback walk over the packed nibbles written by K2.
+//
+// Replaces the reference's end-cell choice (praline/component/align.py:401-431), its pointer
+// chase get_paths (praline/util/align.py:144-185) and extend_path_semiglobal
+// (praline/util/align.py:268-297).  One thread walks one pair.
+//
+// K2 stores, per interior cell, 4 bits in kernel orientation (columns = resident sequence):
+//   bits 0-1  first-priority argmax of (M, U, L) AT this cell, as a kernel state
+//             (0 = M, 1 = reached from above, 2 = reached from the left) -- this is the state
+//             the reference's walker enters when it arrives here diagonally, because the
+//             reference's MM > MU > ML flag priority at (y,x) picks the first maximal state of
+//             (y-1,x-1) (exact for integer-valued scores, see gotoh_stream.cu);
+//   bit 2     the from-above state was opened from M (open beats extend on ties);
+//   bit 3     the from-left state was opened from M.
+// Border cells carry no nibble; their flags follow from the border rules of
+// component/align.py:367-385 (ramp borders chain back along the edge, zero borders stop).
+// The path is emitted in the REFERENCE orientation, rows (y, x), written back to front into
+// the pair's region so that no reversal pass is needed.
+#include "common.cuh"
+
+__device__ __forceinline__ float tkey_value(unsigned long long k)
+{
+    uint32_t b = (uint32_t)(k >> 32);
+    b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+    return __uint_as_float(b);
+}
+
+__global__ void k_traceback(const TraceArgs a)
+{
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_slots) return;
+    const int rid = a.slot_resident[slot], sid = a.slot_stream[slot];
+    const int Lr = (int)(a.offs[rid + 1] - a.offs[rid]);   // kernel columns
+    const int Ls = (int)(a.offs[sid + 1] - a.offs[sid]);   // kernel rows
+    const int K = a.K, lr = (Lr - 1) / K;
+    const int emit = a.emit_t[slot];
+    const uint32_t* tbw = a.tb + a.pair_tb[slot];
+    const bool TR = a.transposed != 0;
+    const int L1 = TR ? Lr : Ls, L2 = TR ? Ls : Lr;        // reference lengths
+
+    auto nib_at = [&](int yk, int xk) -> uint32_t {
+        const int lane = (xk - 1) / K, k = (xk - 1) - lane * K;
+        const int step = emit - (Ls - yk) - (lr - lane);
+        const uint32_t w = tbw[(int64_t)(step >> 3) * (K * 32) + k * 32 + lane];
+        return (w >> (4 * (7 - (step & 7)))) & 15u;
+    };
+    auto code_at = [&](int yk, int xk) -> int {
+        if (yk == 0 && xk == 0) return a.code00;
+        if (yk == 0) return 2;
+        if (xk == 0) return 1;
+        return (int)(nib_at(yk, xk) & 3u);
+    };
+
+    // ---- start cell (kernel coordinates) ----------------------------------------------------
+    int yk = Ls, xk = Lr;
+    if (a.mode != PG_GLOBAL) {
+        const unsigned long long rk = a.rowkey[slot], ck = a.colkey[slot];
+        const float rv = tkey_value(rk), cv = tkey_value(ck);
+        const int rx = (int)(uint32_t)rk, cy = (int)(uint32_t)ck;
+        const bool from_row = (a.mode == PG_SG_BOTH || a.mode == PG_SG_TWO);
+        // reference: last row (y = L1) wins only on strict '>' and when allowed; else last column
+        bool take_kernel_row;   // end cell lies on the kernel's last row (yk = Ls)
+        if (!TR) take_kernel_row = (rv > cv) && from_row;
+        else     take_kernel_row = !((cv > rv) && from_row);
+        if (take_kernel_row) { yk = Ls; xk = rx; } else { yk = cy; xk = Lr; }
+    }
+    int s = code_at(yk, xk);
+
+    const int64_t base = a.path_off[slot];
+    const int cap = Lr + Ls + 2;
+    int w = cap;
+    auto push = [&](int yr, int xr) {
+        --w;
+        a.path_buf[2 * (base + w)] = yr;
+        a.path_buf[2 * (base + w) + 1] = xr;
+    };
+
+    if (a.mode != PG_GLOBAL) {  // extend_path_semiglobal, trailing part (util/align.py:283-295)
+        const int ye = TR ? xk : yk, xe = TR ? yk : xk;
+        if (ye != L1) { for (int v = L1; v > ye; v--) push(v, xe); }
+        else if (xe != L2) { for (int v = L2; v > xe; v--) push(ye, v); }
+    }
+
+    for (;;) {
+        push(TR ? xk : yk, TR ? yk : xk);
+        if (yk == 0 && xk == 0) break;
+        if (xk == 0) {
+            if (s == 1 && a.left_ramp) { yk--; continue; }
+            break;
+        }
+        if (yk == 0) {
+            if (s == 2 && a.top_ramp) { xk--; continue; }
+            break;
+        }
+        if (s == 0) {
+            yk--; xk--;
+            s = code_at(yk, xk);
+        } else {
+            const uint32_t nib = nib_at(yk, xk);
+            if (s == 1) { s = ((nib >> 2) & 1u) ? 0 : 1; yk--; }
+            else        { s = ((nib >> 3) & 1u) ? 0 : 2; xk--; }
+        }
+    }
+
+    if (a.mode != PG_GLOBAL) {  // leading part (util/align.py:270-279): rows first, then columns
+        const int y0 = TR ? xk : yk, x0 = TR ? yk : xk;
+        if (y0 != 0) { for (int v = y0 - 1; v >= 0; v--) push(v, 0); }
+        else if (x0 != 0) { for (int v = x0 - 1; v >= 0; v--) push(0, v); }
+    }
+    a.path_start[slot] = w;
+    a.path_len[slot] = cap - w;
+}
+
+int pg_launch_traceback(const TraceArgs& a, cudaStream_t st)
+{
+    if (a.n_slots <= 0) return 0;
+    if (a.mode == PG_LOCAL) { pg_set_error("batched traceback does not cover local mode"); return 1; }
+    k_traceback<<<(unsigned)((a.n_slots + 127) / 128), 128, 0, st>>>(a);
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,462 @@
+"""Host side of the B200 alignment core: tiling, device buffers, C-ABI calls.
+
+PyTorch is used for device memory, streams and (in parallel.py) torch.distributed only; all
+arithmetic of the hot path runs in libpraline_b200.so.  Mirrors what the reference does around
+its C extension in praline/component/align.py (array prep :119-221, border init :357-385,
+end-cell choice and traceback :401-433), but for whole batches of pairs at once.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MODES = {"global": 0, "local": 1, "semiglobal_both": 2, "semiglobal_one": 3, "semiglobal_two": 4}
+
+TILE_DTYPE = np.dtype([("resident", np.int32), ("stream_begin", np.int32), ("stream_end", np.int32),
+                       ("reserved", np.int32), ("out_base", np.int64)])
+
+
+def _gaps(gap_series):
+    """component/align.py:182-189: one value = linear, two = affine, more is an error."""
+    gs = [float(g) for g in gap_series]
+    if len(gs) == 1:
+        return np.float32(gs[0]), np.float32(gs[0])
+    if len(gs) == 2:
+        return np.float32(gs[0]), np.float32(gs[1])
+    raise ValueError("the fast aligner only supports linear and affine gap penalties at the moment")
+
+
+def borders(mode, go, ge, maxlen, transposed=False):
+    """max(M, U, L) along row 0 and column 0 in the kernel's orientation, built with the same
+    numpy arithmetic as the reference (component/align.py:367-385): int64 arange times f32
+    array is f64, plus an f32 scalar, cast to f32 on store."""
+    go, ge = np.float32(go), np.float32(ge)
+    ramp = np.empty(maxlen + 1, np.float32)
+    ramp[1:] = np.arange(maxlen) * np.full(maxlen, ge, np.float32) + go
+    u_zero = mode in (2, 3)
+    l_zero = mode in (2, 4)
+    u00 = np.float32(0) if u_zero else np.float32(go - ge)
+    l00 = np.float32(0) if l_zero else np.float32(go - ge)
+    col_u = np.zeros(maxlen + 1, np.float32) if u_zero else ramp.copy()
+    row_l = np.zeros(maxlen + 1, np.float32) if l_zero else ramp.copy()
+    vals = [np.float32(0), u00, l00]
+    d00 = max(vals)
+    code00 = int(np.argmax(vals))
+    col_u[0] = d00
+    row_l[0] = d00
+    if not transposed:
+        return dict(topD=row_l, leftD=col_u, code00=code00, top_ramp=int(not l_zero), left_ramp=int(not u_zero))
+    return dict(topD=col_u, leftD=row_l, code00={0: 0, 1: 2, 2: 1}[code00], top_ramp=int(not u_zero),
+                left_ramp=int(not l_zero))
+
+
+class SeqBatch(object):
+    """A set of index sequences resident on the device (uint8 symbols + int64 offsets)."""
+
+    def __init__(self, engine, seqs):
+        self.lens = np.asarray([len(s) for s in seqs], np.int64)
+        if len(seqs) == 0 or (self.lens <= 0).any():
+            raise ValueError("empty sequences cannot be aligned")
+        flat = np.concatenate([np.asarray(s) for s in seqs])
+        if flat.min() < 0 or flat.max() > 63:
+            raise ValueError("symbol indices must lie in 0..63")
+        self.n = len(seqs)
+        self.offs = np.zeros(self.n + 1, np.int64)
+        np.cumsum(self.lens, out=self.offs[1:])
+        self.flat_host = torch.from_numpy(flat.astype(np.uint8)).pin_memory() if engine.pin else \
+            torch.from_numpy(flat.astype(np.uint8))
+        self.offs_host = torch.from_numpy(self.offs)
+        self.flat_dev = self.flat_host.to(engine.device, non_blocking=True)
+        self.offs_dev = self.offs_host.to(engine.device, non_blocking=True)
+        self.max_sym = int(flat.max())
+
+    @property
+    def h2d_bytes(self):
+        return self.flat_host.numel() + self.offs_host.numel() * 8
+
+
+class Engine(object):
+    def __init__(self, device=0, pin=True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.PralineGpuError("no CUDA device visible: praline_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        _lib.check(self.lib.pgpu_init(device))
+        self.pin = pin
+        self.nw = self.lib.pgpu_warps_per_tile()
+        self.k_set = [k for k in range(1, 65) if self.lib.pgpu_supported_k(k)]
+        self.launches = 0          # kernels of ours launched (bench.py reports it)
+        self.tb_budget_words = 1 << 30
+        self._borders = {}
+
+    # -- helpers -------------------------------------------------------------------------------
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dev(self, arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if self.pin and t.numel() * t.element_size() >= (1 << 20):
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=True)
+
+    @staticmethod
+    def ptr(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def k_for(self, length):
+        for k in self.k_set:
+            if 32 * k >= length:
+                return k
+        return None
+
+    def batch(self, seqs):
+        return SeqBatch(self, seqs)
+
+    # -- inter-task batch ----------------------------------------------------------------------
+    def _make_tiles(self, res_sorted, n_stream_total, tile):
+        """res_sorted: resident id per stream element, grouped.  -> structured tile array whose
+        out_base equals stream_begin (slot == stream element)."""
+        n = n_stream_total
+        change = np.flatnonzero(np.diff(res_sorted)) + 1
+        starts = np.concatenate([[0], change]).astype(np.int64)
+        ends = np.concatenate([change, [n]]).astype(np.int64)
+        ntile = (ends - starts + tile - 1) // tile
+        grp = np.repeat(np.arange(len(starts)), ntile)
+        first = np.cumsum(ntile) - ntile
+        tb = starts[grp] + (np.arange(int(ntile.sum())) - first[grp]) * tile
+        te = np.minimum(tb + tile, ends[grp])
+        tiles = np.zeros(len(tb), TILE_DTYPE)
+        tiles["resident"] = res_sorted[tb]
+        tiles["stream_begin"] = tb
+        tiles["stream_end"] = te
+        tiles["out_base"] = tb
+        return tiles
+
+    def _tb_words(self, tiles, K, cs):
+        """Traceback words per (tile, warp); cs = prefix sum of stream-element lengths."""
+        nw = self.nw
+        tb_, te_ = tiles["stream_begin"].astype(np.int64), tiles["stream_end"].astype(np.int64)
+        per = (te_ - tb_ + nw - 1) // nw
+        w = np.arange(nw)[None, :]
+        sb = tb_[:, None] + w * per[:, None]
+        se = np.minimum(sb + per[:, None], te_[:, None])
+        sb = np.minimum(sb, se)
+        rows = cs[se] - cs[sb]
+        T = np.where(se > sb, (rows + 1 + 31 + 7) // 8 * 8, 0)
+        return (T // 8) * (K * 32)
+
+    def _pick_tile(self, n_pairs):
+        # enough tiles to fill 148 SMs several times over, but streams of >= 2 sequences per warp
+        spw = 16
+        while spw > 2 and n_pairs // (self.nw * spw) < 148 * 6:
+            spw //= 2
+        return self.nw * spw
+
+    def run_tiles(self, mode, K, transposed, batch, stream_ids_dev, tiles, n_slots, S_dev, A, go, ge,
+                  scores_dev, cs=None, slot_res_dev=None, slot_str_dev=None, want_paths=False, caps=None,
+                  tiles_dev=None):
+        """Launch K2 (+K4) for one K class.  Returns list of (slot_lo, slot_hi, path_off, path_buf,
+        path_start, path_len) per wave when want_paths."""
+        lib = self.lib
+        md = MODES[mode] if isinstance(mode, str) else mode
+        maxlen = max(32 * K, int(batch.lens.max())) + 2
+        bkey = (md, float(go), float(ge), maxlen, bool(transposed))
+        if bkey not in self._borders:
+            B = borders(md, go, ge, maxlen, transposed)
+            self._borders[bkey] = (B, self.dev(B["topD"]), self.dev(B["leftD"]))
+        B, top_dev, left_dev = self._borders[bkey]
+        semi = md != 0   # local and semiglobal results are reduced through the keys scratch
+        out = []
+        if not want_paths:
+            if tiles_dev is None:
+                tiles_dev = self.dev(tiles.view(np.uint8))
+            keys = torch.empty(2 * n_slots, dtype=torch.int64, device=self.device) if semi else None
+            _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
+                                            self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles), n_slots,
+                                            self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
+                                            self.ptr(left_dev), maxlen + 1, self.ptr(scores_dev), self.ptr(keys),
+                                            None, None, None, None, self.stream()))
+            self.launches += 1 + int(semi)
+            return out
+        # traced: waves bounded by the traceback budget; tiles are in slot order
+        words = self._tb_words(tiles, K, cs)
+        per_tile = words.sum(axis=1)
+        lo = 0
+        while lo < len(tiles):
+            acc = np.cumsum(per_tile[lo:])
+            hi = lo + max(1, int(np.searchsorted(acc, self.tb_budget_words, side="right")))
+            wt = tiles[lo:hi].copy()
+            s_lo, s_hi = int(wt["stream_begin"][0]), int(wt["stream_end"][-1])
+            ns = s_hi - s_lo
+            wt["out_base"] -= s_lo
+            wbase = np.zeros(words[lo:hi].size, np.int64)
+            np.cumsum(words[lo:hi].ravel()[:-1], out=wbase[1:])
+            tb = torch.empty(int(words[lo:hi].sum()), dtype=torch.int32, device=self.device)
+            tiles_dev, wbase_dev = self.dev(wt.view(np.uint8)), self.dev(wbase)
+            emit_t = torch.empty(ns, dtype=torch.int32, device=self.device)
+            pair_tb = torch.empty(ns, dtype=torch.int64, device=self.device)
+            keys = torch.empty(2 * ns, dtype=torch.int64, device=self.device) if semi else None
+            sc = scores_dev[s_lo:s_hi]
+            _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
+                                            self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(wt), ns,
+                                            self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
+                                            self.ptr(left_dev), maxlen + 1, self.ptr(sc), self.ptr(keys),
+                                            self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
+                                            self.stream()))
+            cap = caps[s_lo:s_hi]
+            poff = np.zeros(ns, np.int64)
+            np.cumsum(cap[:-1], out=poff[1:])
+            poff_dev = self.dev(poff)
+            pbuf = torch.empty((int(cap.sum()), 2), dtype=torch.int32, device=self.device)
+            pstart = torch.empty(ns, dtype=torch.int32, device=self.device)
+            plen = torch.empty(ns, dtype=torch.int32, device=self.device)
+            _lib.check(lib.pgpu_traceback_tiles(md, K, int(transposed), self.ptr(batch.offs_dev),
+                                                self.ptr(slot_res_dev[s_lo:s_hi]), self.ptr(slot_str_dev[s_lo:s_hi]),
+                                                ns, self.ptr(keys), self.ptr(tb), self.ptr(emit_t), self.ptr(pair_tb),
+                                                B["code00"], B["top_ramp"], B["left_ramp"], self.ptr(poff_dev),
+                                                self.ptr(pbuf), self.ptr(pstart), self.ptr(plen), self.stream()))
+            self.launches += 2 + int(semi)
+            out.append((s_lo, s_hi, poff, pbuf, pstart, plen))
+            lo = hi
+        return out
+
+    def integer_exact(self, S, go, ge, maxlen):
+        """Traced batches derive tie flags from unrounded operands: exact iff all scores are
+        integers small enough that every f32 sum is exact (see gotoh_stream.cu)."""
+        S = np.asarray(S, np.float64)
+        vals = np.concatenate([S.ravel(), [float(go), float(ge)]])
+        if not np.all(vals == np.round(vals)):
+            return False
+        bound = np.abs(S).max() * maxlen + abs(float(go)) + abs(float(ge)) * 2 * maxlen
+        return bound < 2 ** 23
+
+    def align_pairs(self, batch, pi, pj, S, gap_series, mode="global", want_paths=False, resident=None):
+        """Scores (and reference-format paths) of pairs (sequence_one = pi[k], sequence_two = pj[k]).
+
+        Returns np.float32 scores [n] and, if want_paths, a list of int32 [rows, 2] arrays."""
+        md = MODES[mode]
+        go, ge = _gaps(gap_series)
+        pi = np.asarray(pi, np.int64)
+        pj = np.asarray(pj, np.int64)
+        n = len(pi)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        if batch.max_sym >= A:
+            raise ValueError("sequence symbol outside the score matrix")
+        if n == 0:
+            return np.zeros(0, np.float32), ([] if want_paths else None)
+        if want_paths:
+            if md == 1:
+                raise _lib.PralineGpuError("batched local traceback is served by the general kernel")
+            if not self.integer_exact(S, go, ge, int(batch.lens.max())):
+                raise _lib.PralineGpuError("non-integer scores: use align_general for traced alignments")
+        if resident is None:  # share the side with fewer distinct sequences
+            resident = "one" if len(np.unique(pi)) < len(np.unique(pj)) else "two"
+        transposed = resident == "one"
+        res, strm = (pi, pj) if transposed else (pj, pi)
+        kcls = np.asarray([self.k_for(int(l)) or -1 for l in batch.lens])
+        if (kcls[res] < 0).any():
+            raise _lib.PralineGpuError("resident sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
+        order = np.lexsort((np.arange(n), res, kcls[res]))
+        res_s, str_s = res[order], strm[order]
+        S_dev = self.dev(S)
+        stream_ids_dev = self.dev(str_s.astype(np.int32))
+        scores_dev = torch.empty(n, dtype=torch.float32, device=self.device)
+        cs = np.zeros(n + 1, np.int64)
+        np.cumsum(batch.lens[str_s], out=cs[1:])
+        caps = (batch.lens[res_s] + batch.lens[str_s] + 2).astype(np.int64)
+        slot_res_dev = self.dev(res_s.astype(np.int32)) if want_paths else None
+        paths_sorted = [None] * n if want_paths else None
+        kk = kcls[res_s]
+        bounds = np.flatnonzero(np.diff(kk)) + 1
+        tile = self._pick_tile(n)
+        pending = []
+        for a, b in zip(np.concatenate([[0], bounds]), np.concatenate([bounds, [n]])):
+            K = int(kk[a])
+            tiles = self._make_tiles(res_s[a:b], b - a, tile)
+            tiles["stream_begin"] += a
+            tiles["stream_end"] += a
+            tiles["out_base"] += a
+            waves = self.run_tiles(md, K, transposed, batch, stream_ids_dev, tiles, n, S_dev, A, go, ge,
+                                   scores_dev, cs=cs, slot_res_dev=slot_res_dev, slot_str_dev=stream_ids_dev,
+                                   want_paths=want_paths, caps=caps)
+            pending.extend(waves)
+        scores_sorted = scores_dev.cpu().numpy()
+        scores = np.empty(n, np.float32)
+        scores[order] = scores_sorted
+        if not want_paths:
+            return scores, None
+        for (s_lo, s_hi, poff, pbuf, pstart, plen) in pending:
+            pb, ps, pl = pbuf.cpu().numpy(), pstart.cpu().numpy(), plen.cpu().numpy()
+            for k in range(s_hi - s_lo):
+                o = poff[k] + ps[k]
+                paths_sorted[s_lo + k] = pb[o:o + pl[k]]
+        paths = [None] * n
+        for k, o in enumerate(order):
+            paths[o] = paths_sorted[k]
+        return scores, paths
+
+    def allpairs_tiles(self, batch, shard=(0, 1), tile=None):
+        """All unordered pairs (i < j), sequence_one = i resident, sequence_two = j streamed, slots
+        in condensed (np.triu_indices) order.  Returns {K: tiles} for this shard and its slot range."""
+        n = batch.n
+        rank, world = shard
+        tile = tile or self._pick_tile(n * (n - 1) // 2)
+        i = np.arange(n - 1, dtype=np.int64)
+        cnt = n - 1 - i
+        ntile = (cnt + tile - 1) // tile
+        grp = np.repeat(i, ntile)
+        first = np.cumsum(ntile) - ntile
+        tb = grp + 1 + (np.arange(int(ntile.sum())) - first[grp]) * tile
+        te = np.minimum(tb + tile, n)
+        base = grp * n - grp * (grp + 1) // 2 + (tb - grp - 1)
+        cs = np.zeros(n + 1, np.int64)
+        np.cumsum(batch.lens, out=cs[1:])
+        cells = batch.lens[grp] * (cs[te] - cs[tb])
+        cum = np.concatenate([[0], np.cumsum(cells)])
+        cuts = np.searchsorted(cum, cum[-1] * np.arange(world + 1) / world, side="left")
+        cuts[0], cuts[-1] = 0, len(tb)
+        lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+        tiles = np.zeros(hi - lo, TILE_DTYPE)
+        tiles["resident"] = grp[lo:hi]
+        tiles["stream_begin"] = tb[lo:hi]
+        tiles["stream_end"] = te[lo:hi]
+        tiles["out_base"] = base[lo:hi]
+        n_pairs = n * (n - 1) // 2
+        slot_lo = int(base[lo]) if lo < len(tb) else n_pairs
+        slot_hi = int(base[hi]) if hi < len(tb) else n_pairs
+        slot_cuts = [int(base[c]) if c < len(tb) else n_pairs for c in cuts]
+        kk = np.asarray([self.k_for(int(l)) or -1 for l in batch.lens])[tiles["resident"]]
+        if (kk < 0).any():
+            raise _lib.PralineGpuError("sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
+        by_k = {int(K): tiles[kk == K] for K in np.unique(kk)}
+        return by_k, (slot_lo, slot_hi), int(cells[lo:hi].sum()), slot_cuts, {}
+
+    def allpairs_scores(self, batch, S_dev, A, gap_series, mode="global", shard=(0, 1), out=None, plan=None):
+        """Condensed all-vs-all score vector on the device (this shard's slots filled)."""
+        md = MODES[mode]
+        go, ge = _gaps(gap_series)
+        n_pairs = batch.n * (batch.n - 1) // 2
+        if plan is None:
+            plan = self.allpairs_tiles(batch, shard)
+        by_k, rng, cells = plan[0], plan[1], plan[2]
+        cache = plan[4] if len(plan) > 4 else {}
+        if out is None:
+            out = torch.empty(n_pairs, dtype=torch.float32, device=self.device)
+        for K, tiles in by_k.items():
+            if K not in cache:
+                cache[K] = self.dev(tiles.view(np.uint8))
+            self.run_tiles(md, K, True, batch, None, tiles, n_pairs, S_dev, A, go, ge, out, tiles_dev=cache[K])
+        return out, rng, cells
+
+    # -- general single alignment ----------------------------------------------------------------
+    def build_scores(self, P1s, P2s, Ss):
+        """m = sum_sets P1 . S . P2^T on the device, reference evaluation order (cext.c:308-455)."""
+        n = len(P1s)
+        d1 = [self.dev(np.asarray(p, np.float32)) for p in P1s]
+        d2 = [self.dev(np.asarray(p, np.float32)) for p in P2s]
+        ds = [self.dev(np.asarray(s, np.float32)) for s in Ss]
+        L1, L2 = d1[0].shape[0], d2[0].shape[0]
+        m = torch.empty((L1, L2), dtype=torch.float32, device=self.device)
+        arr = ctypes.c_void_p * n
+        A = (ctypes.c_int * n)(*[int(p.shape[1]) for p in d1])
+        _lib.check(self.lib.pgpu_build_scores(n, arr(*[t.data_ptr() for t in d1]), arr(*[t.data_ptr() for t in d2]),
+                                              arr(*[t.data_ptr() for t in ds]), A, L1, L2, self.ptr(m), L2,
+                                              self.stream()))
+        self.launches += 1
+        return m
+
+    def align_general(self, mode, m, g1, g2, zero_idxs=None, want_path=True, want_matrices=False):
+        """One RawPairwiseAligner call (component/align.py:302-447).  m may be a device tensor."""
+        md = MODES[mode]
+        m_dev = m if isinstance(m, torch.Tensor) else self.dev(np.asarray(m, np.float32))
+        L1, L2 = int(m_dev.shape[0]), int(m_dev.shape[1])
+        if L1 < 1 or L2 < 1:
+            raise ValueError("empty sequences cannot be aligned")
+        g1_dev = self.dev(np.asarray(g1, np.float32).reshape(L1, 2))
+        g2_dev = self.dev(np.asarray(g2, np.float32).reshape(L2, 2))
+        z_dev = None
+        if zero_idxs is not None and len(zero_idxs):
+            z = np.zeros((L1 + 1, L2 + 1), np.uint8)
+            for idx in zero_idxs:
+                z[tuple(idx)] = 1
+            z_dev = self.dev(z)
+        ws = torch.empty(int(self.lib.pgpu_general_workspace_bytes(L1, L2)), dtype=torch.uint8, device=self.device)
+        outb = torch.zeros(8, dtype=torch.int32, device=self.device)   # score | cell[3] | start | len
+        pbuf = torch.empty((L1 + L2 + 2, 2), dtype=torch.int32, device=self.device) if want_path else None
+        o = t = None
+        if want_matrices:
+            o = torch.zeros((L1 + 1, L2 + 1, 3), dtype=torch.float32, device=self.device)
+            t = torch.zeros((L1 + 1, L2 + 1, 3), dtype=torch.uint8, device=self.device)
+        base = outb.data_ptr()
+        _lib.check(self.lib.pgpu_align_general(md, L1, L2, self.ptr(m_dev), int(m_dev.stride(0)), self.ptr(g1_dev),
+                                               self.ptr(g2_dev), self.ptr(z_dev), L2 + 1, self.ptr(ws),
+                                               ctypes.c_void_p(base), ctypes.c_void_p(base + 4),
+                                               self.ptr(pbuf), ctypes.c_void_p(base + 16) if want_path else None,
+                                               ctypes.c_void_p(base + 20) if want_path else None,
+                                               self.ptr(o), self.ptr(t), self.stream()))
+        self.launches += 3 + int(want_path)
+        h = outb.cpu()
+        score = float(h[:1].view(torch.float32)[0])
+        res = dict(score=score, cell=tuple(int(v) for v in h[1:4]))
+        if want_path:
+            st, ln = int(h[4]), int(h[5])
+            res["path"] = pbuf[st:st + ln].cpu().numpy()
+        if want_matrices:
+            res["o"], res["t"] = o.cpu().numpy(), t.cpu().numpy()
+        return res
+
+    def build_scores_seq(self, batch, i, j, S_dev, A):
+        """m[y][x] = S[a_y][b_x] for sequences i (rows) and j (columns) of a batch."""
+        L1, L2 = int(batch.lens[i]), int(batch.lens[j])
+        m = torch.empty((L1, L2), dtype=torch.float32, device=self.device)
+        base = batch.flat_dev.data_ptr()
+        _lib.check(self.lib.pgpu_build_scores_seq(ctypes.c_void_p(base + int(batch.offs[i])),
+                                                  ctypes.c_void_p(base + int(batch.offs[j])), self.ptr(S_dev), A,
+                                                  L1, L2, self.ptr(m), L2, self.stream()))
+        self.launches += 1
+        return m
+
+    def align_seq_pair_general(self, batch, i, j, S, gap_series, mode, zero_idxs=None, want_matrices=False):
+        """One PairwiseAligner call through the general kernels (any gaps, masks, local paths)."""
+        go, ge = _gaps(gap_series)
+        S = np.ascontiguousarray(S, np.float32)
+        m = self.build_scores_seq(batch, i, j, self.dev(S), S.shape[0])
+        L1, L2 = int(batch.lens[i]), int(batch.lens[j])
+        g1 = np.empty((L1, 2), np.float32)
+        g2 = np.empty((L2, 2), np.float32)
+        g1[:] = (go, ge)
+        g2[:] = (go, ge)
+        return self.align_general(mode, m, g1, g2, zero_idxs=zero_idxs, want_matrices=want_matrices)
+
+    def fill_debug(self, mode, m, g1, g2, z=None):
+        """B3 shim: host arrays in, the reference's full o and t arrays out."""
+        m = np.ascontiguousarray(m, np.float32)
+        g1 = np.ascontiguousarray(g1, np.float32)
+        g2 = np.ascontiguousarray(g2, np.float32)
+        L1, L2 = m.shape
+        o = np.zeros((L1 + 1, L2 + 1, 3), np.float32)
+        t = np.zeros((L1 + 1, L2 + 1, 3), np.uint8)
+        zc = np.ascontiguousarray(z, np.uint8) if z is not None else None
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(self.lib.pgpu_fill_debug(MODES[mode], vp(m), vp(g1), vp(g2), vp(o), vp(t),
+                                            vp(zc) if zc is not None else None, L1, L2))
+        return o, t
+
+    def microbench(self):
+        out = (ctypes.c_double * 9)()
+        _lib.check(self.lib.pgpu_microbench(out, 9))
+        names = ["fadd", "fmnmx", "fmnmx3", "cell_mix", "viaddmnmx_s32", "viaddmnmx_s16x2", "shfl", "lds128", "sm_mhz"]
+        return dict(zip(names, [float(v) for v in out]))
+
+
+_ENGINES = {}
+
+
+def get_engine(device=0):
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]

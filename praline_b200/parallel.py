@@ -1,0 +1,40 @@
+"""Multi-GPU plumbing of the all-vs-all path: one process per GPU, pairs sharded by equal DP
+cell count (engine.allpairs_tiles), one NCCL all-gather of the per-shard score slices.
+
+The reference's only parallel strategy farms pickled tasks to worker processes
+(praline/core/manager.py:248-463); the pair list shards with no data-path exchange, so the
+only collective is the assembly of the condensed score vector that GuideTreeBuilder turns into
+its distance matrix (praline/component/tree.py:137-147).
+"""
+import torch
+import torch.distributed as dist
+
+
+def allgather_condensed(out, slot_cuts, group=None):
+    """Every rank has filled out[slot_cuts[r]:slot_cuts[r+1]]; after the call every rank holds
+    the complete vector.  Slices are padded to the longest one so that one equal-sized
+    all-gather does the exchange (works for NCCL on GPU and gloo on CPU tensors)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return out
+    rank = dist.get_rank(group)
+    sizes = [slot_cuts[r + 1] - slot_cuts[r] for r in range(world)]
+    width = max(max(sizes), 1)
+    send = torch.zeros(width, dtype=out.dtype, device=out.device)
+    send[:sizes[rank]] = out[slot_cuts[rank]:slot_cuts[rank + 1]]
+    recv = torch.empty(world * width, dtype=out.dtype, device=out.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    for r in range(world):
+        if r != rank and sizes[r]:
+            out[slot_cuts[r]:slot_cuts[r + 1]] = recv[r * width:r * width + sizes[r]]
+    return out
+
+
+def scores_to_distance(cond, n):
+    """Condensed scores -> the distance matrix of GuideTreeBuilder (tree.py:98-147):
+    d[i][j] = d[j][i] = score, diagonal MINUS_INFINITY = -(2**32), dist = -d + d.max()."""
+    d = torch.full((n, n), float(-(2 ** 32)), dtype=torch.float32, device=cond.device)
+    iu = torch.triu_indices(n, n, offset=1, device=cond.device)
+    d[iu[0], iu[1]] = cond
+    d[iu[1], iu[0]] = cond
+    return (-d) + d.max()

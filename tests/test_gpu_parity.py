@@ -1,0 +1,218 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden vectors.
+All tests here need a B200; they are the parity tests proper."""
+import numpy as np
+import pytest
+
+import oracle
+from praline_b200 import matrices, synth
+from conftest import MODES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from praline_b200 import get_engine
+    return get_engine(0)
+
+
+def _check_batch(eng, seqs, pi, pj, S, gaps, mode, resident, paths=True):
+    batch = eng.batch(seqs)
+    flat, offs = synth.pack(seqs)
+    if mode == "local":
+        paths = False
+    scores, got_paths = eng.align_pairs(batch, pi, pj, S, gaps, mode=mode, want_paths=paths, resident=resident)
+    if paths:
+        want, want_paths = oracle.align_batch(mode, flat, offs, pi, pj, S, gaps, want_paths=True)
+    else:
+        want = oracle.align_batch(mode, flat, offs, pi, pj, S, gaps)
+    assert np.array_equal(scores, want), (mode, gaps, resident)
+    if paths:
+        for k, (a, b) in enumerate(zip(got_paths, want_paths)):
+            assert np.array_equal(a, b), (mode, gaps, resident, k)
+
+
+def test_golden_sequence_cases(eng, golden_seq, golden_mats):
+    """Every golden vector of the reference's PairwiseAligner, one pair per call."""
+    for c in golden_seq:
+        S = golden_mats["blosum62"] if c["alphabet"] == "aa" else golden_mats["nucleotide"]
+        batch = eng.batch([np.asarray(c["a"]), np.asarray(c["b"])])
+        integer = all(float(g).is_integer() for g in c["gaps"])
+        if c["zero_idxs"] is None and c["mode"] != "local" and integer:
+            for resident in ("one", "two"):
+                scores, paths = eng.align_pairs(batch, [0], [1], S, c["gaps"], mode=c["mode"], want_paths=True,
+                                                resident=resident)
+                assert float(scores[0]) == c["score"], (c["name"], c["mode"], resident)
+                assert paths[0].tolist() == c["path"], (c["name"], c["mode"], resident)
+        if c["zero_idxs"] is None:
+            for resident in ("one", "two"):
+                scores, _ = eng.align_pairs(batch, [0], [1], S, c["gaps"], mode=c["mode"], resident=resident)
+                assert float(scores[0]) == c["score"], (c["name"], c["mode"], resident)
+        zero = None if c["zero_idxs"] is None else [tuple(z) for z in c["zero_idxs"]]
+        r = eng.align_seq_pair_general(batch, 0, 1, S, c["gaps"], c["mode"], zero_idxs=zero)
+        assert r["score"] == c["score"], (c["name"], c["mode"])
+        assert r["path"].tolist() == c["path"], (c["name"], c["mode"])
+
+
+@pytest.mark.parametrize("resident", ["one", "two"])
+@pytest.mark.parametrize("mode", MODES)
+def test_batches_vs_oracle(eng, mode, resident):
+    S = matrices.blosum62()
+    rng = np.random.default_rng(5)
+    for trial, (n, length, gaps) in enumerate([(24, 37, [-11.0, -1.0]), (16, 150, [-8.0]), (12, 300, [-11.0, -1.0]),
+                                               (10, 90, [-1.0, -1.0]), (8, 420, [-4.0, -2.0])]):
+        seqs = synth.family(300 + trial, n, length)
+        seqs += [rng.integers(0, 20, int(rng.integers(1, 2 * length))).astype(np.int32) for _ in range(4)]
+        pi, pj = synth.all_pairs(len(seqs))
+        if trial % 2:   # ordered pairs both ways and self pairs
+            pi, pj = np.concatenate([pi, pj[:20], np.arange(5)]), np.concatenate([pj, pi[:20], np.arange(5)])
+        _check_batch(eng, seqs, pi, pj, S, gaps, mode, resident)
+
+
+def test_mixed_length_classes(eng):
+    """Pairs whose resident sequences fall in different K classes in one call."""
+    S = matrices.blosum62()
+    seqs = []
+    for k, length in enumerate([5, 33, 70, 129, 200, 260, 330, 390, 450, 600, 700, 900]):
+        seqs += synth.family(500 + k, 2, length)
+    pi, pj = synth.all_pairs(len(seqs))
+    for mode in ("global", "semiglobal_both"):
+        _check_batch(eng, seqs, pi, pj, S, [-11.0, -1.0], mode, None)
+
+
+def test_dna_and_asymmetric_matrix(eng):
+    S = matrices.nucleotide().copy()
+    S[0, 1] = 3.0   # break symmetry: catches a transposed profile lookup
+    seqs = synth.family(9, 10, 80, n_sym=4)
+    pi, pj = synth.all_pairs(len(seqs))
+    for resident in ("one", "two"):
+        for mode in ("global", "semiglobal_one", "semiglobal_two"):
+            _check_batch(eng, seqs, pi, pj, S, [-5.0, -2.0], mode, resident)
+
+
+def test_allpairs_condensed(eng):
+    S = matrices.blosum62()
+    seqs = synth.family(21, 70, 64) + synth.family(22, 9, 140)
+    batch = eng.batch(seqs)
+    flat, offs = synth.pack(seqs)
+    pi, pj = synth.all_pairs(len(seqs))
+    for mode in ("global", "semiglobal_both", "local"):
+        out, rng, cells = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode=mode)
+        want = oracle.align_batch(mode, flat, offs, pi, pj, S, [-11.0, -1.0])
+        assert np.array_equal(out.cpu().numpy(), want), mode
+        assert cells == int((batch.lens[pi] * batch.lens[pj]).sum())
+    # shards tile the condensed vector without gaps or overlap
+    full = out.cpu().numpy()
+    acc = np.full_like(full, np.nan)
+    for r in range(3):
+        o, (lo, hi), _ = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode="local", shard=(r, 3))
+        acc[lo:hi] = o.cpu().numpy()[lo:hi]
+    assert np.array_equal(acc, full)
+
+
+def test_fill_debug_matches_golden_cells(eng, golden_cells):
+    for c in golden_cells:
+        mode = MODES[int(c["mode"])]
+        o, t = eng.fill_debug(mode, c["m"], c["g1"], c["g2"], c["z"] if c["z"].any() else None)
+        assert np.array_equal(o, c["o"]), mode
+        assert np.array_equal(t, c["t"]), mode
+        zero = [tuple(i) for i in np.argwhere(c["z"] != 0)]
+        r = eng.align_general(mode, c["m"], c["g1"], c["g2"], zero_idxs=zero)
+        assert r["score"] == float(c["score"])
+        assert np.array_equal(r["path"], c["path"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_general_random_vs_oracle(eng, mode):
+    rng = np.random.default_rng(11)
+    for trial, (L1, L2) in enumerate([(1, 1), (1, 40), (50, 1), (63, 65), (130, 257), (300, 90), (40, 700)]):
+        if trial % 2:
+            m = rng.integers(-4, 12, (L1, L2)).astype(np.float32)
+            g1, g2 = oracle.gap_arrays(L1, L2, [[-11.0, -1.0], [-3.0]][trial % 4 // 2])
+        else:
+            m = (rng.standard_normal((L1, L2)) * 3).astype(np.float32)
+            g1, g2 = oracle.gap_arrays(L1, L2, [-4.25, -0.625])
+            g1 = (g1 * rng.uniform(0.5, 1.5, g1.shape)).astype(np.float32)   # per-position gaps
+            g2 = (g2 * rng.uniform(0.5, 1.5, g2.shape)).astype(np.float32)
+        zero = None
+        if trial in (3, 4):
+            zero = [(int(rng.integers(1, L1 + 1)), int(rng.integers(1, L2 + 1))) for _ in range(30)]
+        r = eng.align_general(mode, m, g1, g2, zero_idxs=zero, want_matrices=True)
+        o, t, z = oracle.fill(mode, m, g1, g2, zero)
+        assert np.array_equal(r["o"], o), (mode, trial)
+        assert np.array_equal(r["t"], t), (mode, trial)
+        ws, wp = oracle.align_raw(mode, m, g1, g2, zero_idxs=zero)
+        assert r["score"] == ws, (mode, trial)
+        assert np.array_equal(r["path"], wp), (mode, trial)
+
+
+def test_profiles_vs_golden(eng, golden_prof, golden_mats):
+    for c in golden_prof:
+        A = int(c["alphabet"])
+        S = golden_mats["blosum62"] if A == 27 else golden_mats["nucleotide"]
+        p1 = synth.profile_from_counts(c["counts1"])
+        p2 = synth.profile_from_counts(c["counts2"])
+        m = eng.build_scores([p1], [p2], [S])
+        assert np.array_equal(m.cpu().numpy(), c["m"])      # bit-exact, reference evaluation order
+        g1, g2 = oracle.gap_arrays(p1.shape[0], p2.shape[0], list(c["gaps"]))
+        r = eng.align_general(MODES[int(c["mode"])], m, g1, g2)
+        assert abs(r["score"] - float(c["score"])) <= 1e-5 * max(1.0, abs(float(c["score"])))  # stated tolerance
+        assert r["score"] == float(c["score"])                                               # and in fact exact
+        assert np.array_equal(r["path"], c["path"])
+
+
+def test_two_track_sets(eng):
+    rng = np.random.default_rng(3)
+    S1, S2 = matrices.blosum62(), rng.standard_normal((15, 15)).astype(np.float32)
+    p1 = synth.profile_from_counts(synth.count_profile(1, 33, 5, 20, 27))
+    p2 = synth.profile_from_counts(synth.count_profile(2, 47, 7, 20, 27))
+    q1 = synth.profile_from_counts(synth.count_profile(3, 33, 3, 4, 15))
+    q2 = synth.profile_from_counts(synth.count_profile(4, 47, 2, 4, 15))
+    m = eng.build_scores([p1, q1], [p2, q2], [S1, S2]).cpu().numpy()
+    assert np.array_equal(m, oracle.build_scores([p1, q1], [p2, q2], [S1, S2]))
+
+
+def test_full_size_properties(eng):
+    """BASELINE config 2 shape (1,000 x 300 aa): properties that need no oracle pass, plus a
+    sample of pairs checked against the oracle."""
+    S = matrices.blosum62()
+    seqs = synth.family(2, 1000, 300)
+    batch = eng.batch(seqs)
+    n = len(seqs)
+    out, _, cells = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode="global")
+    full = out.cpu().numpy()
+    pi, pj = synth.all_pairs(n)
+    assert cells == int((batch.lens[pi] * batch.lens[pj]).sum())
+    # (1) the other orientation (resident = sequence two) gives the same scores
+    rng = np.random.default_rng(0)
+    pick = rng.choice(len(pi), 4000, replace=False)
+    s2, _ = eng.align_pairs(batch, pi[pick], pj[pick], S, [-11.0, -1.0], mode="global", resident="two")
+    assert np.array_equal(s2, full[pick])
+    # (2) global alignment score is symmetric for a symmetric matrix
+    s3, _ = eng.align_pairs(batch, pj[pick], pi[pick], S, [-11.0, -1.0], mode="global")
+    assert np.array_equal(s3, full[pick])
+    # (3) a sequence against itself scores the sum of its diagonal substitution scores
+    ii = np.arange(0, n, 7)
+    s4, p4 = eng.align_pairs(batch, ii, ii, S, [-11.0, -1.0], mode="global", want_paths=True)
+    assert np.array_equal(s4, np.asarray([S[seqs[i], seqs[i]].sum() for i in ii], np.float32))
+    assert all(np.array_equal(p, np.stack([np.arange(len(seqs[i]) + 1)] * 2, 1)) for p, i in zip(p4, ii))
+    # (4) oracle on a sample, with paths
+    flat, offs = synth.pack(seqs)
+    sm = pick[:300]
+    want, wpaths = oracle.align_batch("global", flat, offs, pi[sm], pj[sm], S, [-11.0, -1.0], want_paths=True)
+    assert np.array_equal(full[sm], want)
+    got, gpaths = eng.align_pairs(batch, pi[sm], pj[sm], S, [-11.0, -1.0], mode="global", want_paths=True)
+    assert np.array_equal(got, want)
+    assert all(np.array_equal(a, b) for a, b in zip(gpaths, wpaths))
+    # (5) a traced path re-scores to the reported score
+    for k in range(0, 300, 37):
+        a, b, p = seqs[pi[sm[k]]], seqs[pj[sm[k]]], gpaths[k]
+        sc, gap = 0.0, None
+        for (y0, x0), (y1, x1) in zip(p[:-1], p[1:]):
+            if y1 > y0 and x1 > x0:
+                sc += S[a[y1 - 1], b[x1 - 1]]; gap = None
+            else:
+                kind = "u" if y1 > y0 else "l"
+                sc += -1.0 if gap == kind else -11.0
+                gap = kind
+        assert sc == got[k]

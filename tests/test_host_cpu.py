@@ -1,0 +1,118 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, and the host
+tiling logic (no kernel is launched here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from praline_b200 import _lib, synth
+from praline_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "praline_b200.h")).read()
+    declared = set(re.findall(r"\b(pgpu_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().pgpu_abi_version() == 1
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.PralineGpuError):
+        E.Engine(0)
+    assert _lib.load().pgpu_init(0) != 0
+    assert b"CUDA" in _lib.load().pgpu_last_error() or b"device" in _lib.load().pgpu_last_error()
+
+
+def test_gap_series_rules():
+    assert E._gaps([-8.0]) == (np.float32(-8), np.float32(-8))
+    assert E._gaps([-11.0, -1.0]) == (np.float32(-11), np.float32(-1))
+    with pytest.raises(ValueError):
+        E._gaps([-11.0, -2.0, -1.0])
+
+
+def test_borders_match_reference_init():
+    import oracle
+    for mode, name in enumerate(["global", "local", "semiglobal_both", "semiglobal_one", "semiglobal_two"]):
+        g1, g2 = oracle.gap_arrays(40, 40, [-11.0, -1.0])
+        o, t = oracle.ref_init_borders(name, g1, g2, 40, 40)
+        B = E.borders(mode, -11.0, -1.0, 40, transposed=False)
+        assert np.array_equal(B["topD"], o[0].max(axis=1))
+        assert np.array_equal(B["leftD"], o[:, 0].max(axis=1))
+        Bt = E.borders(mode, -11.0, -1.0, 40, transposed=True)
+        assert np.array_equal(Bt["topD"], B["leftD"]) and np.array_equal(Bt["leftD"], B["topD"])
+        assert B["top_ramp"] == int(t[0, 1, 2] != 0) and B["left_ramp"] == int(t[1, 0, 1] != 0)
+
+
+class _FakeEngine(E.Engine):
+    def __init__(self):
+        self.nw = 8
+        self.k_set = [1, 2, 3, 4, 6, 8, 10, 12, 13, 14, 16, 20, 24, 32]
+        self.pin = False
+
+
+def test_tiles_cover_every_pair_once():
+    eng = _FakeEngine()
+    rng = np.random.default_rng(0)
+    res = np.sort(rng.integers(0, 30, 5000))
+    tiles = eng._make_tiles(res, len(res), 48)
+    seen = np.zeros(len(res), int)
+    for t in tiles:
+        assert t["stream_end"] - t["stream_begin"] <= 48 and t["out_base"] == t["stream_begin"]
+        assert (res[t["stream_begin"]:t["stream_end"]] == t["resident"]).all()
+        seen[t["stream_begin"]:t["stream_end"]] += 1
+    assert (seen == 1).all()
+
+
+def test_allpairs_tiles_partition_condensed_vector():
+    eng = _FakeEngine()
+
+    class B(object):
+        pass
+    for n, world in [(2, 1), (37, 1), (37, 4), (200, 8)]:
+        b = B()
+        b.n = n
+        b.lens = np.random.default_rng(n).integers(20, 400, n).astype(np.int64)
+        pi, pj = synth.all_pairs(n)
+        seen = np.zeros(n * (n - 1) // 2, int)
+        tot = 0
+        prev_hi = 0
+        for r in range(world):
+            by_k, (lo, hi), cells, cuts, _ = eng.allpairs_tiles(b, (r, world), tile=16)
+            assert lo == prev_hi
+            prev_hi = hi
+            tot += cells
+            for K, tiles in by_k.items():
+                for t in tiles:
+                    i = t["resident"]
+                    assert 32 * K >= b.lens[i]
+                    for s in range(t["stream_begin"], t["stream_end"]):
+                        slot = t["out_base"] + s - t["stream_begin"]
+                        assert pi[slot] == i and pj[slot] == s and lo <= slot < hi
+                        seen[slot] += 1
+        assert prev_hi == len(seen) and (seen == 1).all()
+        assert tot == int((b.lens[pi] * b.lens[pj]).sum())
+
+
+def test_tb_words_formula():
+    eng = _FakeEngine()
+    lens = np.asarray([5, 7, 3, 9, 4, 4, 6, 8, 2, 10, 11], np.int64)
+    cs = np.concatenate([[0], np.cumsum(lens)])
+    tiles = np.zeros(1, E.TILE_DTYPE)
+    tiles["stream_begin"], tiles["stream_end"] = 0, 11
+    w = eng._tb_words(tiles, 3, cs)[0]
+    per = 2
+    for k in range(8):
+        sb, se = min(k * per, 11), min(k * per + per, 11)
+        rows = lens[sb:se].sum()
+        T = (rows + 1 + 31 + 7) // 8 * 8 if se > sb else 0
+        assert w[k] == T // 8 * 3 * 32
