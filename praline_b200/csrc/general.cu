@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
             // lane 0 needs rows up to y of the left strip; wait for the producer
             int need = min(t + 1, L1);
             if (avail < need) {
-                if (lane == 0) { while ((avail = *pin) < need) { __nanosleep(20); } }
+                if (lane == 0) {
+                    // bounded spin: a protocol bug must fail a test, not hang the GPU
+                    for (long long spins = 0; (avail = *pin) < need && spins < (1ll << 26); spins++) __nanosleep(32);
+                }
                 avail = __shfl_sync(FULL, avail, 0);
                 __threadfence();
             }

@@ -1,0 +1,467 @@
+"""PRALINE plug-in: GPU pairwise aligner components and a batching manager.
+
+Drop-in boundary.  Needs the `praline` package (the reference) importable; it
+is not imported by praline_b200 itself.
+
+B1  GpuPairwiseAligner / GpuRawPairwiseAligner carry the SAME type ids, ports, options and
+    defaults as the reference's PairwiseAligner / RawPairwiseAligner
+    (praline/component/align.py:75-86, 289-300), raise the same ComponentError / DataError
+    for the same conditions (:114-189, :319-341) and return the same container types
+    (Alignment with a list-of-tuples path for global/local, an int ndarray for semiglobal,
+    :401-433; score a Python float).  Registering them in a TypeIndex replaces the CPU
+    aligners for every caller that resolves env['aligner'] (preprofile.py:129, tree.py:117,
+    msa.py:175,421,529).
+B2  GpuBatchManager(Manager).execute_many (praline/core/manager.py:154-170) sees the whole
+    list of requests of one Execution (execution.py:164-175).  PairwiseAligner requests on
+    sequence tracks are aligned by ONE batched kernel launch per group; everything else goes
+    through the stock Manager path.  N GlobalMasterSlaveAligner requests
+    (workflow.py:139-161) are flattened into one N(N-1) ordered-pair batch.
+
+All arithmetic runs in libpraline_b200.so; without a GPU these components raise.
+"""
+from __future__ import division, absolute_import, print_function
+
+import numpy as np
+
+from praline.core import (Component, Port, Environment, Execution, Manager, T, BeginMessage, CompleteMessage,
+                          ProgressMessage, LogMessage, ComponentError, DataError, LogBundle, ROOT_LOG_NAME,
+                          path_to_url)
+from praline.container import (Sequence, Alignment, ScoreMatrix, PlainTrack, ProfileTrack, MatchScoreModel,
+                               GapScoreModel)
+from praline.util import compress_path
+
+from . import _lib
+from .engine import get_engine, MODES
+
+PAIRWISE_TID = "praline.component.PairwiseAligner"
+RAW_TID = "praline.component.RawPairwiseAligner"
+GLOBAL_MS_TID = "praline.component.GlobalMasterSlaveAligner"
+
+
+def _path_container(mode, path):
+    """Reference container types: list of 2-tuples for global/local (util/align.py:183), int
+    ndarray for the semiglobal modes (component/align.py:425-426)."""
+    if mode in ("global", "local"):
+        return [(int(y), int(x)) for y, x in path]
+    return np.asarray(path, dtype=int)
+
+
+class LazyAlignment(Alignment):
+    """An Alignment whose path is produced on first access.  GuideTreeBuilder only reads the
+    score of its N(N-1)/2 alignments (tree.py:142-145), so the batched path is score-only
+    until somebody asks for a path; the first access traces the whole batch at once."""
+    tid = Alignment.tid
+
+    def __init__(self, items, resolver, key):
+        self.items = items
+        self._resolver = resolver
+        self._key = key
+        self._path = None
+
+    @property
+    def path(self):
+        if self._path is None:
+            self._path = self._resolver(self._key)
+            self._resolver = None
+        return self._path
+
+    @path.setter
+    def path(self, value):
+        self._path = value
+
+    def __reduce__(self):
+        return (Alignment, (self.items, self.path))
+
+
+def _seq_like(track):
+    """Index sequence of a track if it is a plain track or a one-symbol-per-column profile
+    (then P.S.P^T is exactly S[a][b], cext.c:84-89), else None."""
+    if track.tid == PlainTrack.tid:
+        return np.asarray(track.values)
+    if track.tid == ProfileTrack.tid:
+        counts = track.counts
+        if counts.ndim == 2 and counts.shape[0] > 0 and ((counts != 0).sum(axis=1) == 1).all() and (counts >= 0).all():
+            return np.argmax(counts != 0, axis=1).astype(np.int32)
+    return None
+
+
+def _prepare(sequence_one, sequence_two, track_id_sets_one, track_id_sets_two, score_matrices, gap_series):
+    """The checks and array preparation of PairwiseAligner.execute (component/align.py:114-189),
+    same exceptions, same messages.  Returns (sets, gaps) with sets = [(track1, track2, S)]."""
+    if len(track_id_sets_one) != len(track_id_sets_two):
+        raise ComponentError("should have an identical number of track id sets"
+                             "for both sequences")
+    sets = []
+    for n, (track_ids_one, track_ids_two) in enumerate(zip(track_id_sets_one, track_id_sets_two)):
+        score_matrix = score_matrices[n]
+        if len(track_ids_one) != 1 or len(track_ids_two) != 1:
+            raise ComponentError("the fast aligner only supports single-track"
+                                 " alignments at the moment")
+        total = len(track_ids_one) + len(track_ids_two)
+        if score_matrix.matrix.ndim != total:
+            s = "the score matrix must consist of as many dimensions as" \
+                "there are tracks to be aligned ({0}), but it contains " \
+                "{1}"
+            raise ComponentError(s.format(total, score_matrix.matrix.ndim))
+        track_one = sequence_one.get_track(track_ids_one[0])
+        track_two = sequence_two.get_track(track_ids_two[0])
+        if score_matrix.alphabets[0].aid != track_one.alphabet.aid:
+            s = "track {0} for sequence one has alphabet '{1}' but " \
+                "the corresponding dimension in the score matrix " \
+                "has alphabet '{2}'"
+            raise DataError(s.format(0, track_one.alphabet.aid, score_matrix.alphabets[0].aid))
+        if score_matrix.alphabets[1].aid != track_two.alphabet.aid:
+            s = "track {0} for sequence two has alphabet '{1}' but " \
+                "the corresponding dimension in the score matrix " \
+                "has alphabet '{2}'"
+            raise DataError(s.format(0, track_two.alphabet.aid, score_matrix.alphabets[1].aid))
+        for track in (track_one, track_two):
+            if track.tid not in (PlainTrack.tid, ProfileTrack.tid):
+                raise DataError("unknown track type id for this aligner: '{0}'".format(track.tid))
+        sets.append((track_one, track_two, score_matrix))
+    if len(gap_series) == 1:
+        gaps = [gap_series[0], gap_series[0]]
+    elif len(gap_series) == 2:
+        gaps = list(gap_series)
+    else:
+        raise ComponentError("the fast aligner only supports linear and affine gap"
+                             " penalties at the moment")
+    return sets, gaps
+
+
+def _profile_of(track):
+    """component/align.py:163-172: one-hot f32 for plain tracks, .profile as f32 for profiles."""
+    if track.tid == PlainTrack.tid:
+        p = np.zeros((len(track), track.alphabet.size), dtype=np.float32)
+        p[np.arange(len(track)), track.values] = 1.0
+        return p
+    return track.profile.astype(np.float32)
+
+
+def _check_mode(mode):
+    if mode not in MODES:
+        raise ComponentError("unknown alignment mode: '{0}'".format(mode))
+
+
+def _batchable(sets, gaps, zero_idxs, mode, engine):
+    """One sequence-like track set, no mask, integer-exact scores: the inter-task kernel."""
+    if len(sets) != 1 or zero_idxs:
+        return None
+    t1, t2, sm = sets[0]
+    a, b = _seq_like(t1), _seq_like(t2)
+    if a is None or b is None:
+        return None
+    S = sm.matrix.astype(np.float32)
+    longest = max(len(a), len(b))
+    if engine.k_for(longest) is None or not engine.integer_exact(S, gaps[0], gaps[1], longest):
+        return None
+    return a, b, S
+
+
+class GpuPairwiseAligner(Component):
+    """GPU drop-in for praline.component.PairwiseAligner (component/align.py:37-251)."""
+    tid = PAIRWISE_TID
+    inputs = {'mode': Port(str),
+              'sequence_one': Port(Sequence.tid),
+              'sequence_two': Port(Sequence.tid),
+              'track_id_sets_one': Port([[str]]),
+              'track_id_sets_two': Port([[str]]),
+              'zero_idxs': Port([(int, int)], optional=True),
+              'score_matrices': Port([ScoreMatrix.tid])}
+    outputs = {'alignment': Port(Alignment.tid), 'score': Port(float)}
+    options = {'gap_series': [float], 'debug': int}
+    defaults = {'gap_series': [-11.0, -1.0], 'debug': 0}
+
+    def execute(self, mode, sequence_one, sequence_two, track_id_sets_one, track_id_sets_two, zero_idxs,
+                score_matrices):
+        gap_series = self.environment['gap_series']
+        debug = self.environment['debug']
+        sets, gaps = _prepare(sequence_one, sequence_two, track_id_sets_one, track_id_sets_two, score_matrices,
+                              gap_series)
+        _check_mode(mode)
+        eng = get_engine()
+        hit = _batchable(sets, gaps, zero_idxs, mode, eng) if (debug == 0 and mode != "local") else None
+        if hit is not None:
+            a, b, S = hit
+            batch = eng.batch([a, b])
+            scores, paths = eng.align_pairs(batch, [0], [1], S, gaps, mode=mode, want_paths=True, resident="two")
+            score, path = float(scores[0]), paths[0]
+            alignment = Alignment([sequence_one, sequence_two], _path_container(mode, path))
+            yield CompleteMessage(outputs={'alignment': alignment, 'score': score})
+            return
+        # general path: score models on the device, then the raw aligner (component/align.py:200-237)
+        m = eng.build_scores([_profile_of(t1) for t1, _, _ in sets], [_profile_of(t2) for _, t2, _ in sets],
+                             [sm.matrix.astype(np.float32) for _, _, sm in sets])
+        L1, L2 = int(m.shape[0]), int(m.shape[1])
+        g1 = np.empty((L1, 2), dtype=np.float32)
+        g2 = np.empty((L2, 2), dtype=np.float32)
+        g1[:] = gaps
+        g2[:] = gaps
+        execution = Execution(self.manager, self.tag)
+        task = execution.add_task(GpuRawPairwiseAligner)
+        task.environment(self.environment)
+        task.inputs(mode=mode, sequence_one=sequence_one, sequence_two=sequence_two,
+                    match_score_model=DeviceMatchScoreModel(sequence_one, sequence_two, m),
+                    gap_score_model_one=GapScoreModel(sequence_one, g1),
+                    gap_score_model_two=GapScoreModel(sequence_two, g2), zero_idxs=zero_idxs)
+        for msg in execution.run():
+            yield msg
+        yield CompleteMessage(outputs=execution.outputs[0])
+
+
+class DeviceMatchScoreModel(MatchScoreModel):
+    """A MatchScoreModel whose scores stay on the device between the score-matrix kernel and the
+    fill (the reference materialises them on the host, component/align.py:205-219)."""
+    tid = MatchScoreModel.tid
+
+    def __init__(self, sequence_one, sequence_two, scores_dev):
+        if len(sequence_one) != scores_dev.shape[0]:
+            s = "sequence length {0} does not correspond to array shape {1}"
+            raise DataError(s.format(len(sequence_one), scores_dev.shape[0]))
+        if len(sequence_two) != scores_dev.shape[1]:
+            s = "sequence length {0} does not correspond to array shape {1}"
+            raise DataError(s.format(len(sequence_two), scores_dev.shape[1]))
+        self.sequence_one = sequence_one
+        self.sequence_two = sequence_two
+        self.scores_dev = scores_dev
+
+    @property
+    def scores(self):
+        return self.scores_dev.cpu().numpy()
+
+
+class GpuRawPairwiseAligner(Component):
+    """GPU drop-in for praline.component.RawPairwiseAligner (component/align.py:254-447)."""
+    tid = RAW_TID
+    inputs = {'mode': Port(str),
+              'sequence_one': Port(Sequence.tid),
+              'sequence_two': Port(Sequence.tid),
+              'match_score_model': Port(MatchScoreModel.tid),
+              'gap_score_model_one': Port(GapScoreModel.tid),
+              'gap_score_model_two': Port(GapScoreModel.tid),
+              'zero_idxs': Port([(int, int)], optional=True)}
+    outputs = {'alignment': Port(Alignment.tid), 'score': Port(float)}
+    options = {'debug': int, 'accelerate': bool}
+    defaults = {'debug': 0, 'accelerate': True}
+
+    def execute(self, mode, sequence_one, sequence_two, match_score_model, gap_score_model_one,
+                gap_score_model_two, zero_idxs):
+        debug = self.environment['debug']
+        if debug > 0:
+            log = LogBundle()
+            log.message(ROOT_LOG_NAME, "Entering component '{0}'".format(self.tid))
+            log.message(ROOT_LOG_NAME, "Alignment mode: '{0}'".format(mode))
+            msg = "Sequence one: '{0}', sequence two: '{1}'"
+            log.message(ROOT_LOG_NAME, msg.format(sequence_one.name, sequence_two.name))
+        _check_mode(mode)
+        eng = get_engine()
+        m = getattr(match_score_model, "scores_dev", None)
+        if m is None:
+            m = np.ascontiguousarray(match_score_model.scores, dtype=np.float32)
+        r = eng.align_general(mode, m, gap_score_model_one.scores, gap_score_model_two.scores,
+                              zero_idxs=zero_idxs, want_matrices=debug > 1)
+        if debug > 1:   # component/align.py:390-399
+            log.message(ROOT_LOG_NAME, "Dumping DP & traceback matrices...")
+            for k in range(3):
+                np.savetxt(log.path("dp_{0}_matrix.csv".format(k)), r["o"][:, :, k], delimiter=",")
+                np.savetxt(log.path("tb_{0}_matrix.csv".format(k)), r["t"][:, :, k], delimiter=",")
+        alignment = Alignment([sequence_one, sequence_two], _path_container(mode, r["path"]))
+        outputs = {'alignment': alignment, 'score': float(r["score"])}
+        if debug > 0:
+            log.message(ROOT_LOG_NAME, "Alignment score: {0}".format(r["score"]))
+            log.message(ROOT_LOG_NAME, "Done!")
+            archive_path = log.archive()
+            log.delete()
+            yield LogMessage(path_to_url(archive_path))
+        yield CompleteMessage(outputs=outputs)
+
+
+def register(index):
+    """Replace the CPU aligners of a TypeIndex (manager.py:49-57) by the GPU ones."""
+    index.register(GpuPairwiseAligner)
+    index.register(GpuRawPairwiseAligner)
+    return index
+
+
+class _Group(object):
+    """Pairs of one (mode, matrix, gaps) class collected from a request list."""
+
+    def __init__(self, mode, S, gaps):
+        self.mode, self.S, self.gaps = mode, S, gaps
+        self.seq_index = {}
+        self.seqs = []
+        self.pi, self.pj = [], []
+        self.scores = None
+        self.paths = None
+        self.batch = None
+
+    def add_seq(self, track, arr):
+        k = id(track)
+        if k not in self.seq_index:
+            self.seq_index[k] = len(self.seqs)
+            self.seqs.append(arr)
+        return self.seq_index[k]
+
+    def add_pair(self, t1, a, t2, b):
+        self.pi.append(self.add_seq(t1, a))
+        self.pj.append(self.add_seq(t2, b))
+        return len(self.pi) - 1
+
+    def run_scores(self, eng):
+        self.batch = eng.batch(self.seqs)
+        self.scores, _ = eng.align_pairs(self.batch, self.pi, self.pj, self.S, self.gaps, mode=self.mode)
+
+    def path(self, k):
+        if self.paths is None:   # first access traces the whole group at once
+            eng = get_engine()
+            if self.mode == "local":
+                self.paths = {}
+            else:
+                _, self.paths = eng.align_pairs(self.batch, self.pi, self.pj, self.S, self.gaps, mode=self.mode,
+                                                want_paths=True)
+        if self.mode == "local":
+            if k not in self.paths:
+                r = get_engine().align_seq_pair_general(self.batch, self.pi[k], self.pj[k], self.S, self.gaps,
+                                                        self.mode)
+                self.paths[k] = r["path"]
+            return _path_container(self.mode, self.paths[k])
+        return _path_container(self.mode, self.paths[k])
+
+
+class GpuBatchManager(Manager):
+    """Manager whose execute_many aligns all PairwiseAligner requests of an Execution in one
+    batched launch per (mode, matrix, gaps) group (manager.py:154-170)."""
+
+    def __init__(self, index, register_gpu=True):
+        super(GpuBatchManager, self).__init__(register(index) if register_gpu else index)
+        self.batched_requests = 0
+
+    def execute_many(self, requests, parent_tag):
+        if not self.open:
+            from praline.core import PralineError
+            raise PralineError("manager has been closed")
+        requests = list(requests)
+        plain, ms = [], []
+        for n, (tid, inputs, tag, env) in enumerate(requests):
+            if tid == PAIRWISE_TID and self.index.resolve(tid) is GpuPairwiseAligner:
+                plain.append(n)
+            elif tid == GLOBAL_MS_TID and len(requests) > 0:
+                ms.append(n)
+        handled = set()
+        if plain:
+            for msg in self._batched_pairwise(requests, plain, parent_tag, handled):
+                yield msg
+        if ms:
+            for msg in self._batched_master_slave(requests, ms, parent_tag, handled):
+                yield msg
+        for n, (tid, inputs, tag, env) in enumerate(requests):
+            if n in handled:
+                continue
+            for msg in self._invoke(tid, inputs, tag, env, parent_tag=parent_tag):
+                yield msg
+
+    # -- PairwiseAligner requests ----------------------------------------------------------------
+    def _collect(self, tid, inputs, env, groups, eng):
+        """Validate one PairwiseAligner request like Manager._invoke + PairwiseAligner.execute do and
+        file it into a group; returns (group, k) or None when it needs the general path."""
+        comp = GpuPairwiseAligner
+        env = Environment(keys=env.keys, component=comp) if 'gap_series' not in env.keys else env
+        if env['debug'] != 0 or inputs.get('zero_idxs'):
+            return None
+        mode = inputs['mode']
+        sets, gaps = _prepare(inputs['sequence_one'], inputs['sequence_two'], inputs['track_id_sets_one'],
+                              inputs['track_id_sets_two'], inputs['score_matrices'], env['gap_series'])
+        _check_mode(mode)
+        hit = _batchable(sets, gaps, None, mode, eng)
+        if hit is None:
+            return None
+        a, b, S = hit
+        key = (mode, id(sets[0][2]), float(gaps[0]), float(gaps[1]))
+        if key not in groups:
+            groups[key] = _Group(mode, S, gaps)
+        g = groups[key]
+        return g, g.add_pair(sets[0][0], a, sets[0][1], b)
+
+    def _batched_pairwise(self, requests, idxs, parent_tag, handled):
+        eng = get_engine()
+        groups, where = {}, {}
+        for n in idxs:
+            tid, inputs, tag, env = requests[n]
+            hit = self._collect(tid, inputs, env, groups, eng)
+            if hit is not None:
+                where[n] = hit
+        if len(where) < 2:
+            return
+        for g in groups.values():
+            g.run_scores(eng)
+        for n in idxs:
+            if n not in where:
+                continue
+            tid, inputs, tag, env = requests[n]
+            g, k = where[n]
+            begin = BeginMessage(parent_tag)
+            begin.tag = tag
+            yield begin
+            alignment = LazyAlignment([inputs['sequence_one'], inputs['sequence_two']], g.path, k)
+            done = CompleteMessage(outputs={'alignment': alignment, 'score': float(g.scores[k])})
+            done.tag = tag
+            yield done
+            handled.add(n)
+            self.batched_requests += 1
+
+    # -- GlobalMasterSlaveAligner requests (preprofile.py:67-156) --------------------------------
+    def _batched_master_slave(self, requests, idxs, parent_tag, handled):
+        eng = get_engine()
+        groups, plans = {}, {}
+        for n in idxs:
+            tid, inputs, tag, env = requests[n]
+            comp = self.index.resolve(tid)
+            env = Environment(keys=env.keys, component=comp)
+            if env['aligner'] != PAIRWISE_TID or self.index.resolve(PAIRWISE_TID) is not GpuPairwiseAligner:
+                continue
+            sub_env = Environment(keys=env['aligner_env'].keys, component=GpuPairwiseAligner, parent=env)
+            master = inputs['master_sequence']
+            slaves = inputs['slave_sequences']
+            items = []
+            ok = True
+            for slave in slaves:
+                sub_inputs = dict(mode="global", sequence_one=master, sequence_two=slave,
+                                  track_id_sets_one=inputs['track_id_sets'], track_id_sets_two=inputs['track_id_sets'],
+                                  score_matrices=inputs['score_matrices'])
+                hit = self._collect(PAIRWISE_TID, sub_inputs, sub_env, groups, eng)
+                if hit is None:
+                    ok = False
+                    break
+                items.append(hit)
+            if ok:
+                plans[n] = (env, items)
+        if not plans:
+            return
+        for g in groups.values():
+            g.run_scores(eng)
+        for n in idxs:
+            if n not in plans:
+                continue
+            tid, inputs, tag, env0 = requests[n]
+            env, items = plans[n]
+            begin = BeginMessage(parent_tag)
+            begin.tag = tag
+            yield begin
+            master, slaves = inputs['master_sequence'], inputs['slave_sequences']
+            threshold = env['score_threshold']
+            path = np.arange(len(master) + 1).reshape(len(master) + 1, 1)
+            alignment = Alignment([master], path)
+            for j, (slave, (g, k)) in enumerate(zip(slaves, items)):   # preprofile.py:144-154
+                score = float(g.scores[k])
+                if threshold is None or score >= threshold:
+                    p = compress_path(np.array(g.path(k)), 0)
+                    merge_path = np.arange(len(slave) + 1).reshape(len(slave) + 1, 1)
+                    alignment = alignment.merge(Alignment([slave], merge_path), p)
+                prog = ProgressMessage((j + 1) / len(slaves))
+                prog.tag = tag
+                yield prog
+            done = CompleteMessage({'alignment': alignment})
+            done.tag = tag
+            yield done
+            handled.add(n)
+            self.batched_requests += len(items)

@@ -1,0 +1,208 @@
+"""The PRALINE plug-in boundary (B1 components, B2 batch manager) against the reference's own
+components.  CPU part: interface mirror and error behaviour.  GPU part: identical outputs."""
+import numpy as np
+import pytest
+
+import ref_praline as R
+from praline_b200 import synth
+from conftest import MODES
+
+pytestmark = pytest.mark.skipif(not R.HAVE_PRALINE, reason="reference package (baseline/_ref) not present")
+
+if R.HAVE_PRALINE:
+    import praline
+    import praline.component as pc
+    from praline.core import Manager, ComponentError, DataError, Environment
+    from praline.container import (Sequence, PlainTrack, ProfileTrack, ALPHABET_AA, ALPHABET_DNA, TRACK_ID_INPUT,
+                                   TRACK_ID_PREPROFILE, MatchScoreModel, GapScoreModel)
+    from praline_b200 import plugin
+
+
+def _blosum():
+    with praline.open_builtin('matrices/blosum62') as f:
+        return praline.load_score_matrix(f, alphabet=ALPHABET_AA)
+
+
+def _seq(name, idx, alpha=None):
+    alpha = alpha or ALPHABET_AA
+    return Sequence(name, [(TRACK_ID_INPUT, PlainTrack(None, alpha, raw_indices=np.asarray(idx)))])
+
+
+# ---- CPU: the interface is the reference's ------------------------------------------------------
+def test_components_mirror_reference_interface():
+    for gpu, ref in ((plugin.GpuPairwiseAligner, pc.PairwiseAligner), (plugin.GpuRawPairwiseAligner, pc.RawPairwiseAligner)):
+        assert gpu.tid == ref.tid
+        assert set(gpu.inputs) == set(ref.inputs) and set(gpu.outputs) == set(ref.outputs)
+        for k in ref.inputs:
+            assert gpu.inputs[k].signature == ref.inputs[k].signature and gpu.inputs[k].optional == ref.inputs[k].optional
+        assert gpu.options == ref.options and gpu.defaults == ref.defaults
+    index = plugin.register(R.reference_index())
+    assert index.resolve(pc.PairwiseAligner.tid) is plugin.GpuPairwiseAligner
+    assert index.resolve(pc.RawPairwiseAligner.tid) is plugin.GpuRawPairwiseAligner
+
+
+@pytest.mark.parametrize("case", ["track_sets", "multi_track", "gap_series", "alphabet", "matrix_dims"])
+def test_same_errors_as_reference(case):
+    sm = _blosum()
+    a, b = _seq("a", [1, 2, 3]), _seq("b", [3, 2, 1])
+    kw = dict(mode="global", sequence_one=a, sequence_two=b, track_id_sets_one=[[TRACK_ID_INPUT]],
+              track_id_sets_two=[[TRACK_ID_INPUT]], score_matrices=[sm])
+    env = {'gap_series': [-11.0, -1.0]}
+    if case == "track_sets":
+        kw['track_id_sets_two'] = [[TRACK_ID_INPUT], [TRACK_ID_INPUT]]
+        kw['score_matrices'] = [sm, sm]
+    elif case == "multi_track":
+        kw['track_id_sets_one'] = [[TRACK_ID_INPUT, TRACK_ID_INPUT]]
+    elif case == "gap_series":
+        env = {'gap_series': [-11.0, -2.0, -1.0]}
+    elif case == "alphabet":
+        kw['sequence_two'] = _seq("b", [1, 2, 3], ALPHABET_DNA)
+    elif case == "matrix_dims":
+        class Fake(type(sm)):
+            pass
+        f = Fake.__new__(Fake)
+        f.__dict__.update(sm.__dict__)
+        f.matrix = np.zeros((27, 27, 27), np.float32)
+        kw['score_matrices'] = [f]
+    errs = []
+    for index in (R.reference_index(), plugin.register(R.reference_index())):
+        with pytest.raises((ComponentError, DataError)) as ei:
+            R.run_task(Manager(index), pc.PairwiseAligner, env, **kw)
+        errs.append((type(ei.value), str(ei.value)))
+    assert errs[0] == errs[1]
+
+
+def test_unknown_mode_is_component_error():
+    sm = _blosum()
+    a, b = _seq("a", [1, 2, 3]), _seq("b", [3, 2, 1])
+    m = np.zeros((3, 3), np.float32)
+    g = np.full((3, 2), -1, np.float32)
+    for index in (R.reference_index(), plugin.register(R.reference_index())):
+        with pytest.raises(ComponentError) as ei:
+            R.run_task(Manager(index), pc.RawPairwiseAligner, {}, mode="bogus", sequence_one=a, sequence_two=b,
+                       match_score_model=MatchScoreModel(a, b, m), gap_score_model_one=GapScoreModel(a, g),
+                       gap_score_model_two=GapScoreModel(b, g))
+        assert "unknown alignment mode: 'bogus'" in str(ei.value)
+
+
+# ---- GPU: identical results through the component API ----------------------------------------------
+def _same_alignment(got, want):
+    assert type(got['score']) is float and got['score'] == want['score']
+    gp, wp = got['alignment'].path, want['alignment'].path
+    assert isinstance(gp, np.ndarray) == isinstance(wp, np.ndarray)
+    assert np.array_equal(np.asarray(gp), np.asarray(wp))
+    assert got['alignment'].items == want['alignment'].items
+
+
+@pytest.mark.gpu
+def test_pairwise_component_matches_reference():
+    sm = _blosum()
+    fam = synth.family(31, 6, 70)
+    ref_mgr, gpu_mgr = Manager(R.reference_index()), Manager(plugin.register(R.reference_index()))
+    for k, mode in enumerate(MODES):
+        for gaps in ([-11.0, -1.0], [-8.0], [-2.5, -0.5]):
+            a, b = _seq("a", fam[k]), _seq("b", fam[(k + 1) % 6])
+            kw = dict(mode=mode, sequence_one=a, sequence_two=b, track_id_sets_one=[[TRACK_ID_INPUT]],
+                      track_id_sets_two=[[TRACK_ID_INPUT]], score_matrices=[sm])
+            zero = [(y, x) for y in range(3, 9) for x in range(2, 12)] if mode == "local" else None
+            for z in (None, zero):
+                if z is not None:
+                    kw['zero_idxs'] = z
+                want, wm = R.run_task(ref_mgr, pc.PairwiseAligner, {'gap_series': gaps}, **kw)
+                got, gm = R.run_task(gpu_mgr, pc.PairwiseAligner, {'gap_series': gaps}, **kw)
+                _same_alignment(got, want)
+                assert [m.kind for m in gm][0] == "begin" and [m.kind for m in gm][-1] == "complete"
+
+
+@pytest.mark.gpu
+def test_profile_component_matches_reference():
+    sm = _blosum()
+    ref_mgr, gpu_mgr = Manager(R.reference_index()), Manager(plugin.register(R.reference_index()))
+    for k, mode in enumerate(MODES):
+        c1 = synth.count_profile(40 + k, 50 + 7 * k, 4 + k, 20, 27)
+        c2 = synth.count_profile(60 + k, 64, 3, 20, 27)
+        a = Sequence("p1", [(TRACK_ID_PREPROFILE, ProfileTrack(c1, ALPHABET_AA))])
+        b = Sequence("p2", [(TRACK_ID_PREPROFILE, ProfileTrack(c2, ALPHABET_AA))])
+        kw = dict(mode=mode, sequence_one=a, sequence_two=b, track_id_sets_one=[[TRACK_ID_PREPROFILE]],
+                  track_id_sets_two=[[TRACK_ID_PREPROFILE]], score_matrices=[sm])
+        want, _ = R.run_task(ref_mgr, pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
+        got, _ = R.run_task(gpu_mgr, pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
+        assert abs(got['score'] - want['score']) <= 1e-5 * max(1.0, abs(want['score']))
+        _same_alignment(got, want)
+
+
+@pytest.mark.gpu
+def test_raw_component_matches_reference():
+    rng = np.random.default_rng(4)
+    ref_mgr, gpu_mgr = Manager(R.reference_index()), Manager(plugin.register(R.reference_index()))
+    a, b = _seq("a", rng.integers(0, 20, 45)), _seq("b", rng.integers(0, 20, 61))
+    m = (rng.standard_normal((45, 61)) * 4).astype(np.float32)
+    g1 = (-rng.random((45, 2)) * 5 - 0.1).astype(np.float32)
+    g2 = (-rng.random((61, 2)) * 5 - 0.1).astype(np.float32)
+    for mode in MODES:
+        kw = dict(mode=mode, sequence_one=a, sequence_two=b, match_score_model=MatchScoreModel(a, b, m),
+                  gap_score_model_one=GapScoreModel(a, g1), gap_score_model_two=GapScoreModel(b, g2),
+                  zero_idxs=[(5, 5), (6, 6), (7, 7)])
+        want, _ = R.run_task(ref_mgr, pc.RawPairwiseAligner, {}, **kw)
+        got, _ = R.run_task(gpu_mgr, pc.RawPairwiseAligner, {}, **kw)
+        _same_alignment(got, want)
+
+
+@pytest.mark.gpu
+def test_guide_tree_through_batch_manager():
+    sm = _blosum()
+    fam = synth.family(77, 14, 90)
+    seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+    kw = dict(sequences=seqs, track_id_sets=[[TRACK_ID_INPUT]], score_matrices=[sm])
+    for dist in ("global", "semiglobal", "semiglobal_auto"):
+        env = {'gap_series': [-11.0, -1.0], 'linkage_method': 'average', 'dist_mode': dist,
+               'aligner': pc.PairwiseAligner.tid}
+        want, _ = R.run_task(Manager(R.reference_index()), pc.GuideTreeBuilder, env, **kw)
+        mgr = plugin.GpuBatchManager(R.reference_index())
+        got, msgs = R.run_task(mgr, pc.GuideTreeBuilder, env, **kw)
+        assert got['guide_tree'].merge_orders == want['guide_tree'].merge_orders
+        assert mgr.batched_requests == 14 * 13 // 2
+        assert sum(1 for m in msgs if m.kind == "complete") >= 14 * 13 // 2
+
+
+@pytest.mark.gpu
+def test_lazy_alignment_paths_from_batch():
+    sm = _blosum()
+    fam = synth.family(78, 6, 50)
+    seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+    from praline.core import Execution
+    for mode in ("global", "semiglobal_both", "local"):
+        outs = []
+        for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+            ex = Execution(mgr, R.ROOT_TAG)
+            for i in range(6):
+                for j in range(6):
+                    if i != j:
+                        t = ex.add_task(pc.PairwiseAligner)
+                        t.environment(Environment(keys={'gap_series': [-11.0, -1.0]}))
+                        t.inputs(mode=mode, sequence_one=seqs[i], sequence_two=seqs[j],
+                                 track_id_sets_one=[[TRACK_ID_INPUT]], track_id_sets_two=[[TRACK_ID_INPUT]],
+                                 score_matrices=[sm])
+            for _ in ex.run():
+                pass
+            outs.append(ex.outputs)
+        for want, got in zip(*outs):
+            _same_alignment(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preprofile,msa", [("global", "tree"), ("dummy", "tree"), ("global", "ad_hoc")])
+def test_msa_workflow_identical_to_reference(preprofile, msa):
+    sm = _blosum()
+    seqs = praline.load_sequence_fasta(R.ROOT + "/tests/golden/BBA0184.tfa", ALPHABET_AA)
+    want = R.workflow_fasta(Manager(R.reference_index()), seqs, sm, preprofile, msa)
+    seqs = praline.load_sequence_fasta(R.ROOT + "/tests/golden/BBA0184.tfa", ALPHABET_AA)
+    got = R.workflow_fasta(plugin.GpuBatchManager(R.reference_index()), seqs, sm, preprofile, msa)
+    assert got == want
+    if (preprofile, msa) == ("global", "tree"):
+        assert got == open(R.ROOT + "/tests/golden/BBA0184.aln").read()     # the reference's golden file
+    fam = synth.family(5, 12, 60)
+    mk = lambda: [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+    want = R.workflow_fasta(Manager(R.reference_index()), mk(), sm, preprofile, msa)
+    got = R.workflow_fasta(plugin.GpuBatchManager(R.reference_index()), mk(), sm, preprofile, msa)
+    assert got == want
