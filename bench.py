@@ -54,24 +54,41 @@ def config_dict(extra=None, world=1):
 
 # ---- clocks sampling -------------------------------------------------------------------------
 class ClockSampler(object):
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~3 ms)."""
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop = False
         self.th = threading.Thread(target=self._run, daemon=True)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
 
     def _run(self):
+        nv = self.nv
+        if nv is None:
+            return
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.samples.append([v.strip() for v in out.stdout.strip().split(",")])
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.mx.append(mx)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.003)
 
     def __enter__(self):
         self.th.start()
@@ -82,21 +99,9 @@ class ClockSampler(object):
         self.th.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            if len(s) < 6:
-                continue
-            try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ---- CPU baselines ---------------------------------------------------------------------------
@@ -315,9 +320,10 @@ def main():
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         clk_sum = clk.summary()
         mhz = clk_sum["sm_mhz"] or mb["sm_mhz"]
-        # peak f32 add/max lane-ops per second on this box: measured issue rate of the 4 add : 3 max
-        # cell mix (warp-instructions / clk / SM) x 32 lanes x SMs x SM clock under load
-        peak = mb["cell_mix"] * 32 * sms * mhz * 1e6
+        # peak f32 add/max lane-ops per second on this box: the measured
+        # full-rate f32 issue (FADD, warp-instructions / clk / SM) x 32 lanes x SMs x SM clock
+        # sampled during the timed region
+        peak = mb["fadd"] * 32 * sms * mhz * 1e6
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
         for a, b in kev:
             a.record()
@@ -328,11 +334,26 @@ def main():
         achieved = my_cells * W_FLOPS_PER_CELL / (kms * 1e-3)
         roof = {"bound": "cuda_core_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak, "traffic": None,
-                "note": "DP-cell roofline (SURVEY 8d): 11 f32 add/max per cell; peak = measured issue rate of the "
-                        "recurrence's add:max mix x 32 lanes x %d SMs x %.0f MHz (of measured); HBM is not the bound: "
-                        "4 B/pair out" % (sms, mhz),
+                "note": "DP-cell roofline (SURVEY 8d): algorithmic 11 f32 add/max per cell (the kernel issues 7); "
+                        "peak = measured f32 issue rate (%.2f warp-instr/clk/SM) x 32 lanes x %d SMs x %.0f MHz "
+                        "(of measured); f32 max / compare / integer ops issue at half that rate on this part "
+                        "(pipe_rates); HBM is not the bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
                 "kernel": "k_stream<10,global,score-only>", "kernel_ms": kms,
                 "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
+        # traced variant (what the preprofile master-slave alignments need): K2 with packed traceback
+        # + K4 walk, device time only, on the first 120k pairs of the same workload
+        tpi, tpj = synth.all_pairs(n)
+        tpi, tpj = tpi[:120000], tpj[:120000]
+        tcells = int((batch.lens[tpi] * batch.lens[tpj]).sum())
+        eng.align_pairs(batch, tpi, tpj, S, gaps, mode=mode, want_paths=True, resident="one", device_only=True)
+        torch.cuda.synchronize(dev)
+        ta, tb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta.record()
+        eng.align_pairs(batch, tpi, tpj, S, gaps, mode=mode, want_paths=True, resident="one", device_only=True)
+        tb_.record()
+        torch.cuda.synchronize(dev)
+        roof["traced_gcups"] = tcells / (ta.elapsed_time(tb_) * 1e-3) / 1e9
+        roof["traced_note"] = "120000 pairs, fill with 4-bit traceback + per-pair path walk, device time incl. plan upload"
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_port(seqs, S)
 

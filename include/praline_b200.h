@@ -68,7 +68,8 @@ int pgpu_warps_per_tile(void);
  *                1: resident sequences are `sequence_one`
  *   stream_ids   sequence id per stream element, or NULL when element s is sequence s
  *   topD/leftD   DP border values max(M,U,L) along row 0 / column 0 in the KERNEL orientation
- *                (component/align.py:367-385), border_len >= 32*K+1 and > every stream length
+ *                (component/align.py:367-385), border_len >= 32*K+1 and > every stream length;
+ *                left0/left1: the same column-0 border in closed form, D(y,0) = left0 + (y-1)*left1
  *   scores       [n_slots] f32
  *   keys         [2*n_slots] u64 scratch, local and semiglobal modes (running maxima); only
  *                slots produced by this call have their score written
@@ -78,7 +79,8 @@ int pgpu_warps_per_tile(void);
 int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
                      const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, int64_t n_slots,
                      const float* S_dev, int A, float gap_open, float gap_extend, const float* topD_dev,
-                     const float* leftD_dev, int border_len, float* scores_dev, uint64_t* keys_dev,
+                     const float* leftD_dev, float left0, float left1, int border_len, float* scores_dev,
+                     uint64_t* keys_dev,
                      uint32_t* tb_dev, const int64_t* tb_base_dev, int32_t* emit_t_dev,
                      int64_t* pair_tb_dev, void* stream);
 
@@ -135,7 +137,8 @@ int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, 
  * Pipe-rate micro-benchmarks used for the DP roofline denominator: returns in out[0..n) the
  * measured warp-instructions per clock per SM for (0) FADD, (1) FMNMX, (2) FMNMX3,
  * (3) the 4 FADD : 3 FMNMX mix of the score-only recurrence, (4) VIADDMNMX.S32,
- * (5) VIADDMNMX.S16x2, (6) SHFL, (7) LDS.128, and out[8] = SM clock in MHz seen by the run.
+ * (5) VIADDMNMX.S16x2, (6) SHFL, (7) LDS.128, out[8] = SM clock in MHz held during a burst,
+ * (9) SHF, (10) IMAD, (11) LOP3, (12) IADD3.  n must be >= 13.
  */
 int pgpu_microbench(double* out, int n);
 

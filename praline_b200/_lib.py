@@ -19,8 +19,8 @@ _SIGNATURES = {
     "pgpu_supported_k": (c_int, [c_int]),
     "pgpu_warps_per_tile": (c_int, []),
     "pgpu_align_tiles": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
-                                 c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_float, c_float, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgpu_traceback_tiles": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),

@@ -48,7 +48,7 @@ int pgpu_warps_per_tile(void) { return 8; }
 int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs, const int64_t* offs,
                      const int32_t* stream_ids, const void* tiles, int n_tiles, int64_t n_slots,
                      const float* S, int A, float gap_open, float gap_extend, const float* topD,
-                     const float* leftD, int border_len, float* scores, uint64_t* keys, uint32_t* tb,
+                     const float* leftD, float left0, float left1, int border_len, float* scores, uint64_t* keys, uint32_t* tb,
                      const int64_t* tb_base, int32_t* emit_t, int64_t* pair_tb, void* stream)
 {
     if (mode < 0 || mode > 4) { pg_set_error("unknown alignment mode %d", mode); return 1; }
@@ -62,6 +62,7 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs, const
     a.seqs = seqs; a.offs = offs; a.stream_ids = stream_ids; a.tiles = (const PgTile*)tiles;
     a.S = S; a.A = A; a.transposed = transposed; a.go = gap_open; a.ge = gap_extend;
     a.topD = topD; a.leftD = leftD; a.border_len = border_len;
+    a.left0 = left0; a.left1 = left1;
     a.scores = scores;
     a.rowkey = (unsigned long long*)keys;
     a.colkey = keys ? (unsigned long long*)keys + n_slots : nullptr;

@@ -42,7 +42,8 @@ struct StreamArgs {
     int transposed;              // resident is the reference's sequence one
     float go, ge;
     const float* topD;           // D(0, x), x = 0 .. border_len-1 (kernel orientation)
-    const float* leftD;          // D(y, 0)
+    const float* leftD;          // D(y, 0) (kept for callers; the kernel uses left0/left1)
+    float left0, left1;          // D(y, 0) = left0 + (y-1)*left1, y >= 1
     int border_len;
     float* scores;               // global / local: one per output slot
     unsigned long long* rowkey;  // semiglobal: (ordered f32 << 32 | x) of the last row

@@ -55,11 +55,12 @@ __device__ __forceinline__ float pick(const float (&v)[K], int k)
 template <int K, int KM, bool TB, bool TR, int NW>
 __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
 {
+    constexpr int UNR = TB ? 8 : 4;   // steps unrolled per inner iteration (8 = one traceback word)
     constexpr int NCH = (K + 3) / 4;
     constexpr int ROWB = NCH * 512;
     extern __shared__ __align__(16) unsigned char smem[];
     float* prof = reinterpret_cast<float*>(smem);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)a.A * ROWB) + (threadIdx.x >> 5) * 64;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)a.A * ROWB) + (threadIdx.x >> 5) * 128;
 
     const PgTile tile = a.tiles[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,8 +81,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
             }
             prof[idx] = v;
         }
-        ring[lane] = 0;
-        ring[lane + 32] = 0;
+        for (int i = lane; i < 128; i += 32) ring[i] = (uint32_t)__cvta_generic_to_shared(smem);
     }
     __syncthreads();
 
@@ -103,25 +103,30 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
     for (int s = sb + lane; s < se; s += 32) total += seq_len(s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-    int T = total + 1 + 31;
-    if (TB) T = (T + 7) & ~7;
+    const int T = (total + 1 + 31 + 31) & ~31;   // dummy row + stream + drain, whole 32-step blocks
 
     const int lr = (Lr - 1) / K, klast = (Lr - 1) % K;
     const float go = a.go, ge = a.ge;
+    const float left0 = a.left0, left1 = a.left1;
     const int64_t tbw0 = TB ? a.tb_base[(int64_t)blockIdx.x * NW + warp] : 0;
+    const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t lane16 = (uint32_t)lane << 4;
+    if (prof_s & 511u) __trap();   // row addresses are OR-ed with the lane offset below
 
     float Mo[K], U[K], D[K];
     uint32_t acc[K];
 #pragma unroll
     for (int k = 0; k < K; k++) { Mo[k] = 0.f; U[k] = 0.f; D[k] = 0.f; acc[k] = 0u; }
     float Mo_last = 0.f, L_last = 0.f, D_last = 0.f, Dleft_prev = 0.f;
-    float best = 0.f, colbest = 0.f;
-    int colbest_y = 0, y = 0, q = sb;
-    int ps = sb - 1, pp = 0;  // producer cursor: stream element / offset of stream position t
+    float best = 0.f, colbest = 0.f, yf = 0.f;   // yf = rows of the current sequence already done
+    int colbest_y = 0, q = sb;
+    int ps = sb - 1, pp = 0;  // producer cursor: stream element / offset of stream position t0
 
-    for (int t = 0; t < T; t++) {
-        // ---- every 32 steps: decode the next 32 stream positions into the ring -------------
-        if ((t & 31) == 0) {
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        // ---- decode the next 32 stream positions into the ring (kept twice, 64 apart, so that
+        //      the 32 reads below never wrap) -------------------------------------------------
+        {
             int s = ps, p = pp + lane;
             int len = (s < se) ? seq_len(s) : 0;
             while (s < se && p >= len) {
@@ -129,17 +134,18 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
                 s++;
                 len = (s < se) ? seq_len(s) : 0;
             }
-            uint32_t word = 0;
+            uint32_t word = prof_s;
             if (s < se) {
                 if (s < sb) {
-                    word = FLAG_LAST;
+                    word |= FLAG_LAST;
                 } else {
                     const int sym = a.seqs[a.offs[seq_id(s)] + p];
-                    word = (uint32_t)(sym * ROWB) | ((p == len - 1) ? (FLAG_LAST | FLAG_EMIT) : 0u);
+                    word = (prof_s + (uint32_t)(sym * ROWB)) | ((p == len - 1) ? (FLAG_LAST | FLAG_EMIT) : 0u);
                 }
             }
             __syncwarp();
-            ring[(t + lane) & 63] = word;
+            ring[(t0 + lane) & 63] = word;
+            ring[((t0 + lane) & 63) + 64] = word;
             __syncwarp();
             int s31 = __shfl_sync(FULL, s, 31), p31 = __shfl_sync(FULL, p, 31) + 1;
             const int len31 = __shfl_sync(FULL, len, 31);
@@ -147,113 +153,124 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
             ps = s31;
             pp = p31;
         }
+        const uint32_t rp0 = ring_s + ((uint32_t)((t0 - lane) & 63) << 2);
 
-        const uint32_t w = ring[(t - lane) & 63];
-        const float4* prow = reinterpret_cast<const float4*>(smem + (w & 0x00ffffffu)) + lane;
-        float sc[NCH * 4];
+#pragma unroll 1
+        for (int g = 0; g < 32; g += UNR) {
+            const uint32_t rp = rp0 + (uint32_t)g * 4u;
 #pragma unroll
-        for (int j = 0; j < NCH; j++) {
-            const float4 v = prow[j * 32];
-            sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
-        }
-        y++;
+            for (int i = 0; i < UNR; i++) {
+                const int t = t0 + g + i;
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)i * 4u) : "memory");
+                const uint32_t pa = (w & 0x00ffffffu) | lane16;
+                float sc[NCH * 4];
+#pragma unroll
+                for (int j = 0; j < NCH; j++)
+                    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                        : "=f"(sc[4 * j]), "=f"(sc[4 * j + 1]), "=f"(sc[4 * j + 2]), "=f"(sc[4 * j + 3])
+                        : "r"(pa + (uint32_t)j * 512u));
 
-        // ---- strip edge from the left lane (its results of step t-1 = my row) --------------
-        float Ml = __shfl_up_sync(FULL, Mo_last, 1);
-        float Ll = __shfl_up_sync(FULL, L_last, 1);
-        float Dn = __shfl_up_sync(FULL, D_last, 1);
-        if (lane == 0) {
-            Ml = -INFINITY;
-            Ll = -INFINITY;
-            Dn = a.leftD[min(y, a.border_len - 1)];
-        }
-        float diag = Dleft_prev;
-        Dleft_prev = Dn;
+                // ---- strip edge from the left lane (its results of the previous step = my row)
+                float Ml = __shfl_up_sync(FULL, Mo_last, 1);
+                float Ll = __shfl_up_sync(FULL, L_last, 1);
+                float Dn = __shfl_up_sync(FULL, D_last, 1);
+                if (lane == 0) {   // column 0: M = L = -inf, max3 = the U border (align.py:371-377)
+                    Ml = -INFINITY;
+                    Ll = -INFINITY;
+                    Dn = fmaf(yf, left1, left0);
+                }
+                yf += 1.f;
+                float diag = Dleft_prev;
+                Dleft_prev = Dn;
 
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            float m = diag + sc[k];
-            if (KM == 1) { m = fmaxf(m, 0.f); best = fmaxf(best, m); }
-            const float ue = U[k] + ge;
-            const float le = Ll + ge;
-            const float u = fmaxf(Mo[k], ue);
-            const float l = fmaxf(Ml, le);
-            diag = D[k];
-            float d;
-            if (TB) {
-                const float ul = fmaxf(u, l);
-                d = fmaxf(m, ul);
-                const bool pm = m >= ul;
-                const bool p2 = TR ? (l >= u) : (u >= l);
-                uint32_t nib = pm ? 0u : (p2 ? (TR ? 2u : 1u) : (TR ? 1u : 2u));
-                nib |= (Mo[k] >= ue) ? 4u : 0u;
-                nib |= (Ml >= le) ? 8u : 0u;
-                acc[k] = (acc[k] << 4) | nib;
-            } else {
-                d = fmaxf(fmaxf(m, u), l);
-            }
-            const float mo = m + go;
-            Mo[k] = mo;
-            U[k] = u;
-            D[k] = d;
-            Ml = mo;
-            Ll = l;
-        }
-        Mo_last = Ml;
-        L_last = Ll;
-        D_last = D[K - 1];
+                for (int k = 0; k < K; k++) {
+                    float m = diag + sc[k];
+                    if (KM == 1) { m = fmaxf(m, 0.f); best = fmaxf(best, m); }
+                    const float ue = U[k] + ge;
+                    const float le = Ll + ge;
+                    const float u = fmaxf(Mo[k], ue);
+                    const float l = fmaxf(Ml, le);
+                    diag = D[k];
+                    float d;
+                    if (TB) {
+                        // four sign bits per cell, shifted straight into the column's word: 1 = the
+                        // SECOND operand won (strictly), so ties keep the reference's priority
+                        // (open before extend, M before U before L; util/align.py:161-174)
+                        const float ul = fmaxf(u, l);
+                        d = fmaxf(m, ul);
+                        uint32_t w4 = __funnelshift_l(__float_as_uint(Ml - le), acc[k], 1);      // L: extend
+                        w4 = __funnelshift_l(__float_as_uint(Mo[k] - ue), w4, 1);               // U: extend
+                        w4 = __funnelshift_l(__float_as_uint(TR ? (l - u) : (u - l)), w4, 1);   // second gap state
+                        acc[k] = __funnelshift_l(__float_as_uint(m - ul), w4, 1);               // not M
+                    } else {
+                        d = fmaxf(fmaxf(m, u), l);
+                    }
+                    const float mo = m + go;
+                    Mo[k] = mo;
+                    U[k] = u;
+                    D[k] = d;
+                    Ml = mo;
+                    Ll = l;
+                }
+                Mo_last = Ml;
+                L_last = Ll;
+                D_last = D[K - 1];
 
-        if (TB && (t & 7) == 7) {
-            uint32_t* dst = a.tb + tbw0 + (int64_t)(t >> 3) * (K * 32) + lane;
+                if (TB && (i & 7) == 7) {
+                    uint32_t* dst = a.tb + tbw0 + (int64_t)(t >> 3) * (K * 32) + lane;
 #pragma unroll
-            for (int k = 0; k < K; k++) dst[k * 32] = acc[k];
-        }
-        if (KM == 2 && lane == lr) {
-            const float dl = pick<K>(D, klast);
-            if (dl >= colbest) { colbest = dl; colbest_y = y; }
-        }
+                    for (int k = 0; k < K; k++) dst[k * 32] = acc[k];
+                }
+                if (KM == 2 && lane == lr) {
+                    const float dl = pick<K>(D, klast);
+                    if (dl >= colbest) { colbest = dl; colbest_y = (int)yf; }
+                }
 
-        if (w & FLAG_LAST) {
-            if (w & FLAG_EMIT) {
-                const int64_t slot = tile.out_base + (q - tile.stream_begin);
-                if (KM == 0) {
-                    if (lane == lr) a.scores[slot] = pick<K>(D, klast);
-                } else if (KM == 1) {
-                    atomicMax(a.rowkey + slot, pack_key(best, 0));
-                    if (lane == lr) a.colkey[slot] = 1ull;   // marks the slot as produced
-                } else {
-                    float bv = -INFINITY;
-                    int bx = -1;
+                if ((int)w < 0) {   // FLAG_LAST
+                    if (w & FLAG_EMIT) {
+                        const int64_t slot = tile.out_base + (q - tile.stream_begin);
+                        if (KM == 0) {
+                            if (lane == lr) a.scores[slot] = pick<K>(D, klast);
+                        } else if (KM == 1) {
+                            atomicMax(a.rowkey + slot, pack_key(best, 0));
+                            if (lane == lr) a.colkey[slot] = 1ull;   // marks the slot as produced
+                        } else {
+                            float bv = -INFINITY;
+                            int bx = -1;
+#pragma unroll
+                            for (int k = 0; k < K; k++) {
+                                const int x = lane * K + k + 1;
+                                if (x <= Lr && D[k] >= bv) { bv = D[k]; bx = x; }
+                            }
+                            if (lane == 0) {
+                                const float v = fmaf(yf - 1.f, left1, left0);   // D(y, 0) of this last row
+                                if (v > bv) { bv = v; bx = 0; }
+                            }
+                            if (bx >= 0) atomicMax(a.rowkey + slot, pack_key(bv, bx));
+                            if (lane == lr) a.colkey[slot] = pack_key(colbest, colbest_y);
+                        }
+                        if (TB && lane == lr) {
+                            a.emit_t[slot] = t;
+                            a.pair_tb[slot] = tbw0;
+                        }
+                        q++;
+                    }
+                    // re-arm the top border for the next streamed sequence
 #pragma unroll
                     for (int k = 0; k < K; k++) {
-                        const int x = lane * K + k + 1;
-                        if (x <= Lr && D[k] >= bv) { bv = D[k]; bx = x; }
+                        Mo[k] = -INFINITY;
+                        U[k] = -INFINITY;
+                        D[k] = a.topD[lane * K + k + 1];
                     }
-                    if (lane == 0) {
-                        const float v = a.leftD[min(y, a.border_len - 1)];
-                        if (v > bv) { bv = v; bx = 0; }
-                    }
-                    if (bx >= 0) atomicMax(a.rowkey + slot, pack_key(bv, bx));
-                    if (lane == lr) a.colkey[slot] = pack_key(colbest, colbest_y);
+                    Dleft_prev = a.topD[lane * K];
+                    yf = 0.f;
+                    best = 0.f;
+                    colbest = a.topD[Lr];
+                    colbest_y = 0;
                 }
-                if (TB && lane == lr) {
-                    a.emit_t[slot] = t;
-                    a.pair_tb[slot] = tbw0;
-                }
-                q++;
             }
-            // re-arm the top border for the next streamed sequence
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                Mo[k] = -INFINITY;
-                U[k] = -INFINITY;
-                D[k] = a.topD[lane * K + k + 1];
-            }
-            Dleft_prev = a.topD[lane * K];
-            y = 0;
-            best = 0.f;
-            colbest = a.topD[Lr];
-            colbest_y = 0;
         }
     }
 }
@@ -286,7 +303,7 @@ template <int K, int KM, bool TB, bool TR>
 static int launch_one(const StreamArgs& a, int n_tiles, cudaStream_t st)
 {
     constexpr int NCH = (K + 3) / 4;
-    const size_t smem = (size_t)a.A * NCH * 512 + kNW * 64 * sizeof(uint32_t);
+    const size_t smem = (size_t)a.A * NCH * 512 + kNW * 128 * sizeof(uint32_t);
     auto kern = k_stream<K, KM, TB, TR, kNW>;
     PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_tiles, kNW * 32, smem, st>>>(a);

@@ -13,7 +13,8 @@
 #define ITERS 2048
 
 template <int OP>
-__global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin, float* fout, long long* cyc)
+__global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin, float* fout, long long* cyc,
+                                               unsigned long long* ns = nullptr)
 {
     float f[CH];
     int v[CH];
@@ -24,12 +25,18 @@ __global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin,
     __shared__ float4 sh[1024];
     sh[threadIdx.x] = make_float4(c1, c2, c1, c2);
     __syncthreads();
+    unsigned long long g0 = 0, g1 = 0;
+    if (ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
+#pragma unroll 2
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             if (OP == 0) asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
-            if (OP == 1) asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+            if (OP == 1) {   // alternate max / min so that ptxas cannot fuse pairs into FMNMX3
+                if (it & 1) asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
+                else asm volatile("min.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2));
+            }
             if (OP == 2) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(c1), "f"(c2));
             if (OP == 3) {  // the score-only cell: 4 FADD, 2 FMNMX, 1 FMNMX3
                 asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
@@ -43,6 +50,10 @@ __global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin,
             if (OP == 4) v[i] = __viaddmax_s32(v[i], i1, i2);
             if (OP == 5) v[i] = (int)__viaddmax_s16x2((unsigned)v[i], (unsigned)i1, (unsigned)i2);
             if (OP == 6) f[i] = __shfl_up_sync(0xffffffffu, f[i], 1);
+            if (OP == 9) v[i] = (int)__funnelshift_l((unsigned)i1, (unsigned)v[i], 1);
+            if (OP == 10) v[i] = v[i] * i1 + i2;
+            if (OP == 11) v[i] = (v[i] & i1) ^ i2;
+            if (OP == 12) v[i] = v[i] + i1 + i2;
             if (OP == 7) {
                 const float4 q = sh[(threadIdx.x + i + it) & 1023];
                 f[i] += q.x;
@@ -50,6 +61,8 @@ __global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin,
         }
     }
     const long long t1 = clock64();
+    if (ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (ns && threadIdx.x == 0) ns[blockIdx.x] = g1 - g0;
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < CH; i++) acc += f[i] + (float)v[i];
@@ -78,7 +91,7 @@ static int run_rate(int sms, const float* fin, const int* iin, float* fout, long
 
 extern "C" int pgpu_microbench(double* out, int n)
 {
-    if (n < 9) { pg_set_error("pgpu_microbench needs room for 9 doubles"); return 1; }
+    if (n < 13) { pg_set_error("pgpu_microbench needs room for 13 doubles"); return 1; }
     int dev = 0, sms = 0, khz = 0;
     PG_CUDA_OK(cudaGetDevice(&dev));
     PG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -103,21 +116,21 @@ extern "C" int pgpu_microbench(double* out, int n)
     rc |= run_rate<5>(sms, fin, iin, fout, cyc, &out[5]);
     rc |= run_rate<6>(sms, fin, iin, fout, cyc, &out[6]);
     rc |= run_rate<7>(sms, fin, iin, fout, cyc, &out[7]);
-    // SM clock actually held during a timed burst: cycles (clock64) over wall time (events)
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0);
-    k_rate<3><<<sms, 1024>>>(fin, iin, fout, cyc);
-    cudaEventRecord(e1);
+    rc |= run_rate<9>(sms, fin, iin, fout, cyc, &out[9]);
+    rc |= run_rate<10>(sms, fin, iin, fout, cyc, &out[10]);
+    rc |= run_rate<11>(sms, fin, iin, fout, cyc, &out[11]);
+    rc |= run_rate<12>(sms, fin, iin, fout, cyc, &out[12]);
+    // SM clock held during a burst of the cell mix: SM cycles (clock64) over %globaltimer ns
+    unsigned long long* ns = nullptr;
+    PG_CUDA_OK(cudaMalloc((void**)&ns, sizeof(unsigned long long) * sms));
+    for (int rep = 0; rep < 20; rep++) k_rate<3><<<sms, 1024>>>(fin, iin, fout, cyc, ns);
     PG_CUDA_OK(cudaDeviceSynchronize());
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
     long long c0 = 0;
+    unsigned long long n0 = 0;
     PG_CUDA_OK(cudaMemcpy(&c0, cyc, sizeof(long long), cudaMemcpyDeviceToHost));
-    out[8] = (ms > 0) ? (double)c0 / (ms * 1e3) : (double)khz / 1e3;   // MHz
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    PG_CUDA_OK(cudaMemcpy(&n0, ns, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    out[8] = (n0 > 0) ? (double)c0 / (double)n0 * 1e3 : (double)khz / 1e3;   // MHz
+    cudaFree(ns);
     cudaFree(fin); cudaFree(iin); cudaFree(fout); cudaFree(cyc);
     return rc;
 }

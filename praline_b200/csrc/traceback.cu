@@ -4,14 +4,16 @@
 // chase get_paths (praline/util/align.py:144-185) and extend_path_semiglobal
 // (praline/util/align.py:268-297).  One thread walks one pair.
 //
-// K2 stores, per interior cell, 4 bits in kernel orientation (columns = resident sequence):
-//   bits 0-1  first-priority argmax of (M, U, L) AT this cell, as a kernel state
-//             (0 = M, 1 = reached from above, 2 = reached from the left) -- this is the state
-//             the reference's walker enters when it arrives here diagonally, because the
+// K2 stores, per interior cell, 4 sign bits in kernel orientation (columns = resident
+// sequence; states 0 = M, 1 = reached from above, 2 = reached from the left):
+//   bit 0     max3 of (M, U, L) AT this cell is not M (M lost strictly)
+//   bit 1     among the two gap states the lower-priority one won strictly
+//             bits 0-1 together give the first-priority argmax of (M, U, L) at this cell -- the
+//             state the reference's walker enters when it arrives here diagonally, because the
 //             reference's MM > MU > ML flag priority at (y,x) picks the first maximal state of
 //             (y-1,x-1) (exact for integer-valued scores, see gotoh_stream.cu);
-//   bit 2     the from-above state was opened from M (open beats extend on ties);
-//   bit 3     the from-left state was opened from M.
+//   bit 2     the from-above state was EXTENDED (open beats extend on ties);
+//   bit 3     the from-left state was EXTENDED.
 // Border cells carry no nibble; their flags follow from the border rules of
 // component/align.py:367-385 (ramp borders chain back along the edge, zero borders stop).
 // The path is emitted in the REFERENCE orientation, rows (y, x), written back to front into
@@ -48,7 +50,10 @@ __global__ void k_traceback(const TraceArgs a)
         if (yk == 0 && xk == 0) return a.code00;
         if (yk == 0) return 2;
         if (xk == 0) return 1;
-        return (int)(nib_at(yk, xk) & 3u);
+        const uint32_t nb = nib_at(yk, xk);
+        if (!(nb & 1u)) return 0;
+        const bool second = (nb & 2u) != 0;
+        return TR ? (second ? 1 : 2) : (second ? 2 : 1);   // reference priority U before L
     };
 
     // ---- start cell (kernel coordinates) ----------------------------------------------------
@@ -97,8 +102,8 @@ __global__ void k_traceback(const TraceArgs a)
             s = code_at(yk, xk);
         } else {
             const uint32_t nib = nib_at(yk, xk);
-            if (s == 1) { s = ((nib >> 2) & 1u) ? 0 : 1; yk--; }
-            else        { s = ((nib >> 3) & 1u) ? 0 : 2; xk--; }
+            if (s == 1) { s = ((nib >> 2) & 1u) ? 1 : 0; yk--; }
+            else        { s = ((nib >> 3) & 1u) ? 2 : 0; xk--; }
         }
     }
 

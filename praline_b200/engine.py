@@ -47,9 +47,10 @@ def borders(mode, go, ge, maxlen, transposed=False):
     col_u[0] = d00
     row_l[0] = d00
     if not transposed:
-        return dict(topD=row_l, leftD=col_u, code00=code00, top_ramp=int(not l_zero), left_ramp=int(not u_zero))
+        return dict(topD=row_l, leftD=col_u, code00=code00, top_ramp=int(not l_zero), left_ramp=int(not u_zero),
+                    left0=0.0 if u_zero else float(go), left1=0.0 if u_zero else float(ge))
     return dict(topD=col_u, leftD=row_l, code00={0: 0, 1: 2, 2: 1}[code00], top_ramp=int(not u_zero),
-                left_ramp=int(not l_zero))
+                left_ramp=int(not l_zero), left0=0.0 if l_zero else float(go), left1=0.0 if l_zero else float(ge))
 
 
 class SeqBatch(object):
@@ -145,7 +146,7 @@ class Engine(object):
         se = np.minimum(sb + per[:, None], te_[:, None])
         sb = np.minimum(sb, se)
         rows = cs[se] - cs[sb]
-        T = np.where(se > sb, (rows + 1 + 31 + 7) // 8 * 8, 0)
+        T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
         return (T // 8) * (K * 32)
 
     def _pick_tile(self, n_pairs):
@@ -177,7 +178,8 @@ class Engine(object):
             _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
                                             self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles), n_slots,
                                             self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
-                                            self.ptr(left_dev), maxlen + 1, self.ptr(scores_dev), self.ptr(keys),
+                                            self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1,
+                                            self.ptr(scores_dev), self.ptr(keys),
                                             None, None, None, None, self.stream()))
             self.launches += 1 + int(semi)
             return out
@@ -203,7 +205,8 @@ class Engine(object):
             _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
                                             self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(wt), ns,
                                             self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
-                                            self.ptr(left_dev), maxlen + 1, self.ptr(sc), self.ptr(keys),
+                                            self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1, self.ptr(sc),
+                                            self.ptr(keys),
                                             self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
                                             self.stream()))
             cap = caps[s_lo:s_hi]
@@ -233,7 +236,8 @@ class Engine(object):
         bound = np.abs(S).max() * maxlen + abs(float(go)) + abs(float(ge)) * 2 * maxlen
         return bound < 2 ** 23
 
-    def align_pairs(self, batch, pi, pj, S, gap_series, mode="global", want_paths=False, resident=None):
+    def align_pairs(self, batch, pi, pj, S, gap_series, mode="global", want_paths=False, resident=None,
+                    device_only=False):
         """Scores (and reference-format paths) of pairs (sequence_one = pi[k], sequence_two = pj[k]).
 
         Returns np.float32 scores [n] and, if want_paths, a list of int32 [rows, 2] arrays."""
@@ -284,6 +288,8 @@ class Engine(object):
                                    scores_dev, cs=cs, slot_res_dev=slot_res_dev, slot_str_dev=stream_ids_dev,
                                    want_paths=want_paths, caps=caps)
             pending.extend(waves)
+        if device_only:
+            return scores_dev, order, pending
         scores_sorted = scores_dev.cpu().numpy()
         scores = np.empty(n, np.float32)
         scores[order] = scores_sorted
@@ -447,9 +453,10 @@ class Engine(object):
         return o, t
 
     def microbench(self):
-        out = (ctypes.c_double * 9)()
-        _lib.check(self.lib.pgpu_microbench(out, 9))
-        names = ["fadd", "fmnmx", "fmnmx3", "cell_mix", "viaddmnmx_s32", "viaddmnmx_s16x2", "shfl", "lds128", "sm_mhz"]
+        out = (ctypes.c_double * 13)()
+        _lib.check(self.lib.pgpu_microbench(out, 13))
+        names = ["fadd", "fmnmx", "fmnmx3", "cell_mix", "viaddmnmx_s32", "viaddmnmx_s16x2", "shfl", "lds128", "sm_mhz",
+                 "shf", "imad", "lop3", "iadd3"]
         return dict(zip(names, [float(v) for v in out]))
 
 

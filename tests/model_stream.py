@@ -125,10 +125,10 @@ def run_warp(K, resident, streams, S, go, ge, mode, transposed=False, want_tb=Fa
                 ul = np.maximum(u, l)
                 d = np.maximum(m, ul)
                 if want_tb:
-                    pm = m >= ul
-                    p2 = (l >= u) if transposed else (u >= l)
-                    code = np.where(pm, 0, np.where(p2, 2 if transposed else 1, 1 if transposed else 2))
-                    nib = code | ((Mo[:, k] >= ue).astype(np.int64) << 2) | ((Ml >= le).astype(np.int64) << 3)
+                    # four sign bits: 1 = the second operand won strictly (ties keep the priority)
+                    not_m = (m < ul).astype(np.int64)
+                    second = ((l < u) if transposed else (u < l)).astype(np.int64)
+                    nib = not_m | (second << 1) | ((Mo[:, k] < ue).astype(np.int64) << 2) | ((Ml < le).astype(np.int64) << 3)
                     acc[:, k] = ((acc[:, k].astype(np.uint64) << 4) & 0xFFFFFFFF).astype(np.uint32) | nib.astype(np.uint32)
                 mo = m + go
                 Mo[:, k] = mo
@@ -201,7 +201,12 @@ def traceback(tb, K, info, L1, L2, emit_t, start, transposed):
             return 2
         if x_ == 0:
             return 1
-        return fetch_nib(tb, K, emit_t, lr, L1, y_, x_) & 3
+        nb = fetch_nib(tb, K, emit_t, lr, L1, y_, x_)
+        if not nb & 1:
+            return 0
+        if transposed:
+            return 1 if nb & 2 else 2
+        return 2 if nb & 2 else 1
 
     while True:
         path.append((xk, yk) if transposed else (yk, xk))
@@ -222,10 +227,10 @@ def traceback(tb, K, info, L1, L2, emit_t, start, transposed):
             yk, xk = yk - 1, xk - 1
             s = code_at(yk, xk)
         elif s == 1:
-            s = 0 if (nib >> 2) & 1 else 1
+            s = 1 if (nib >> 2) & 1 else 0
             yk -= 1
         else:
-            s = 0 if (nib >> 3) & 1 else 2
+            s = 2 if (nib >> 3) & 1 else 0
             xk -= 1
     path.reverse()
     return path

@@ -114,5 +114,5 @@ def test_tb_words_formula():
     for k in range(8):
         sb, se = min(k * per, 11), min(k * per + per, 11)
         rows = lens[sb:se].sum()
-        T = (rows + 1 + 31 + 7) // 8 * 8 if se > sb else 0
+        T = (rows + 1 + 31 + 31) // 32 * 32 if se > sb else 0
         assert w[k] == T // 8 * 3 * 32

@@ -34,7 +34,12 @@ def finish(mode, transposed, o, info, tb, K, L_res, L_str):
             return 2
         if xk == 0:
             return 1
-        return ms.fetch_nib(tb, K, o["emit_t"], info["lr"], L_str, yk, xk) & 3
+        nb = ms.fetch_nib(tb, K, o["emit_t"], info["lr"], L_str, yk, xk)
+        if not nb & 1:
+            return 0
+        if transposed:
+            return 1 if nb & 2 else 2
+        return 2 if nb & 2 else 1
 
     if mode == 0:
         start = (L_str, L_res, code_at(L_str, L_res))
