@@ -323,7 +323,7 @@ def main():
         # peak f32 add/max lane-ops per second on this box: the measured
         # full-rate f32 issue (FADD, warp-instructions / clk / SM) x 32 lanes x SMs x SM clock
         # sampled during the timed region
-        peak = mb["fadd"] * 32 * sms * mhz * 1e6
+        peak = mb["fadd"] * 32 * sms * 1e9     # warp-instr/ns/SM x lanes x SMs -> lane-ops/s, wall clock
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
         for a, b in kev:
             a.record()
@@ -335,9 +335,13 @@ def main():
         roof = {"bound": "cuda_core_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak, "traffic": None,
                 "note": "DP-cell roofline (SURVEY 8d): algorithmic 11 f32 add/max per cell (the kernel issues 7); "
-                        "peak = measured f32 issue rate (%.2f warp-instr/clk/SM) x 32 lanes x %d SMs x %.0f MHz "
-                        "(of measured); f32 max / compare / integer ops issue at half that rate on this part "
-                        "(pipe_rates); HBM is not the bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
+                        "peak = measured f32 add issue rate (%.2f warp-instr/ns/SM, wall clock) x 32 lanes x %d SMs "
+                        "(of measured; SM clock %.0f MHz during the run); f32 max / compare / shift / integer ops "
+                        "issue at half that rate on this part (pipe_rates, warp-instr/ns/SM); HBM is not the "
+                        "bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
+                "issue_bound_frac": (my_cells / (kms * 1e-3)) * 7.0 / 32.0 / (mb["fadd"] * sms * 1e9),
+                "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence: "
+                                    "7 warp-instructions per 32 cells at the measured full issue rate",
                 "kernel": "k_stream<10,global,score-only>", "kernel_ms": kms,
                 "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
         # traced variant (what the preprofile master-slave alignments need): K2 with packed traceback

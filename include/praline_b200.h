@@ -75,6 +75,10 @@ int pgpu_warps_per_tile(void);
  *                slots produced by this call have their score written
  *   tb .. pair_tb  NULL for score-only runs; else packed traceback words, per-(tile,warp) word
  *                offsets, and per-slot outputs consumed by pgpu_traceback_tiles
+ *   mwave, mrow_base  NULL for sequence batches.  Profile x profile batches (score only): the
+ *                match scores of the wave made by pgpu_build_rows, one row of 32*K floats per
+ *                stream position, and the first row per (tile, warp); seqs_dev is then unused and
+ *                offs_dev holds profile ROW offsets per sequence
  */
 int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
                      const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, int64_t n_slots,
@@ -82,7 +86,7 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, c
                      const float* leftD_dev, float left0, float left1, int border_len, float* scores_dev,
                      uint64_t* keys_dev,
                      uint32_t* tb_dev, const int64_t* tb_base_dev, int32_t* emit_t_dev,
-                     int64_t* pair_tb_dev, void* stream);
+                     int64_t* pair_tb_dev, const float* mwave_dev, const int64_t* mrow_base_dev, void* stream);
 
 /*
  * Traceback of an inter-task batch (K4).  Replaces get_paths (util/align.py:144-185), the
@@ -106,6 +110,15 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs_de
 int pgpu_build_scores(int n_sets, const float* const* P1_dev, const float* const* P2_dev,
                       const float* const* S_dev, const int* A, int L1, int L2, float* m_dev, int m_pitch,
                       void* stream);
+/*
+ * Match scores of a wave of profile x profile pairs in stream order (feeds pgpu_align_tiles).
+ * Same evaluation order as cext_build_scores (cext.c:63-95) for ONE track set.  prof [rows][A]
+ * holds all profiles, rowoff [n_seqs+1] their row offsets; rowsrc[r] is the profile row of the
+ * streamed sequence for matrix row r (-1: dummy row), rowres[r] the resident sequence id.
+ */
+int pgpu_build_rows(const float* prof_dev, const int64_t* rowoff_dev, int A, const float* S_dev,
+                    const int32_t* rowsrc_dev, const int32_t* rowres_dev, int64_t n_rows, int width,
+                    int transposed, int local_mode, float* mwave_dev, void* stream);
 int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
                           int L2, float* m_dev, int m_pitch, void* stream);
 
@@ -135,7 +148,7 @@ int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, 
 
 /*
  * Pipe-rate micro-benchmarks used for the DP roofline denominator: returns in out[0..n) the
- * measured warp-instructions per clock per SM for (0) FADD, (1) FMNMX, (2) FMNMX3,
+ * measured warp-instructions per NANOSECOND per SM (wall clock, CUDA events) for (0) FADD, (1) FMNMX, (2) FMNMX3,
  * (3) the 4 FADD : 3 FMNMX mix of the score-only recurrence, (4) VIADDMNMX.S32,
  * (5) VIADDMNMX.S16x2, (6) SHFL, (7) LDS.128, out[8] = SM clock in MHz held during a burst,
  * (9) SHF, (10) IMAD, (11) LOP3, (12) IADD3.  n must be >= 13.

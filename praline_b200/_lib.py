@@ -20,12 +20,15 @@ _SIGNATURES = {
     "pgpu_warps_per_tile": (c_int, []),
     "pgpu_align_tiles": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
                                  c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_float, c_float, c_int,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "pgpu_traceback_tiles": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "pgpu_build_scores": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                   c_void_p]),
+    "pgpu_build_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                c_void_p, c_void_p]),
     "pgpu_build_scores_seq": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                       c_void_p]),
     "pgpu_general_workspace_bytes": (c_int64, [c_int, c_int]),

@@ -49,7 +49,8 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs, const
                      const int32_t* stream_ids, const void* tiles, int n_tiles, int64_t n_slots,
                      const float* S, int A, float gap_open, float gap_extend, const float* topD,
                      const float* leftD, float left0, float left1, int border_len, float* scores, uint64_t* keys, uint32_t* tb,
-                     const int64_t* tb_base, int32_t* emit_t, int64_t* pair_tb, void* stream)
+                     const int64_t* tb_base, int32_t* emit_t, int64_t* pair_tb, const float* mwave,
+                     const int64_t* mrow_base, void* stream)
 {
     if (mode < 0 || mode > 4) { pg_set_error("unknown alignment mode %d", mode); return 1; }
     if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
@@ -67,6 +68,7 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs, const
     a.rowkey = (unsigned long long*)keys;
     a.colkey = keys ? (unsigned long long*)keys + n_slots : nullptr;
     a.tb = tb; a.tb_base = tb_base; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    a.mwave = mwave; a.mrow_base = mrow_base;
     // kernel-orientation mode: a transposed launch swaps the roles of sequence one and two
     int kmode = mode;
     if (transposed && (mode == PG_SG_ONE || mode == PG_SG_TWO)) kmode = (mode == PG_SG_ONE) ? PG_SG_TWO : PG_SG_ONE;
@@ -99,17 +101,20 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, c
 int pgpu_build_scores(int n_sets, const float* const* P1, const float* const* P2, const float* const* S,
                       const int* A, int L1, int L2, float* m, int m_pitch, void* stream)
 {
-    if (n_sets < 1 || n_sets > 16) { pg_set_error("n_sets %d outside 1..16", n_sets); return 1; }
-    cudaStream_t st = (cudaStream_t)stream;
-    ScoreSet h[16];
-    for (int i = 0; i < n_sets; i++) { h[i].P1 = P1[i]; h[i].P2 = P2[i]; h[i].S = S[i]; h[i].A = A[i]; }
-    ScoreSet* d = nullptr;
-    PG_CUDA_OK(cudaMallocAsync((void**)&d, sizeof(ScoreSet) * n_sets, st));
-    PG_CUDA_OK(cudaMemcpyAsync(d, h, sizeof(ScoreSet) * n_sets, cudaMemcpyHostToDevice, st));
-    PG_CUDA_OK(cudaStreamSynchronize(st));  // h is on this stack frame
-    int rc = pg_launch_build_scores(n_sets, d, L1, L2, m, m_pitch, st);
-    cudaFreeAsync(d, st);
-    return rc;
+    if (n_sets < 1 || n_sets > 8) { pg_set_error("n_sets %d outside 1..8", n_sets); return 1; }
+    ScoreSets h;
+    h.n = n_sets;
+    for (int i = 0; i < n_sets; i++) { h.s[i].P1 = P1[i]; h.s[i].P2 = P2[i]; h.s[i].S = S[i]; h.s[i].A = A[i]; }
+    return pg_launch_build_scores(h, L1, L2, m, m_pitch, (cudaStream_t)stream);
+}
+
+int pgpu_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const int32_t* rowsrc,
+                    const int32_t* rowres, int64_t n_rows, int width, int transposed, int local_mode, float* mwave,
+                    void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    return pg_launch_build_rows(prof, rowoff, A, S, rowsrc, rowres, n_rows, width, transposed,
+                                local_mode ? -INFINITY : 0.f, mwave, (cudaStream_t)stream);
 }
 
 int pgpu_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,

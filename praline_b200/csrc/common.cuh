@@ -52,6 +52,8 @@ struct StreamArgs {
     const int64_t* tb_base;      // word offset per (tile, warp)
     int32_t* emit_t;             // per slot: step at which the owning lane saw the last row
     int64_t* pair_tb;            // per slot: word offset of its warp's traceback region
+    const float* mwave;          // profile batches: match scores [row][32*K], rows in stream order
+    const int64_t* mrow_base;    // first matrix row per (tile, warp); row 0 of a region is the dummy row
 };
 
 // Arguments of the per-pair traceback walk (traceback.cu).
@@ -97,10 +99,14 @@ struct GenArgs {
 };
 
 struct ScoreSet { const float* P1; const float* P2; const float* S; int A; };
+struct ScoreSets { ScoreSet s[8]; int n; };   // passed by value as a kernel argument
 
 void pg_set_error(const char* fmt, ...);
 int pg_launch_general(GenArgs a, int kg, cudaStream_t st);
-int pg_launch_build_scores(int n_sets, const ScoreSet* sets_dev, int L1, int L2, float* m, int m_pitch, cudaStream_t st);
+int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st);
+int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const int32_t* rowsrc,
+                         const int32_t* rowres, int64_t n_rows, int width, int transposed, float padv, float* mwave,
+                         cudaStream_t st);
 int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,
                                float* m, int m_pitch, cudaStream_t st);
 int pg_stream_supported_k(int k);

@@ -110,9 +110,33 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
         float bv = NINF; uint32_t bl = 0xffffffffu;  // local: best value / smallest linear index
         const int T = L1 + 31;
 
+        // software pipeline: everything a row needs from memory (match scores, the row's gap
+        // pair, mask bits, lane 0's left edge) is requested one step ahead, so that no L2 round
+        // trip sits on the per-step critical path of the wavefront
+        float cm[KG], nm[KG];
+        float cg1o = 0.f, cg1e = 0.f, ng1o = 0.f, ng1e = 0.f;
+        uint32_t cz = 0, nz = 0;
+        float pMe = 0.f, pUe = 0.f, pLe = 0.f;       // lane 0: prefetched left edge
+        bool have_edge = false;
+        auto fetch_row = [&](int yy, float (&mm)[KG], float& go1, float& ge1, uint32_t& zz) {
+            zz = 0;
+            if (yy >= 1 && yy <= L1 && x0 <= L2) {
+                go1 = a.g1[(size_t)(yy - 1) * 2];
+                ge1 = a.g1[(size_t)(yy - 1) * 2 + 1];
+                const float* mrow = a.m + (size_t)(yy - 1) * a.m_pitch + (x0 - 1);
+#pragma unroll
+                for (int k = 0; k < KG; k++) {
+                    mm[k] = (x0 + k <= L2) ? __ldg(mrow + k) : 0.f;
+                    if (a.z && x0 + k <= L2 && a.z[(size_t)yy * a.z_pitch + x0 + k]) zz |= 1u << k;
+                }
+            }
+        };
+        fetch_row(1 - lane, cm, cg1o, cg1e, cz);
+
         for (int t = 0; t < T; t++) {
             const int y = t - lane + 1;               // my row this step (1-based)
             const bool active = (y >= 1) && (y <= L1) && (x0 <= L2);
+            fetch_row(y + 1, nm, ng1o, ng1e, nz);     // in flight while this row is computed
             // lane 0 needs rows up to y of the left strip; wait for the producer
             int need = min(t + 1, L1);
             if (avail < need) {
@@ -127,12 +151,13 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
             float Ul = __shfl_up_sync(FULL, Ue, 1);
             float Ll = __shfl_up_sync(FULL, Le, 1);
             if (lane == 0 && y <= L1) {
-                const float* e = ein + (size_t)y * 3;
-                Ml = __ldcg(e); Ul = __ldcg(e + 1); Ll = __ldcg(e + 2);
+                if (have_edge) { Ml = pMe; Ul = pUe; Ll = pLe; }
+                else { const float* e = ein + (size_t)y * 3; Ml = __ldcg(e); Ul = __ldcg(e + 1); Ll = __ldcg(e + 2); }
+                have_edge = (y + 1 <= L1) && (y + 1 <= avail);
+                if (have_edge) { const float* e = ein + (size_t)(y + 1) * 3; pMe = __ldcg(e); pUe = __ldcg(e + 1); pLe = __ldcg(e + 2); }
             }
             if (active) {
-                const float g1o = a.g1[(size_t)(y - 1) * 2], g1e = a.g1[(size_t)(y - 1) * 2 + 1];
-                const float* mrow = a.m + (size_t)(y - 1) * a.m_pitch + (x0 - 1);
+                const float g1o = cg1o, g1e = cg1e;
                 const float dM = Ml, dU = Ul, dL = Ll;   // become next row's diagonal seed
                 float cMl = Ml, cLl = Ll;                // left neighbour M / L in this row
                 uint8_t fl[KG];
@@ -142,9 +167,9 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
                     float M = 0.f, U = 0.f, L = 0.f;
                     uint8_t f = 0;
                     const bool valid = x <= L2;
-                    const bool masked = valid && a.z && a.z[(size_t)y * a.z_pitch + x];
+                    const bool masked = (cz >> k) & 1u;
                     if (valid && !masked) {
-                        const float s = mrow[k];
+                        const float s = cm[k];
                         const float up_open = Mp[k] + g1o, up_ext = Up[k] + g1e;
                         const float lf_open = cMl + go2[k], lf_ext = cLl + ge2[k];
                         const float mm = Md + s, mu = Ud + s, ml = Ld + s;
@@ -203,6 +228,9 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
                 Me = Mp[KG - 1]; Ue = Up[KG - 1]; Le = Lp[KG - 1];
                 if (lane == 31) { float* e = eout + (size_t)y * 3; e[0] = Me; e[1] = Ue; e[2] = Le; }
             }
+#pragma unroll
+            for (int k = 0; k < KG; k++) cm[k] = nm[k];
+            cg1o = ng1o; cg1e = ng1e; cz = nz;
             // publish progress of the right edge every 8 rows and at the end
             const int done = t - 31 + 1;   // rows finished by lane 31 after this step
             if (done >= 1 && ((done & 7) == 0 || done == L1)) {
@@ -267,9 +295,15 @@ __global__ void k_gen_finalize(const GenArgs a)
 }
 
 // ---- traceback (reference util/align.py:144-185, :268-297) -----------------------------------
-__global__ void k_gen_traceback(const GenArgs a)
+// One warp.  The walk is a chain of dependent byte loads; instead of paying an L2 round trip per
+// step, the warp stages a 16 x 64 tile of flag bytes ending at the current cell in shared memory
+// (two coalesced 16-byte loads per lane) and lane 0 walks inside it until it leaves the tile.
+#define TB_TR 16
+#define TB_TC 64
+__global__ void __launch_bounds__(32) k_gen_traceback(const GenArgs a)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ __align__(16) uint8_t tile[TB_TR][TB_TC];
+    const int lane = threadIdx.x;
     const int L1 = a.L1, L2 = a.L2;
     const bool u_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_ONE);
     const bool l_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_TWO);
@@ -278,35 +312,61 @@ __global__ void k_gen_traceback(const GenArgs a)
     int w = cap;
     auto push = [&](int yy, int xx) { --w; a.path_buf[2 * w] = yy; a.path_buf[2 * w + 1] = xx; };
     const bool semi = (a.mode >= PG_SG_BOTH);
-    if (semi) {
+    if (lane == 0 && semi) {
         if (y != L1) { for (int v = L1; v > y; v--) push(v, x); }
         else if (x != L2) { for (int v = L2; v > x; v--) push(y, v); }
     }
-    for (;;) {
-        push(y, x);
-        uint8_t f;
-        if (y == 0 && x == 0) f = 0;
-        else if (x == 0) f = (u_ramp && k == 1) ? TB_UE : 0;
-        else if (y == 0) f = (l_ramp && k == 2) ? TB_LE : 0;
-        else {
-            f = a.flags[(size_t)y * a.f_pitch + x];
-            f &= (k == 0) ? (TB_MM | TB_MU | TB_ML) : (k == 1 ? (TB_UO | TB_UE) : (TB_LO | TB_LE));
+    int done = 0;
+    while (!done) {
+        // stage the tile whose bottom-right region holds (y, x); border cells need no tile
+        int ty0 = max(0, y - TB_TR + 1);
+        int tx0 = max(0, (x - (TB_TC - 16)) & ~15);
+        tx0 = min(tx0, a.f_pitch - TB_TC);
+        if (y >= 1 && x >= 1) {
+            const int r = lane >> 1, h = lane & 1;
+            const int row = min(ty0 + r, L1);
+            const uint4* src = reinterpret_cast<const uint4*>(a.flags + (size_t)row * a.f_pitch + tx0 + h * 32);
+            uint4* dst = reinterpret_cast<uint4*>(&tile[r][h * 32]);
+            dst[0] = src[0];
+            dst[1] = src[1];
         }
-        if (f & TB_MM) { y--; x--; k = 0; }
-        else if (f & TB_MU) { y--; x--; k = 1; }
-        else if (f & TB_ML) { y--; x--; k = 2; }
-        else if (f & TB_UO) { y--; k = 0; }
-        else if (f & TB_UE) { y--; k = 1; }
-        else if (f & TB_LO) { x--; k = 0; }
-        else if (f & TB_LE) { x--; k = 2; }
-        else break;
+        __syncwarp();
+        if (lane == 0) {
+            for (;;) {
+                push(y, x);
+                uint8_t f;
+                if (y == 0 && x == 0) f = 0;
+                else if (x == 0) f = (u_ramp && k == 1) ? TB_UE : 0;
+                else if (y == 0) f = (l_ramp && k == 2) ? TB_LE : 0;
+                else {
+                    f = tile[y - ty0][x - tx0];
+                    f &= (k == 0) ? (TB_MM | TB_MU | TB_ML) : (k == 1 ? (TB_UO | TB_UE) : (TB_LO | TB_LE));
+                }
+                if (f & TB_MM) { y--; x--; k = 0; }
+                else if (f & TB_MU) { y--; x--; k = 1; }
+                else if (f & TB_ML) { y--; x--; k = 2; }
+                else if (f & TB_UO) { y--; k = 0; }
+                else if (f & TB_UE) { y--; k = 1; }
+                else if (f & TB_LO) { x--; k = 0; }
+                else if (f & TB_LE) { x--; k = 2; }
+                else { done = 1; break; }
+                // still inside the staged tile (or on a border, which needs none)?
+                if (y >= 1 && x >= 1 && (y < ty0 || x < tx0)) break;
+            }
+        }
+        __syncwarp();
+        done = __shfl_sync(FULL, done, 0);
+        y = __shfl_sync(FULL, y, 0);
+        x = __shfl_sync(FULL, x, 0);
     }
-    if (semi) {
-        if (y != 0) { for (int v = y - 1; v >= 0; v--) push(v, 0); }
-        else if (x != 0) { for (int v = x - 1; v >= 0; v--) push(0, v); }
+    if (lane == 0) {
+        if (semi) {
+            if (y != 0) { for (int v = y - 1; v >= 0; v--) push(v, 0); }
+            else if (x != 0) { for (int v = x - 1; v >= 0; v--) push(0, v); }
+        }
+        *a.path_start = w;
+        *a.path_len = cap - w;
     }
-    *a.path_start = w;
-    *a.path_len = cap - w;
 }
 
 // ---- K1: match-score matrix in the reference's evaluation order ------------------------------
@@ -314,14 +374,15 @@ __global__ void k_gen_traceback(const GenArgs a)
 // accumulated sequentially per set, sets added in order (cext.c:63-95, :388-421).  Explicit
 // _rn intrinsics keep ptxas from contracting the multiply-add.
 
-__global__ void k_build_scores(int n_sets, const ScoreSet* sets, int L1, int L2, float* m, int m_pitch)
+__global__ void k_build_scores(const ScoreSets sets, int L1, int L2, float* m, int m_pitch)
 {
+    const int n_sets = sets.n;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= L2 || y >= L1) return;
     float score = 0.f;
     for (int n = 0; n < n_sets; n++) {
-        const ScoreSet st = sets[n];
+        const ScoreSet st = sets.s[n];
         const float* r1 = st.P1 + (size_t)y * st.A;
         const float* r2 = st.P2 + (size_t)x * st.A;
         float acc = 0.f;
@@ -338,6 +399,52 @@ __global__ void k_build_scores(int n_sets, const ScoreSet* sets, int L1, int L2,
         score = __fadd_rn(score, acc);
     }
     m[(size_t)y * m_pitch + x] = score;
+}
+
+// Batched form for the matrix-fed streaming kernel: one matrix row per stream position of a
+// wave (rows in stream order, `width` = 32*K floats each).  rowsrc[r] is the global profile row
+// of the STREAMED sequence at that position (-1: dummy row), rowres[r] the resident sequence.
+// Same evaluation order as above; `transposed` says the resident is sequence one.
+__global__ void __launch_bounds__(128) k_build_rows(const float* __restrict__ prof, const int64_t* __restrict__ rowoff,
+                                                    int A, const float* __restrict__ S,
+                                                    const int32_t* __restrict__ rowsrc,
+                                                    const int32_t* __restrict__ rowres, int64_t n_rows, int width,
+                                                    int transposed, float padv, float* __restrict__ mwave)
+{
+    extern __shared__ float sh[];   // S [A*A] then the streamed profile row [A]
+    const int xblocks = (width + 127) / 128;
+    const int64_t r = blockIdx.x / xblocks;
+    const int x = (int)(blockIdx.x % xblocks) * 128 + threadIdx.x;
+    if (r >= n_rows) return;
+    const int src = rowsrc[r];
+    for (int i = threadIdx.x; i < A * A; i += 128) sh[i] = S[i];
+    if (src >= 0) for (int i = threadIdx.x; i < A; i += 128) sh[A * A + i] = prof[(size_t)src * A + i];
+    __syncthreads();
+    if (x >= width) return;
+    float v = padv;
+    if (src >= 0) {
+        const int res = rowres[r];
+        const int64_t r0 = rowoff[res];
+        const int Lr = (int)(rowoff[res + 1] - r0);
+        if (x < Lr) {
+            const float* rr = prof + (size_t)(r0 + x) * A;   // resident profile row
+            const float* sr = sh + A * A;                    // streamed profile row
+            float acc = 0.f;
+            for (int i = 0; i < A; i++) {
+                const float p1 = transposed ? rr[i] : sr[i];
+                if (p1 == 0.f) continue;
+                for (int j = 0; j < A; j++) {
+                    const float p2 = transposed ? sr[j] : rr[j];
+                    if (p2 == 0.f) continue;
+                    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p2, sh[i * A + j]), p1));
+                }
+            }
+            v = __fadd_rn(0.f, acc);
+        }
+    } else {
+        v = 0.f;
+    }
+    mwave[(size_t)r * width + x] = v;
 }
 
 // Sequence x sequence: one-hot profiles make the sum collapse to exactly S[a_y][b_x].
@@ -386,12 +493,24 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
     return 0;
 }
 
-int pg_launch_build_scores(int n_sets, const ScoreSet* sets_dev, int L1, int L2, float* m, int m_pitch,
-                           cudaStream_t st)
+int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st)
 {
     if (L1 <= 0 || L2 <= 0) return 0;
     dim3 b(32, 8), g((L2 + 31) / 32, (L1 + 7) / 8);
-    k_build_scores<<<g, b, 0, st>>>(n_sets, sets_dev, L1, L2, m, m_pitch);
+    k_build_scores<<<g, b, 0, st>>>(sets, L1, L2, m, m_pitch);
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const int32_t* rowsrc,
+                         const int32_t* rowres, int64_t n_rows, int width, int transposed, float padv, float* mwave,
+                         cudaStream_t st)
+{
+    if (n_rows <= 0) return 0;
+    const int64_t blocks = n_rows * ((width + 127) / 128);
+    if (blocks > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)blocks); return 1; }
+    k_build_rows<<<(unsigned)blocks, 128, sizeof(float) * (A * A + A), st>>>(prof, rowoff, A, S, rowsrc, rowres, n_rows,
+                                                                           width, transposed, padv, mwave);
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -52,7 +52,9 @@ __device__ __forceinline__ float pick(const float (&v)[K], int k)
 
 // KM: 0 = global, 1 = local (score only), 2 = semiglobal.  TB: write packed traceback.
 // TR: traceback tie order for a transposed (resident = sequence one) launch.
-template <int K, int KM, bool TB, bool TR, int NW>
+// MS: match scores come from a materialised matrix in HBM (profile x profile batches, rows in
+//     stream order, 32*K floats per row) instead of the shared-memory substitution profile.
+template <int K, int KM, bool TB, bool TR, bool MS, int NW>
 __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
 {
     constexpr int UNR = TB ? 8 : 4;   // steps unrolled per inner iteration (8 = one traceback word)
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
     constexpr int ROWB = NCH * 512;
     extern __shared__ __align__(16) unsigned char smem[];
     float* prof = reinterpret_cast<float*>(smem);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (size_t)a.A * ROWB) + (threadIdx.x >> 5) * 128;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + (MS ? 0 : (size_t)a.A * ROWB)) + (threadIdx.x >> 5) * 128;
 
     const PgTile tile = a.tiles[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
     const int Lr = (int)(a.offs[tile.resident + 1] - roff);
 
     // ---- substitution profile of the resident, [a][chunk][lane][4] ------------------------
-    {
+    if (!MS) {
         const float padv = (KM == 1) ? -INFINITY : 0.f;
         const int n = a.A * NCH * 128;
         for (int idx = threadIdx.x; idx < n; idx += NW * 32) {
@@ -81,8 +83,8 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
             }
             prof[idx] = v;
         }
-        for (int i = lane; i < 128; i += 32) ring[i] = (uint32_t)__cvta_generic_to_shared(smem);
     }
+    for (int i = lane; i < 128; i += 32) ring[i] = MS ? 0u : (uint32_t)__cvta_generic_to_shared(smem);
     __syncthreads();
 
     // ---- this warp's slice of the tile's stream --------------------------------------------
@@ -109,10 +111,11 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
     const float go = a.go, ge = a.ge;
     const float left0 = a.left0, left1 = a.left1;
     const int64_t tbw0 = TB ? a.tb_base[(int64_t)blockIdx.x * NW + warp] : 0;
+    const float* mwarp = MS ? a.mwave + a.mrow_base[(int64_t)blockIdx.x * NW + warp] * (32 * K) : nullptr;
     const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t lane16 = (uint32_t)lane << 4;
-    if (prof_s & 511u) __trap();   // row addresses are OR-ed with the lane offset below
+    if (!MS && (prof_s & 511u)) __trap();   // row addresses are OR-ed with the lane offset below
 
     float Mo[K], U[K], D[K];
     uint32_t acc[K];
@@ -134,10 +137,12 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
                 s++;
                 len = (s < se) ? seq_len(s) : 0;
             }
-            uint32_t word = prof_s;
+            uint32_t word = MS ? 0u : prof_s;
             if (s < se) {
                 if (s < sb) {
                     word |= FLAG_LAST;
+                } else if (MS) {   // the matrix row of stream position t0 + lane is that position itself
+                    word = (uint32_t)(t0 + lane) | ((p == len - 1) ? (FLAG_LAST | FLAG_EMIT) : 0u);
                 } else {
                     const int sym = a.seqs[a.offs[seq_id(s)] + p];
                     word = (prof_s + (uint32_t)(sym * ROWB)) | ((p == len - 1) ? (FLAG_LAST | FLAG_EMIT) : 0u);
@@ -163,13 +168,27 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
                 const int t = t0 + g + i;
                 uint32_t w;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)i * 4u) : "memory");
-                const uint32_t pa = (w & 0x00ffffffu) | lane16;
                 float sc[NCH * 4];
+                if (MS) {
+                    const float* mr = mwarp + (size_t)(w & 0x00ffffffu) * (32 * K) + lane * K;
+                    if (K % 4 == 0) {
 #pragma unroll
-                for (int j = 0; j < NCH; j++)
-                    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                        : "=f"(sc[4 * j]), "=f"(sc[4 * j + 1]), "=f"(sc[4 * j + 2]), "=f"(sc[4 * j + 3])
-                        : "r"(pa + (uint32_t)j * 512u));
+                        for (int j = 0; j < K / 4; j++) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(mr) + j);
+                            sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; k++) sc[k] = __ldg(mr + k);
+                    }
+                } else {
+                    const uint32_t pa = (w & 0x00ffffffu) | lane16;
+#pragma unroll
+                    for (int j = 0; j < NCH; j++)
+                        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                            : "=f"(sc[4 * j]), "=f"(sc[4 * j + 1]), "=f"(sc[4 * j + 2]), "=f"(sc[4 * j + 3])
+                            : "r"(pa + (uint32_t)j * 512u));
+                }
 
                 // ---- strip edge from the left lane (its results of the previous step = my row)
                 float Ml = __shfl_up_sync(FULL, Mo_last, 1);
@@ -299,12 +318,12 @@ __global__ void k_semi_scores(int64_t n, const unsigned long long* rowkey, const
 // ---- launch ------------------------------------------------------------------------------------
 constexpr int kNW = 8;
 
-template <int K, int KM, bool TB, bool TR>
+template <int K, int KM, bool TB, bool TR, bool MS = false>
 static int launch_one(const StreamArgs& a, int n_tiles, cudaStream_t st)
 {
     constexpr int NCH = (K + 3) / 4;
-    const size_t smem = (size_t)a.A * NCH * 512 + kNW * 128 * sizeof(uint32_t);
-    auto kern = k_stream<K, KM, TB, TR, kNW>;
+    const size_t smem = (MS ? 0 : (size_t)a.A * NCH * 512) + kNW * 128 * sizeof(uint32_t);
+    auto kern = k_stream<K, KM, TB, TR, MS, kNW>;
     PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_tiles, kNW * 32, smem, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
@@ -314,6 +333,12 @@ static int launch_one(const StreamArgs& a, int n_tiles, cudaStream_t st)
 template <int K>
 static int launch_k(const StreamArgs& a, int n_tiles, int km, bool tb, cudaStream_t st)
 {
+    if (a.mwave) {   // profile batches: score only, scores read from the materialised matrix
+        if (tb) { pg_set_error("matrix-fed batches are score-only; traced profile alignments use the general kernel"); return 1; }
+        if (km == 0) return launch_one<K, 0, false, false, true>(a, n_tiles, st);
+        if (km == 1) return launch_one<K, 1, false, false, true>(a, n_tiles, st);
+        return launch_one<K, 2, false, false, true>(a, n_tiles, st);
+    }
     if (!tb) {
         if (km == 0) return launch_one<K, 0, false, false>(a, n_tiles, st);
         if (km == 1) return launch_one<K, 1, false, false>(a, n_tiles, st);

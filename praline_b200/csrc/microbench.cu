@@ -3,18 +3,19 @@
 // the DP fill is bound by CUDA-core instruction issue, and
 // MEASURED_PEAKS.json has no such figure, so the box is probed directly.  Each kernel runs
 // 32 warps per SM, every thread carrying 8 independent dependency chains of one instruction
-// kind, and reports warp-instructions per clock per SM from clock64 deltas on the SM itself.
+// kind; rates are wall-clock (CUDA events) warp-instructions per nanosecond per SM.
 #include "common.cuh"
 #include "../../include/praline_b200.h"
 
 #include <vector>
 
 #define CH 8
-#define ITERS 2048
+#define ITERS 2048          // clock64-timed burst (SM clock probe)
+#define LONG_ITERS 32768    // event-timed runs behind the reported rates
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin, float* fout, long long* cyc,
-                                               unsigned long long* ns = nullptr)
+                                               unsigned long long* ns = nullptr, int iters = ITERS)
 {
     float f[CH];
     int v[CH];
@@ -28,8 +29,8 @@ __global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin,
     unsigned long long g0 = 0, g1 = 0;
     if (ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
-#pragma unroll 2
-    for (int it = 0; it < ITERS; it++) {
+#pragma unroll 4
+    for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < CH; i++) {
             if (OP == 0) asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c1));
@@ -70,22 +71,27 @@ __global__ void __launch_bounds__(1024) k_rate(const float* fin, const int* iin,
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// Rate of one instruction kind in warp-instructions per NANOSECOND per SM, wall-clock timed with
+// CUDA events over a ~ms run (independent of any on-chip counter); divide by the SM clock in
+// GHz for a per-clock figure.
 template <int OP>
 static int run_rate(int sms, const float* fin, const int* iin, float* fout, long long* cyc, double* rate)
 {
-    k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc);   // warm-up
-    k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc);
+    k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc, nullptr, ITERS);   // warm-up
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc, nullptr, LONG_ITERS);
+    cudaEventRecord(e1);
     PG_CUDA_OK(cudaGetLastError());
     PG_CUDA_OK(cudaDeviceSynchronize());
-    std::vector<long long> h(sms);
-    PG_CUDA_OK(cudaMemcpy(h.data(), cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
-    double mean = 0;
-    for (int i = 0; i < sms; i++) mean += (double)h[i];
-    mean /= sms;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     const double per_it = (OP == 3) ? 7.0 : 1.0;
-    double extra = (OP == 7) ? 2.0 : 1.0;   // the LDS kernel issues LDS + FADD
-    (void)extra;
-    *rate = 32.0 * CH * ITERS * per_it / mean;   // warp-instructions of the probed kind per clock per SM
+    *rate = 32.0 * CH * (double)LONG_ITERS * per_it / ((double)ms * 1e6);
     return 0;
 }
 
@@ -123,7 +129,7 @@ extern "C" int pgpu_microbench(double* out, int n)
     // SM clock held during a burst of the cell mix: SM cycles (clock64) over %globaltimer ns
     unsigned long long* ns = nullptr;
     PG_CUDA_OK(cudaMalloc((void**)&ns, sizeof(unsigned long long) * sms));
-    for (int rep = 0; rep < 20; rep++) k_rate<3><<<sms, 1024>>>(fin, iin, fout, cyc, ns);
+    for (int rep = 0; rep < 20; rep++) k_rate<3><<<sms, 1024>>>(fin, iin, fout, cyc, ns, ITERS);
     PG_CUDA_OK(cudaDeviceSynchronize());
     long long c0 = 0;
     unsigned long long n0 = 0;

@@ -78,6 +78,56 @@ class SeqBatch(object):
         return self.flat_host.numel() + self.offs_host.numel() * 8
 
 
+def plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, offs):
+    """Row layout of one wave of a profile batch.  Every (tile, warp) region holds one dummy row
+    followed by the profile rows of its streamed sequences in stream order, so that the matrix
+    row of a stream position IS that position.  Returns (first row per region, profile row per
+    matrix row or -1, resident id per matrix row, number of rows)."""
+    tb_, te_ = wt["stream_begin"].astype(np.int64), wt["stream_end"].astype(np.int64)
+    per = (te_ - tb_ + nw - 1) // nw
+    w = np.arange(nw)[None, :]
+    sb = tb_[:, None] + w * per[:, None]
+    se = np.minimum(sb + per[:, None], te_[:, None])
+    sb = np.minimum(sb, se)
+    reg_rows = np.where(se > sb, cs[se] - cs[sb] + 1, 0).ravel()      # +1: the dummy row
+    mrow_base = np.zeros(reg_rows.size, np.int64)
+    np.cumsum(reg_rows[:-1], out=mrow_base[1:])
+    n_rows = int(reg_rows.sum())
+    e_lo, e_hi = int(tb_[0]), int(te_[-1])
+    el = lens_s[e_lo:e_hi]
+    reg_of = np.repeat(np.arange(reg_rows.size), (se - sb).ravel())   # region of every stream element
+    e_start = mrow_base[reg_of] + 1 + (cs[e_lo:e_hi] - cs[sb.ravel()[reg_of]])
+    rowsrc = np.full(n_rows, -1, np.int32)
+    rowres = np.zeros(n_rows, np.int32)
+    tot = int(el.sum())
+    within = np.arange(tot) - np.repeat(np.cumsum(el) - el, el)
+    dst = np.repeat(e_start, el) + within
+    rowsrc[dst] = (np.repeat(offs[str_s[e_lo:e_hi]], el) + within).astype(np.int32)
+    rowres[dst] = np.repeat(res_s[e_lo:e_hi], el).astype(np.int32)
+    return mrow_base, rowsrc, rowres, n_rows
+
+
+class ProfileBatch(object):
+    """A set of f32 profiles [L x A] resident on the device: one [rows x A] array plus int64 row
+    offsets (the analogue of SeqBatch for ProfileTrack inputs, component/align.py:171-172)."""
+
+    def __init__(self, engine, profiles):
+        profiles = [np.ascontiguousarray(p, np.float32) for p in profiles]
+        self.lens = np.asarray([p.shape[0] for p in profiles], np.int64)
+        if len(profiles) == 0 or (self.lens <= 0).any():
+            raise ValueError("empty sequences cannot be aligned")
+        self.A = int(profiles[0].shape[1])
+        if any(p.shape[1] != self.A for p in profiles):
+            raise ValueError("profiles of one batch must share an alphabet")
+        self.n = len(profiles)
+        self.offs = np.zeros(self.n + 1, np.int64)
+        np.cumsum(self.lens, out=self.offs[1:])
+        self.prof_dev = engine.dev(np.concatenate(profiles, axis=0))
+        self.offs_dev = engine.dev(self.offs)
+        self.flat_dev = None
+        self.max_sym = self.A - 1
+
+
 class Engine(object):
     def __init__(self, device=0, pin=True):
         self.lib = _lib.load()
@@ -92,6 +142,7 @@ class Engine(object):
         self.launches = 0          # kernels of ours launched (bench.py reports it)
         self.tb_budget_words = 1 << 30
         self._borders = {}
+        self.m_budget_floats = 1 << 31     # 8 GiB of match scores per wave of a profile batch
 
     # -- helpers -------------------------------------------------------------------------------
     def stream(self):
@@ -115,6 +166,9 @@ class Engine(object):
 
     def batch(self, seqs):
         return SeqBatch(self, seqs)
+
+    def profile_batch(self, profiles):
+        return ProfileBatch(self, profiles)
 
     # -- inter-task batch ----------------------------------------------------------------------
     def _make_tiles(self, res_sorted, n_stream_total, tile):
@@ -158,7 +212,7 @@ class Engine(object):
 
     def run_tiles(self, mode, K, transposed, batch, stream_ids_dev, tiles, n_slots, S_dev, A, go, ge,
                   scores_dev, cs=None, slot_res_dev=None, slot_str_dev=None, want_paths=False, caps=None,
-                  tiles_dev=None):
+                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None):
         """Launch K2 (+K4) for one K class.  Returns list of (slot_lo, slot_hi, path_off, path_buf,
         path_start, path_len) per wave when want_paths."""
         lib = self.lib
@@ -180,7 +234,8 @@ class Engine(object):
                                             self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
                                             self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1,
                                             self.ptr(scores_dev), self.ptr(keys),
-                                            None, None, None, None, self.stream()))
+                                            None, None, None, None, self.ptr(mwave_dev), self.ptr(mrow_base_dev),
+                                            self.stream()))
             self.launches += 1 + int(semi)
             return out
         # traced: waves bounded by the traceback budget; tiles are in slot order
@@ -208,7 +263,7 @@ class Engine(object):
                                             self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1, self.ptr(sc),
                                             self.ptr(keys),
                                             self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
-                                            self.stream()))
+                                            None, None, self.stream()))
             cap = caps[s_lo:s_hi]
             poff = np.zeros(ns, np.int64)
             np.cumsum(cap[:-1], out=poff[1:])
@@ -305,6 +360,69 @@ class Engine(object):
             paths[o] = paths_sorted[k]
         return scores, paths
 
+    def align_profile_pairs(self, pbatch, pi, pj, S, gap_series, mode="global", resident=None):
+        """Scores of profile x profile pairs (sequence_one = pi[k], sequence_two = pj[k]), one track
+        set, constant gaps: K1 rows in the reference's evaluation order feed the streaming kernel.
+        Score only (GuideTreeBuilder, ad-hoc rounds); traced profile alignments use align_general."""
+        md = MODES[mode]
+        go, ge = _gaps(gap_series)
+        pi = np.asarray(pi, np.int64)
+        pj = np.asarray(pj, np.int64)
+        n = len(pi)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        if A != pbatch.A:
+            raise ValueError("profile alphabet does not match the score matrix")
+        if n == 0:
+            return np.zeros(0, np.float32)
+        if resident is None:
+            resident = "one" if len(np.unique(pi)) < len(np.unique(pj)) else "two"
+        transposed = resident == "one"
+        res, strm = (pi, pj) if transposed else (pj, pi)
+        kcls = np.asarray([self.k_for(int(l)) or -1 for l in pbatch.lens])
+        if (kcls[res] < 0).any():
+            raise _lib.PralineGpuError("resident profile longer than %d: use the general kernel" % (32 * self.k_set[-1]))
+        order = np.lexsort((np.arange(n), res, kcls[res]))
+        res_s, str_s = res[order], strm[order]
+        S_dev = self.dev(S)
+        stream_ids_dev = self.dev(str_s.astype(np.int32))
+        scores_dev = torch.empty(n, dtype=torch.float32, device=self.device)
+        lens_s = pbatch.lens[str_s]
+        cs = np.zeros(n + 1, np.int64)
+        np.cumsum(lens_s, out=cs[1:])
+        kk = kcls[res_s]
+        bounds = np.flatnonzero(np.diff(kk)) + 1
+        tile = self._pick_tile(n)
+        nw = self.nw
+        for a, b in zip(np.concatenate([[0], bounds]), np.concatenate([bounds, [n]])):
+            K = int(kk[a])
+            width = 32 * K
+            tiles = self._make_tiles(res_s[a:b], b - a, tile)
+            for f in ("stream_begin", "stream_end", "out_base"):
+                tiles[f] += a
+            rows_per_tile = (cs[tiles["stream_end"]] - cs[tiles["stream_begin"]]) + nw
+            lo = 0
+            while lo < len(tiles):   # waves bounded by the matrix budget
+                acc = np.cumsum(rows_per_tile[lo:]) * width
+                hi = lo + max(1, int(np.searchsorted(acc, self.m_budget_floats, side="right")))
+                wt = tiles[lo:hi]
+                mrow_base, rowsrc, rowres, n_rows = plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, pbatch.offs)
+                mwave = torch.empty(n_rows * width, dtype=torch.float32, device=self.device)
+                # keep every device temporary referenced until the launches that read it are queued:
+                # a tensor freed right after data_ptr() is handed to the next allocation
+                rowsrc_dev, rowres_dev = self.dev(rowsrc), self.dev(rowres)
+                _lib.check(self.lib.pgpu_build_rows(self.ptr(pbatch.prof_dev), self.ptr(pbatch.offs_dev), A,
+                                                    self.ptr(S_dev), self.ptr(rowsrc_dev), self.ptr(rowres_dev),
+                                                    n_rows, width, int(transposed), int(md == 1), self.ptr(mwave),
+                                                    self.stream()))
+                self.launches += 1
+                self.run_tiles(md, K, transposed, pbatch, stream_ids_dev, wt, n, S_dev, A, go, ge, scores_dev,
+                               mwave_dev=mwave, mrow_base_dev=self.dev(mrow_base))
+                lo = hi
+        out = np.empty(n, np.float32)
+        out[order] = scores_dev.cpu().numpy()
+        return out
+
     def allpairs_tiles(self, batch, shard=(0, 1), tile=None):
         """All unordered pairs (i < j), sequence_one = i resident, sequence_two = j streamed, slots
         in condensed (np.triu_indices) order.  Returns {K: tiles} for this shard and its slot range."""
@@ -391,8 +509,9 @@ class Engine(object):
                 z[tuple(idx)] = 1
             z_dev = self.dev(z)
         ws = torch.empty(int(self.lib.pgpu_general_workspace_bytes(L1, L2)), dtype=torch.uint8, device=self.device)
-        outb = torch.zeros(8, dtype=torch.int32, device=self.device)   # score | cell[3] | start | len
-        pbuf = torch.empty((L1 + L2 + 2, 2), dtype=torch.int32, device=self.device) if want_path else None
+        # one int32 buffer: [score | cell y x k | path start | path len | pad 2] + path rows
+        nrows = (L1 + L2 + 2) if want_path else 0
+        outb = torch.zeros(8 + 2 * nrows, dtype=torch.int32, device=self.device)
         o = t = None
         if want_matrices:
             o = torch.zeros((L1 + 1, L2 + 1, 3), dtype=torch.float32, device=self.device)
@@ -401,16 +520,17 @@ class Engine(object):
         _lib.check(self.lib.pgpu_align_general(md, L1, L2, self.ptr(m_dev), int(m_dev.stride(0)), self.ptr(g1_dev),
                                                self.ptr(g2_dev), self.ptr(z_dev), L2 + 1, self.ptr(ws),
                                                ctypes.c_void_p(base), ctypes.c_void_p(base + 4),
-                                               self.ptr(pbuf), ctypes.c_void_p(base + 16) if want_path else None,
+                                               ctypes.c_void_p(base + 32) if want_path else None,
+                                               ctypes.c_void_p(base + 16) if want_path else None,
                                                ctypes.c_void_p(base + 20) if want_path else None,
                                                self.ptr(o), self.ptr(t), self.stream()))
         self.launches += 3 + int(want_path)
-        h = outb.cpu()
-        score = float(h[:1].view(torch.float32)[0])
+        h = outb.cpu().numpy()          # the single device -> host read of this alignment
+        score = float(h[:1].view(np.float32)[0])
         res = dict(score=score, cell=tuple(int(v) for v in h[1:4]))
         if want_path:
             st, ln = int(h[4]), int(h[5])
-            res["path"] = pbuf[st:st + ln].cpu().numpy()
+            res["path"] = h[8:].reshape(-1, 2)[st:st + ln].copy()
         if want_matrices:
             res["o"], res["t"] = o.cpu().numpy(), t.cpu().numpy()
         return res

@@ -42,7 +42,7 @@ def _path_container(mode, path):
     """Reference container types: list of 2-tuples for global/local (util/align.py:183), int
     ndarray for the semiglobal modes (component/align.py:425-426)."""
     if mode in ("global", "local"):
-        return [(int(y), int(x)) for y, x in path]
+        return list(map(tuple, np.asarray(path).tolist()))
     return np.asarray(path, dtype=int)
 
 
@@ -328,6 +328,47 @@ class _Group(object):
         return _path_container(self.mode, self.paths[k])
 
 
+class _ProfileGroup(object):
+    """Profile x profile pairs of one (mode, matrix, gaps) class: scores from one matrix-fed
+    batch launch, paths (rarely asked for) from the exact general path, pair by pair."""
+
+    def __init__(self, mode, S, gaps):
+        self.mode, self.S, self.gaps = mode, S, gaps
+        self.index = {}
+        self.profiles = []
+        self.pi, self.pj = [], []
+        self.scores = None
+        self.paths = {}
+
+    def add_profile(self, track):
+        k = id(track)
+        if k not in self.index:
+            self.index[k] = len(self.profiles)
+            self.profiles.append(_profile_of(track))
+        return self.index[k]
+
+    def add_pair(self, t1, a, t2, b):
+        self.pi.append(self.add_profile(t1))
+        self.pj.append(self.add_profile(t2))
+        return len(self.pi) - 1
+
+    def run_scores(self, eng):
+        pb = eng.profile_batch(self.profiles)
+        self.scores = eng.align_profile_pairs(pb, self.pi, self.pj, self.S, self.gaps, mode=self.mode)
+
+    def path(self, k):
+        if k not in self.paths:
+            eng = get_engine()
+            p1, p2 = self.profiles[self.pi[k]], self.profiles[self.pj[k]]
+            m = eng.build_scores([p1], [p2], [self.S])
+            g1 = np.empty((p1.shape[0], 2), np.float32)
+            g2 = np.empty((p2.shape[0], 2), np.float32)
+            g1[:] = self.gaps
+            g2[:] = self.gaps
+            self.paths[k] = eng.align_general(self.mode, m, g1, g2)["path"]
+        return _path_container(self.mode, self.paths[k])
+
+
 class GpuBatchManager(Manager):
     """Manager whose execute_many aligns all PairwiseAligner requests of an Execution in one
     batched launch per (mode, matrix, gaps) group (manager.py:154-170)."""
@@ -374,7 +415,17 @@ class GpuBatchManager(Manager):
         _check_mode(mode)
         hit = _batchable(sets, gaps, None, mode, eng)
         if hit is None:
-            return None
+            # profile x profile, one track set: matrix-fed batch (scores), exact general path (paths)
+            if len(sets) != 1:
+                return None
+            t1, t2, sm = sets[0]
+            if eng.k_for(max(len(t1), len(t2))) is None:
+                return None
+            key = ("prof", mode, id(sm), float(gaps[0]), float(gaps[1]))
+            if key not in groups:
+                groups[key] = _ProfileGroup(mode, sm.matrix.astype(np.float32), gaps)
+            g = groups[key]
+            return g, g.add_pair(t1, None, t2, None)
         a, b, S = hit
         key = (mode, id(sets[0][2]), float(gaps[0]), float(gaps[1]))
         if key not in groups:

@@ -161,6 +161,31 @@ def test_profiles_vs_golden(eng, golden_prof, golden_mats):
         assert np.array_equal(r["path"], c["path"])
 
 
+@pytest.mark.parametrize("resident", ["one", "two"])
+def test_profile_batches_vs_oracle(eng, resident):
+    """Matrix-fed batch: scores of profile x profile pairs are bit-identical to the oracle
+    (same evaluation order for m, same recurrence), all modes, ragged lengths."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(8)
+    profs = []
+    for k in range(14):
+        L = int(rng.integers(5, 200))
+        profs.append(synth.profile_from_counts(synth.count_profile(300 + k, L, int(rng.integers(1, 9)), 20, 27)))
+    pb = eng.profile_batch(profs)
+    pi, pj = synth.all_pairs(len(profs))
+    pi, pj = np.concatenate([pi, pj[:15]]), np.concatenate([pj, pi[:15]])
+    for mode, gaps in (("global", [-11.0, -1.0]), ("semiglobal_both", [-2.5, -0.5]), ("local", [-11.0, -1.0]),
+                       ("semiglobal_one", [-4.0]), ("semiglobal_two", [-11.0, -1.0])):
+        got = eng.align_profile_pairs(pb, pi, pj, S, gaps, mode=mode, resident=resident)
+        for k in range(len(pi)):
+            p1, p2 = profs[pi[k]], profs[pj[k]]
+            m = oracle.build_scores([p1], [p2], [S])
+            g1, g2 = oracle.gap_arrays(p1.shape[0], p2.shape[0], gaps)
+            want, _ = oracle.align_raw(mode, m, g1, g2)
+            assert abs(float(got[k]) - want) <= 1e-5 * max(1.0, abs(want)), (mode, k)   # stated tolerance
+            assert float(got[k]) == want, (mode, k)                                     # and in fact exact
+
+
 def test_two_track_sets(eng):
     rng = np.random.default_rng(3)
     S1, S2 = matrices.blosum62(), rng.standard_normal((15, 15)).astype(np.float32)
