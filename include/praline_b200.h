@@ -93,14 +93,22 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, c
  * semiglobal end-cell scan (component/align.py:405-426) and extend_path_semiglobal
  * (util/align.py:268-297).  Paths are (y, x) rows in the reference orientation, written
  * right-aligned into each slot's region of capacity len(resident)+len(stream)+2 rows:
- * rows [path_off[s] + path_start[s], +path_len[s]).
+ * rows [path_off[s] + path_start[s], +path_len[s]).  path_buf may be NULL when counts is given.
+ *
+ * Preprofile mode (counts_dev != NULL, global mode): every pair is (master = sequence one,
+ * slave = sequence two); the walk adds the slave's aligned residues into the master's count
+ * table counts_dev + cnt_off[slot] ([len(master)][A] int32), which is what compress_path +
+ * Alignment.merge + get_frequencies produce on the host in the reference (util/align.py:187-232,
+ * container/align.py:30-61; preprofile.py:127-154).  Pairs with score < threshold are skipped.
  */
 int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs_dev,
                          const int32_t* slot_resident_dev, const int32_t* slot_stream_dev, int64_t n_slots,
                          const uint64_t* keys_dev, const uint32_t* tb_dev, const int32_t* emit_t_dev,
                          const int64_t* pair_tb_dev, int code00, int top_ramp, int left_ramp,
                          const int64_t* path_off_dev, int32_t* path_buf_dev, int32_t* path_start_dev,
-                         int32_t* path_len_dev, void* stream);
+                         int32_t* path_len_dev, const uint8_t* seqs_dev, int32_t* counts_dev,
+                         const int64_t* cnt_off_dev, int A, const float* scores_dev, int use_threshold,
+                         float threshold, void* stream);
 
 /*
  * Match-score matrix (K1).  Replaces cext_build_scores (cext.c:308-455): m[y][x] = sum over

@@ -84,7 +84,8 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, c
                          const int32_t* slot_stream, int64_t n_slots, const uint64_t* keys,
                          const uint32_t* tb, const int32_t* emit_t, const int64_t* pair_tb, int code00,
                          int top_ramp, int left_ramp, const int64_t* path_off, int32_t* path_buf,
-                         int32_t* path_start, int32_t* path_len, void* stream)
+                         int32_t* path_start, int32_t* path_len, const uint8_t* seqs, int32_t* counts,
+                         const int64_t* cnt_off, int A, const float* scores, int use_thr, float thr, void* stream)
 {
     TraceArgs a;
     memset(&a, 0, sizeof(a));
@@ -95,6 +96,10 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, c
     a.colkey = keys ? (const unsigned long long*)keys + n_slots : nullptr;
     a.code00 = code00; a.top_ramp = top_ramp; a.left_ramp = left_ramp;
     a.path_off = path_off; a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
+    a.seqs = seqs; a.counts = counts; a.cnt_off = cnt_off; a.A = A; a.scores = scores; a.use_thr = use_thr; a.thr = thr;
+    if (counts && (!seqs || !cnt_off || (use_thr && !scores))) { pg_set_error("preprofile mode needs seqs, cnt_off and scores"); return 1; }
+    if (counts && mode != PG_GLOBAL) { pg_set_error("preprofile counts are defined for global master-slave alignments"); return 1; }
+    if (!counts && !path_buf) { pg_set_error("nothing to produce: neither paths nor counts requested"); return 1; }
     return pg_launch_traceback(a, (cudaStream_t)stream);
 }
 

@@ -73,6 +73,14 @@ struct TraceArgs {
     int32_t* path_buf;              // [rows][2] = (y, x) in the REFERENCE orientation
     int32_t* path_start;            // per slot: first used row within its region
     int32_t* path_len;              // per slot: rows used
+    // preprofile mode (counts != NULL): per-master symbol counts instead of / besides paths
+    const uint8_t* seqs;            // symbols (with offs)
+    int32_t* counts;                // all masters' [L x A] tables
+    const int64_t* cnt_off;         // per slot: offset of its master's table
+    int A;
+    const float* scores;            // per slot, for the score threshold
+    int use_thr;
+    float thr;
 };
 
 // Arguments of the general single-alignment path (general.cu).

@@ -18,6 +18,15 @@
 // component/align.py:367-385 (ramp borders chain back along the edge, zero borders stop).
 // The path is emitted in the REFERENCE orientation, rows (y, x), written back to front into
 // the pair's region so that no reversal pass is needed.
+//
+// Preprofile mode (a.counts != NULL).  The walk also does, on the fly, what the reference does
+// on the host for every master-slave pair: compress_path(path, 0) (util/align.py:215-232),
+// Alignment.merge (container/align.py:30-61) and get_frequencies (util/align.py:187-213).  Their
+// net effect on the master's count table is: for each master position y, the slave residue at
+// x_y is counted iff x_y > x_{y-1}, where x_y is the slave index of the FIRST path row whose
+// master index is y.  Counts are order-independent sums, so pairs add with atomics straight
+// into the master's [L x A] table and no path ever leaves the device.  Pairs below the score
+// threshold are skipped (preprofile.py:144-145).
 #include "common.cuh"
 
 __device__ __forceinline__ float tkey_value(unsigned long long k)
@@ -31,6 +40,7 @@ __global__ void k_traceback(const TraceArgs a)
 {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.n_slots) return;
+    if (a.counts && a.use_thr && !(a.scores[slot] >= a.thr)) return;
     const int rid = a.slot_resident[slot], sid = a.slot_stream[slot];
     const int Lr = (int)(a.offs[rid + 1] - a.offs[rid]);   // kernel columns
     const int Ls = (int)(a.offs[sid + 1] - a.offs[sid]);   // kernel rows
@@ -71,13 +81,25 @@ __global__ void k_traceback(const TraceArgs a)
     }
     int s = code_at(yk, xk);
 
-    const int64_t base = a.path_off[slot];
+    const int64_t base = a.path_buf ? a.path_off[slot] : 0;
     const int cap = Lr + Ls + 2;
     int w = cap;
+    const bool want_path = a.path_buf != nullptr;
     auto push = [&](int yr, int xr) {
         --w;
-        a.path_buf[2 * (base + w)] = yr;
-        a.path_buf[2 * (base + w) + 1] = xr;
+        if (want_path) {
+            a.path_buf[2 * (base + w)] = yr;
+            a.path_buf[2 * (base + w) + 1] = xr;
+        }
+    };
+    // preprofile mode: sequence one is the master, sequence two the slave
+    int* cnt = a.counts ? a.counts + a.cnt_off[slot] : nullptr;
+    const uint8_t* slave = a.seqs ? a.seqs + a.offs[TR ? sid : rid] : nullptr;
+    int pend_y = -1, pend_x = 0;
+    auto kept = [&](int yr, int xr) {   // (yr, xr) is the first path row with master index yr
+        if (cnt && pend_y == yr + 1 && pend_x > xr) atomicAdd(cnt + (int64_t)(pend_y - 1) * a.A + slave[pend_x - 1], 1);
+        pend_y = yr;
+        pend_x = xr;
     };
 
     if (a.mode != PG_GLOBAL) {  // extend_path_semiglobal, trailing part (util/align.py:283-295)
@@ -87,24 +109,26 @@ __global__ void k_traceback(const TraceArgs a)
     }
 
     for (;;) {
-        push(TR ? xk : yk, TR ? yk : xk);
-        if (yk == 0 && xk == 0) break;
-        if (xk == 0) {
-            if (s == 1 && a.left_ramp) { yk--; continue; }
-            break;
-        }
-        if (yk == 0) {
-            if (s == 2 && a.top_ramp) { xk--; continue; }
-            break;
-        }
-        if (s == 0) {
-            yk--; xk--;
-            s = code_at(yk, xk);
+        const int cy = TR ? xk : yk, cx = TR ? yk : xk;   // reference coordinates of this cell
+        push(cy, cx);
+        int ny = yk, nx = xk;
+        bool moved = true;
+        if (yk == 0 && xk == 0) moved = false;
+        else if (xk == 0) {
+            if (s == 1 && a.left_ramp) ny--; else moved = false;
+        } else if (yk == 0) {
+            if (s == 2 && a.top_ramp) nx--; else moved = false;
+        } else if (s == 0) {
+            ny--; nx--;
+            s = code_at(ny, nx);
         } else {
             const uint32_t nib = nib_at(yk, xk);
-            if (s == 1) { s = ((nib >> 2) & 1u) ? 1 : 0; yk--; }
-            else        { s = ((nib >> 3) & 1u) ? 2 : 0; xk--; }
+            if (s == 1) { s = ((nib >> 2) & 1u) ? 1 : 0; ny--; }
+            else        { s = ((nib >> 3) & 1u) ? 2 : 0; nx--; }
         }
+        if (!moved) { kept(cy, cx); break; }              // row 0 of the path is always kept
+        if ((TR ? nx : ny) == cy - 1) kept(cy, cx);       // the master index steps here
+        yk = ny; xk = nx;
     }
 
     if (a.mode != PG_GLOBAL) {  // leading part (util/align.py:270-279): rows first, then columns
@@ -112,8 +136,10 @@ __global__ void k_traceback(const TraceArgs a)
         if (y0 != 0) { for (int v = y0 - 1; v >= 0; v--) push(v, 0); }
         else if (x0 != 0) { for (int v = x0 - 1; v >= 0; v--) push(0, v); }
     }
-    a.path_start[slot] = w;
-    a.path_len[slot] = cap - w;
+    if (want_path) {
+        a.path_start[slot] = w;
+        a.path_len[slot] = cap - w;
+    }
 }
 
 int pg_launch_traceback(const TraceArgs& a, cudaStream_t st)

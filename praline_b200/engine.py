@@ -212,7 +212,7 @@ class Engine(object):
 
     def run_tiles(self, mode, K, transposed, batch, stream_ids_dev, tiles, n_slots, S_dev, A, go, ge,
                   scores_dev, cs=None, slot_res_dev=None, slot_str_dev=None, want_paths=False, caps=None,
-                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None):
+                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None):
         """Launch K2 (+K4) for one K class.  Returns list of (slot_lo, slot_hi, path_off, path_buf,
         path_start, path_len) per wave when want_paths."""
         lib = self.lib
@@ -264,6 +264,20 @@ class Engine(object):
                                             self.ptr(keys),
                                             self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
                                             None, None, self.stream()))
+            if counts is not None:
+                # preprofile mode: the walk adds into the masters' count tables, no path leaves the device
+                cnt_dev, cnt_off_dev, thr = counts
+                _lib.check(lib.pgpu_traceback_tiles(md, K, int(transposed), self.ptr(batch.offs_dev),
+                                                    self.ptr(slot_res_dev[s_lo:s_hi]), self.ptr(slot_str_dev[s_lo:s_hi]),
+                                                    ns, self.ptr(keys), self.ptr(tb), self.ptr(emit_t), self.ptr(pair_tb),
+                                                    B["code00"], B["top_ramp"], B["left_ramp"], None, None, None, None,
+                                                    self.ptr(batch.flat_dev), self.ptr(cnt_dev),
+                                                    self.ptr(cnt_off_dev[s_lo:s_hi]), A, self.ptr(sc),
+                                                    int(thr is not None), float(thr if thr is not None else 0.0),
+                                                    self.stream()))
+                self.launches += 2 + int(semi)
+                lo = hi
+                continue
             cap = caps[s_lo:s_hi]
             poff = np.zeros(ns, np.int64)
             np.cumsum(cap[:-1], out=poff[1:])
@@ -275,7 +289,8 @@ class Engine(object):
                                                 self.ptr(slot_res_dev[s_lo:s_hi]), self.ptr(slot_str_dev[s_lo:s_hi]),
                                                 ns, self.ptr(keys), self.ptr(tb), self.ptr(emit_t), self.ptr(pair_tb),
                                                 B["code00"], B["top_ramp"], B["left_ramp"], self.ptr(poff_dev),
-                                                self.ptr(pbuf), self.ptr(pstart), self.ptr(plen), self.stream()))
+                                                self.ptr(pbuf), self.ptr(pstart), self.ptr(plen),
+                                                None, None, None, A, None, 0, 0.0, self.stream()))
             self.launches += 2 + int(semi)
             out.append((s_lo, s_hi, poff, pbuf, pstart, plen))
             lo = hi
@@ -292,7 +307,7 @@ class Engine(object):
         return bound < 2 ** 23
 
     def align_pairs(self, batch, pi, pj, S, gap_series, mode="global", want_paths=False, resident=None,
-                    device_only=False):
+                    device_only=False, counts=None):
         """Scores (and reference-format paths) of pairs (sequence_one = pi[k], sequence_two = pj[k]).
 
         Returns np.float32 scores [n] and, if want_paths, a list of int32 [rows, 2] arrays."""
@@ -329,6 +344,10 @@ class Engine(object):
         caps = (batch.lens[res_s] + batch.lens[str_s] + 2).astype(np.int64)
         slot_res_dev = self.dev(res_s.astype(np.int32)) if want_paths else None
         paths_sorted = [None] * n if want_paths else None
+        counts_ctx = None
+        if counts is not None:   # (count tables on the device, offset of the master's table per pair, threshold)
+            cnt_dev, cnt_off, thr = counts
+            counts_ctx = (cnt_dev, self.dev(np.asarray(cnt_off, np.int64)[order]), thr)
         kk = kcls[res_s]
         bounds = np.flatnonzero(np.diff(kk)) + 1
         tile = self._pick_tile(n)
@@ -341,7 +360,7 @@ class Engine(object):
             tiles["out_base"] += a
             waves = self.run_tiles(md, K, transposed, batch, stream_ids_dev, tiles, n, S_dev, A, go, ge,
                                    scores_dev, cs=cs, slot_res_dev=slot_res_dev, slot_str_dev=stream_ids_dev,
-                                   want_paths=want_paths, caps=caps)
+                                   want_paths=want_paths, caps=caps, counts=counts_ctx)
             pending.extend(waves)
         if device_only:
             return scores_dev, order, pending
@@ -359,6 +378,37 @@ class Engine(object):
         for k, o in enumerate(order):
             paths[o] = paths_sorted[k]
         return scores, paths
+
+    def preprofile_counts(self, batch, masters, slaves, S, gap_series, threshold=None):
+        """Count tables of global master-slave preprofiles, entirely on the device.
+
+        masters / slaves: sequence ids of every (master, slave) pair (sequence_one = master,
+        preprofile.py:131-137).  Returns (counts int64 [sum L_master x A] on the host, offsets per
+        distinct master id, scores per pair).  Replaces N(N-1) x (PairwiseAligner + compress_path +
+        Alignment.merge) and the per-master get_frequencies of ProfileBuilder (profile.py:56)."""
+        masters = np.asarray(masters, np.int64)
+        slaves = np.asarray(slaves, np.int64)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        uniq = np.unique(masters)
+        lens = batch.lens[uniq]
+        off = np.zeros(len(uniq) + 1, np.int64)
+        np.cumsum(lens * A, out=off[1:])
+        slot_of = np.full(batch.n, -1, np.int64)
+        slot_of[uniq] = np.arange(len(uniq))
+        cnt = torch.zeros(int(off[-1]), dtype=torch.int32, device=self.device)
+        # the master itself occupies every column of its own alignment (util/align.py:205-211)
+        rows = np.concatenate([np.arange(l) for l in lens]) if len(lens) else np.zeros(0, np.int64)
+        base = np.repeat(off[:-1], lens)
+        syms = np.concatenate([batch.flat_host.numpy()[batch.offs[u]:batch.offs[u + 1]] for u in uniq]).astype(np.int64)
+        own = self.dev(base + rows * A + syms)
+        cnt[own] = 1
+        scores_dev, order, _ = self.align_pairs(batch, masters, slaves, S, gap_series, mode="global", want_paths=True,
+                                                resident="one", device_only=True,
+                                                counts=(cnt, off[slot_of[masters]], threshold))
+        scores = np.empty(len(masters), np.float32)
+        scores[order] = scores_dev.cpu().numpy()
+        return cnt.cpu().numpy().astype(np.int64), {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, scores
 
     def align_profile_pairs(self, pbatch, pi, pj, S, gap_series, mode="global", resident=None):
         """Scores of profile x profile pairs (sequence_one = pi[k], sequence_two = pj[k]), one track

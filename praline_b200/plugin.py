@@ -36,6 +36,7 @@ from .engine import get_engine, MODES
 PAIRWISE_TID = "praline.component.PairwiseAligner"
 RAW_TID = "praline.component.RawPairwiseAligner"
 GLOBAL_MS_TID = "praline.component.GlobalMasterSlaveAligner"
+PROFILE_BUILDER_TID = "praline.component.ProfileBuilder"
 
 
 def _path_container(mode, path):
@@ -68,6 +69,75 @@ class LazyAlignment(Alignment):
     @path.setter
     def path(self, value):
         self._path = value
+
+    def __reduce__(self):
+        return (Alignment, (self.items, self.path))
+
+
+class _PreprofileBatch(object):
+    """All master-slave pairs of one execute_many call that share a (matrix, gaps, threshold)
+    class.  The count tables of every master are produced by ONE device pass on first use."""
+
+    def __init__(self, group, threshold):
+        self.group, self.threshold = group, threshold
+        self.masters, self.slaves = [], []
+        self.result = None
+
+    def add(self, master_idx, slave_idx):
+        self.masters.append(master_idx)
+        self.slaves.append(slave_idx)
+
+    def counts(self, master_idx):
+        if self.result is None:
+            g = self.group
+            self.result = get_engine().preprofile_counts(g.batch, self.masters, self.slaves, g.S, g.gaps,
+                                                         self.threshold)
+        cnt, where, _ = self.result
+        off, length = where[int(master_idx)]
+        A = self.group.S.shape[0]
+        return cnt[off:off + length * A].reshape(length, A).copy()
+
+
+class LazyMasterSlaveAlignment(Alignment):
+    """The master-slave alignment of GlobalMasterSlaveAligner (preprofile.py:67-156), built on
+    first access.  The workflow only hands it to ProfileBuilder (workflow.py:211-224), whose
+    count table GpuBatchManager takes from the device (`gpu_counts`) without ever materialising
+    the paths; anybody else who touches .items / .path gets the reference's host-side merge."""
+    tid = Alignment.tid
+
+    def __init__(self, master, slaves, picks, threshold, track_id, batch, master_idx):
+        self._master, self._slaves, self._picks = master, slaves, picks
+        self._threshold, self._track_id = threshold, track_id
+        self._batch, self._master_idx = batch, master_idx
+        self._built = None
+
+    def _build(self):
+        if self._built is None:
+            master = self._master
+            path = np.arange(len(master) + 1).reshape(len(master) + 1, 1)
+            alignment = Alignment([master], path)
+            for slave, (g, k) in zip(self._slaves, self._picks):     # preprofile.py:144-152
+                score = float(g.scores[k])
+                if self._threshold is None or score >= self._threshold:
+                    p = compress_path(np.array(g.path(k)), 0)
+                    merge_path = np.arange(len(slave) + 1).reshape(len(slave) + 1, 1)
+                    alignment = alignment.merge(Alignment([slave], merge_path), p)
+            self._built = alignment
+        return self._built
+
+    @property
+    def items(self):
+        return self._build().items
+
+    @property
+    def path(self):
+        return self._build().path
+
+    def gpu_counts(self, track_id):
+        """Count table of ProfileBuilder (profile.py:56) or None when the device path does not apply."""
+        if track_id != self._track_id or self._built is not None:
+            return None
+        return self._batch.counts(self._master_idx)
 
     def __reduce__(self):
         return (Alignment, (self.items, self.path))
@@ -398,8 +468,32 @@ class GpuBatchManager(Manager):
         for n, (tid, inputs, tag, env) in enumerate(requests):
             if n in handled:
                 continue
+            if tid == PROFILE_BUILDER_TID:
+                done = self._device_profile(inputs, env)
+                if done is not None:
+                    begin = BeginMessage(parent_tag)
+                    begin.tag = tag
+                    yield begin
+                    done.tag = tag
+                    yield done
+                    continue
             for msg in self._invoke(tid, inputs, tag, env, parent_tag=parent_tag):
                 yield msg
+
+    def _device_profile(self, inputs, env):
+        """ProfileBuilder (profile.py:41-74) on a lazily built master-slave alignment: the count
+        table comes from the device, the alignment itself is never materialised."""
+        alignment = inputs.get('alignment')
+        if not isinstance(alignment, LazyMasterSlaveAlignment):
+            return None
+        comp = self.index.resolve(PROFILE_BUILDER_TID)
+        if Environment(keys=env.keys, component=comp)['debug'] != 0:
+            return None
+        freqs = alignment.gpu_counts(inputs.get('track_id'))
+        if freqs is None:
+            return None
+        track = alignment._master.get_track(inputs['track_id'])
+        return CompleteMessage(outputs={'profile_track': ProfileTrack(freqs, track.alphabet)})
 
     # -- PairwiseAligner requests ----------------------------------------------------------------
     def _collect(self, tid, inputs, env, groups, eng):
@@ -490,6 +584,7 @@ class GpuBatchManager(Manager):
             return
         for g in groups.values():
             g.run_scores(eng)
+        pre = {}
         for n in idxs:
             if n not in plans:
                 continue
@@ -500,17 +595,23 @@ class GpuBatchManager(Manager):
             yield begin
             master, slaves = inputs['master_sequence'], inputs['slave_sequences']
             threshold = env['score_threshold']
-            path = np.arange(len(master) + 1).reshape(len(master) + 1, 1)
-            alignment = Alignment([master], path)
-            for j, (slave, (g, k)) in enumerate(zip(slaves, items)):   # preprofile.py:144-154
-                score = float(g.scores[k])
-                if threshold is None or score >= threshold:
-                    p = compress_path(np.array(g.path(k)), 0)
-                    merge_path = np.arange(len(slave) + 1).reshape(len(slave) + 1, 1)
-                    alignment = alignment.merge(Alignment([slave], merge_path), p)
-                prog = ProgressMessage((j + 1) / len(slaves))
-                prog.tag = tag
-                yield prog
+            track_ids = inputs['track_id_sets']
+            plain = len(track_ids) == 1 and all(s_.get_track(track_ids[0][0]).tid == PlainTrack.tid
+                                                for s_ in [master] + list(slaves))
+            if plain and items and isinstance(items[0][0], _Group):
+                g = items[0][0]
+                key = (id(g), threshold)
+                if key not in pre:
+                    pre[key] = _PreprofileBatch(g, threshold)
+                midx = g.pi[items[0][1]]
+                for (gg, k) in items:
+                    pre[key].add(gg.pi[k], gg.pj[k])
+                alignment = LazyMasterSlaveAlignment(master, slaves, items, threshold, track_ids[0][0], pre[key], midx)
+            else:   # not plain tracks: the reference's host-side merge, paths from the traced batch
+                alignment = LazyMasterSlaveAlignment(master, slaves, items, threshold, None, None, None)._build()
+            prog = ProgressMessage(1.0)
+            prog.tag = tag
+            yield prog
             done = CompleteMessage({'alignment': alignment})
             done.tag = tag
             yield done

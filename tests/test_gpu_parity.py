@@ -186,6 +186,39 @@ def test_profile_batches_vs_oracle(eng, resident):
             assert float(got[k]) == want, (mode, k)                                     # and in fact exact
 
 
+def test_preprofile_counts_on_device(eng):
+    """Count tables of global master-slave preprofiles from the device equal the reference's
+    host pipeline compress_path -> Alignment.merge -> get_frequencies (restated literally here
+    from util/align.py:187-232 on oracle paths), with and without a score threshold."""
+    S = matrices.blosum62()
+    seqs = synth.family(91, 9, 70) + [np.random.default_rng(2).integers(0, 20, 33).astype(np.int32)]
+    n = len(seqs)
+    batch = eng.batch(seqs)
+    masters = np.repeat(np.arange(n), n - 1)
+    slaves = np.concatenate([[j for j in range(n) if j != i] for i in range(n)])
+    for thr in (None, 60.0):
+        cnt, where, scores = eng.preprofile_counts(batch, masters, slaves, S, [-11.0, -1.0], threshold=thr)
+        for i in range(n):
+            want = np.zeros((len(seqs[i]), 27), np.int64)
+            want[np.arange(len(seqs[i])), seqs[i]] += 1
+            for j in range(n):
+                if j == i:
+                    continue
+                score, path = oracle.align_seqs("global", seqs[i], seqs[j], S, [-11.0, -1.0])
+                if thr is not None and score < thr:
+                    continue
+                keep = [0] + [r for r in range(1, len(path)) if path[r, 0] > path[r - 1, 0]]   # compress_path
+                cp = path[keep]
+                for c in range(len(cp) - 1):                                                 # get_frequencies
+                    if cp[c + 1, 1] > cp[c, 1]:
+                        want[c, seqs[j][cp[c + 1, 1] - 1]] += 1
+            off, length = where[i]
+            got = cnt[off:off + length * 27].reshape(length, 27)
+            assert np.array_equal(got, want), (thr, i)
+        pairs_scores = oracle.align_batch("global", *synth.pack(seqs), masters, slaves, S, [-11.0, -1.0])
+        assert np.array_equal(scores, pairs_scores)
+
+
 def test_two_track_sets(eng):
     rng = np.random.default_rng(3)
     S1, S2 = matrices.blosum62(), rng.standard_normal((15, 15)).astype(np.float32)
