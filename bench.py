@@ -204,6 +204,23 @@ def cpu_baseline_port(seqs, S, seconds=12.0):
                       % (n, dt)}
 
 
+def msa_e2e(n=50, length=300):
+    """Second half of the BASELINE metric: wall time of the reference's MSA workflow
+    (`praline --preprofile-global --msa-tree`, 50 x 300 aa, BASELINE configs[0] scale) on the
+    GPU manager and on the reference's own single-process Manager; outputs must be identical.
+    Needs the reference package (baseline/_ref); returns None when it is absent."""
+    import subprocess
+    tool = os.path.join(ROOT, "tools", "msa_e2e.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "praline")):
+        return None
+    try:
+        out = subprocess.run([sys.executable, tool, str(n), str(length), "global", "tree"], capture_output=True,
+                             text=True, timeout=600)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:   # the DP numbers above stand on their own
+        return {"error": str(e)[:200]}
+
+
 # ---- our arm ---------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -333,7 +350,11 @@ def main():
         kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
         achieved = my_cells * W_FLOPS_PER_CELL / (kms * 1e-3)
         roof = {"bound": "cuda_core_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+                # (profiles/r01_kstream_v2_raw.csv): 443 KB read, 0 B written (the 2 MB of scores stay in L2);
+                # algorithmic bytes per launch: 0.3 MB sequences + 0.1 MB tiles in, 2.0 MB scores out
+                "traffic": 443392,
                 "note": "DP-cell roofline (SURVEY 8d): algorithmic 11 f32 add/max per cell (the kernel issues 7); "
                         "peak = measured f32 add issue rate (%.2f warp-instr/ns/SM, wall clock) x 32 lanes x %d SMs "
                         "(of measured; SM clock %.0f MHz during the run); f32 max / compare / shift / integer ops "
@@ -360,6 +381,7 @@ def main():
         roof["traced_note"] = "120000 pairs, fill with 4-bit traceback + per-pair path walk, device time incl. plan upload"
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_port(seqs, S)
+            roof["msa_e2e"] = msa_e2e()
 
     if rank == 0:
         line = {"metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS", "n_gpus": world,

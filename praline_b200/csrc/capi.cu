@@ -5,6 +5,7 @@
 #include "../../include/praline_b200.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -130,17 +131,28 @@ int pgpu_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, in
 
 static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int general_kg(int L2) { return L2 <= 2048 ? 2 : 8; }
+// Columns per lane of the general wavefront kernel.  `full` (debug dumps of o and t) runs the
+// reference-flag kernel, instantiated for 2 and 8.  The production kernel uses ONE strip (no
+// inter-strip handshake at all) while the columns fit 32 lanes x 16, and thin strips beyond
+// that so that many warps ride the anti-diagonal.  PGPU_KG overrides for experiments.
+static int general_kg(int L2, bool full)
+{
+    if (full) return L2 <= 2048 ? 2 : 8;
+    const char* e = getenv("PGPU_KG");
+    if (e && atoi(e) > 0) return atoi(e);
+    if (L2 <= 512) { int kg = 1; while (32 * kg < L2) kg *= 2; return kg; }
+    return L2 <= 8192 ? 4 : 2;
+}
+static int general_strips(int L2, int kg) { int ns = (L2 + 32 * kg - 1) / (32 * kg); return ns < 1 ? 1 : ns; }
 
 int64_t pgpu_general_workspace_bytes(int L1, int L2)
 {
-    const int kg = general_kg(L2);
-    int ns = (L2 + 32 * kg - 1) / (32 * kg);
-    if (ns < 1) ns = 1;
+    const int nsa = general_strips(L2, general_kg(L2, false)), nsb = general_strips(L2, general_kg(L2, true));
+    const int ns = nsa > nsb ? nsa : nsb;
     const size_t fp = up256((size_t)L2 + 1);
     size_t b = 0;
     b += up256((size_t)(L1 + 1) * fp);                              // flags
-    b += up256(sizeof(float) * 3 * (size_t)(ns + 1) * (L1 + 1));    // edge
+    b += up256(sizeof(float) * 4 * (size_t)(ns + 1) * (L1 + 1));    // edge (16-byte records)
     b += up256(sizeof(int) * (size_t)(ns + 1));                     // progress
     b += 2 * up256(sizeof(float) * 3 * (size_t)(L2 + 1));           // top, lastrow
     b += up256(sizeof(float) * 3 * (size_t)(L1 + 1));               // lastcol
@@ -155,8 +167,9 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
 {
     if (mode < 0 || mode > 4) { pg_set_error("unknown alignment mode %d", mode); return 1; }
     if (L1 < 1 || L2 < 1) { pg_set_error("empty sequence (L1=%d, L2=%d)", L1, L2); return 1; }
-    const int kg = general_kg(L2);
-    int ns = (L2 + 32 * kg - 1) / (32 * kg);
+    const int kg = general_kg(L2, o_full != nullptr);
+    const int nsa = general_strips(L2, general_kg(L2, false)), nsb = general_strips(L2, general_kg(L2, true));
+    const int ns = nsa > nsb ? nsa : nsb;   // workspace carved for the larger of the two layouts
     GenArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = mode; a.L1 = L1; a.L2 = L2; a.m = m; a.m_pitch = m_pitch; a.g1 = g1; a.g2 = g2;
@@ -164,7 +177,7 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
     unsigned char* w = (unsigned char*)workspace;
     const size_t fp = up256((size_t)L2 + 1);
     a.flags = w; a.f_pitch = (int)fp; w += up256((size_t)(L1 + 1) * fp);
-    a.edge = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(ns + 1) * (L1 + 1));
+    a.edge = (float*)w; w += up256(sizeof(float) * 4 * (size_t)(ns + 1) * (L1 + 1));
     a.progress = (int*)w; w += up256(sizeof(int) * (size_t)(ns + 1));
     a.top = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));
     a.lastrow = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));

@@ -91,13 +91,14 @@ struct GenArgs {
     const uint8_t* z; int z_pitch;       // [(L1+1)][z_pitch] or NULL
     uint8_t* flags;  int f_pitch;        // [(L1+1)][f_pitch], one byte per cell
     float* o_full;   uint8_t* t_full;    // optional [(L1+1)][(L2+1)][3] (debug / B3 shim)
-    float* edge;                         // [n_strips+1][L1+1][3]
+    float* edge;                         // [n_strips+1][L1+1][4]: M, U, L, pad (16-byte records)
     int* progress;                       // [n_strips+1]
     float* top;                          // [3][L2+1]  border row 0
     float* lastrow;                      // [3][L2+1]
     float* lastcol;                      // [3][L1+1]
     unsigned long long* best;            // local mode: (ordered value << 32 | ~linear index)
     int n_strips;
+    int flag_fmt;                        // 0: the reference's seven flag bits, 1: compact sign bits
     // finalize / traceback outputs
     float* score_out;                    // [1]
     int32_t* cell_out;                   // [3] y, x, state

@@ -44,8 +44,8 @@ __global__ void k_gen_init(const GenArgs a)
         else if (y == 0) U = a.g1[0] - a.g1[1];
         else U = (float)((double)(y - 1) * (double)a.g1[(size_t)(y - 1) * 2 + 1] + (double)a.g1[0]);
         if (y == 0) L = l_zero ? 0.f : (a.g2[0] - a.g2[1]);
-        float* e = a.edge + (size_t)y * 3;
-        e[0] = M; e[1] = U; e[2] = L;
+        float* e = a.edge + (size_t)y * 4;
+        e[0] = M; e[1] = U; e[2] = L; e[3] = 0.f;
         if (a.o_full) {
             float* o = a.o_full + ((size_t)y * (L2 + 1)) * 3;
             o[0] = M; o[1] = U; o[2] = L;
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
 
     for (int strip = gw; strip < a.n_strips; strip += nw) {
         const int x0 = strip * (32 * KG) + lane * KG + 1;   // my first column (1-based)
-        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 3;
-        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 3;
+        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 4;
+        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 4;
         volatile int* pin = a.progress + strip;
         volatile int* pout = a.progress + strip + 1;
 
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
             float Ll = __shfl_up_sync(FULL, Le, 1);
             if (lane == 0 && y <= L1) {
                 if (have_edge) { Ml = pMe; Ul = pUe; Ll = pLe; }
-                else { const float* e = ein + (size_t)y * 3; Ml = __ldcg(e); Ul = __ldcg(e + 1); Ll = __ldcg(e + 2); }
+                else { const float* e = ein + (size_t)y * 4; Ml = __ldcg(e); Ul = __ldcg(e + 1); Ll = __ldcg(e + 2); }
                 have_edge = (y + 1 <= L1) && (y + 1 <= avail);
-                if (have_edge) { const float* e = ein + (size_t)(y + 1) * 3; pMe = __ldcg(e); pUe = __ldcg(e + 1); pLe = __ldcg(e + 2); }
+                if (have_edge) { const float* e = ein + (size_t)(y + 1) * 4; pMe = __ldcg(e); pUe = __ldcg(e + 1); pLe = __ldcg(e + 2); }
             }
             if (active) {
                 const float g1o = cg1o, g1e = cg1e;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
                 }
                 // my right edge = last valid column of my strip part (pad lanes forward nothing useful)
                 Me = Mp[KG - 1]; Ue = Up[KG - 1]; Le = Lp[KG - 1];
-                if (lane == 31) { float* e = eout + (size_t)y * 3; e[0] = Me; e[1] = Ue; e[2] = Le; }
+                if (lane == 31) { float* e = eout + (size_t)y * 4; e[0] = Me; e[1] = Ue; e[2] = Le; }
             }
 #pragma unroll
             for (int k = 0; k < KG; k++) cm[k] = nm[k];
@@ -243,52 +243,279 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
     }
 }
 
-// ---- end cell (reference component/align.py:401-431) -----------------------------------------
-__global__ void k_gen_finalize(const GenArgs a)
+
+// ---- the production fill: same wavefront, compact flags ---------------------------------------
+// The walker only ever follows the FIRST set flag in the reference's priority order
+// (util/align.py:161-174), so one byte per cell with five sign bits is enough:
+//   bit 0  M+s lost strictly against the maximum        (not MM)
+//   bit 1  U+s lost strictly                            (not MU)
+//   bit 2  the up state was extended, open lost strictly (open beats extend on ties)
+//   bit 3  the left state was extended
+//   bit 4  local mode only: L+s lost strictly too       (with bits 0,1: no flag -> path stops)
+//   bit 7  masked cell (reference leaves all three flag bytes 0, cext.c:141-149)
+// "x == max" for x <= max is "sign(x - max) == 0": distinct finite floats never subtract to
+// zero, -inf minus -inf gives the positive default NaN (equal, as in C), so the bits are exact
+// for ANY f32 input, like the three-sum comparison of the reference they encode.
+#define GEN_R 8            // depth of the per-lane prefetch ring (rows in flight per lane)
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async4_cg(uint32_t dst, const void* src)   // through L2: data of other SMs
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+
+template <int KG, bool LOCAL, bool MASK>
+__global__ void __launch_bounds__(256) k_gen_fill_fast(const GenArgs a)
+{
+    // per warp: GEN_R slots of [32 lanes][KG match scores + 2 gap values], filled by cp.async
+    // GEN_R - 1 rows ahead of use, so that no global-memory latency sits on the wavefront's
+    // per-step critical path (each lane only ever reads back what it requested itself)
+    extern __shared__ __align__(16) float gsm[];
+    constexpr int EOFF = (KG + 2 + 3) & ~3;        // lane 0: the left-edge record (M, U, L, pad) of the row
+    constexpr int SLOTP = EOFF + 4;                // floats per lane per slot, 16 B aligned
+    const int L1 = a.L1, L2 = a.L2, W = L2 + 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const float NINF = -INFINITY;
+    float* ring = gsm + (size_t)wib * (GEN_R * 32 * SLOTP) + lane * SLOTP;     // + slot * 32 * SLOTP
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const bool vec = (KG % 4 == 0) && (a.m_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.m) & 15) == 0);
+
+    for (int strip = gw; strip < a.n_strips; strip += nw) {
+        const int x0 = strip * (32 * KG) + lane * KG + 1;   // my first column (1-based)
+        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 4;
+        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 4;
+        volatile int* pin = a.progress + strip;
+        volatile int* pout = a.progress + strip + 1;
+        const bool last_strip = strip == a.n_strips - 1;
+        const bool lane_on = x0 <= L2;
+
+        float Mp[KG], Up[KG], Lp[KG], go2[KG], ge2[KG];
+#pragma unroll
+        for (int k = 0; k < KG; k++) {
+            const int x = x0 + k;
+            const bool v = x <= L2;
+            Mp[k] = v ? a.top[x] : NINF;
+            Up[k] = v ? a.top[W + x] : NINF;
+            Lp[k] = v ? a.top[2 * W + x] : NINF;
+            go2[k] = v ? a.g2[(size_t)(x - 1) * 2] : 0.f;
+            ge2[k] = v ? a.g2[(size_t)(x - 1) * 2 + 1] : 0.f;
+        }
+        float Md = NINF, Ud = NINF, Ld = NINF;
+        if (lane_on) { Md = a.top[x0 - 1]; Ud = a.top[W + x0 - 1]; Ld = a.top[2 * W + x0 - 1]; }
+        float Me = 0.f, Ue = 0.f, Le = 0.f;
+        int avail = 0;
+        float bv = NINF; uint32_t bl = 0xffffffffu;
+        const int T = L1 + 31;
+
+        // request everything row yy needs into its ring slot; always commits a group
+        auto request = [&](int yy) {
+            if (yy >= 1 && yy <= L1 && lane_on) {
+                const uint32_t dst = ring_s + (uint32_t)((yy & (GEN_R - 1)) * 32 * SLOTP) * 4u;
+                const float* mrow = a.m + (size_t)(yy - 1) * a.m_pitch + (x0 - 1);
+                if (vec && x0 + KG - 1 <= L2) {
+#pragma unroll
+                    for (int k = 0; k < KG; k += 4) cp_async16(dst + k * 4, mrow + k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KG; k++) if (x0 + k <= L2) cp_async4(dst + k * 4, mrow + k);
+                }
+                cp_async4(dst + KG * 4, a.g1 + (size_t)(yy - 1) * 2);
+                cp_async4(dst + KG * 4 + 4, a.g1 + (size_t)(yy - 1) * 2 + 1);
+                // lane 0: the left strip's edge record, through L2 (.cg): it was written by another SM
+                if (lane == 0) cp_async16(dst + EOFF * 4, ein + (size_t)yy * 4);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // the consumer keeps GEN_R - 1 rows of slack to its producer so that every edge record
+        // can be requested ahead of use
+        auto wait_rows = [&](int need) {
+            if (avail < need) {
+                if (lane == 0) {
+                    // bounded spin: a protocol bug must fail a test, not hang the GPU.  ld.acquire
+                    // pairs with the producer's st.release; lane 0 is also the only reader of the edge
+                    for (long long spins = 0; spins < (1ll << 26); spins++) {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(avail) : "l"(const_cast<int*>(pin)) : "memory");
+                        if (avail >= need) break;
+                        __nanosleep(32);
+                    }
+                }
+                avail = __shfl_sync(FULL, avail, 0);
+            }
+        };
+        __syncwarp();
+        wait_rows(min(GEN_R - 1, L1));
+#pragma unroll 1
+        for (int d = 0; d < GEN_R - 1; d++) request(1 - lane + d);
+        uint32_t cz = 0, nz = 0;
+        auto fetch_mask = [&](int yy) -> uint32_t {
+            uint32_t zz = 0;
+            if (MASK && yy >= 1 && yy <= L1 && lane_on) {
+#pragma unroll
+                for (int k = 0; k < KG; k++)
+                    if (x0 + k <= L2 && a.z[(size_t)yy * a.z_pitch + x0 + k]) zz |= 1u << k;
+            }
+            return zz;
+        };
+        cz = fetch_mask(1 - lane);
+
+        for (int t = 0; t < T; t++) {
+            __syncwarp();                               // lanes took different branches last step
+            const int y = t - lane + 1;
+            const bool active = (y >= 1) && (y <= L1) && lane_on;
+            wait_rows(min(t + GEN_R, L1));              // lane 0 is about to request row t + GEN_R
+            request(y + GEN_R - 1);
+            if (MASK) nz = fetch_mask(y + 1);
+            float Ml = __shfl_up_sync(FULL, Me, 1);
+            float Ul = __shfl_up_sync(FULL, Ue, 1);
+            float Ll = __shfl_up_sync(FULL, Le, 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(GEN_R - 1) : "memory");   // row y has landed
+            const float* slot = ring + (y & (GEN_R - 1)) * 32 * SLOTP;
+            if (lane == 0 && y <= L1) { Ml = slot[EOFF]; Ul = slot[EOFF + 1]; Ll = slot[EOFF + 2]; }
+            if (active) {
+                const float cg1o = slot[KG], cg1e = slot[KG + 1];
+                const float dM = Ml, dU = Ul, dL = Ll;
+                float cMl = Ml, cLl = Ll;
+                uint32_t fl[KG];
+#pragma unroll
+                for (int k = 0; k < KG; k++) {
+                    const float s = slot[k];
+                    const float mm = Md + s, mu = Ud + s, ml = Ld + s;
+                    float M = fmaxf(fmaxf(mm, mu), ml);
+                    if (LOCAL) M = fmaxf(M, 0.f);
+                    const float uo = Mp[k] + cg1o, ue = Up[k] + cg1e;
+                    const float lo = cMl + go2[k], le = cLl + ge2[k];
+                    float U = fmaxf(uo, ue), L = fmaxf(lo, le);
+                    uint32_t f = 0;
+                    if (LOCAL) f = __funnelshift_l(__float_as_uint(ml - M), f, 1);
+                    f = __funnelshift_l(__float_as_uint(lo - L), f, 1);
+                    f = __funnelshift_l(__float_as_uint(uo - U), f, 1);
+                    f = __funnelshift_l(__float_as_uint(mu - M), f, 1);
+                    f = __funnelshift_l(__float_as_uint(mm - M), f, 1);
+                    if (MASK && ((cz >> k) & 1u)) { M = 0.f; U = 0.f; L = 0.f; f = 0x80u; }
+                    Md = Mp[k]; Ud = Up[k]; Ld = Lp[k];
+                    if (x0 + k <= L2) {
+                        Mp[k] = M; Up[k] = U; Lp[k] = L;
+                        cMl = M; cLl = L;
+                        if (LOCAL) {
+                            const float v3 = fmaxf(fmaxf(M, U), L);
+                            if (v3 >= bv) {
+                                const uint32_t lin = (uint32_t)(((size_t)y * W + x0 + k) * 3);
+                                const float vs[3] = {M, U, L};
+#pragma unroll
+                                for (int j = 0; j < 3; j++)
+                                    if (vs[j] > bv || (vs[j] == bv && lin + j < bl)) { bv = vs[j]; bl = lin + j; }
+                            }
+                        }
+                    }
+                    fl[k] = f;
+                }
+                Md = dM; Ud = dU; Ld = dL;
+                {
+                    uint8_t* frow = a.flags + (size_t)y * a.f_pitch + x0;
+#pragma unroll
+                    for (int k = 0; k < KG; k++) if (x0 + k <= L2) frow[k] = (uint8_t)fl[k];
+                }
+                if (y == L1) {
+#pragma unroll
+                    for (int k = 0; k < KG; k++)
+                        if (x0 + k <= L2) { a.lastrow[x0 + k] = Mp[k]; a.lastrow[W + x0 + k] = Up[k]; a.lastrow[2 * W + x0 + k] = Lp[k]; }
+                }
+                if (last_strip) {
+#pragma unroll
+                    for (int k = 0; k < KG; k++)
+                        if (x0 + k == L2) { a.lastcol[y] = Mp[k]; a.lastcol[(L1 + 1) + y] = Up[k]; a.lastcol[2 * (L1 + 1) + y] = Lp[k]; }
+                }
+                Me = Mp[KG - 1]; Ue = Up[KG - 1]; Le = Lp[KG - 1];
+                if (lane == 31 && !last_strip) { float* e = eout + (size_t)y * 4; e[0] = Me; e[1] = Ue; e[2] = Le; }
+            }
+            if (MASK) cz = nz;
+            // lane 31 wrote the edge records; its release store orders them before the counter
+            const int done = t - 31 + 1;
+            if (!last_strip && lane == 31 && done >= 1 && ((done & 7) == 0 || done == L1))
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(const_cast<int*>(pout)), "r"(done) : "memory");
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (LOCAL && bl != 0xffffffffu) atomicMax(a.best, gkey(bv, bl));
+    }
+}
+
+// ---- end cell (reference component/align.py:401-431) -----------------------------------------
+// One CTA.  global: first argmax of the three states at (L1, L2).  semiglobal: max of the last
+// row vs max of the last column (strict '>' and only when tracing from the row is allowed), then
+// the FIRST hit scanning from the far end backwards, states 0,1,2 -- as a parallel reduction:
+// every candidate gets the key (ordered value, position from the far end descending, state
+// ascending) and the maximum key wins.  local: first argmax of the whole o array in
+// (y, x, state) order; the interior part was reduced by the fill, the borders are added here.
+__device__ __forceinline__ unsigned long long fkey(float v, uint32_t pos, int k)
+{
+    uint32_t b = __float_as_uint(v);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)b << 32) | ((unsigned long long)pos << 2) | (unsigned)(3 - k);
+}
+
+__global__ void __launch_bounds__(256) k_gen_finalize(const GenArgs a)
+{
+    __shared__ unsigned long long red[2][256];
     const int L1 = a.L1, L2 = a.L2, W = L2 + 1, H = L1 + 1;
+    const int tid = threadIdx.x;
+    auto row_at = [&](int x, int k) -> float { return (L1 == 0) ? a.top[k * W + x] : (x == 0 ? a.edge[(size_t)L1 * 4 + k] : a.lastrow[k * W + x]); };
+    auto col_at = [&](int y, int k) -> float { return (y == 0) ? a.top[k * W + L2] : (L2 == 0 ? a.edge[(size_t)y * 4 + k] : a.lastcol[k * H + y]); };
+    unsigned long long kr = 0ull, kc = 0ull;
+    if (a.mode == PG_LOCAL) {
+        // borders of o in linear (y, x, state) order: smaller linear index wins ties
+        auto lkey = [&](float v, uint32_t lin) { return gkey(v, lin); };
+        for (int x = tid; x <= L2; x += 256)
+            for (int k = 0; k < 3; k++) { const unsigned long long c = lkey(a.top[k * W + x], (uint32_t)(x * 3 + k)); if (c > kr) kr = c; }
+        for (int y = 1 + tid; y <= L1; y += 256)
+            for (int k = 0; k < 3; k++) { const unsigned long long c = lkey(a.edge[(size_t)y * 4 + k], (uint32_t)(((size_t)y * W) * 3 + k)); if (c > kr) kr = c; }
+    } else if (a.mode != PG_GLOBAL) {
+        for (int x = tid; x <= L2; x += 256)
+            for (int k = 0; k < 3; k++) { const unsigned long long c = fkey(row_at(x, k), (uint32_t)x, k); if (c > kr) kr = c; }
+        for (int y = tid; y <= L1; y += 256)
+            for (int k = 0; k < 3; k++) { const unsigned long long c = fkey(col_at(y, k), (uint32_t)y, k); if (c > kc) kc = c; }
+    }
+    red[0][tid] = kr;
+    red[1][tid] = kc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+            if (red[0][tid + o] > red[0][tid]) red[0][tid] = red[0][tid + o];
+            if (red[1][tid + o] > red[1][tid]) red[1][tid] = red[1][tid + o];
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
     int cy = L1, cx = L2, ck = 0;
     float score;
-    // seed the border entries of lastrow / lastcol
-    auto row_at = [&](int x, int k) -> float { return (L1 == 0) ? a.top[k * W + x] : (x == 0 ? a.edge[(size_t)L1 * 3 + k] : a.lastrow[k * W + x]); };
-    auto col_at = [&](int y, int k) -> float { return (y == 0) ? a.top[k * W + L2] : (L2 == 0 ? a.edge[(size_t)y * 3 + k] : a.lastcol[k * H + y]); };
+    auto kval = [](unsigned long long k) -> float {
+        uint32_t b = (uint32_t)(k >> 32);
+        b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+        return __uint_as_float(b);
+    };
     if (a.mode == PG_GLOBAL) {
-        ck = 0;
         for (int k = 1; k < 3; k++) if (row_at(L2, k) > row_at(L2, ck)) ck = k;
         score = row_at(L2, ck);
     } else if (a.mode == PG_LOCAL) {
-        // interior best from the fill; borders (row 0, column 0) scanned here in linear order
-        float bv = -INFINITY; uint32_t bl = 0xffffffffu;
-        if (*a.best) {
-            uint32_t b = (uint32_t)(*a.best >> 32);
-            b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
-            bv = __uint_as_float(b); bl = ~(uint32_t)(*a.best);
-        }
-        for (int x = 0; x <= L2; x++) for (int k = 0; k < 3; k++) {
-            const float v = a.top[k * W + x]; const uint32_t lin = (uint32_t)(x * 3 + k);
-            if (v > bv || (v == bv && lin < bl)) { bv = v; bl = lin; }
-        }
-        for (int y = 1; y <= L1; y++) for (int k = 0; k < 3; k++) {
-            const float v = a.edge[(size_t)y * 3 + k]; const uint32_t lin = (uint32_t)(((size_t)y * W) * 3 + k);
-            if (v > bv || (v == bv && lin < bl)) { bv = v; bl = lin; }
-        }
-        ck = bl % 3; cx = (bl / 3) % W; cy = bl / 3 / W; score = bv;
+        unsigned long long best = red[0][0];
+        if (*a.best > best) best = *a.best;
+        const uint32_t bl = ~(uint32_t)best;
+        ck = bl % 3; cx = (bl / 3) % W; cy = bl / 3 / W; score = kval(best);
     } else {
-        float rmax = -INFINITY, cmax = -INFINITY;
-        for (int x = 0; x <= L2; x++) for (int k = 0; k < 3; k++) rmax = fmaxf(rmax, row_at(x, k));
-        for (int y = 0; y <= L1; y++) for (int k = 0; k < 3; k++) cmax = fmaxf(cmax, col_at(y, k));
+        const unsigned long long br = red[0][0], bc = red[1][0];
+        const float rmax = kval(br), cmax = kval(bc);
         const bool from_row = (a.mode == PG_SG_BOTH || a.mode == PG_SG_TWO);
-        bool found = false;
-        if (rmax > cmax && from_row) {
-            for (int x = L2; x >= 0 && !found; x--) for (int k = 0; k < 3; k++)
-                if (row_at(x, k) == rmax) { cy = L1; cx = x; ck = k; found = true; break; }
-            score = rmax;
-        } else {
-            for (int y = L1; y >= 0 && !found; y--) for (int k = 0; k < 3; k++)
-                if (col_at(y, k) == cmax) { cy = y; cx = L2; ck = k; found = true; break; }
-            score = cmax;
-        }
+        if (rmax > cmax && from_row) { cy = L1; cx = (int)((br & 0xffffffffull) >> 2); ck = 3 - (int)(br & 3ull); score = rmax; }
+        else { cy = (int)((bc & 0xffffffffull) >> 2); cx = L2; ck = 3 - (int)(bc & 3ull); score = cmax; }
     }
     *a.score_out = score;
     a.cell_out[0] = cy; a.cell_out[1] = cx; a.cell_out[2] = ck;
@@ -340,7 +567,15 @@ __global__ void __launch_bounds__(32) k_gen_traceback(const GenArgs a)
                 else if (y == 0) f = (l_ramp && k == 2) ? TB_LE : 0;
                 else {
                     f = tile[y - ty0][x - tx0];
-                    f &= (k == 0) ? (TB_MM | TB_MU | TB_ML) : (k == 1 ? (TB_UO | TB_UE) : (TB_LO | TB_LE));
+                    if (a.flag_fmt) {   // compact sign bits of k_gen_fill_fast -> the first reference flag
+                        const uint8_t c = f;
+                        if (c & 0x80) f = 0;
+                        else if (k == 0) f = !(c & 1) ? TB_MM : (!(c & 2) ? TB_MU : ((c & 16) ? 0 : TB_ML));
+                        else if (k == 1) f = (c & 4) ? TB_UE : TB_UO;
+                        else f = (c & 8) ? TB_LE : TB_LO;
+                    } else {
+                        f &= (k == 0) ? (TB_MM | TB_MU | TB_ML) : (k == 1 ? (TB_UO | TB_UE) : (TB_LO | TB_LE));
+                    }
                 }
                 if (f & TB_MM) { y--; x--; k = 0; }
                 else if (f & TB_MU) { y--; x--; k = 1; }
@@ -374,31 +609,52 @@ __global__ void __launch_bounds__(32) k_gen_traceback(const GenArgs a)
 // accumulated sequentially per set, sets added in order (cext.c:63-95, :388-421).  Explicit
 // _rn intrinsics keep ptxas from contracting the multiply-add.
 
-__global__ void k_build_scores(const ScoreSets sets, int L1, int L2, float* m, int m_pitch)
+// Block = 32 columns x 8 rows of m.  Per track set the block stages its 8 rows of P1, its 32 rows
+// of P2 and S in shared memory and compacts the NONZERO entries of every staged profile row
+// (ascending index, as build_nonzero_matrix does on the host, component/align.py:449-458), so a
+// cell costs nnz1 x nnz2 terms like the reference instead of A x A.
+#define BS_MAXA 64
+__global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int L1, int L2, float* m, int m_pitch)
 {
-    const int n_sets = sets.n;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= L2 || y >= L1) return;
+    extern __shared__ float bsm[];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
     float score = 0.f;
-    for (int n = 0; n < n_sets; n++) {
+    for (int n = 0; n < sets.n; n++) {
         const ScoreSet st = sets.s[n];
-        const float* r1 = st.P1 + (size_t)y * st.A;
-        const float* r2 = st.P2 + (size_t)x * st.A;
+        const int A = st.A;
+        float* sS = bsm;                         // [A][A]
+        float* v1 = sS + A * A;                  // [8][A]  nonzero values of P1 rows, compacted
+        float* v2 = v1 + 8 * A;                  // [32][A]
+        uint8_t* i1 = reinterpret_cast<uint8_t*>(v2 + 32 * A);   // [8][A] their symbol indices
+        uint8_t* i2 = i1 + 8 * A;                                 // [32][A]
+        int* c1 = reinterpret_cast<int*>(i2 + 32 * A + ((4 - ((40 * A) & 3)) & 3));   // [8] counts
+        int* c2 = c1 + 8;                                                            // [32]
+        __syncthreads();
+        for (int i = tid; i < A * A; i += 256) sS[i] = st.S[i];
+        if (tid < 8) {          // one thread compacts one P1 row
+            const int yy = blockIdx.y * 8 + tid;
+            int c = 0;
+            if (yy < L1) for (int i = 0; i < A; i++) { const float p = st.P1[(size_t)yy * A + i]; if (p != 0.f) { v1[tid * A + c] = p; i1[tid * A + c] = (uint8_t)i; c++; } }
+            c1[tid] = c;
+        } else if (tid >= 32 && tid < 64) {   // and one thread one P2 row
+            const int r = tid - 32, xx = blockIdx.x * 32 + r;
+            int c = 0;
+            if (xx < L2) for (int j = 0; j < A; j++) { const float p = st.P2[(size_t)xx * A + j]; if (p != 0.f) { v2[r * A + c] = p; i2[r * A + c] = (uint8_t)j; c++; } }
+            c2[r] = c;
+        }
+        __syncthreads();
         float acc = 0.f;
-        for (int i = 0; i < st.A; i++) {
-            const float p1 = r1[i];
-            if (p1 == 0.f) continue;
-            const float* srow = st.S + (size_t)i * st.A;
-            for (int j = 0; j < st.A; j++) {
-                const float p2 = r2[j];
-                if (p2 == 0.f) continue;
-                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p2, srow[j]), p1));
-            }
+        const int n1 = c1[ty], n2 = c2[tx];
+        for (int a = 0; a < n1; a++) {
+            const float p1 = v1[ty * A + a];
+            const float* srow = sS + (int)i1[ty * A + a] * A;
+            for (int b = 0; b < n2; b++)
+                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(v2[tx * A + b], srow[i2[tx * A + b]]), p1));
         }
         score = __fadd_rn(score, acc);
     }
-    m[(size_t)y * m_pitch + x] = score;
+    if (x < L2 && y < L1) m[(size_t)y * m_pitch + x] = score;
 }
 
 // Batched form for the matrix-fed streaming kernel: one matrix row per stream position of a
@@ -472,19 +728,44 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
         int ctas = (a.n_strips + wpc - 1) / wpc;
         if (ctas > sms) ctas = sms;    // all warps co-resident: strips wait on lower strips only
         const bool local = a.mode == PG_LOCAL;
-        if (kg == 2) {
-            if (local) k_gen_fill<2, true><<<ctas, wpc * 32, 0, st>>>(a);
-            else k_gen_fill<2, false><<<ctas, wpc * 32, 0, st>>>(a);
-        } else if (kg == 8) {
-            if (local) k_gen_fill<8, true><<<ctas, wpc * 32, 0, st>>>(a);
-            else k_gen_fill<8, false><<<ctas, wpc * 32, 0, st>>>(a);
+        if (a.o_full) {               // debug / B3 shim: the reference's complete flag bytes and o
+            a.flag_fmt = 0;
+            if (kg == 2) {
+                if (local) k_gen_fill<2, true><<<ctas, wpc * 32, 0, st>>>(a);
+                else k_gen_fill<2, false><<<ctas, wpc * 32, 0, st>>>(a);
+            } else {
+                if (local) k_gen_fill<8, true><<<ctas, wpc * 32, 0, st>>>(a);
+                else k_gen_fill<8, false><<<ctas, wpc * 32, 0, st>>>(a);
+            }
         } else {
-            pg_set_error("general kernel: unsupported strip width kg=%d", kg);
-            return 1;
+            a.flag_fmt = 1;
+            const bool mask = a.z != nullptr;
+#define PG_FAST1(KGV, LO, MA)                                                                      \
+    do {                                                                                           \
+        auto kern = k_gen_fill_fast<KGV, LO, MA>;                                                  \
+        const int w2 = a.n_strips < wpc ? a.n_strips : wpc;                                        \
+        const int c2 = (a.n_strips + w2 - 1) / w2 > sms ? sms : (a.n_strips + w2 - 1) / w2;        \
+        const size_t sm = (size_t)w2 * GEN_R * 32 * ((((KGV + 2) + 3) & ~3) + 4) * sizeof(float);        \
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        kern<<<c2, w2 * 32, sm, st>>>(a);                                                          \
+    } while (0)
+#define PG_FAST(KGV)                                                                               \
+    do {                                                                                           \
+        if (local) { if (mask) PG_FAST1(KGV, true, true); else PG_FAST1(KGV, true, false); }       \
+        else { if (mask) PG_FAST1(KGV, false, true); else PG_FAST1(KGV, false, false); }           \
+    } while (0)
+            if (kg == 1) PG_FAST(1);
+            else if (kg == 2) PG_FAST(2);
+            else if (kg == 4) PG_FAST(4);
+            else if (kg == 8) PG_FAST(8);
+            else if (kg == 16) PG_FAST(16);
+            else { pg_set_error("general kernel: unsupported strip width kg=%d", kg); return 1; }
+#undef PG_FAST
+#undef PG_FAST1
         }
         PG_CUDA_OK(cudaGetLastError());
     }
-    k_gen_finalize<<<1, 32, 0, st>>>(a);
+    k_gen_finalize<<<1, 256, 0, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
     if (a.path_buf) {
         k_gen_traceback<<<1, 32, 0, st>>>(a);
@@ -497,7 +778,13 @@ int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int 
 {
     if (L1 <= 0 || L2 <= 0) return 0;
     dim3 b(32, 8), g((L2 + 31) / 32, (L1 + 7) / 8);
-    k_build_scores<<<g, b, 0, st>>>(sets, L1, L2, m, m_pitch);
+    int amax = 1;
+    for (int i = 0; i < sets.n; i++) {
+        if (sets.s[i].A > BS_MAXA) { pg_set_error("alphabet size %d above %d", sets.s[i].A, BS_MAXA); return 1; }
+        if (sets.s[i].A > amax) amax = sets.s[i].A;
+    }
+    const size_t sm = sizeof(float) * (amax * amax + 40 * amax) + 40 * amax + 4 + sizeof(int) * 40;
+    k_build_scores<<<g, b, sm, st>>>(sets, L1, L2, m, m_pitch);
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -274,3 +274,52 @@ def test_full_size_properties(eng):
                 sc += -1.0 if gap == kind else -11.0
                 gap = kind
         assert sc == got[k]
+
+
+def test_long_profile_alignment_vs_oracle(eng):
+    """BASELINE config 5 shape, scaled to what the oracle finishes in seconds: two depth-8 DNA
+    count profiles (nucleotide matrix), global + semiglobal_both, affine [-11,-1] and linear [-2]."""
+    S = matrices.nucleotide()
+    c1 = synth.count_profile(5, 2600, 8, 4, 15)
+    c2 = synth.count_profile(6, 3100, 8, 4, 15)
+    p1, p2 = synth.profile_from_counts(c1), synth.profile_from_counts(c2)
+    m = eng.build_scores([p1], [p2], [S])
+    want_m = oracle.build_scores([p1], [p2], [S])
+    assert np.array_equal(m.cpu().numpy(), want_m)
+    for mode in ("global", "semiglobal_both"):
+        for gaps in ([-11.0, -1.0], [-2.0]):
+            g1, g2 = oracle.gap_arrays(2600, 3100, gaps)
+            r = eng.align_general(mode, m, g1, g2)
+            ws, wp = oracle.align_raw(mode, want_m, g1, g2)
+            assert r["score"] == ws, (mode, gaps)
+            assert np.array_equal(r["path"], wp), (mode, gaps)
+
+
+def test_config5_full_size_properties(eng):
+    """20,000 x 20,000 (BASELINE config 5): too large for the oracle in a test, so size-independent
+    properties: the traced path is monotone, spans the matrix and re-scores to the reported score;
+    a linear-gap score is bounded by the affine one with the same extension."""
+    S = matrices.nucleotide()
+    L = 20000
+    a = synth.family(5, 2, L, n_sym=4, n_indels=0)
+    seqs = [a[0], a[1]]
+    batch = eng.batch(seqs)
+    scores = {}
+    for gaps in ([-11.0, -1.0], [-1.0]):
+        r = eng.align_seq_pair_general(batch, 0, 1, S, gaps, "global")
+        p = r["path"]
+        assert tuple(p[0]) == (0, 0) and tuple(p[-1]) == (L, L)
+        d = np.diff(p, axis=0)
+        assert ((d >= 0).all() and (d.max(axis=1) == 1).all())
+        go, ge = (gaps + gaps)[:2]
+        sc, gap = 0.0, None
+        diag = (d[:, 0] == 1) & (d[:, 1] == 1)
+        sc = float(S[seqs[0][p[1:, 0][diag] - 1], seqs[1][p[1:, 1][diag] - 1]].sum())
+        kinds = np.where(diag, 0, np.where(d[:, 0] == 1, 1, 2))
+        prev = np.r_[0, kinds[:-1]]
+        opens = (kinds != 0) & (kinds != prev)
+        exts = (kinds != 0) & (kinds == prev)
+        sc += go * opens.sum() + ge * exts.sum()
+        assert sc == r["score"], gaps
+        scores[tuple(gaps)] = r["score"]
+    assert scores[(-1.0,)] >= scores[(-11.0, -1.0)]
