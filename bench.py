@@ -271,7 +271,8 @@ def main():
     total_cells = int(sum(len(seqs[i]) for i in range(n)) ** 2 - sum(len(s) ** 2 for s in seqs)) // 2
 
     def step_resident():
-        eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan)
+        eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan,
+                            S_host=S)
         if world > 1:
             parallel.allgather_condensed(out, slot_cuts)
 
@@ -307,7 +308,8 @@ def main():
         b = eng.batch(seqs)                                  # pinned host -> device
         sd = eng.dev(S)
         pl = eng.allpairs_tiles(b, (rank, world))
-        o, (lo, hi), _ = eng.allpairs_scores(b, sd, S.shape[0], gaps, mode=mode, shard=(rank, world), plan=pl)
+        o, (lo, hi), _ = eng.allpairs_scores(b, sd, S.shape[0], gaps, mode=mode, shard=(rank, world), plan=pl,
+                                             S_host=S)
         if world > 1:
             parallel.allgather_condensed(o, pl[3])
             lo, hi = 0, n_pairs
@@ -344,7 +346,8 @@ def main():
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
         for a, b in kev:
             a.record()
-            eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan)
+            eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan,
+                            S_host=S)
             b.record()
         torch.cuda.synchronize(dev)
         kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
@@ -363,7 +366,7 @@ def main():
                 "issue_bound_frac": (my_cells / (kms * 1e-3)) * 7.0 / 32.0 / (mb["fadd"] * sms * 1e9),
                 "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence: "
                                     "7 warp-instructions per 32 cells at the measured full issue rate",
-                "kernel": "k_stream<10,global,score-only>", "kernel_ms": kms,
+                "kernel": "k_stream16<10> (packed s16x2)" if eng.use_s16 else "k_stream<10,global,score-only>", "kernel_ms": kms,
                 "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
         # traced variant (what the preprofile master-slave alignments need): K2 with packed traceback
         # + K4 walk, device time only, on the first 120k pairs of the same workload
@@ -386,7 +389,9 @@ def main():
     if rank == 0:
         line = {"metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "i16" if (eng.use_s16 and eng.fits_s16(S, gaps[0], gaps[1], batch.lens) is not None) else "f32",
+                "data": "synthetic",
                 "config": config_dict({"parallelism": "pairs sharded by DP cells over %d rank(s)%s"
                                        % (world, ", NCCL all-gather of scores" if world > 1 else "")}, world),
                 "clocks": clk_sum,

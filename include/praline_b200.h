@@ -89,6 +89,17 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, c
                      int64_t* pair_tb_dev, const float* mwave_dev, const int64_t* mrow_base_dev, void* stream);
 
 /*
+ * Inter-task batch in packed 16-bit integers (DPX, two streamed sequences per warp): global
+ * mode, score per pair, INTEGER matrix and gaps whose DP values fit int16 (the caller checks,
+ * Engine.fits_s16).  Same tiles, sequences and outputs as pgpu_align_tiles; `neg` is the -inf
+ * sentinel, left0/left1 the column-0 border D(y,0) = left0 + (y-1)*left1 as integers.
+ */
+int pgpu_align_tiles16(int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
+                       const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, const float* S_dev,
+                       int A, int gap_open, int gap_extend, int neg, const float* topD_dev, int left0,
+                       int left1, int border_len, float* scores_dev, void* stream);
+
+/*
  * Traceback of an inter-task batch (K4).  Replaces get_paths (util/align.py:144-185), the
  * semiglobal end-cell scan (component/align.py:405-426) and extend_path_semiglobal
  * (util/align.py:268-297).  Paths are (y, x) rows in the reference orientation, written

@@ -52,6 +52,7 @@ struct StreamArgs {
     const int64_t* tb_base;      // word offset per (tile, warp)
     int32_t* emit_t;             // per slot: step at which the owning lane saw the last row
     int64_t* pair_tb;            // per slot: word offset of its warp's traceback region
+    int go16, ge16, neg16, left0_16, left1_16;   // packed s16x2 variant (gotoh_stream16.cu)
     const float* mwave;          // profile batches: match scores [row][32*K], rows in stream order
     const int64_t* mrow_base;    // first matrix row per (tile, warp); row 0 of a region is the dummy row
 };
@@ -120,6 +121,7 @@ int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* 
                                float* m, int m_pitch, cudaStream_t st);
 int pg_stream_supported_k(int k);
 int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb, cudaStream_t st);
+int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, cudaStream_t st);
 int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,
                           int mode, int transposed, float* scores, cudaStream_t st);
 int pg_launch_traceback(const TraceArgs& a, cudaStream_t st);

@@ -6,6 +6,7 @@ its C extension in praline/component/align.py (array prep :119-221, border init 
 end-cell choice and traceback :401-433), but for whole batches of pairs at once.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -142,6 +143,7 @@ class Engine(object):
         self.launches = 0          # kernels of ours launched (bench.py reports it)
         self.tb_budget_words = 1 << 30
         self._borders = {}
+        self.use_s16 = os.environ.get("PGPU_NO_S16", "") == ""
         self.m_budget_floats = 1 << 31     # 8 GiB of match scores per wave of a profile batch
 
     # -- helpers -------------------------------------------------------------------------------
@@ -212,7 +214,7 @@ class Engine(object):
 
     def run_tiles(self, mode, K, transposed, batch, stream_ids_dev, tiles, n_slots, S_dev, A, go, ge,
                   scores_dev, cs=None, slot_res_dev=None, slot_str_dev=None, want_paths=False, caps=None,
-                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None):
+                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None, S_host=None):
         """Launch K2 (+K4) for one K class.  Returns list of (slot_lo, slot_hi, path_off, path_buf,
         path_start, path_len) per wave when want_paths."""
         lib = self.lib
@@ -228,6 +230,16 @@ class Engine(object):
         if not want_paths:
             if tiles_dev is None:
                 tiles_dev = self.dev(tiles.view(np.uint8))
+            neg = self.fits_s16(S_host, go, ge, batch.lens) if (
+                md == 0 and mwave_dev is None and self.use_s16) else None
+            if neg is not None:   # packed 16-bit DPX kernel: two streamed sequences per warp
+                _lib.check(lib.pgpu_align_tiles16(K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
+                                                  self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles),
+                                                  self.ptr(S_dev), A, int(go), int(ge), neg, self.ptr(top_dev),
+                                                  int(B["left0"]), int(B["left1"]), maxlen + 1,
+                                                  self.ptr(scores_dev), self.stream()))
+                self.launches += 1
+                return out
             keys = torch.empty(2 * n_slots, dtype=torch.int64, device=self.device) if semi else None
             _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
                                             self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles), n_slots,
@@ -296,6 +308,22 @@ class Engine(object):
             lo = hi
         return out
 
+    def fits_s16(self, S, go, ge, lens):
+        """Sentinel for the packed int16 kernel, or None when the batch must stay in f32: integer
+        scores, and |go| + (|ge| + max|S|) * (L1 + L2) plus the sentinel arithmetic inside int16."""
+        if S is None:
+            return None
+        vals = np.concatenate([S.ravel().astype(np.float64), [float(go), float(ge)]])
+        if not np.all(vals == np.round(vals)):
+            return None
+        smax = float(np.abs(S).max())
+        lmax = int(np.max(lens))
+        v = abs(float(go)) + (abs(float(ge)) + smax) * 2 * lmax
+        neg = -(v + smax + 1)
+        if neg - abs(float(go)) - 2 * abs(float(ge)) - smax < -32000 or smax * lmax > 32000:
+            return None
+        return int(neg)
+
     def integer_exact(self, S, go, ge, maxlen):
         """Traced batches derive tie flags from unrounded operands: exact iff all scores are
         integers small enough that every f32 sum is exact (see gotoh_stream.cu)."""
@@ -360,7 +388,7 @@ class Engine(object):
             tiles["out_base"] += a
             waves = self.run_tiles(md, K, transposed, batch, stream_ids_dev, tiles, n, S_dev, A, go, ge,
                                    scores_dev, cs=cs, slot_res_dev=slot_res_dev, slot_str_dev=stream_ids_dev,
-                                   want_paths=want_paths, caps=caps, counts=counts_ctx)
+                                   want_paths=want_paths, caps=caps, counts=counts_ctx, S_host=S)
             pending.extend(waves)
         if device_only:
             return scores_dev, order, pending
@@ -509,7 +537,8 @@ class Engine(object):
         by_k = {int(K): tiles[kk == K] for K in np.unique(kk)}
         return by_k, (slot_lo, slot_hi), int(cells[lo:hi].sum()), slot_cuts, {}
 
-    def allpairs_scores(self, batch, S_dev, A, gap_series, mode="global", shard=(0, 1), out=None, plan=None):
+    def allpairs_scores(self, batch, S_dev, A, gap_series, mode="global", shard=(0, 1), out=None, plan=None,
+                        S_host=None):
         """Condensed all-vs-all score vector on the device (this shard's slots filled)."""
         md = MODES[mode]
         go, ge = _gaps(gap_series)
@@ -523,7 +552,8 @@ class Engine(object):
         for K, tiles in by_k.items():
             if K not in cache:
                 cache[K] = self.dev(tiles.view(np.uint8))
-            self.run_tiles(md, K, True, batch, None, tiles, n_pairs, S_dev, A, go, ge, out, tiles_dev=cache[K])
+            self.run_tiles(md, K, True, batch, None, tiles, n_pairs, S_dev, A, go, ge, out, tiles_dev=cache[K],
+                           S_host=S_host)
         return out, rng, cells
 
     # -- general single alignment ----------------------------------------------------------------

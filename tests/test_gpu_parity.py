@@ -219,6 +219,31 @@ def test_preprofile_counts_on_device(eng):
         assert np.array_equal(scores, pairs_scores)
 
 
+def test_packed_int16_kernel_matches_f32_kernel(eng):
+    """The DPX s16x2 kernel (global, score only, integer scores) and the f32 kernel agree on
+    every pair, ragged lengths, both orientations; out-of-range batches fall back to f32."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(17)
+    seqs = synth.family(401, 40, 180) + [rng.integers(0, 20, int(rng.integers(1, 330))).astype(np.int32) for _ in range(25)]
+    batch = eng.batch(seqs)
+    pi, pj = synth.all_pairs(len(seqs))
+    flat, offs = synth.pack(seqs)
+    want = oracle.align_batch("global", flat, offs, pi, pj, S, [-11.0, -1.0])
+    for resident in ("one", "two"):
+        for use in (True, False):
+            eng.use_s16 = use
+            got, _ = eng.align_pairs(batch, pi, pj, S, [-11.0, -1.0], mode="global", resident=resident)
+            assert np.array_equal(got, want), (resident, use)
+    eng.use_s16 = True
+    assert eng.fits_s16(S, -11.0, -1.0, batch.lens) is not None
+    assert eng.fits_s16(S * 0.5, -11.0, -1.0, batch.lens) is None            # non-integer scores
+    assert eng.fits_s16(S * 40, -11.0, -1.0, batch.lens) is None             # would leave int16
+    big, _ = eng.align_pairs(batch, pi[:50], pj[:50], S * 40, [-11.0, -1.0], mode="global")
+    assert np.array_equal(big, oracle.align_batch("global", flat, offs, pi[:50], pj[:50], S * 40, [-11.0, -1.0]))
+    out, _, _ = eng.allpairs_scores(batch, eng.dev(S), 27, [-8.0], mode="global", S_host=S)
+    assert np.array_equal(out.cpu().numpy(), oracle.align_batch("global", flat, offs, pi, pj, S, [-8.0]))
+
+
 def test_two_track_sets(eng):
     rng = np.random.default_rng(3)
     S1, S2 = matrices.blosum62(), rng.standard_normal((15, 15)).astype(np.float32)
