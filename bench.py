@@ -263,7 +263,8 @@ def main():
     # ---- resident-input arm: sequences, matrix and tile plan already in HBM ------------------
     batch = eng.batch(seqs)
     S_dev = eng.dev(S)
-    plan = eng.allpairs_tiles(batch, (rank, world))
+    go_, ge_ = float(gaps[0]), float(gaps[-1])
+    plan = eng.allpairs_tiles(batch, (rank, world), paired=eng.wants_paired(S, go_, ge_, 0, batch))
     slot_cuts = plan[3]
     my_cells = plan[2]
     out = torch.empty(n_pairs, dtype=torch.float32, device=dev)
@@ -307,7 +308,7 @@ def main():
         nonlocal h2d, d2h
         b = eng.batch(seqs)                                  # pinned host -> device
         sd = eng.dev(S)
-        pl = eng.allpairs_tiles(b, (rank, world))
+        pl = eng.allpairs_tiles(b, (rank, world), paired=eng.wants_paired(S, go_, ge_, 0, b))
         o, (lo, hi), _ = eng.allpairs_scores(b, sd, S.shape[0], gaps, mode=mode, shard=(rank, world), plan=pl,
                                              S_host=S)
         if world > 1:
@@ -366,7 +367,7 @@ def main():
                 "issue_bound_frac": (my_cells / (kms * 1e-3)) * 7.0 / 32.0 / (mb["fadd"] * sms * 1e9),
                 "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence: "
                                     "7 warp-instructions per 32 cells at the measured full issue rate",
-                "kernel": "k_stream16<10> (packed s16x2)" if eng.use_s16 else "k_stream<10,global,score-only>", "kernel_ms": kms,
+                "kernel": "k_stream16r<10> (packed s16x2, paired residents)" if plan[5] else "k_stream<10,global,score-only>", "kernel_ms": kms,
                 "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
         # traced variant (what the preprofile master-slave alignments need): K2 with packed traceback
         # + K4 walk, device time only, on the first 120k pairs of the same workload

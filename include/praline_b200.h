@@ -44,8 +44,11 @@ typedef struct pgpu_tile {
     int32_t resident;
     int32_t stream_begin;
     int32_t stream_end;
-    int32_t reserved;
+    int32_t resident2;      /* paired-resident int16 launches: second resident or -1; else unused */
     int64_t out_base;
+    int64_t out_base2;      /* paired-resident launches: first output slot of resident2 */
+    int32_t b_skip;         /* leading stream elements that have no pair with resident2 */
+    int32_t reserved;
 } pgpu_tile;
 
 int pgpu_abi_version(void);
@@ -93,8 +96,11 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, c
  * mode, score per pair, INTEGER matrix and gaps whose DP values fit int16 (the caller checks,
  * Engine.fits_s16).  Same tiles, sequences and outputs as pgpu_align_tiles; `neg` is the -inf
  * sentinel, left0/left1 the column-0 border D(y,0) = left0 + (y-1)*left1 as integers.
+ * paired = 0: the two halves carry two STREAMED sequences of the tile (any pair list).
+ * paired = 1: the two halves carry two RESIDENT sequences (tile.resident, tile.resident2) that
+ *             share one stream -- the all-vs-all shape; results of resident2 go to out_base2.
  */
-int pgpu_align_tiles16(int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
+int pgpu_align_tiles16(int K, int paired, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
                        const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, const float* S_dev,
                        int A, int gap_open, int gap_extend, int neg, const float* topD_dev, int left0,
                        int left1, int border_len, float* scores_dev, void* stream);

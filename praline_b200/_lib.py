@@ -22,7 +22,7 @@ _SIGNATURES = {
                                  c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_float, c_float, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
-    "pgpu_align_tiles16": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+    "pgpu_align_tiles16": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pgpu_traceback_tiles": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

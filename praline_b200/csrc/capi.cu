@@ -81,7 +81,7 @@ int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs, const
     return rc;
 }
 
-int pgpu_align_tiles16(int K, int transposed, const uint8_t* seqs, const int64_t* offs, const int32_t* stream_ids,
+int pgpu_align_tiles16(int K, int paired, int transposed, const uint8_t* seqs, const int64_t* offs, const int32_t* stream_ids,
                        const void* tiles, int n_tiles, const float* S, int A, int gap_open, int gap_extend,
                        int neg, const float* topD, int left0, int left1, int border_len, float* scores,
                        void* stream)
@@ -94,7 +94,7 @@ int pgpu_align_tiles16(int K, int transposed, const uint8_t* seqs, const int64_t
     a.seqs = seqs; a.offs = offs; a.stream_ids = stream_ids; a.tiles = (const PgTile*)tiles;
     a.S = S; a.A = A; a.transposed = transposed; a.topD = topD; a.border_len = border_len; a.scores = scores;
     a.go16 = gap_open; a.ge16 = gap_extend; a.neg16 = neg; a.left0_16 = left0; a.left1_16 = left1;
-    return pg_launch_stream16(a, n_tiles, K, (cudaStream_t)stream);
+    return pg_launch_stream16(a, n_tiles, K, paired, (cudaStream_t)stream);
 }
 
 int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, const int32_t* slot_resident,

@@ -19,8 +19,11 @@ struct PgTile {
     int32_t resident;       // sequence id of the resident sequence
     int32_t stream_begin;   // [begin, end) into stream_ids (or sequence ids when stream_ids == NULL)
     int32_t stream_end;
-    int32_t _pad;
+    int32_t resident2;      // paired-resident launches: second resident (high half), -1 = none
     int64_t out_base;       // output slot of the first streamed sequence; slots are consecutive
+    int64_t out_base2;      // paired-resident launches: first slot of the second resident
+    int32_t b_skip;         // leading stream elements that have no pair with resident2
+    int32_t _pad;
 };
 
 struct PgBorder {
@@ -121,7 +124,7 @@ int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* 
                                float* m, int m_pitch, cudaStream_t st);
 int pg_stream_supported_k(int k);
 int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb, cudaStream_t st);
-int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, cudaStream_t st);
+int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, int paired, cudaStream_t st);
 int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,
                           int mode, int transposed, float* scores, cudaStream_t st);
 int pg_launch_traceback(const TraceArgs& a, cudaStream_t st);

@@ -226,39 +226,234 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
     }
 }
 
+// ---- paired RESIDENTS: the all-vs-all shape -------------------------------------------------------
+// The low and high halves carry two RESIDENT sequences (tile.resident, tile.resident2) and ONE
+// stream runs through both: the substitution profile is stored pre-packed,
+//     prof2[a][x] = { S[a][resA[x]] , S[a][resB[x]] },
+// so a single shared-memory row feeds both halves without the per-column PRMT, there is one
+// ring, one set of row flags, and the border re-arm is a plain register reload.  In an
+// all-vs-all, residents i and i+1 share every streamed j > i+1; the pair (i, i+1) itself rides
+// along as the first stream element with its high half ignored (tile.b_skip).
+template <int K, int NW>
+__global__ void __launch_bounds__(NW * 32) k_stream16r(const StreamArgs a)
+{
+    constexpr int UNR = 4;
+    constexpr int NCH = (K + 3) / 4;        // 16-byte chunks of 4 packed columns per lane
+    constexpr int ROWB = NCH * 512;
+    constexpr int KP = (K + 3) & ~3;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* prof = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* top2 = reinterpret_cast<uint32_t*>(smem + (size_t)a.A * ROWB);            // [32][KP + 4]
+    uint32_t* ring = top2 + 32 * (KP + 4) + (threadIdx.x >> 5) * 128;
+
+    const PgTile tile = a.tiles[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t roffA = a.offs[tile.resident];
+    const int LrA = (int)(a.offs[tile.resident + 1] - roffA);
+    const bool hasB = tile.resident2 >= 0;
+    const int64_t roffB = hasB ? a.offs[tile.resident2] : 0;
+    const int LrB = hasB ? (int)(a.offs[tile.resident2 + 1] - roffB) : 1;
+
+    {
+        const int n = a.A * NCH * 128;
+        for (int idx = threadIdx.x; idx < n; idx += NW * 32) {
+            const int c = idx & 3, l = (idx >> 2) & 31, j = (idx >> 7) % NCH, sym = idx / (NCH * 128);
+            const int k = 4 * j + c, x = l * K + k;
+            int va = 0, vb = 0;
+            if (k < K && x < LrA) {
+                const int b = a.seqs[roffA + x];
+                va = (int)(a.transposed ? a.S[b * a.A + sym] : a.S[sym * a.A + b]);
+            }
+            if (hasB && k < K && x < LrB) {
+                const int b = a.seqs[roffB + x];
+                vb = (int)(a.transposed ? a.S[b * a.A + sym] : a.S[sym * a.A + b]);
+            }
+            prof[idx] = ((uint32_t)(va & 0xffff)) | ((uint32_t)vb << 16);
+        }
+        for (int idx = threadIdx.x; idx < 32 * (KP + 4); idx += NW * 32) {
+            const int l = idx / (KP + 4), k = idx % (KP + 4);
+            int v = 0;
+            if (k < K) v = (int)a.topD[l * K + k + 1];
+            else if (k == KP) v = (int)a.topD[l * K];
+            top2[idx] = pack2(v);
+        }
+    }
+    const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(smem);
+    for (int i = lane; i < 128; i += 32) ring[i] = prof_s;
+    __syncthreads();
+    if (prof_s & 511u) __trap();
+
+    const int n_str = tile.stream_end - tile.stream_begin;
+    const int per = (n_str + NW - 1) / NW;
+    const int sb = tile.stream_begin + warp * per;
+    const int se = min(sb + per, tile.stream_end);
+    if (sb >= se) return;
+
+    auto seq_id = [&](int s) -> int { return a.stream_ids ? a.stream_ids[s] : s; };
+    auto seq_len = [&](int s) -> int {
+        if (s < sb) return 1;
+        const int id = seq_id(s);
+        return (int)(a.offs[id + 1] - a.offs[id]);
+    };
+    int total = 0;
+    for (int s = sb + lane; s < se; s += 32) total += seq_len(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+    const int T = (total + 1 + 31 + 31) & ~31;
+
+    const int lrA = (LrA - 1) / K, klA = (LrA - 1) % K, lrB = (LrB - 1) / K, klB = (LrB - 1) % K;
+    const uint32_t go2 = pack2(a.go16), ge2 = pack2(a.ge16), NEG2 = pack2(a.neg16);
+    const uint32_t left0_2 = pack2(a.left0_16), left1_2 = pack2(a.left1_16);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t lane16 = (uint32_t)lane << 4;
+    const uint32_t* mytop = top2 + lane * (KP + 4);
+
+    uint32_t Mo[K], U[K], D[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { Mo[k] = 0u; U[k] = 0u; D[k] = 0u; }
+    uint32_t Mo_last = 0u, L_last = 0u, D_last = 0u, Dleft_prev = 0u, bord = 0u;
+    int q = sb;
+    int ps = sb - 1, pp = 0;
+
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        {
+            int s = ps, p = pp + lane;
+            int len = (s < se) ? seq_len(s) : 0;
+            while (s < se && p >= len) {
+                p -= len;
+                s++;
+                len = (s < se) ? seq_len(s) : 0;
+            }
+            uint32_t word = prof_s;
+            if (s < se) {
+                if (s < sb) {
+                    word |= FLAG_LAST;
+                } else {
+                    const int sym = a.seqs[a.offs[seq_id(s)] + p];
+                    word = (prof_s + (uint32_t)(sym * ROWB)) | ((p == len - 1) ? (FLAG_LAST | FLAG_EMIT) : 0u);
+                }
+            }
+            __syncwarp();
+            ring[(t0 + lane) & 63] = word;
+            ring[((t0 + lane) & 63) + 64] = word;
+            __syncwarp();
+            int s31 = __shfl_sync(FULL, s, 31), p31 = __shfl_sync(FULL, p, 31) + 1;
+            const int len31 = __shfl_sync(FULL, len, 31);
+            if (s31 < se && p31 >= len31) { p31 = 0; s31++; }
+            ps = s31;
+            pp = p31;
+        }
+        const uint32_t rp0 = ring_s + ((uint32_t)((t0 - lane) & 63) << 2);
+
+#pragma unroll 1
+        for (int g = 0; g < 32; g += UNR) {
+            const uint32_t rp = rp0 + (uint32_t)g * 4u;
+#pragma unroll
+            for (int i = 0; i < UNR; i++) {
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)i * 4u) : "memory");
+                const uint32_t pa = (w & 0x00ffffffu) | lane16;
+                uint32_t sc[NCH * 4];
+#pragma unroll
+                for (int j = 0; j < NCH; j++)
+                    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                        : "=r"(sc[4 * j]), "=r"(sc[4 * j + 1]), "=r"(sc[4 * j + 2]), "=r"(sc[4 * j + 3])
+                        : "r"(pa + (uint32_t)j * 512u));
+
+                uint32_t Ml = __shfl_up_sync(FULL, Mo_last, 1);
+                uint32_t Ll = __shfl_up_sync(FULL, L_last, 1);
+                uint32_t Dn = __shfl_up_sync(FULL, D_last, 1);
+                if (lane == 0) {
+                    Ml = NEG2;
+                    Ll = NEG2;
+                    Dn = bord;
+                }
+                bord = __vadd2(bord, left1_2);
+                uint32_t diag = Dleft_prev;
+                Dleft_prev = Dn;
+
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const uint32_t m = __vadd2(diag, sc[k]);
+                    const uint32_t u = __viaddmax_s16x2(U[k], ge2, Mo[k]);
+                    const uint32_t l = __viaddmax_s16x2(Ll, ge2, Ml);
+                    diag = D[k];
+                    const uint32_t d = __vimax3_s16x2(m, u, l);
+                    const uint32_t mo = __vadd2(m, go2);
+                    Mo[k] = mo;
+                    U[k] = u;
+                    D[k] = d;
+                    Ml = mo;
+                    Ll = l;
+                }
+                Mo_last = Ml;
+                L_last = Ll;
+                D_last = D[K - 1];
+
+                if ((int)w < 0) {   // FLAG_LAST
+                    if (w & FLAG_EMIT) {
+                        const int e = q - tile.stream_begin;
+                        if (lane == lrA) a.scores[tile.out_base + e] = (float)(int)(int16_t)(pick_u<K>(D, klA) & 0xffffu);
+                        if (hasB && lane == lrB && e >= tile.b_skip)
+                            a.scores[tile.out_base2 + (e - tile.b_skip)] = (float)(int)(int16_t)(pick_u<K>(D, klB) >> 16);
+                        q++;
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        Mo[k] = NEG2;
+                        U[k] = NEG2;
+                        D[k] = mytop[k];
+                    }
+                    Dleft_prev = mytop[KP];
+                    bord = left0_2;
+                }
+            }
+        }
+    }
+}
+
 // ---- launch ------------------------------------------------------------------------------------
 constexpr int kNW16 = 8;
 
 template <int K>
-static int launch16(const StreamArgs& a, int n_tiles, cudaStream_t st)
+static int launch16(const StreamArgs& a, int n_tiles, int paired, cudaStream_t st)
 {
-    constexpr int NCH = (K + 7) / 8, KP = (K + 3) & ~3;
-    const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16 * 256 * sizeof(uint32_t);
-    auto kern = k_stream16<K, kNW16>;
-    PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_tiles, kNW16 * 32, smem, st>>>(a);
+    constexpr int KP = (K + 3) & ~3;
+    if (paired) {
+        constexpr int NCH = (K + 3) / 4;
+        const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16 * 128 * sizeof(uint32_t);
+        auto kern = k_stream16r<K, kNW16>;
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_tiles, kNW16 * 32, smem, st>>>(a);
+    } else {
+        constexpr int NCH = (K + 7) / 8;
+        const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16 * 256 * sizeof(uint32_t);
+        auto kern = k_stream16<K, kNW16>;
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_tiles, kNW16 * 32, smem, st>>>(a);
+    }
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, cudaStream_t st)
+int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, int paired, cudaStream_t st)
 {
     if (n_tiles <= 0) return 0;
     switch (K) {
-        case 1: return launch16<1>(a, n_tiles, st);
-        case 2: return launch16<2>(a, n_tiles, st);
-        case 3: return launch16<3>(a, n_tiles, st);
-        case 4: return launch16<4>(a, n_tiles, st);
-        case 6: return launch16<6>(a, n_tiles, st);
-        case 8: return launch16<8>(a, n_tiles, st);
-        case 10: return launch16<10>(a, n_tiles, st);
-        case 12: return launch16<12>(a, n_tiles, st);
-        case 13: return launch16<13>(a, n_tiles, st);
-        case 14: return launch16<14>(a, n_tiles, st);
-        case 16: return launch16<16>(a, n_tiles, st);
-        case 20: return launch16<20>(a, n_tiles, st);
-        case 24: return launch16<24>(a, n_tiles, st);
-        case 32: return launch16<32>(a, n_tiles, st);
+        case 1: return launch16<1>(a, n_tiles, paired, st);
+        case 2: return launch16<2>(a, n_tiles, paired, st);
+        case 3: return launch16<3>(a, n_tiles, paired, st);
+        case 4: return launch16<4>(a, n_tiles, paired, st);
+        case 6: return launch16<6>(a, n_tiles, paired, st);
+        case 8: return launch16<8>(a, n_tiles, paired, st);
+        case 10: return launch16<10>(a, n_tiles, paired, st);
+        case 12: return launch16<12>(a, n_tiles, paired, st);
+        case 13: return launch16<13>(a, n_tiles, paired, st);
+        case 14: return launch16<14>(a, n_tiles, paired, st);
+        case 16: return launch16<16>(a, n_tiles, paired, st);
+        case 20: return launch16<20>(a, n_tiles, paired, st);
+        case 24: return launch16<24>(a, n_tiles, paired, st);
+        case 32: return launch16<32>(a, n_tiles, paired, st);
         default: pg_set_error("unsupported columns-per-lane K=%d", K); return 1;
     }
 }

@@ -16,7 +16,8 @@ from . import _lib
 MODES = {"global": 0, "local": 1, "semiglobal_both": 2, "semiglobal_one": 3, "semiglobal_two": 4}
 
 TILE_DTYPE = np.dtype([("resident", np.int32), ("stream_begin", np.int32), ("stream_end", np.int32),
-                       ("reserved", np.int32), ("out_base", np.int64)])
+                       ("resident2", np.int32), ("out_base", np.int64), ("out_base2", np.int64),
+                       ("b_skip", np.int32), ("reserved", np.int32)])
 
 
 def _gaps(gap_series):
@@ -207,6 +208,8 @@ class Engine(object):
 
     def _pick_tile(self, n_pairs):
         # enough tiles to fill 148 SMs several times over, but streams of >= 2 sequences per warp
+        if os.environ.get("PGPU_TILE"):
+            return int(os.environ["PGPU_TILE"])
         spw = 16
         while spw > 2 and n_pairs // (self.nw * spw) < 148 * 6:
             spw //= 2
@@ -214,7 +217,7 @@ class Engine(object):
 
     def run_tiles(self, mode, K, transposed, batch, stream_ids_dev, tiles, n_slots, S_dev, A, go, ge,
                   scores_dev, cs=None, slot_res_dev=None, slot_str_dev=None, want_paths=False, caps=None,
-                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None, S_host=None):
+                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None, S_host=None, paired=False):
         """Launch K2 (+K4) for one K class.  Returns list of (slot_lo, slot_hi, path_off, path_buf,
         path_start, path_len) per wave when want_paths."""
         lib = self.lib
@@ -233,7 +236,7 @@ class Engine(object):
             neg = self.fits_s16(S_host, go, ge, batch.lens) if (
                 md == 0 and mwave_dev is None and self.use_s16) else None
             if neg is not None:   # packed 16-bit DPX kernel: two streamed sequences per warp
-                _lib.check(lib.pgpu_align_tiles16(K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
+                _lib.check(lib.pgpu_align_tiles16(K, int(paired), int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
                                                   self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles),
                                                   self.ptr(S_dev), A, int(go), int(ge), neg, self.ptr(top_dev),
                                                   int(B["left0"]), int(B["left1"]), maxlen + 1,
@@ -501,41 +504,61 @@ class Engine(object):
         out[order] = scores_dev.cpu().numpy()
         return out
 
-    def allpairs_tiles(self, batch, shard=(0, 1), tile=None):
+    def allpairs_tiles(self, batch, shard=(0, 1), tile=None, paired=False):
         """All unordered pairs (i < j), sequence_one = i resident, sequence_two = j streamed, slots
-        in condensed (np.triu_indices) order.  Returns {K: tiles} for this shard and its slot range."""
+        in condensed (np.triu_indices) order.  Returns (tiles per K, this shard's slot range, its
+        DP cells, slot cut per rank, device cache, paired).
+
+        paired=True lays residents out two by two (2p, 2p+1) for the packed int16 kernel whose
+        register halves carry two residents over one shared stream (pgpu_align_tiles16, paired=1):
+        the stream of a pair starts at j = 2p+1, where the high half has no partner yet (b_skip)."""
         n = batch.n
         rank, world = shard
         tile = tile or self._pick_tile(n * (n - 1) // 2)
-        i = np.arange(n - 1, dtype=np.int64)
-        cnt = n - 1 - i
-        ntile = (cnt + tile - 1) // tile
-        grp = np.repeat(i, ntile)
-        first = np.cumsum(ntile) - ntile
-        tb = grp + 1 + (np.arange(int(ntile.sum())) - first[grp]) * tile
-        te = np.minimum(tb + tile, n)
-        base = grp * n - grp * (grp + 1) // 2 + (tb - grp - 1)
-        cs = np.zeros(n + 1, np.int64)
-        np.cumsum(batch.lens, out=cs[1:])
-        cells = batch.lens[grp] * (cs[te] - cs[tb])
-        cum = np.concatenate([[0], np.cumsum(cells)])
-        cuts = np.searchsorted(cum, cum[-1] * np.arange(world + 1) / world, side="left")
-        cuts[0], cuts[-1] = 0, len(tb)
-        lo, hi = int(cuts[rank]), int(cuts[rank + 1])
-        tiles = np.zeros(hi - lo, TILE_DTYPE)
-        tiles["resident"] = grp[lo:hi]
-        tiles["stream_begin"] = tb[lo:hi]
-        tiles["stream_end"] = te[lo:hi]
-        tiles["out_base"] = base[lo:hi]
         n_pairs = n * (n - 1) // 2
-        slot_lo = int(base[lo]) if lo < len(tb) else n_pairs
-        slot_hi = int(base[hi]) if hi < len(tb) else n_pairs
-        slot_cuts = [int(base[c]) if c < len(tb) else n_pairs for c in cuts]
-        kk = np.asarray([self.k_for(int(l)) or -1 for l in batch.lens])[tiles["resident"]]
-        if (kk < 0).any():
+        lens = batch.lens
+        cs = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=cs[1:])
+        kcls = np.asarray([self.k_for(int(l)) or -1 for l in lens])
+        if (kcls[:max(n - 1, 1)] < 0).any():
             raise _lib.PralineGpuError("sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
+        cond = lambda i, j: i * n - i * (i + 1) // 2 + (j - i - 1)
+        step = 2 if paired else 1
+        i = np.arange(0, n - 1, step, dtype=np.int64)            # first resident of every unit
+        has_b = (i + 1 <= n - 2) if paired else np.zeros(len(i), bool)
+        cnt = n - 1 - i                                           # stream elements j = i+1 .. n-1
+        ntile = (cnt + tile - 1) // tile
+        unit = np.repeat(np.arange(len(i)), ntile)
+        first = np.cumsum(ntile) - ntile
+        gi = i[unit]
+        tb = gi + 1 + (np.arange(int(ntile.sum())) - first[unit]) * tile
+        te = np.minimum(tb + tile, n)
+        hb = has_b[unit]
+        rows = cs[te] - cs[tb]
+        cells = lens[gi] * rows + np.where(hb, lens[np.minimum(gi + 1, n - 1)] * (cs[te] - cs[np.maximum(tb, gi + 2)]), 0)
+        # shard at unit boundaries so that every rank owns whole condensed rows
+        ucells = np.zeros(len(i) + 1, np.int64)
+        np.add.at(ucells, unit + 1, cells)
+        ucum = np.cumsum(ucells)
+        ucuts = np.searchsorted(ucum, ucum[-1] * np.arange(world + 1) / world, side="left")
+        ucuts[0], ucuts[-1] = 0, len(i)
+        ucuts = np.maximum.accumulate(ucuts)
+        sel = (unit >= ucuts[rank]) & (unit < ucuts[rank + 1])
+        tiles = np.zeros(int(sel.sum()), TILE_DTYPE)
+        tiles["resident"] = gi[sel]
+        tiles["resident2"] = np.where(hb[sel], gi[sel] + 1, -1)
+        tiles["stream_begin"] = tb[sel]
+        tiles["stream_end"] = te[sel]
+        tiles["out_base"] = cond(gi[sel], tb[sel])
+        tiles["out_base2"] = np.where(hb[sel], cond(gi[sel] + 1, np.maximum(tb[sel], gi[sel] + 2)), 0)
+        tiles["b_skip"] = np.where(hb[sel] & (tb[sel] == gi[sel] + 1), 1, 0)
+        row_cut = lambda u: int(cond(i[u], i[u] + 1)) if u < len(i) else n_pairs
+        slot_cuts = [row_cut(int(u)) for u in ucuts]
+        kk = kcls[tiles["resident"]]
+        if paired:
+            kk = np.maximum(kk, np.where(tiles["resident2"] >= 0, kcls[np.maximum(tiles["resident2"], 0)], 0))
         by_k = {int(K): tiles[kk == K] for K in np.unique(kk)}
-        return by_k, (slot_lo, slot_hi), int(cells[lo:hi].sum()), slot_cuts, {}
+        return by_k, (slot_cuts[rank], slot_cuts[rank + 1]), int(cells[sel].sum()), slot_cuts, {}, bool(paired)
 
     def allpairs_scores(self, batch, S_dev, A, gap_series, mode="global", shard=(0, 1), out=None, plan=None,
                         S_host=None):
@@ -544,17 +567,25 @@ class Engine(object):
         go, ge = _gaps(gap_series)
         n_pairs = batch.n * (batch.n - 1) // 2
         if plan is None:
-            plan = self.allpairs_tiles(batch, shard)
+            plan = self.allpairs_tiles(batch, shard, paired=self.wants_paired(S_host, go, ge, md, batch))
         by_k, rng, cells = plan[0], plan[1], plan[2]
         cache = plan[4] if len(plan) > 4 else {}
+        paired = bool(plan[5]) if len(plan) > 5 else False
+        if paired and not self.wants_paired(S_host, go, ge, md, batch):
+            raise _lib.PralineGpuError("a paired-resident plan needs the packed int16 kernel (global mode, integer scores)")
         if out is None:
             out = torch.empty(n_pairs, dtype=torch.float32, device=self.device)
         for K, tiles in by_k.items():
             if K not in cache:
                 cache[K] = self.dev(tiles.view(np.uint8))
             self.run_tiles(md, K, True, batch, None, tiles, n_pairs, S_dev, A, go, ge, out, tiles_dev=cache[K],
-                           S_host=S_host)
+                           S_host=S_host, paired=paired)
         return out, rng, cells
+
+    def wants_paired(self, S_host, go, ge, md, batch):
+        """All-vs-all runs on the paired-resident int16 kernel when the packed path applies."""
+        return bool(self.use_s16 and md == 0 and S_host is not None and
+                    self.fits_s16(np.asarray(S_host), go, ge, batch.lens) is not None)
 
     # -- general single alignment ----------------------------------------------------------------
     def build_scores(self, P1s, P2s, Ss):

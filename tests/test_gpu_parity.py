@@ -240,8 +240,20 @@ def test_packed_int16_kernel_matches_f32_kernel(eng):
     assert eng.fits_s16(S * 40, -11.0, -1.0, batch.lens) is None             # would leave int16
     big, _ = eng.align_pairs(batch, pi[:50], pj[:50], S * 40, [-11.0, -1.0], mode="global")
     assert np.array_equal(big, oracle.align_batch("global", flat, offs, pi[:50], pj[:50], S * 40, [-11.0, -1.0]))
-    out, _, _ = eng.allpairs_scores(batch, eng.dev(S), 27, [-8.0], mode="global", S_host=S)
+    out, _, _ = eng.allpairs_scores(batch, eng.dev(S), 27, [-8.0], mode="global", S_host=S)        # paired residents
     assert np.array_equal(out.cpu().numpy(), oracle.align_batch("global", flat, offs, pi, pj, S, [-8.0]))
+    for n_odd in (2, 3, 7, 64):                                    # odd counts, sharded plans
+        sub = eng.batch(seqs[:n_odd])
+        f2, o2 = synth.pack(seqs[:n_odd])
+        qi, qj = synth.all_pairs(n_odd)
+        want2 = oracle.align_batch("global", f2, o2, qi, qj, S, [-11.0, -1.0])
+        acc = np.full(len(qi), np.nan, np.float32)
+        for r in range(2):
+            plan = eng.allpairs_tiles(sub, (r, 2), tile=16, paired=True)
+            o, (lo, hi), _ = eng.allpairs_scores(sub, eng.dev(S), 27, [-11.0, -1.0], mode="global", shard=(r, 2),
+                                                 plan=plan, S_host=S)
+            acc[lo:hi] = o.cpu().numpy()[lo:hi]
+        assert np.array_equal(acc, want2), n_odd
 
 
 def test_two_track_sets(eng):
@@ -262,8 +274,10 @@ def test_full_size_properties(eng):
     seqs = synth.family(2, 1000, 300)
     batch = eng.batch(seqs)
     n = len(seqs)
-    out, _, cells = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode="global")
+    out, _, cells = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode="global", S_host=S)   # packed kernel
     full = out.cpu().numpy()
+    out32, _, _ = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode="global")                # f32 kernel
+    assert np.array_equal(out32.cpu().numpy(), full)
     pi, pj = synth.all_pairs(n)
     assert cells == int((batch.lens[pi] * batch.lens[pj]).sum())
     # (1) the other orientation (resident = sequence two) gives the same scores

@@ -87,7 +87,7 @@ def test_allpairs_tiles_partition_condensed_vector():
         tot = 0
         prev_hi = 0
         for r in range(world):
-            by_k, (lo, hi), cells, cuts, _ = eng.allpairs_tiles(b, (r, world), tile=16)
+            by_k, (lo, hi), cells, cuts, _, _ = eng.allpairs_tiles(b, (r, world), tile=16)
             assert lo == prev_hi
             prev_hi = hi
             tot += cells
@@ -116,3 +116,38 @@ def test_tb_words_formula():
         rows = lens[sb:se].sum()
         T = (rows + 1 + 31 + 31) // 32 * 32 if se > sb else 0
         assert w[k] == T // 8 * 3 * 32
+
+
+def test_paired_allpairs_tiles_cover_every_pair_once():
+    """Paired-resident plan of the packed int16 kernel: slots of resident A and resident B."""
+    eng = _FakeEngine()
+
+    class B(object):
+        pass
+    for n, world in [(2, 1), (3, 1), (38, 1), (37, 3), (120, 8)]:
+        b = B()
+        b.n = n
+        b.lens = np.random.default_rng(n).integers(20, 400, n).astype(np.int64)
+        pi, pj = synth.all_pairs(n)
+        seen = np.zeros(n * (n - 1) // 2, int)
+        prev_hi = 0
+        for r in range(world):
+            by_k, (lo, hi), cells, cuts, _, paired = eng.allpairs_tiles(b, (r, world), tile=16, paired=True)
+            assert paired and lo == prev_hi
+            prev_hi = hi
+            for K, tiles in by_k.items():
+                for t in tiles:
+                    i, i2 = int(t["resident"]), int(t["resident2"])
+                    assert 32 * K >= b.lens[i] and (i2 < 0 or (i2 == i + 1 and 32 * K >= b.lens[i2]))
+                    for s in range(t["stream_begin"], t["stream_end"]):
+                        e = s - t["stream_begin"]
+                        slot = t["out_base"] + e
+                        assert pi[slot] == i and pj[slot] == s and lo <= slot < hi
+                        seen[slot] += 1
+                        if i2 >= 0 and e >= t["b_skip"]:
+                            slot2 = t["out_base2"] + e - t["b_skip"]
+                            assert pi[slot2] == i2 and pj[slot2] == s and lo <= slot2 < hi
+                            seen[slot2] += 1
+                        elif i2 >= 0:
+                            assert s == i2          # the skipped element is resident2 itself
+        assert prev_hi == len(seen) and (seen == 1).all()

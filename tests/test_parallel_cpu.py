@@ -37,7 +37,7 @@ def _worker(rank, world, port, n, q):
     b.n = n
     b.lens = np.random.default_rng(1).integers(30, 300, n).astype(np.int64)
     eng = _FakeEngine()
-    by_k, (lo, hi), cells, cuts, _ = eng.allpairs_tiles(b, (rank, world), tile=16)
+    by_k, (lo, hi), cells, cuts, _, _ = eng.allpairs_tiles(b, (rank, world), tile=16)
     n_pairs = n * (n - 1) // 2
     out = torch.full((n_pairs,), float("nan"))
     # stand-in for the kernel: every slot of this shard gets a value derived from its pair
