@@ -364,9 +364,11 @@ def main():
                         "(of measured; SM clock %.0f MHz during the run); f32 max / compare / shift / integer ops "
                         "issue at half that rate on this part (pipe_rates, warp-instr/ns/SM); HBM is not the "
                         "bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
-                "issue_bound_frac": (my_cells / (kms * 1e-3)) * 7.0 / 32.0 / (mb["fadd"] * sms * 1e9),
-                "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence: "
-                                    "7 warp-instructions per 32 cells at the measured full issue rate",
+                "issue_bound_frac": (my_cells / (kms * 1e-3)) * (2.5 if plan[5] else 7.0) / 32.0 / (mb["fadd"] * sms * 1e9),
+                "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence at the "
+                                    "measured full issue rate: 5 packed DPX/add instructions per 2 cells (int16 "
+                                    "kernel) or 7 per cell (f32 kernel); the DPX and max instructions themselves "
+                                    "issue at half rate (pipe_rates), which is the binding pipe",
                 "kernel": "k_stream16r<10> (packed s16x2, paired residents)" if plan[5] else "k_stream<10,global,score-only>", "kernel_ms": kms,
                 "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
         # traced variant (what the preprofile master-slave alignments need): K2 with packed traceback
