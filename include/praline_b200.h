@@ -135,15 +135,34 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs_de
 int pgpu_build_scores(int n_sets, const float* const* P1_dev, const float* const* P2_dev,
                       const float* const* S_dev, const int* A, int L1, int L2, float* m_dev, int m_pitch,
                       void* stream);
+/* <= 32 consecutive matrix rows of one streamed sequence in a wave of a profile batch */
+typedef struct pgpu_row_block {
+    int64_t row0;     /* first matrix row */
+    int64_t src0;     /* profile row feeding matrix row row0 */
+    int32_t rows;
+    int32_t res;      /* resident sequence id */
+    int32_t dummy;    /* row0 is the region's dummy row (no profile row) */
+    int32_t reserved;
+} pgpu_row_block;
+
 /*
  * Match scores of a wave of profile x profile pairs in stream order (feeds pgpu_align_tiles).
  * Same evaluation order as cext_build_scores (cext.c:63-95) for ONE track set.  prof [rows][A]
- * holds all profiles, rowoff [n_seqs+1] their row offsets; rowsrc[r] is the profile row of the
- * streamed sequence for matrix row r (-1: dummy row), rowres[r] the resident sequence id.
+ * holds all profiles, rowoff [n_seqs+1] their row offsets; the wave is described by row blocks.
  */
 int pgpu_build_rows(const float* prof_dev, const int64_t* rowoff_dev, int A, const float* S_dev,
-                    const int32_t* rowsrc_dev, const int32_t* rowres_dev, int64_t n_rows, int width,
-                    int transposed, int local_mode, float* mwave_dev, void* stream);
+                    const void* blocks_dev, int n_blocks, int width, int transposed, int local_mode,
+                    float* mwave_dev, void* stream);
+/*
+ * Tolerance-mode (<= 1e-5 relative, not the reference's evaluation order) variant for score-only
+ * profile batches: W = P . S^T (transposed = 0) or P . S (transposed = 1) per profile row from
+ * pgpu_profile_times_matrix, then A fused multiply-adds per cell.
+ */
+int pgpu_profile_times_matrix(const float* prof_dev, const float* S_dev, int A, int64_t n_rows, int transposed,
+                              float* out_dev, void* stream);
+int pgpu_build_rows_fast(const float* prof_dev, const float* wres_dev, const int64_t* rowoff_dev, int A,
+                         const void* blocks_dev, int n_blocks, int width, int local_mode, float* mwave_dev,
+                         void* stream);
 int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
                           int L2, float* m_dev, int m_pitch, void* stream);
 

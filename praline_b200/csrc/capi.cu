@@ -130,13 +130,25 @@ int pgpu_build_scores(int n_sets, const float* const* P1, const float* const* P2
     return pg_launch_build_scores(h, L1, L2, m, m_pitch, (cudaStream_t)stream);
 }
 
-int pgpu_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const int32_t* rowsrc,
-                    const int32_t* rowres, int64_t n_rows, int width, int transposed, int local_mode, float* mwave,
-                    void* stream)
+int pgpu_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const void* blocks, int n_blocks,
+                    int width, int transposed, int local_mode, float* mwave, void* stream)
 {
     if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
-    return pg_launch_build_rows(prof, rowoff, A, S, rowsrc, rowres, n_rows, width, transposed,
+    return pg_launch_build_rows(prof, rowoff, A, S, (const PgRowBlock*)blocks, n_blocks, width, transposed,
                                 local_mode ? -INFINITY : 0.f, mwave, (cudaStream_t)stream);
+}
+
+int pgpu_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const void* blocks,
+                         int n_blocks, int width, int local_mode, float* mwave, void* stream)
+{
+    return pg_launch_build_rows_fast(prof, wres, rowoff, A, (const PgRowBlock*)blocks, n_blocks, width,
+                                     local_mode ? -INFINITY : 0.f, mwave, (cudaStream_t)stream);
+}
+
+int pgpu_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,
+                              void* stream)
+{
+    return pg_launch_profile_times_matrix(prof, S, A, n_rows, transposed, out, (cudaStream_t)stream);
 }
 
 int pgpu_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,

@@ -117,9 +117,21 @@ struct ScoreSets { ScoreSet s[8]; int n; };   // passed by value as a kernel arg
 void pg_set_error(const char* fmt, ...);
 int pg_launch_general(GenArgs a, int kg, cudaStream_t st);
 int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st);
-int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const int32_t* rowsrc,
-                         const int32_t* rowres, int64_t n_rows, int width, int transposed, float padv, float* mwave,
-                         cudaStream_t st);
+// <= 32 consecutive matrix rows of one streamed sequence in a wave of a profile batch
+struct PgRowBlock {
+    int64_t row0;     // first matrix row
+    int64_t src0;     // profile row feeding matrix row row0 (row0 + r is fed by src0 + r)
+    int32_t rows;
+    int32_t res;      // resident sequence id
+    int32_t dummy;    // matrix row row0 is the region's dummy row (no profile row)
+    int32_t _pad;
+};
+int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const PgRowBlock* blocks,
+                         int n_blocks, int width, int transposed, float padv, float* mwave, cudaStream_t st);
+int pg_launch_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
+                              int n_blocks, int width, float padv, float* mwave, cudaStream_t st);
+int pg_launch_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,
+                                   cudaStream_t st);
 int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,
                                float* m, int m_pitch, cudaStream_t st);
 int pg_stream_supported_k(int k);

@@ -658,49 +658,102 @@ __global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int 
 }
 
 // Batched form for the matrix-fed streaming kernel: one matrix row per stream position of a
-// wave (rows in stream order, `width` = 32*K floats each).  rowsrc[r] is the global profile row
-// of the STREAMED sequence at that position (-1: dummy row), rowres[r] the resident sequence.
-// Same evaluation order as above; `transposed` says the resident is sequence one.
+// wave (rows in stream order, `width` = 32*K floats each).  Work arrives as BLOCKS of <= 32
+// consecutive matrix rows that belong to one streamed sequence (so their profile rows are
+// consecutive too): PgRowBlock = {first matrix row, profile row of that matrix row, rows,
+// resident sequence, first row is the region's dummy row}.  Same evaluation order as
+// k_build_scores; `transposed` says the resident is sequence one.
 __global__ void __launch_bounds__(128) k_build_rows(const float* __restrict__ prof, const int64_t* __restrict__ rowoff,
                                                     int A, const float* __restrict__ S,
-                                                    const int32_t* __restrict__ rowsrc,
-                                                    const int32_t* __restrict__ rowres, int64_t n_rows, int width,
+                                                    const PgRowBlock* __restrict__ blocks, int width,
                                                     int transposed, float padv, float* __restrict__ mwave)
 {
-    extern __shared__ float sh[];   // S [A*A] then the streamed profile row [A]
+    extern __shared__ float sh[];   // S [A*A] then the streamed profile rows [32][A]
     const int xblocks = (width + 127) / 128;
-    const int64_t r = blockIdx.x / xblocks;
+    const PgRowBlock blk = blocks[blockIdx.x / xblocks];
     const int x = (int)(blockIdx.x % xblocks) * 128 + threadIdx.x;
-    if (r >= n_rows) return;
-    const int src = rowsrc[r];
+    float* srows = sh + A * A;
     for (int i = threadIdx.x; i < A * A; i += 128) sh[i] = S[i];
-    if (src >= 0) for (int i = threadIdx.x; i < A; i += 128) sh[A * A + i] = prof[(size_t)src * A + i];
+    for (int i = threadIdx.x; i < blk.rows * A; i += 128) {
+        const int rr = i / A, c = i % A;
+        srows[i] = (blk.dummy && rr == 0) ? 0.f : prof[(size_t)(blk.src0 + rr) * A + c];
+    }
     __syncthreads();
     if (x >= width) return;
-    float v = padv;
-    if (src >= 0) {
-        const int res = rowres[r];
-        const int64_t r0 = rowoff[res];
-        const int Lr = (int)(rowoff[res + 1] - r0);
-        if (x < Lr) {
-            const float* rr = prof + (size_t)(r0 + x) * A;   // resident profile row
-            const float* sr = sh + A * A;                    // streamed profile row
+    const int64_t q0 = rowoff[blk.res];
+    const int Lr = (int)(rowoff[blk.res + 1] - q0);
+    const float* rr_ = prof + (size_t)(q0 + x) * A;   // resident profile row (x < Lr)
+    for (int r = 0; r < blk.rows; r++) {
+        float v = padv;
+        if (blk.dummy && r == 0) v = 0.f;
+        else if (x < Lr) {
+            const float* sr = srows + r * A;
             float acc = 0.f;
             for (int i = 0; i < A; i++) {
-                const float p1 = transposed ? rr[i] : sr[i];
+                const float p1 = transposed ? rr_[i] : sr[i];
                 if (p1 == 0.f) continue;
                 for (int j = 0; j < A; j++) {
-                    const float p2 = transposed ? sr[j] : rr[j];
+                    const float p2 = transposed ? sr[j] : rr_[j];
                     if (p2 == 0.f) continue;
                     acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p2, sh[i * A + j]), p1));
                 }
             }
             v = __fadd_rn(0.f, acc);
         }
-    } else {
-        v = 0.f;
+        mwave[(size_t)(blk.row0 + r) * width + x] = v;
     }
-    mwave[(size_t)r * width + x] = v;
+}
+
+// Tolerance-mode variant of k_build_rows for score-only profile batches (guide tree on deep
+// preprofiles): the contraction P1 . S . P2^T is factored through W = P_resident . S^T (or . S),
+// precomputed per sequence, so a cell costs A fused multiply-adds instead of nnz1 x nnz2
+// mul-mul-add triples.  Not the reference's evaluation order: scores agree to ~1e-6 relative
+// (the stated tolerance is 1e-5), so this path is opt-in and never used for traced alignments.
+// Block = 32 matrix rows x 128 columns of ONE region (all its rows share a resident): the thread
+// keeps its column's W row in registers and sweeps the 32 staged profile rows.
+template <int AP>
+__global__ void __launch_bounds__(128) k_build_rows_fast(const float* __restrict__ prof, const float* __restrict__ wres,
+                                                         const int64_t* __restrict__ rowoff, int A,
+                                                         const PgRowBlock* __restrict__ blocks, int width, float padv,
+                                                         float* __restrict__ mwave)
+{
+    __shared__ float srow[32][AP];
+    const int xblocks = (width + 127) / 128;
+    const PgRowBlock blk = blocks[blockIdx.x / xblocks];
+    const int x = (int)(blockIdx.x % xblocks) * 128 + threadIdx.x;
+    for (int i = threadIdx.x; i < 32 * AP; i += 128) {
+        const int rr = i / AP, c = i % AP;
+        float v = 0.f;
+        if (rr < blk.rows && c < A && !(blk.dummy && rr == 0)) v = prof[(size_t)(blk.src0 + rr) * A + c];
+        srow[rr][c] = v;
+    }
+    __syncthreads();
+    if (x >= width) return;
+    const int64_t q0 = rowoff[blk.res];
+    const int Lr = (int)(rowoff[blk.res + 1] - q0);
+    float w[AP];
+#pragma unroll
+    for (int c = 0; c < AP; c++) w[c] = (x < Lr && c < A) ? wres[(size_t)(q0 + x) * A + c] : 0.f;
+    for (int rr = 0; rr < blk.rows; rr++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < AP; c++) acc = fmaf(srow[rr][c], w[c], acc);
+        const bool dummy = blk.dummy && rr == 0;
+        mwave[(size_t)(blk.row0 + rr) * width + x] = dummy ? 0.f : (x < Lr ? acc : padv);
+    }
+}
+
+// W[row][i] = sum_j S[i][j] * P[row][j]  (transposed = 0)   or   sum_j P[row][j] * S[j][i]  (transposed = 1)
+__global__ void k_profile_times_matrix(const float* __restrict__ prof, const float* __restrict__ S, int A, int64_t n_rows,
+                                       int transposed, float* __restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * A) return;
+    const int64_t r = idx / A;
+    const int i = (int)(idx % A);
+    float acc = 0.f;
+    for (int j = 0; j < A; j++) acc = fmaf(prof[r * A + j], transposed ? S[j * A + i] : S[i * A + j], acc);
+    out[idx] = acc;
 }
 
 // Sequence x sequence: one-hot profiles make the sum collapse to exactly S[a_y][b_x].
@@ -789,15 +842,37 @@ int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int 
     return 0;
 }
 
-int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const int32_t* rowsrc,
-                         const int32_t* rowres, int64_t n_rows, int width, int transposed, float padv, float* mwave,
-                         cudaStream_t st)
+int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const PgRowBlock* blocks,
+                         int n_blocks, int width, int transposed, float padv, float* mwave, cudaStream_t st)
+{
+    if (n_blocks <= 0) return 0;
+    const int64_t nb = (int64_t)n_blocks * ((width + 127) / 128);
+    if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
+    k_build_rows<<<(unsigned)nb, 128, sizeof(float) * (A * A + 32 * A), st>>>(prof, rowoff, A, S, blocks, width, transposed,
+                                                                              padv, mwave);
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pg_launch_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
+                              int n_blocks, int width, float padv, float* mwave, cudaStream_t st)
+{
+    if (n_blocks <= 0) return 0;
+    const int64_t nb = (int64_t)n_blocks * ((width + 127) / 128);
+    if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
+    if (A <= 16) k_build_rows_fast<16><<<(unsigned)nb, 128, 0, st>>>(prof, wres, rowoff, A, blocks, width, padv, mwave);
+    else if (A <= 32) k_build_rows_fast<32><<<(unsigned)nb, 128, 0, st>>>(prof, wres, rowoff, A, blocks, width, padv, mwave);
+    else { pg_set_error("fast profile rows: alphabet size %d above 32", A); return 1; }
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pg_launch_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,
+                                   cudaStream_t st)
 {
     if (n_rows <= 0) return 0;
-    const int64_t blocks = n_rows * ((width + 127) / 128);
-    if (blocks > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)blocks); return 1; }
-    k_build_rows<<<(unsigned)blocks, 128, sizeof(float) * (A * A + A), st>>>(prof, rowoff, A, S, rowsrc, rowres, n_rows,
-                                                                           width, transposed, padv, mwave);
+    const int64_t n = n_rows * A;
+    k_profile_times_matrix<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prof, S, A, n_rows, transposed, out);
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }

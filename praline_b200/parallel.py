@@ -38,3 +38,31 @@ def scores_to_distance(cond, n):
     d[iu[0], iu[1]] = cond
     d[iu[1], iu[0]] = cond
     return (-d) + d.max()
+
+
+def shard_masters(masters, lens, rank, world):
+    """Contiguous shard of the (sorted, distinct) master ids with equal DP cells per rank.
+    A master's work is len(master) * sum(len(slaves)), and every master sees (almost) the same
+    slaves, so balancing on len(master) is enough."""
+    import numpy as np
+    masters = np.asarray(masters)
+    w = np.cumsum(lens[masters].astype(np.float64))
+    cuts = np.searchsorted(w, w[-1] * np.arange(world + 1) / world, side="left")
+    cuts[0], cuts[-1] = 0, len(masters)
+    return masters[cuts[rank]:cuts[rank + 1]], [int(c) for c in cuts]
+
+
+def allgather_counts(local_counts, sizes, group=None):
+    """Preprofile stage: every rank owns the whole [L x A] count tables of its masters
+    (SURVEY.md 8e); one padded all-gather hands every rank all tables.  local_counts: 1-D tensor
+    of this rank's tables; sizes[r]: number of elements rank r owns.  Returns the concatenation
+    in rank order."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_counts
+    width = max(max(sizes), 1)
+    send = torch.zeros(width, dtype=local_counts.dtype, device=local_counts.device)
+    send[:local_counts.numel()] = local_counts
+    recv = torch.empty(world * width, dtype=local_counts.dtype, device=local_counts.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return torch.cat([recv[r * width:r * width + sizes[r]] for r in range(world)])

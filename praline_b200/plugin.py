@@ -423,8 +423,12 @@ class _ProfileGroup(object):
         return len(self.pi) - 1
 
     def run_scores(self, eng):
+        # PGPU_FAST_PROFILES=1 opts into the tolerance-mode score rows (<= 1e-5 relative, A FMAs per
+        # cell); the default keeps the reference's evaluation order, bit for bit
+        import os
+        fast = os.environ.get("PGPU_FAST_PROFILES", "") not in ("", "0")
         pb = eng.profile_batch(self.profiles)
-        self.scores = eng.align_profile_pairs(pb, self.pi, self.pj, self.S, self.gaps, mode=self.mode)
+        self.scores = eng.align_profile_pairs(pb, self.pi, self.pj, self.S, self.gaps, mode=self.mode, fast=fast)
 
     def path(self, k):
         if k not in self.paths:

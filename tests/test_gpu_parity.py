@@ -256,6 +256,27 @@ def test_packed_int16_kernel_matches_f32_kernel(eng):
         assert np.array_equal(acc, want2), n_odd
 
 
+def test_fast_profile_batches_within_tolerance(eng):
+    """Tolerance mode of the profile batch (W = P.S^T, A FMAs per cell): every score within the
+    stated 1e-5 relative of the oracle, all modes, both orientations."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(9)
+    profs = [synth.profile_from_counts(synth.count_profile(700 + k, int(rng.integers(20, 260)), int(rng.integers(2, 30)), 20, 27))
+             for k in range(12)]
+    pb = eng.profile_batch(profs)
+    pi, pj = synth.all_pairs(len(profs))
+    for resident in ("one", "two"):
+        for mode, gaps in (("global", [-11.0, -1.0]), ("semiglobal_both", [-2.5, -0.5]), ("local", [-11.0, -1.0])):
+            got = eng.align_profile_pairs(pb, pi, pj, S, gaps, mode=mode, resident=resident, fast=True)
+            exact = eng.align_profile_pairs(pb, pi, pj, S, gaps, mode=mode, resident=resident)
+            for k in range(len(pi)):
+                m = oracle.build_scores([profs[pi[k]]], [profs[pj[k]]], [S])
+                g1, g2 = oracle.gap_arrays(m.shape[0], m.shape[1], gaps)
+                want, _ = oracle.align_raw(mode, m, g1, g2)
+                assert float(exact[k]) == want
+                assert abs(float(got[k]) - want) <= 1e-5 * max(1.0, abs(want)), (mode, resident, k, float(got[k]), want)
+
+
 def test_two_track_sets(eng):
     rng = np.random.default_rng(3)
     S1, S2 = matrices.blosum62(), rng.standard_normal((15, 15)).astype(np.float32)

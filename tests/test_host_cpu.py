@@ -151,3 +151,43 @@ def test_paired_allpairs_tiles_cover_every_pair_once():
                         elif i2 >= 0:
                             assert s == i2          # the skipped element is resident2 itself
         assert prev_hi == len(seen) and (seen == 1).all()
+
+
+def test_profile_wave_blocks_cover_rows():
+    """Row blocks of a profile wave: every matrix row exactly once, fed by the right profile row."""
+    rng = np.random.default_rng(0)
+    nseq = 9
+    lens = rng.integers(3, 80, nseq).astype(np.int64)
+    offs = np.r_[0, np.cumsum(lens)]
+    n = 40
+    res_s = np.sort(rng.integers(0, nseq, n))
+    str_s = rng.integers(0, nseq, n)
+    eng = _FakeEngine()
+    tiles = eng._make_tiles(res_s, n, 16)
+    lens_s = lens[str_s]
+    cs = np.r_[0, np.cumsum(lens_s)]
+    mb, blocks, nr = E.plan_profile_wave(tiles, 8, cs, lens_s, str_s, res_s, offs)
+    src = np.full(nr, -9, np.int64)
+    res = np.full(nr, -9, np.int64)
+    for b in blocks:
+        assert 1 <= b["rows"] <= 32
+        for r in range(b["rows"]):
+            assert src[b["row0"] + r] == -9
+            src[b["row0"] + r] = -1 if (b["dummy"] and r == 0) else b["src0"] + r
+            res[b["row0"] + r] = b["res"]
+    for ti, t in enumerate(tiles):
+        bb, e = int(t["stream_begin"]), int(t["stream_end"])
+        per = (e - bb + 7) // 8
+        for w in range(8):
+            sb = min(bb + w * per, e)
+            se = min(sb + per, e)
+            if se <= sb:
+                continue
+            r = mb[ti * 8 + w]
+            assert src[r] == -1 and res[r] == t["resident"]
+            r += 1
+            for el in range(sb, se):
+                for y in range(lens_s[el]):
+                    assert src[r] == offs[str_s[el]] + y and res[r] == res_s[el]
+                    r += 1
+    assert (src != -9).all()

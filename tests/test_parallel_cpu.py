@@ -52,6 +52,14 @@ def _worker(rank, world, port, n, q):
     ok = bool(torch.equal(out, truth))
     d = parallel.scores_to_distance(out, n)
     ok = ok and bool(d[3, 5] == d[5, 3]) and bool(d.min() == 0)
+    # preprofile stage: masters sharded by rank, count tables all-gathered
+    mine, cuts = parallel.shard_masters(np.arange(n), b.lens, rank, world)
+    A = 5
+    local = torch.cat([torch.full((int(b.lens[m]) * A,), float(m)) for m in mine]) if len(mine) else torch.zeros(0)
+    sizes = [int(b.lens[cuts[r]:cuts[r + 1]].sum()) * A for r in range(world)]
+    allc = parallel.allgather_counts(local, sizes)
+    want = torch.cat([torch.full((int(b.lens[m]) * A,), float(m)) for m in range(n)])
+    ok = ok and bool(torch.equal(allc, want)) and cuts[0] == 0 and cuts[-1] == n
     q.put((rank, ok, cells))
     dist.barrier()
     dist.destroy_process_group()
