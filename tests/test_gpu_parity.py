@@ -383,3 +383,40 @@ def test_config5_full_size_properties(eng):
         assert sc == r["score"], gaps
         scores[tuple(gaps)] = r["score"]
     assert scores[(-1.0,)] >= scores[(-11.0, -1.0)]
+
+
+def test_length_boundaries(eng):
+    """Resident lengths on both sides of every columns-per-lane class boundary (32*K), traced and
+    score-only, f32 and packed kernels; plus residents beyond the inter-task limit through the
+    general kernels."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(23)
+    lens = [1, 2, 31, 32, 33, 63, 64, 65, 96, 97, 128, 129, 192, 193, 256, 257, 319, 320, 321, 384, 385,
+            416, 417, 448, 449, 512, 513, 640, 641, 768, 769, 1023, 1024]
+    seqs = [rng.integers(0, 20, n).astype(np.int32) for n in lens]
+    partner = synth.family(7, 3, 150)
+    seqs += partner
+    n0 = len(lens)
+    pi = np.concatenate([np.arange(n0), np.full(n0, n0), np.arange(n0 - 1)])
+    pj = np.concatenate([np.full(n0, n0 + 1), np.arange(n0), np.arange(1, n0)])
+    flat, offs = synth.pack(seqs)
+    batch = eng.batch(seqs)
+    for mode in ("global", "semiglobal_both"):
+        want, wpaths = oracle.align_batch(mode, flat, offs, pi, pj, S, [-11.0, -1.0], want_paths=True)
+        for resident in ("one", "two"):
+            for use in (True, False):
+                eng.use_s16 = use
+                got, _ = eng.align_pairs(batch, pi, pj, S, [-11.0, -1.0], mode=mode, resident=resident)
+                assert np.array_equal(got, want), (mode, resident, use)
+            eng.use_s16 = True
+            got, paths = eng.align_pairs(batch, pi, pj, S, [-11.0, -1.0], mode=mode, want_paths=True, resident=resident)
+            assert np.array_equal(got, want)
+            assert all(np.array_equal(a, b) for a, b in zip(paths, wpaths)), (mode, resident)
+    # beyond 1024 columns: the inter-task kernel refuses, the general path serves
+    long_seqs = [rng.integers(0, 20, 1500).astype(np.int32), rng.integers(0, 20, 1100).astype(np.int32)]
+    lb = eng.batch(long_seqs)
+    with pytest.raises(Exception):
+        eng.align_pairs(lb, [0], [1], S, [-11.0, -1.0], mode="global")
+    r = eng.align_seq_pair_general(lb, 0, 1, S, [-11.0, -1.0], "global")
+    ws, wp = oracle.align_seqs("global", long_seqs[0], long_seqs[1], S, [-11.0, -1.0])
+    assert r["score"] == ws and np.array_equal(r["path"], wp)

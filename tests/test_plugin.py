@@ -206,3 +206,16 @@ def test_msa_workflow_identical_to_reference(preprofile, msa):
     want = R.workflow_fasta(Manager(R.reference_index()), mk(), sm, preprofile, msa)
     got = R.workflow_fasta(plugin.GpuBatchManager(R.reference_index()), mk(), sm, preprofile, msa)
     assert got == want
+
+
+@pytest.mark.gpu
+def test_long_sequences_fall_back_to_general_kernels():
+    """Sequences beyond the inter-task limit (1024) still align identically through the plug-in."""
+    sm = _blosum()
+    rng = np.random.default_rng(12)
+    a, b = _seq("a", rng.integers(0, 20, 1300)), _seq("b", rng.integers(0, 20, 1190))
+    kw = dict(mode="global", sequence_one=a, sequence_two=b, track_id_sets_one=[[TRACK_ID_INPUT]],
+              track_id_sets_two=[[TRACK_ID_INPUT]], score_matrices=[sm])
+    want, _ = R.run_task(Manager(R.reference_index()), pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
+    got, _ = R.run_task(plugin.GpuBatchManager(R.reference_index()), pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
+    _same_alignment(got, want)
