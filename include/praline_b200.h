@@ -169,7 +169,10 @@ int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const floa
 /*
  * General single alignment (K3 wavefront + traceback).  Replaces RawPairwiseAligner.execute
  * (component/align.py:302-447): arbitrary match scores m [L1][m_pitch], per-position gap
- * arrays g1 [L1][2], g2 [L2][2], optional mask z [(L1+1)][z_pitch] (zero_idxs), any mode.
+ * arrays g1 [L1][2], g2 [L2][2] (var_gaps = 0 promises that every row of g1 equals g1[0] and
+ * every row of g2 equals g2[0], which is what PairwiseAligner builds, component/align.py:212-217),
+ * optional mask z [(L1+1)][z_pitch] (zero_idxs), any mode.  A match-score matrix whose pitch is a
+ * multiple of 4 floats and covers ceil(L2/128)*128 columns runs the lean wavefront kernel.
  * Outputs: *score_out, cell_out[3] = end cell (y, x, state), path rows right-aligned in
  * path_buf (capacity L1+L2+2 rows) at [path_start[0], +path_len[0]).  path_buf may be NULL
  * (score only).  o_full / t_full, when non-NULL, receive the reference's complete o and t
@@ -177,7 +180,7 @@ int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const floa
  */
 int64_t pgpu_general_workspace_bytes(int L1, int L2);
 int pgpu_align_general(int mode, int L1, int L2, const float* m_dev, int m_pitch, const float* g1_dev,
-                       const float* g2_dev, const uint8_t* z_dev, int z_pitch, void* workspace_dev,
+                       const float* g2_dev, int var_gaps, const uint8_t* z_dev, int z_pitch, void* workspace_dev,
                        float* score_out_dev, int32_t* cell_out_dev, int32_t* path_buf_dev,
                        int32_t* path_start_dev, int32_t* path_len_dev, float* o_full_dev,
                        uint8_t* t_full_dev, void* stream);

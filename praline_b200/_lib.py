@@ -38,7 +38,7 @@ _SIGNATURES = {
     "pgpu_build_scores_seq": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                       c_void_p]),
     "pgpu_general_workspace_bytes": (c_int64, [c_int, c_int]),
-    "pgpu_align_general": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+    "pgpu_align_general": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "pgpu_fill_debug": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),

@@ -176,9 +176,11 @@ static int general_strips(int L2, int kg) { int ns = (L2 + 32 * kg - 1) / (32 * 
 int64_t pgpu_general_workspace_bytes(int L1, int L2)
 {
     const int nsa = general_strips(L2, general_kg(L2, false)), nsb = general_strips(L2, general_kg(L2, true));
-    const int ns = nsa > nsb ? nsa : nsb;
+    const int nsl = (L2 + 127) / 128;
+    const int ns = (nsa > nsb ? nsa : nsb) > nsl ? (nsa > nsb ? nsa : nsb) : nsl;
     const size_t fp = up256((size_t)L2 + 1);
     size_t b = 0;
+    b += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 31));    // lean kernel's flag words
     b += up256((size_t)(L1 + 1) * fp);                              // flags
     b += up256(sizeof(float) * 4 * (size_t)(ns + 1) * (L1 + 1));    // edge (16-byte records)
     b += up256(sizeof(int) * (size_t)(ns + 1));                     // progress
@@ -189,7 +191,7 @@ int64_t pgpu_general_workspace_bytes(int L1, int L2)
 }
 
 int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, const float* g1,
-                       const float* g2, const uint8_t* z, int z_pitch, void* workspace, float* score_out,
+                       const float* g2, int var_gaps, const uint8_t* z, int z_pitch, void* workspace, float* score_out,
                        int32_t* cell_out, int32_t* path_buf, int32_t* path_start, int32_t* path_len,
                        float* o_full, uint8_t* t_full, void* stream)
 {
@@ -197,13 +199,16 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
     if (L1 < 1 || L2 < 1) { pg_set_error("empty sequence (L1=%d, L2=%d)", L1, L2); return 1; }
     const int kg = general_kg(L2, o_full != nullptr);
     const int nsa = general_strips(L2, general_kg(L2, false)), nsb = general_strips(L2, general_kg(L2, true));
-    const int ns = nsa > nsb ? nsa : nsb;   // workspace carved for the larger of the two layouts
+    const int nsl = (L2 + 127) / 128;
+    const int ns = (nsa > nsb ? nsa : nsb) > nsl ? (nsa > nsb ? nsa : nsb) : nsl;   // workspace fits every layout
     GenArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = mode; a.L1 = L1; a.L2 = L2; a.m = m; a.m_pitch = m_pitch; a.g1 = g1; a.g2 = g2;
     a.z = z; a.z_pitch = z_pitch; a.o_full = o_full; a.t_full = t_full;
     unsigned char* w = (unsigned char*)workspace;
     const size_t fp = up256((size_t)L2 + 1);
+    a.flagw = (uint32_t*)w; w += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 31));
+    a.var_gaps = var_gaps;
     a.flags = w; a.f_pitch = (int)fp; w += up256((size_t)(L1 + 1) * fp);
     a.edge = (float*)w; w += up256(sizeof(float) * 4 * (size_t)(ns + 1) * (L1 + 1));
     a.progress = (int*)w; w += up256(sizeof(int) * (size_t)(ns + 1));
@@ -241,7 +246,7 @@ int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, 
         CK(cudaMemset(d + off_o, 0, sizeof(float) * 3 * cells));
         CK(cudaMemset(d + off_t, 0, 3 * cells));
         rc = pgpu_align_general(mode, L1, L2, (const float*)(d + off_m), L2, (const float*)(d + off_g1),
-                                (const float*)(d + off_g2), z ? d + off_z : nullptr, L2 + 1, d + off_ws,
+                                (const float*)(d + off_g2), 1, z ? d + off_z : nullptr, L2 + 1, d + off_ws,
                                 (float*)(d + off_out), (int32_t*)(d + off_out + 16), nullptr, nullptr, nullptr,
                                 (float*)(d + off_o), d + off_t, nullptr);
         if (rc) break;

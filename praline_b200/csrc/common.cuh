@@ -102,7 +102,9 @@ struct GenArgs {
     float* lastcol;                      // [3][L1+1]
     unsigned long long* best;            // local mode: (ordered value << 32 | ~linear index)
     int n_strips;
-    int flag_fmt;                        // 0: the reference's seven flag bits, 1: compact sign bits
+    int flag_fmt;                        // 0: the reference's seven flag bits, 1: compact sign bits, 2: lean words
+    uint32_t* flagw;                     // lean kernel: [n_strips][L1+31][32] flag words (4 cells x 5 bits + mask bits)
+    int var_gaps;                        // gap arrays vary per position (else g1[0..1], g2[0..1] are THE gap pairs)
     // finalize / traceback outputs
     float* score_out;                    // [1]
     int32_t* cell_out;                   // [3] y, x, state

@@ -18,6 +18,7 @@
 // One byte per cell holds all seven tie flags (their bit positions are disjoint,
 // cext.c:9-15), instead of the reference's three traceback planes.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define FULL 0xffffffffu
 
@@ -449,6 +450,253 @@ __global__ void __launch_bounds__(256) k_gen_fill_fast(const GenArgs a)
     }
 }
 
+
+// ---- K3, lean form ------------------------------------------------------------------------------
+// The production wavefront when the match-score matrix has a padded pitch (the engine allocates
+// it so): strips of 128 columns (4 per lane), a step loop in the style of K2 -- every pointer
+// hoisted, no per-column validity tests (pad columns compute harmlessly inside the padded pitch),
+// constant gap pairs as scalars when the gap models are constant (VARG = false), one uniform
+// ring slot per step, the five sign bits of a lane's four cells packed into ONE 32-bit word that
+// is stored in the skewed [strip][step][lane] layout (a coalesced 128-byte line per warp-step).
+#define WV_R 8
+template <bool LOCAL, bool MASK, bool VARG>
+__global__ void __launch_bounds__(256) k_wave(const GenArgs a)
+{
+    extern __shared__ __align__(16) float wsm[];
+    constexpr int SLOTP = VARG ? 12 : 8;    // floats per lane per slot: [m x4][edge M U L pad][gap open, extend, pad x2]
+    const int L1 = a.L1, L2 = a.L2, W = L2 + 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const float NINF = -INFINITY;
+    float* ring = wsm + (size_t)wib * (WV_R * 32 * SLOTP) + lane * SLOTP;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const int TT = L1 + 31;                 // steps per strip == rows of its flag-word block
+
+    for (int strip = gw; strip < a.n_strips; strip += nw) {
+        const int x0 = strip * 128 + lane * 4 + 1;
+        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 4;
+        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 4;
+        int* pin = a.progress + strip;
+        int* pout = a.progress + strip + 1;
+        const bool last_strip = strip == a.n_strips - 1;
+        const bool lane_on = x0 <= L2;
+        const bool multi = strip > 0;       // strip 0 reads the border column written by k_gen_init
+        uint32_t* fout = a.flagw + (size_t)strip * TT * 32 + lane;
+
+        float Mp[4], Up[4], Lp[4], go2[4], ge2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = x0 + k;
+            const bool v = x <= L2;
+            Mp[k] = v ? a.top[x] : NINF;
+            Up[k] = v ? a.top[W + x] : NINF;
+            Lp[k] = v ? a.top[2 * W + x] : NINF;
+            go2[k] = (VARG && v) ? a.g2[(size_t)(x - 1) * 2] : a.g2[0];
+            ge2[k] = (VARG && v) ? a.g2[(size_t)(x - 1) * 2 + 1] : a.g2[1];
+        }
+        const float cgo1 = a.g1[0], cge1 = a.g1[1];
+        float Md = NINF, Ud = NINF, Ld = NINF;
+        if (lane_on) { Md = a.top[x0 - 1]; Ud = a.top[W + x0 - 1]; Ld = a.top[2 * W + x0 - 1]; }
+        float Me = 0.f, Ue = 0.f, Le = 0.f;
+        int avail = multi ? 0 : L1;
+        float bv = NINF; uint32_t bl = 0xffffffffu;
+        const int lcol = (L2 - 1 - strip * 128) >> 2, kcol = (L2 - 1) & 3;   // lane / cell of column L2 (last strip)
+
+        // row yy -> ring slot of the step that consumes it (uniform slot index per step)
+        auto request = [&](int yy, int use_step) {
+            if (yy >= 1 && yy <= L1 && lane_on) {
+                const uint32_t dst = ring_s + (uint32_t)((use_step & (WV_R - 1)) * 32 * SLOTP) * 4u;
+                cp_async16(dst, a.m + (size_t)(yy - 1) * a.m_pitch + (x0 - 1));
+                if (lane == 0) cp_async16(dst + 16, ein + (size_t)yy * 4);
+                if (VARG) {
+                    cp_async4(dst + 32, a.g1 + (size_t)(yy - 1) * 2);
+                    cp_async4(dst + 36, a.g1 + (size_t)(yy - 1) * 2 + 1);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto wait_rows = [&](int need) {
+            if (avail < need) {
+                if (lane == 0) {
+                    for (long long spins = 0; spins < (1ll << 26); spins++) {   // bounded: fail a test, never hang
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(avail) : "l"(pin) : "memory");
+                        if (avail >= need) break;
+                        __nanosleep(32);
+                    }
+                }
+                avail = __shfl_sync(FULL, avail, 0);
+            }
+        };
+        auto fetch_mask = [&](int yy) -> uint32_t {
+            uint32_t zz = 0;
+            if (MASK && yy >= 1 && yy <= L1 && lane_on) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (x0 + k <= L2 && a.z[(size_t)yy * a.z_pitch + x0 + k]) zz |= 1u << k;
+            }
+            return zz;
+        };
+        __syncwarp();
+        wait_rows(min(WV_R - 1, L1));
+#pragma unroll 1
+        for (int d = 0; d < WV_R - 1; d++) request(1 - lane + d, d);
+        uint32_t cz = fetch_mask(1 - lane), nz = 0;
+
+        for (int t = 0; t < TT; t++) {
+            __syncwarp();
+            const int y = t - lane + 1;
+            wait_rows(min(t + WV_R, L1));
+            request(y + WV_R - 1, t + WV_R - 1);
+            if (MASK) nz = fetch_mask(y + 1);
+            float Ml = __shfl_up_sync(FULL, Me, 1);
+            float Ul = __shfl_up_sync(FULL, Ue, 1);
+            float Ll = __shfl_up_sync(FULL, Le, 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(WV_R - 1) : "memory");
+            const float* slot = ring + (t & (WV_R - 1)) * 32 * SLOTP;
+            if (lane == 0) { const float4 e = *reinterpret_cast<const float4*>(slot + 4); Ml = e.x; Ul = e.y; Ll = e.z; }
+            if (y >= 1 && y <= L1 && lane_on) {
+                const float4 sv = *reinterpret_cast<const float4*>(slot);
+                const float sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                const float g1o = VARG ? slot[8] : cgo1, g1e = VARG ? slot[9] : cge1;
+                const float dM = Ml, dU = Ul, dL = Ll;
+                float cMl = Ml, cLl = Ll;
+                uint32_t fw = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float mm = Md + sc[k], mu = Ud + sc[k], ml = Ld + sc[k];
+                    float M = fmaxf(fmaxf(mm, mu), ml);
+                    if (LOCAL) M = fmaxf(M, 0.f);
+                    const float uo = Mp[k] + g1o, ue = Up[k] + g1e;
+                    const float lo = cMl + go2[k], le = cLl + ge2[k];
+                    float U = fmaxf(uo, ue), L = fmaxf(lo, le);
+                    uint32_t f = 0;
+                    if (LOCAL) f = __funnelshift_l(__float_as_uint(ml - M), f, 1);
+                    f = __funnelshift_l(__float_as_uint(lo - L), f, 1);
+                    f = __funnelshift_l(__float_as_uint(uo - U), f, 1);
+                    f = __funnelshift_l(__float_as_uint(mu - M), f, 1);
+                    f = __funnelshift_l(__float_as_uint(mm - M), f, 1);
+                    if (MASK && ((cz >> k) & 1u)) { M = 0.f; U = 0.f; L = 0.f; f = 0; fw |= 1u << (24 + k); }
+                    fw |= f << (5 * k);
+                    Md = Mp[k]; Ud = Up[k]; Ld = Lp[k];
+                    Mp[k] = M; Up[k] = U; Lp[k] = L;
+                    cMl = M; cLl = L;
+                    if (LOCAL && x0 + k <= L2) {
+                        const float v3 = fmaxf(fmaxf(M, U), L);
+                        if (v3 >= bv) {
+                            const uint32_t lin = (uint32_t)(((size_t)y * W + x0 + k) * 3);
+                            const float vs[3] = {M, U, L};
+#pragma unroll
+                            for (int j = 0; j < 3; j++)
+                                if (vs[j] > bv || (vs[j] == bv && lin + j < bl)) { bv = vs[j]; bl = lin + j; }
+                        }
+                    }
+                }
+                Md = dM; Ud = dU; Ld = dL;
+                fout[(size_t)t * 32] = fw;
+                Me = Mp[3]; Ue = Up[3]; Le = Lp[3];
+                if (y == L1) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (x0 + k <= L2) { a.lastrow[x0 + k] = Mp[k]; a.lastrow[W + x0 + k] = Up[k]; a.lastrow[2 * W + x0 + k] = Lp[k]; }
+                }
+                if (last_strip) {
+                    if (lane == lcol) {
+                        float m_ = Mp[0], u_ = Up[0], l_ = Lp[0];
+#pragma unroll
+                        for (int k = 1; k < 4; k++) if (kcol == k) { m_ = Mp[k]; u_ = Up[k]; l_ = Lp[k]; }
+                        a.lastcol[y] = m_; a.lastcol[(L1 + 1) + y] = u_; a.lastcol[2 * (L1 + 1) + y] = l_;
+                    }
+                } else if (lane == 31) {
+                    *reinterpret_cast<float4*>(eout + (size_t)y * 4) = make_float4(Me, Ue, Le, 0.f);
+                }
+            }
+            if (MASK) cz = nz;
+            const int done = t - 31 + 1;
+            if (!last_strip && lane == 31 && done >= 1 && ((done & 7) == 0 || done == L1))
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pout), "r"(done) : "memory");
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (LOCAL && bl != 0xffffffffu) atomicMax(a.best, gkey(bv, bl));
+    }
+}
+
+// Traceback over the lean kernel's flag words: one warp stages 32 steps x 32 lanes of the current
+// strip (4 KB, coalesced) and lane 0 walks inside that window.
+__global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
+{
+    __shared__ uint32_t tile[32][32];
+    const int lane = threadIdx.x;
+    const int L1 = a.L1, L2 = a.L2, TT = L1 + 31;
+    const bool u_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_ONE);
+    const bool l_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_TWO);
+    int y = a.cell_out[0], x = a.cell_out[1], k = a.cell_out[2];
+    const int cap = L1 + L2 + 2;
+    int w = cap;
+    auto push = [&](int yy, int xx) { --w; a.path_buf[2 * w] = yy; a.path_buf[2 * w + 1] = xx; };
+    const bool semi = (a.mode >= PG_SG_BOTH);
+    if (lane == 0 && semi) {
+        if (y != L1) { for (int v = L1; v > y; v--) push(v, x); }
+        else if (x != L2) { for (int v = L2; v > x; v--) push(y, v); }
+    }
+    int done = 0;
+    while (!done) {
+        int strip = 0, tlo = 0;
+        if (y >= 1 && x >= 1) {
+            strip = (x - 1) >> 7;
+            const int tcur = y - 1 + (((x - 1) & 127) >> 2);
+            tlo = max(0, tcur - 31);
+            const uint32_t* src = a.flagw + ((size_t)strip * TT + tlo) * 32 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) tile[r][lane] = (tlo + r < TT) ? src[(size_t)r * 32] : 0u;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (;;) {
+                push(y, x);
+                uint8_t f;
+                if (y == 0 && x == 0) f = 0;
+                else if (x == 0) f = (u_ramp && k == 1) ? TB_UE : 0;
+                else if (y == 0) f = (l_ramp && k == 2) ? TB_LE : 0;
+                else {
+                    const int ln = ((x - 1) & 127) >> 2, kk = (x - 1) & 3;
+                    const uint32_t word = tile[y - 1 + ln - tlo][ln];
+                    const uint32_t c = (word >> (5 * kk)) & 31u;
+                    if ((word >> (24 + kk)) & 1u) f = 0;
+                    else if (k == 0) f = !(c & 1) ? TB_MM : (!(c & 2) ? TB_MU : ((c & 16) ? 0 : TB_ML));
+                    else if (k == 1) f = (c & 4) ? TB_UE : TB_UO;
+                    else f = (c & 8) ? TB_LE : TB_LO;
+                }
+                if (f & TB_MM) { y--; x--; k = 0; }
+                else if (f & TB_MU) { y--; x--; k = 1; }
+                else if (f & TB_ML) { y--; x--; k = 2; }
+                else if (f & TB_UO) { y--; k = 0; }
+                else if (f & TB_UE) { y--; k = 1; }
+                else if (f & TB_LO) { x--; k = 0; }
+                else if (f & TB_LE) { x--; k = 2; }
+                else { done = 1; break; }
+                if (y >= 1 && x >= 1) {   // still inside the staged window of this strip?
+                    const int tn = y - 1 + (((x - 1) & 127) >> 2);
+                    if (((x - 1) >> 7) != strip || tn < tlo) break;
+                }
+            }
+        }
+        __syncwarp();
+        done = __shfl_sync(FULL, done, 0);
+        y = __shfl_sync(FULL, y, 0);
+        x = __shfl_sync(FULL, x, 0);
+    }
+    if (lane == 0) {
+        if (semi) {
+            if (y != 0) { for (int v = y - 1; v >= 0; v--) push(v, 0); }
+            else if (x != 0) { for (int v = x - 1; v >= 0; v--) push(0, v); }
+        }
+        *a.path_start = w;
+        *a.path_len = cap - w;
+    }
+}
+
 // ---- end cell (reference component/align.py:401-431) -----------------------------------------
 // One CTA.  global: first argmax of the three states at (L1, L2).  semiglobal: max of the last
 // row vs max of the last column (strict '>' and only when tracing from the row is allowed), then
@@ -769,18 +1017,43 @@ __global__ void k_build_scores_seq(const uint8_t* a, const uint8_t* b, const flo
 // ---- host side ----------------------------------------------------------------------------------
 int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
 {
-    a.n_strips = (a.L2 + 32 * kg - 1) / (32 * kg);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // the lean kernel needs the padded matrix pitch the engine allocates; anything else (and the
+    // debug dumps) runs the general-layout kernels
+    const int lean_strips = (a.L2 + 127) / 128;
+    const bool lean = !a.o_full && a.flagw && a.m_pitch % 4 == 0 && a.m_pitch >= lean_strips * 128 &&
+                      ((reinterpret_cast<uintptr_t>(a.m) & 15) == 0) && getenv("PGPU_NO_LEAN") == nullptr;
+    a.n_strips = lean ? lean_strips : (a.L2 + 32 * kg - 1) / (32 * kg);
     if (a.n_strips < 1) a.n_strips = 1;
     k_gen_init<<<32, 256, 0, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
-    if (a.L1 > 0 && a.L2 > 0) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool local = a.mode == PG_LOCAL;
+    const bool mask = a.z != nullptr;
+    if (lean) {
+        a.flag_fmt = 2;
+        const int wpc = a.n_strips < 8 ? a.n_strips : 8;
+        int ctas = (a.n_strips + wpc - 1) / wpc;
+        if (ctas > sms) ctas = sms;
+#define PG_WAVE(LO, MA, VG)                                                                          \
+    do {                                                                                             \
+        auto kern = k_wave<LO, MA, VG>;                                                              \
+        const size_t sm = (size_t)wpc * WV_R * 32 * (VG ? 12 : 8) * sizeof(float);                   \
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        kern<<<ctas, wpc * 32, sm, st>>>(a);                                                         \
+    } while (0)
+        const bool vg = a.var_gaps != 0;
+        if (local) { if (mask) { if (vg) PG_WAVE(true, true, true); else PG_WAVE(true, true, false); }
+                     else { if (vg) PG_WAVE(true, false, true); else PG_WAVE(true, false, false); } }
+        else { if (mask) { if (vg) PG_WAVE(false, true, true); else PG_WAVE(false, true, false); }
+               else { if (vg) PG_WAVE(false, false, true); else PG_WAVE(false, false, false); } }
+#undef PG_WAVE
+        PG_CUDA_OK(cudaGetLastError());
+    } else if (a.L1 > 0 && a.L2 > 0) {
         const int wpc = 8;
         int ctas = (a.n_strips + wpc - 1) / wpc;
         if (ctas > sms) ctas = sms;    // all warps co-resident: strips wait on lower strips only
-        const bool local = a.mode == PG_LOCAL;
         if (a.o_full) {               // debug / B3 shim: the reference's complete flag bytes and o
             a.flag_fmt = 0;
             if (kg == 2) {
@@ -792,13 +1065,12 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
             }
         } else {
             a.flag_fmt = 1;
-            const bool mask = a.z != nullptr;
 #define PG_FAST1(KGV, LO, MA)                                                                      \
     do {                                                                                           \
         auto kern = k_gen_fill_fast<KGV, LO, MA>;                                                  \
         const int w2 = a.n_strips < wpc ? a.n_strips : wpc;                                        \
         const int c2 = (a.n_strips + w2 - 1) / w2 > sms ? sms : (a.n_strips + w2 - 1) / w2;        \
-        const size_t sm = (size_t)w2 * GEN_R * 32 * ((((KGV + 2) + 3) & ~3) + 4) * sizeof(float);        \
+        const size_t sm = (size_t)w2 * GEN_R * 32 * ((((KGV + 2) + 3) & ~3) + 4) * sizeof(float);  \
         PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         kern<<<c2, w2 * 32, sm, st>>>(a);                                                          \
     } while (0)
@@ -821,7 +1093,8 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
     k_gen_finalize<<<1, 256, 0, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
     if (a.path_buf) {
-        k_gen_traceback<<<1, 32, 0, st>>>(a);
+        if (lean) k_wave_traceback<<<1, 32, 0, st>>>(a);
+        else k_gen_traceback<<<1, 32, 0, st>>>(a);
         PG_CUDA_OK(cudaGetLastError());
     }
     return 0;

@@ -615,6 +615,12 @@ class Engine(object):
                     self.fits_s16(np.asarray(S_host), go, ge, batch.lens) is not None)
 
     # -- general single alignment ----------------------------------------------------------------
+    def padded_matrix(self, L1, L2):
+        """[L1 x L2] f32 view whose pitch covers whole 128-column strips: the layout the lean
+        wavefront kernel wants (pad columns are computed and ignored)."""
+        pitch = (L2 + 127) // 128 * 128
+        return torch.empty((L1, pitch), dtype=torch.float32, device=self.device)[:, :L2]
+
     def build_scores(self, P1s, P2s, Ss):
         """m = sum_sets P1 . S . P2^T on the device, reference evaluation order (cext.c:308-455)."""
         n = len(P1s)
@@ -622,11 +628,11 @@ class Engine(object):
         d2 = [self.dev(np.asarray(p, np.float32)) for p in P2s]
         ds = [self.dev(np.asarray(s, np.float32)) for s in Ss]
         L1, L2 = d1[0].shape[0], d2[0].shape[0]
-        m = torch.empty((L1, L2), dtype=torch.float32, device=self.device)
+        m = self.padded_matrix(L1, L2)
         arr = ctypes.c_void_p * n
         A = (ctypes.c_int * n)(*[int(p.shape[1]) for p in d1])
         _lib.check(self.lib.pgpu_build_scores(n, arr(*[t.data_ptr() for t in d1]), arr(*[t.data_ptr() for t in d2]),
-                                              arr(*[t.data_ptr() for t in ds]), A, L1, L2, self.ptr(m), L2,
+                                              arr(*[t.data_ptr() for t in ds]), A, L1, L2, self.ptr(m), int(m.stride(0)),
                                               self.stream()))
         self.launches += 1
         return m
@@ -634,12 +640,19 @@ class Engine(object):
     def align_general(self, mode, m, g1, g2, zero_idxs=None, want_path=True, want_matrices=False):
         """One RawPairwiseAligner call (component/align.py:302-447).  m may be a device tensor."""
         md = MODES[mode]
-        m_dev = m if isinstance(m, torch.Tensor) else self.dev(np.asarray(m, np.float32))
+        if isinstance(m, torch.Tensor):
+            m_dev = m
+        else:
+            mh = np.asarray(m, np.float32)
+            m_dev = self.padded_matrix(mh.shape[0], mh.shape[1])
+            m_dev.copy_(torch.from_numpy(np.ascontiguousarray(mh)), non_blocking=False)
         L1, L2 = int(m_dev.shape[0]), int(m_dev.shape[1])
         if L1 < 1 or L2 < 1:
             raise ValueError("empty sequences cannot be aligned")
-        g1_dev = self.dev(np.asarray(g1, np.float32).reshape(L1, 2))
-        g2_dev = self.dev(np.asarray(g2, np.float32).reshape(L2, 2))
+        g1h = np.asarray(g1, np.float32).reshape(L1, 2)
+        g2h = np.asarray(g2, np.float32).reshape(L2, 2)
+        var_gaps = int(not ((g1h == g1h[0]).all() and (g2h == g2h[0]).all()))
+        g1_dev, g2_dev = self.dev(g1h), self.dev(g2h)
         z_dev = None
         if zero_idxs is not None and len(zero_idxs):
             z = np.zeros((L1 + 1, L2 + 1), np.uint8)
@@ -656,7 +669,7 @@ class Engine(object):
             t = torch.zeros((L1 + 1, L2 + 1, 3), dtype=torch.uint8, device=self.device)
         base = outb.data_ptr()
         _lib.check(self.lib.pgpu_align_general(md, L1, L2, self.ptr(m_dev), int(m_dev.stride(0)), self.ptr(g1_dev),
-                                               self.ptr(g2_dev), self.ptr(z_dev), L2 + 1, self.ptr(ws),
+                                               self.ptr(g2_dev), var_gaps, self.ptr(z_dev), L2 + 1, self.ptr(ws),
                                                ctypes.c_void_p(base), ctypes.c_void_p(base + 4),
                                                ctypes.c_void_p(base + 32) if want_path else None,
                                                ctypes.c_void_p(base + 16) if want_path else None,
@@ -676,11 +689,11 @@ class Engine(object):
     def build_scores_seq(self, batch, i, j, S_dev, A):
         """m[y][x] = S[a_y][b_x] for sequences i (rows) and j (columns) of a batch."""
         L1, L2 = int(batch.lens[i]), int(batch.lens[j])
-        m = torch.empty((L1, L2), dtype=torch.float32, device=self.device)
+        m = self.padded_matrix(L1, L2)
         base = batch.flat_dev.data_ptr()
         _lib.check(self.lib.pgpu_build_scores_seq(ctypes.c_void_p(base + int(batch.offs[i])),
                                                   ctypes.c_void_p(base + int(batch.offs[j])), self.ptr(S_dev), A,
-                                                  L1, L2, self.ptr(m), L2, self.stream()))
+                                                  L1, L2, self.ptr(m), int(m.stride(0)), self.stream()))
         self.launches += 1
         return m
 
