@@ -182,7 +182,7 @@ int64_t pgpu_general_workspace_bytes(int L1, int L2)
     size_t b = 0;
     b += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 31));    // lean kernel's flag words
     b += up256((size_t)(L1 + 1) * fp);                              // flags
-    b += up256(sizeof(float) * 4 * (size_t)(ns + 1) * (L1 + 1));    // edge (16-byte records)
+    b += up256(sizeof(float) * 8 * (size_t)(ns + 1) * (L1 + 1));    // edge (16-byte records; 32-byte tagged ones in the lean kernel)
     b += up256(sizeof(int) * (size_t)(ns + 1));                     // progress
     b += 2 * up256(sizeof(float) * 3 * (size_t)(L2 + 1));           // top, lastrow
     b += up256(sizeof(float) * 3 * (size_t)(L1 + 1));               // lastcol
@@ -210,7 +210,7 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
     a.flagw = (uint32_t*)w; w += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 31));
     a.var_gaps = var_gaps;
     a.flags = w; a.f_pitch = (int)fp; w += up256((size_t)(L1 + 1) * fp);
-    a.edge = (float*)w; w += up256(sizeof(float) * 4 * (size_t)(ns + 1) * (L1 + 1));
+    a.edge = (float*)w; w += up256(sizeof(float) * 8 * (size_t)(ns + 1) * (L1 + 1));
     a.progress = (int*)w; w += up256(sizeof(int) * (size_t)(ns + 1));
     a.top = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));
     a.lastrow = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));

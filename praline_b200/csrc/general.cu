@@ -45,8 +45,14 @@ __global__ void k_gen_init(const GenArgs a)
         else if (y == 0) U = a.g1[0] - a.g1[1];
         else U = (float)((double)(y - 1) * (double)a.g1[(size_t)(y - 1) * 2 + 1] + (double)a.g1[0]);
         if (y == 0) L = l_zero ? 0.f : (a.g2[0] - a.g2[1]);
-        float* e = a.edge + (size_t)y * 4;
-        e[0] = M; e[1] = U; e[2] = L; e[3] = 0.f;
+        if (a.flag_fmt == 2) {          // lean kernel: tagged 32-byte records (see k_wave)
+            float* e = a.edge + (size_t)y * 8;
+            const float tg = __uint_as_float((uint32_t)y);
+            e[0] = M; e[1] = tg; e[2] = U; e[3] = tg; e[4] = L; e[5] = tg; e[6] = 0.f; e[7] = 0.f;
+        } else {
+            float* e = a.edge + (size_t)y * 4;
+            e[0] = M; e[1] = U; e[2] = L; e[3] = 0.f;
+        }
         if (a.o_full) {
             float* o = a.o_full + ((size_t)y * (L2 + 1)) * 3;
             o[0] = M; o[1] = U; o[2] = L;
@@ -458,12 +464,69 @@ __global__ void __launch_bounds__(256) k_gen_fill_fast(const GenArgs a)
 // constant gap pairs as scalars when the gap models are constant (VARG = false), one uniform
 // ring slot per step, the five sign bits of a lane's four cells packed into ONE 32-bit word that
 // is stored in the skewed [strip][step][lane] layout (a coalesced 128-byte line per warp-step).
+//
+// Strip-to-strip handoff without fences: the right edge of a strip is a stream of 32-byte
+// records {M, tag, U, tag | L, tag, 0, 0} with tag = row number (the buffer is zeroed before the
+// launch, rows start at 1).  Every 8-byte {value, tag} pair is written and read as part of one
+// aligned vector access, so a record is valid exactly when its three tags match -- no release
+// store, no membar, no progress counter (the first version spent a third of its cycles in the
+// ERRBAR of a predicated st.release, which drained the whole prefetch ring every step).  The
+// consumer prefetches records WV_R-1 rows ahead with cp.async.cg and checks the tags at use; on
+// a miss it waits until its producer is a full ring ahead and reloads the ring's records directly.
 #define WV_R 8
+// every {value, tag} pair is ONE 64-bit scalar access (single-copy atomic); ptxas is free to split
+// a vector access into its elements, so the pairs are never loaded or stored as f32 vectors
+__device__ __forceinline__ void ld_edge(const float* p, float4& e0, float4& e1)
+{
+    unsigned long long a, b, c;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(p + 2) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(p + 4) : "memory");
+    e0.x = __uint_as_float((uint32_t)a); e0.y = __uint_as_float((uint32_t)(a >> 32));
+    e0.z = __uint_as_float((uint32_t)b); e0.w = __uint_as_float((uint32_t)(b >> 32));
+    e1.x = __uint_as_float((uint32_t)c); e1.y = __uint_as_float((uint32_t)(c >> 32));
+    e1.z = 0.f; e1.w = 0.f;
+}
+__device__ __forceinline__ void st_edge(float* p, float M, float U, float L, int y)
+{
+    const unsigned long long tg = (unsigned long long)(uint32_t)y << 32;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(tg | __float_as_uint(M)) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p + 2), "l"(tg | __float_as_uint(U)) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p + 4), "l"(tg | __float_as_uint(L)) : "memory");
+}
+__device__ __forceinline__ bool edge_ok(const float4& e0, const float4& e1, int y)
+{
+    const uint32_t tg = (uint32_t)y;
+    return __float_as_uint(e0.y) == tg && __float_as_uint(e0.w) == tg && __float_as_uint(e1.y) == tg;
+}
+// lane 0, record of row y not there yet: let the producer get a full ring ahead, then put the
+// records of rows y .. y+WV_R-1 (all requested already, possibly too early) into their slots
+__device__ __forceinline__ void wave_refill(const float* ein, float* ring_lane0, int slotp, int y, int t, int L1)
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");      // nothing in flight may land on top of the fix-up
+    const int target = min(y + WV_R - 1, L1);
+    float4 e0, e1;
+    for (long long spins = 0; spins < (1ll << 24); spins++) {  // bounded: fail a test, never hang
+        ld_edge(ein + (size_t)target * 8, e0, e1);
+        if (edge_ok(e0, e1, target)) break;
+        __nanosleep(64);
+    }
+    for (int r = y; r <= target; r++) {
+        for (int spins = 0; spins < (1 << 20); spins++) {
+            ld_edge(ein + (size_t)r * 8, e0, e1);
+            if (edge_ok(e0, e1, r)) break;
+        }
+        float* s = ring_lane0 + ((t + (r - y)) & (WV_R - 1)) * 32 * slotp;
+        *reinterpret_cast<float4*>(s + 4) = e0;
+        *reinterpret_cast<float4*>(s + 8) = e1;
+    }
+}
+
 template <bool LOCAL, bool MASK, bool VARG>
 __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
 {
     extern __shared__ __align__(16) float wsm[];
-    constexpr int SLOTP = VARG ? 12 : 8;    // floats per lane per slot: [m x4][edge M U L pad][gap open, extend, pad x2]
+    constexpr int SLOTP = VARG ? 16 : 12;   // floats per lane per slot: [m x4][edge M tag U tag][edge L tag 0 0][gap open, extend, pad x2]
     const int L1 = a.L1, L2 = a.L2, W = L2 + 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -475,13 +538,10 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
 
     for (int strip = gw; strip < a.n_strips; strip += nw) {
         const int x0 = strip * 128 + lane * 4 + 1;
-        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 4;
-        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 4;
-        int* pin = a.progress + strip;
-        int* pout = a.progress + strip + 1;
+        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 8;
+        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 8;
         const bool last_strip = strip == a.n_strips - 1;
         const bool lane_on = x0 <= L2;
-        const bool multi = strip > 0;       // strip 0 reads the border column written by k_gen_init
         uint32_t* fout = a.flagw + (size_t)strip * TT * 32 + lane;
 
         float Mp[4], Up[4], Lp[4], go2[4], ge2[4];
@@ -499,7 +559,6 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
         float Md = NINF, Ud = NINF, Ld = NINF;
         if (lane_on) { Md = a.top[x0 - 1]; Ud = a.top[W + x0 - 1]; Ld = a.top[2 * W + x0 - 1]; }
         float Me = 0.f, Ue = 0.f, Le = 0.f;
-        int avail = multi ? 0 : L1;
         float bv = NINF; uint32_t bl = 0xffffffffu;
         const int lcol = (L2 - 1 - strip * 128) >> 2, kcol = (L2 - 1) & 3;   // lane / cell of column L2 (last strip)
 
@@ -508,25 +567,16 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
             if (yy >= 1 && yy <= L1 && lane_on) {
                 const uint32_t dst = ring_s + (uint32_t)((use_step & (WV_R - 1)) * 32 * SLOTP) * 4u;
                 cp_async16(dst, a.m + (size_t)(yy - 1) * a.m_pitch + (x0 - 1));
-                if (lane == 0) cp_async16(dst + 16, ein + (size_t)yy * 4);
+                if (lane == 0) {
+                    cp_async16(dst + 16, ein + (size_t)yy * 8);
+                    cp_async16(dst + 32, ein + (size_t)yy * 8 + 4);
+                }
                 if (VARG) {
-                    cp_async4(dst + 32, a.g1 + (size_t)(yy - 1) * 2);
-                    cp_async4(dst + 36, a.g1 + (size_t)(yy - 1) * 2 + 1);
+                    cp_async4(dst + 48, a.g1 + (size_t)(yy - 1) * 2);
+                    cp_async4(dst + 52, a.g1 + (size_t)(yy - 1) * 2 + 1);
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto wait_rows = [&](int need) {
-            if (avail < need) {
-                if (lane == 0) {
-                    for (long long spins = 0; spins < (1ll << 26); spins++) {   // bounded: fail a test, never hang
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(avail) : "l"(pin) : "memory");
-                        if (avail >= need) break;
-                        __nanosleep(32);
-                    }
-                }
-                avail = __shfl_sync(FULL, avail, 0);
-            }
         };
         auto fetch_mask = [&](int yy) -> uint32_t {
             uint32_t zz = 0;
@@ -538,7 +588,6 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
             return zz;
         };
         __syncwarp();
-        wait_rows(min(WV_R - 1, L1));
 #pragma unroll 1
         for (int d = 0; d < WV_R - 1; d++) request(1 - lane + d, d);
         uint32_t cz = fetch_mask(1 - lane), nz = 0;
@@ -546,19 +595,39 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
         for (int t = 0; t < TT; t++) {
             __syncwarp();
             const int y = t - lane + 1;
-            wait_rows(min(t + WV_R, L1));
             request(y + WV_R - 1, t + WV_R - 1);
             if (MASK) nz = fetch_mask(y + 1);
             float Ml = __shfl_up_sync(FULL, Me, 1);
             float Ul = __shfl_up_sync(FULL, Ue, 1);
             float Ll = __shfl_up_sync(FULL, Le, 1);
             asm volatile("cp.async.wait_group %0;" ::"n"(WV_R - 1) : "memory");
-            const float* slot = ring + (t & (WV_R - 1)) * 32 * SLOTP;
-            if (lane == 0) { const float4 e = *reinterpret_cast<const float4*>(slot + 4); Ml = e.x; Ul = e.y; Ll = e.z; }
+            float* slot = ring + (t & (WV_R - 1)) * 32 * SLOTP;
+            // lane 0: the left strip's record of this row.  The miss path is entered by the whole
+            // warp (vote), so the step loop itself never runs diverged.
+            float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+            bool miss = false;
+            if (lane == 0 && y <= L1) {
+                e0 = *reinterpret_cast<const float4*>(slot + 4);
+                e1 = *reinterpret_cast<const float4*>(slot + 8);
+                miss = !edge_ok(e0, e1, y);
+            }
+            if (__any_sync(FULL, miss)) {
+                if (lane == 0) {
+#ifdef WAVE_DEBUG
+                    atomicAdd(a.progress + strip, 1);
+#endif
+                    wave_refill(ein, ring, SLOTP, y, t, L1);
+                    asm volatile("" ::: "memory");
+                    e0 = *reinterpret_cast<const float4*>(slot + 4);
+                    e1 = *reinterpret_cast<const float4*>(slot + 8);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { Ml = e0.x; Ul = e0.z; Ll = e1.x; }
             if (y >= 1 && y <= L1 && lane_on) {
                 const float4 sv = *reinterpret_cast<const float4*>(slot);
                 const float sc[4] = {sv.x, sv.y, sv.z, sv.w};
-                const float g1o = VARG ? slot[8] : cgo1, g1e = VARG ? slot[9] : cge1;
+                const float g1o = VARG ? slot[12] : cgo1, g1e = VARG ? slot[13] : cge1;
                 const float dM = Ml, dU = Ul, dL = Ll;
                 float cMl = Ml, cLl = Ll;
                 uint32_t fw = 0;
@@ -608,17 +677,17 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
                         a.lastcol[y] = m_; a.lastcol[(L1 + 1) + y] = u_; a.lastcol[2 * (L1 + 1) + y] = l_;
                     }
                 } else if (lane == 31) {
-                    *reinterpret_cast<float4*>(eout + (size_t)y * 4) = make_float4(Me, Ue, Le, 0.f);
+                    st_edge(eout + (size_t)y * 8, Me, Ue, Le, y);
                 }
             }
             if (MASK) cz = nz;
-            const int done = t - 31 + 1;
-            if (!last_strip && lane == 31 && done >= 1 && ((done & 7) == 0 || done == L1))
-                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pout), "r"(done) : "memory");
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (LOCAL && bl != 0xffffffffu) atomicMax(a.best, gkey(bv, bl));
+#ifdef WAVE_DEBUG
+        if (lane == 0) printf("strip %d refills %d\n", strip, a.progress[strip]);
+#endif
     }
 }
 
@@ -716,8 +785,8 @@ __global__ void __launch_bounds__(256) k_gen_finalize(const GenArgs a)
     __shared__ unsigned long long red[2][256];
     const int L1 = a.L1, L2 = a.L2, W = L2 + 1, H = L1 + 1;
     const int tid = threadIdx.x;
-    auto row_at = [&](int x, int k) -> float { return (L1 == 0) ? a.top[k * W + x] : (x == 0 ? a.edge[(size_t)L1 * 4 + k] : a.lastrow[k * W + x]); };
-    auto col_at = [&](int y, int k) -> float { return (y == 0) ? a.top[k * W + L2] : (L2 == 0 ? a.edge[(size_t)y * 4 + k] : a.lastcol[k * H + y]); };
+    auto row_at = [&](int x, int k) -> float { return (L1 == 0) ? a.top[k * W + x] : (x == 0 ? a.edge[a.flag_fmt == 2 ? (size_t)L1 * 8 + 2 * k : (size_t)L1 * 4 + k] : a.lastrow[k * W + x]); };
+    auto col_at = [&](int y, int k) -> float { return (y == 0) ? a.top[k * W + L2] : (L2 == 0 ? a.edge[a.flag_fmt == 2 ? (size_t)y * 8 + 2 * k : (size_t)y * 4 + k] : a.lastcol[k * H + y]); };
     unsigned long long kr = 0ull, kc = 0ull;
     if (a.mode == PG_LOCAL) {
         // borders of o in linear (y, x, state) order: smaller linear index wins ties
@@ -725,7 +794,7 @@ __global__ void __launch_bounds__(256) k_gen_finalize(const GenArgs a)
         for (int x = tid; x <= L2; x += 256)
             for (int k = 0; k < 3; k++) { const unsigned long long c = lkey(a.top[k * W + x], (uint32_t)(x * 3 + k)); if (c > kr) kr = c; }
         for (int y = 1 + tid; y <= L1; y += 256)
-            for (int k = 0; k < 3; k++) { const unsigned long long c = lkey(a.edge[(size_t)y * 4 + k], (uint32_t)(((size_t)y * W) * 3 + k)); if (c > kr) kr = c; }
+            for (int k = 0; k < 3; k++) { const unsigned long long c = lkey(a.edge[a.flag_fmt == 2 ? (size_t)y * 8 + 2 * k : (size_t)y * 4 + k], (uint32_t)(((size_t)y * W) * 3 + k)); if (c > kr) kr = c; }
     } else if (a.mode != PG_GLOBAL) {
         for (int x = tid; x <= L2; x += 256)
             for (int k = 0; k < 3; k++) { const unsigned long long c = fkey(row_at(x, k), (uint32_t)x, k); if (c > kr) kr = c; }
@@ -1027,19 +1096,26 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
                       ((reinterpret_cast<uintptr_t>(a.m) & 15) == 0) && getenv("PGPU_NO_LEAN") == nullptr;
     a.n_strips = lean ? lean_strips : (a.L2 + 32 * kg - 1) / (32 * kg);
     if (a.n_strips < 1) a.n_strips = 1;
+    if (lean) {
+        a.flag_fmt = 2;
+        // tags of the strip-to-strip edge records must start invalid (row numbers start at 1)
+        PG_CUDA_OK(cudaMemsetAsync(a.edge + (size_t)(a.L1 + 1) * 8, 0, sizeof(float) * 8 * (size_t)a.n_strips * (a.L1 + 1), st));
+    }
     k_gen_init<<<32, 256, 0, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
     const bool local = a.mode == PG_LOCAL;
     const bool mask = a.z != nullptr;
     if (lean) {
-        a.flag_fmt = 2;
-        const int wpc = a.n_strips < 8 ? a.n_strips : 8;
+        // all strips co-resident, spread over the SMs: a lone warp per scheduler runs its
+        // dependent step loop fastest
+        int wpc = (a.n_strips + sms - 1) / sms;
+        if (wpc > 8) wpc = 8;
         int ctas = (a.n_strips + wpc - 1) / wpc;
         if (ctas > sms) ctas = sms;
 #define PG_WAVE(LO, MA, VG)                                                                          \
     do {                                                                                             \
         auto kern = k_wave<LO, MA, VG>;                                                              \
-        const size_t sm = (size_t)wpc * WV_R * 32 * (VG ? 12 : 8) * sizeof(float);                   \
+        const size_t sm = (size_t)wpc * WV_R * 32 * (VG ? 16 : 12) * sizeof(float);                   \
         PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         kern<<<ctas, wpc * 32, sm, st>>>(a);                                                         \
     } while (0)

@@ -1,0 +1,53 @@
+"""BASELINE config 5: one long nucleotide profile x profile alignment on the intra-task path
+(K1 score matrix + K3 wavefront fill + end cell + traceback).  Two depth-8 DNA count profiles
+drawn from a common root (seed 5, 15-symbol alphabet, `nucleotide` matrix), global and
+semiglobal_both, gaps [-11,-1] and linear [-2].  Device time per stage from
+CUDA events; prints one JSON line per case.
+
+    python tools/run_c5.py [length=20000] [reps=3]
+"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from praline_b200 import get_engine, matrices, synth
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+eng = get_engine(0)
+S = matrices.nucleotide()
+# two profiles from one root: the family generator with a shared seed, split in two halves
+fam = synth.family(5, 16, L, n_sym=4)
+
+
+def prof(members):
+    n = min(len(s) for s in members)
+    c = np.zeros((n, S.shape[0]), np.int64)
+    for s in members:
+        c[np.arange(n), s[:n]] += 1
+    return synth.profile_from_counts(c)
+
+
+p1, p2 = prof(fam[:8]), prof(fam[8:])
+L1, L2 = p1.shape[0], p2.shape[0]
+for mode in ("global", "semiglobal_both"):
+    for gaps in ([-11.0, -1.0], [-2.0]):
+        go, ge = (gaps[0], gaps[-1])
+        g1 = np.empty((L1, 2), np.float32); g1[:] = (go, ge)
+        g2 = np.empty((L2, 2), np.float32); g2[:] = (go, ge)
+        best = None
+        for rep in range(reps):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            m = eng.build_scores([p1], [p2], [S])
+            e[1].record()
+            r = eng.align_general(mode, m, g1, g2)
+            e[2].record()
+            torch.cuda.synchronize()
+            t = (e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]))
+            if best is None or sum(t) < sum(best):
+                best = t
+        cells = L1 * L2
+        print(json.dumps({"stage": "C5 long profile x profile", "L1": L1, "L2": L2, "mode": mode, "gaps": gaps,
+                          "score": r["score"], "path_len": int(len(r["path"])), "build_scores_ms": best[0],
+                          "fill_end_traceback_ms": best[1], "gcups_e2e": cells / (sum(best) * 1e-3) / 1e9,
+                          "gcups_fill": cells / (best[1] * 1e-3) / 1e9}))
