@@ -691,11 +691,13 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
     }
 }
 
-// Traceback over the lean kernel's flag words: one warp stages 32 steps x 32 lanes of the current
-// strip (4 KB, coalesced) and lane 0 walks inside that window.
+// Traceback over the lean kernel's flag words: one warp stages WT_WIN steps x 32 lanes of the
+// current strip (16 KB, every row a coalesced 128-byte line, all requests in flight at once) and
+// lane 0 walks inside that window -- one memory round trip per ~100 path cells.
+#define WT_WIN 128
 __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
 {
-    __shared__ uint32_t tile[32][32];
+    __shared__ uint32_t tile[WT_WIN][32];
     const int lane = threadIdx.x;
     const int L1 = a.L1, L2 = a.L2, TT = L1 + 31;
     const bool u_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_ONE);
@@ -703,48 +705,49 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
     int y = a.cell_out[0], x = a.cell_out[1], k = a.cell_out[2];
     const int cap = L1 + L2 + 2;
     int w = cap;
-    auto push = [&](int yy, int xx) { --w; a.path_buf[2 * w] = yy; a.path_buf[2 * w + 1] = xx; };
+    int2* pb = reinterpret_cast<int2*>(a.path_buf);
+    auto push = [&](int yy, int xx) { pb[--w] = make_int2(yy, xx); };
     const bool semi = (a.mode >= PG_SG_BOTH);
     if (lane == 0 && semi) {
         if (y != L1) { for (int v = L1; v > y; v--) push(v, x); }
         else if (x != L2) { for (int v = L2; v > x; v--) push(y, v); }
     }
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
     int done = 0;
     while (!done) {
         int strip = 0, tlo = 0;
         if (y >= 1 && x >= 1) {
             strip = (x - 1) >> 7;
             const int tcur = y - 1 + (((x - 1) & 127) >> 2);
-            tlo = max(0, tcur - 31);
+            tlo = max(0, tcur - (WT_WIN - 1));
             const uint32_t* src = a.flagw + ((size_t)strip * TT + tlo) * 32 + lane;
+            const int nrow = min(WT_WIN, TT - tlo);
 #pragma unroll 8
-            for (int r = 0; r < 32; r++) tile[r][lane] = (tlo + r < TT) ? src[(size_t)r * 32] : 0u;
+            for (int r = 0; r < nrow; r++) cp_async4(tile_s + (uint32_t)(r * 32 + lane) * 4u, src + (size_t)r * 32);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
         if (lane == 0) {
             for (;;) {
                 push(y, x);
-                uint8_t f;
-                if (y == 0 && x == 0) f = 0;
-                else if (x == 0) f = (u_ramp && k == 1) ? TB_UE : 0;
-                else if (y == 0) f = (l_ramp && k == 2) ? TB_LE : 0;
-                else {
+                int ny = y, nx = x, nk = k;
+                bool stop = false;
+                if (y >= 1 && x >= 1) {
                     const int ln = ((x - 1) & 127) >> 2, kk = (x - 1) & 3;
                     const uint32_t word = tile[y - 1 + ln - tlo][ln];
                     const uint32_t c = (word >> (5 * kk)) & 31u;
-                    if ((word >> (24 + kk)) & 1u) f = 0;
-                    else if (k == 0) f = !(c & 1) ? TB_MM : (!(c & 2) ? TB_MU : ((c & 16) ? 0 : TB_ML));
-                    else if (k == 1) f = (c & 4) ? TB_UE : TB_UO;
-                    else f = (c & 8) ? TB_LE : TB_LO;
-                }
-                if (f & TB_MM) { y--; x--; k = 0; }
-                else if (f & TB_MU) { y--; x--; k = 1; }
-                else if (f & TB_ML) { y--; x--; k = 2; }
-                else if (f & TB_UO) { y--; k = 0; }
-                else if (f & TB_UE) { y--; k = 1; }
-                else if (f & TB_LO) { x--; k = 0; }
-                else if (f & TB_LE) { x--; k = 2; }
-                else { done = 1; break; }
+                    if ((word >> (24 + kk)) & 1u) stop = true;              // masked cell: no flags
+                    else if (k == 0) {
+                        ny = y - 1; nx = x - 1;
+                        if (!(c & 1)) nk = 0; else if (!(c & 2)) nk = 1; else if (c & 16) stop = true; else nk = 2;
+                    } else if (k == 1) { ny = y - 1; nk = (c & 4) ? 1 : 0; }
+                    else { nx = x - 1; nk = (c & 8) ? 2 : 0; }
+                } else if (y == 0 && x == 0) stop = true;
+                else if (x == 0) { if (u_ramp && k == 1) ny = y - 1; else stop = true; }
+                else { if (l_ramp && k == 2) nx = x - 1; else stop = true; }
+                if (stop) { done = 1; break; }
+                y = ny; x = nx; k = nk;
                 if (y >= 1 && x >= 1) {   // still inside the staged window of this strip?
                     const int tn = y - 1 + (((x - 1) & 127) >> 2);
                     if (((x - 1) >> 7) != strip || tn < tlo) break;
@@ -926,52 +929,88 @@ __global__ void __launch_bounds__(32) k_gen_traceback(const GenArgs a)
 // accumulated sequentially per set, sets added in order (cext.c:63-95, :388-421).  Explicit
 // _rn intrinsics keep ptxas from contracting the multiply-add.
 
-// Block = 32 columns x 8 rows of m.  Per track set the block stages its 8 rows of P1, its 32 rows
-// of P2 and S in shared memory and compacts the NONZERO entries of every staged profile row
-// (ascending index, as build_nonzero_matrix does on the host, component/align.py:449-458), so a
-// cell costs nnz1 x nnz2 terms like the reference instead of A x A.
+// Block = (32*CG) columns x (8*RG) rows of m, 256 threads.  Per track set the block stages its
+// rows of P1, its rows of P2 and S in shared memory and compacts the NONZERO entries of every
+// staged profile row (ascending index, as build_nonzero_matrix does on the host,
+// component/align.py:449-458), so a cell costs nnz1 x nnz2 terms like the reference instead of
+// A x A.  Large matrices use CG x RG = 2 x 2 (a thread owns 4 cells and the staging is amortised over
+// 1024 cells); small ones 1 x 1 so that the grid still covers the machine.
 #define BS_MAXA 64
+template <int CG, int RG>
 __global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int L1, int L2, float* m, int m_pitch)
 {
     extern __shared__ float bsm[];
+    constexpr int NR = 8 * RG, NC = 32 * CG;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
-    float score = 0.f;
+    const int x0 = blockIdx.x * NC, y0 = blockIdx.y * NR;
+    float score[RG][CG];
+#pragma unroll
+    for (int r = 0; r < RG; r++)
+#pragma unroll
+        for (int c = 0; c < CG; c++) score[r][c] = 0.f;
     for (int n = 0; n < sets.n; n++) {
         const ScoreSet st = sets.s[n];
         const int A = st.A;
         float* sS = bsm;                         // [A][A]
-        float* v1 = sS + A * A;                  // [8][A]  nonzero values of P1 rows, compacted
-        float* v2 = v1 + 8 * A;                  // [32][A]
-        uint8_t* i1 = reinterpret_cast<uint8_t*>(v2 + 32 * A);   // [8][A] their symbol indices
-        uint8_t* i2 = i1 + 8 * A;                                 // [32][A]
-        int* c1 = reinterpret_cast<int*>(i2 + 32 * A + ((4 - ((40 * A) & 3)) & 3));   // [8] counts
-        int* c2 = c1 + 8;                                                            // [32]
+        float* v1 = sS + A * A;                  // [NR][A]  nonzero values of P1 rows, compacted
+        float* v2 = v1 + NR * A;                 // [NC][A]
+        int* c1 = reinterpret_cast<int*>(v2 + NC * A);             // [NR] counts
+        int* c2 = c1 + NR;                                          // [NC]
+        uint8_t* i1 = reinterpret_cast<uint8_t*>(c2 + NC);          // [NR][A] their symbol indices
+        uint8_t* i2 = i1 + NR * A;                                  // [NC][A]
+        float* raw = reinterpret_cast<float*>(i2 + NC * A + ((4 - ((NR + NC) * A & 3)) & 3));   // [NR + NC][A] staged rows
         __syncthreads();
         for (int i = tid; i < A * A; i += 256) sS[i] = st.S[i];
-        if (tid < 8) {          // one thread compacts one P1 row
-            const int yy = blockIdx.y * 8 + tid;
-            int c = 0;
-            if (yy < L1) for (int i = 0; i < A; i++) { const float p = st.P1[(size_t)yy * A + i]; if (p != 0.f) { v1[tid * A + c] = p; i1[tid * A + c] = (uint8_t)i; c++; } }
-            c1[tid] = c;
-        } else if (tid >= 32 && tid < 64) {   // and one thread one P2 row
-            const int r = tid - 32, xx = blockIdx.x * 32 + r;
-            int c = 0;
-            if (xx < L2) for (int j = 0; j < A; j++) { const float p = st.P2[(size_t)xx * A + j]; if (p != 0.f) { v2[r * A + c] = p; i2[r * A + c] = (uint8_t)j; c++; } }
-            c2[r] = c;
+        {   // all threads stage the raw profile rows (coalesced, one memory round trip) ...
+            const int n1r = min(NR, L1 - y0), n2r = min(NC, L2 - x0);
+            const float* s1 = st.P1 + (size_t)y0 * A;
+            const float* s2 = st.P2 + (size_t)x0 * A;
+            for (int i = tid; i < n1r * A; i += 256) raw[i] = s1[i];
+            for (int i = tid; i < n2r * A; i += 256) raw[NR * A + i] = s2[i];
         }
         __syncthreads();
-        float acc = 0.f;
-        const int n1 = c1[ty], n2 = c2[tx];
-        for (int a = 0; a < n1; a++) {
-            const float p1 = v1[ty * A + a];
-            const float* srow = sS + (int)i1[ty * A + a] * A;
-            for (int b = 0; b < n2; b++)
-                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(v2[tx * A + b], srow[i2[tx * A + b]]), p1));
+        for (int r = tid; r < NR + NC; r += 256) {   // ... then one thread compacts one row from shared memory
+            const float* src = raw + r * A;
+            if (r < NR) {
+                int c = 0;
+                if (y0 + r < L1) for (int i = 0; i < A; i++) { const float p = src[i]; if (p != 0.f) { v1[r * A + c] = p; i1[r * A + c] = (uint8_t)i; c++; } }
+                c1[r] = c;
+            } else {
+                const int q = r - NR;
+                int c = 0;
+                if (x0 + q < L2) for (int j = 0; j < A; j++) { const float p = src[j]; if (p != 0.f) { v2[q * A + c] = p; i2[q * A + c] = (uint8_t)j; c++; } }
+                c2[q] = c;
+            }
         }
-        score = __fadd_rn(score, acc);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < CG; c++) {
+            const int q = c * 32 + tx;
+            const int n2 = c2[q];
+            const float* pv2 = v2 + q * A;
+            const uint8_t* pi2 = i2 + q * A;
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                const int rr = r * 8 + ty;
+                const int n1 = c1[rr];
+                float acc = 0.f;
+                for (int a = 0; a < n1; a++) {
+                    const float p1 = v1[rr * A + a];
+                    const float* srow = sS + (int)i1[rr * A + a] * A;
+                    for (int b = 0; b < n2; b++)
+                        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(pv2[b], srow[pi2[b]]), p1));
+                }
+                score[r][c] = __fadd_rn(score[r][c], acc);
+            }
+        }
     }
-    if (x < L2 && y < L1) m[(size_t)y * m_pitch + x] = score;
+#pragma unroll
+    for (int r = 0; r < RG; r++)
+#pragma unroll
+        for (int c = 0; c < CG; c++) {
+            const int x = x0 + c * 32 + tx, y = y0 + r * 8 + ty;
+            if (x < L2 && y < L1) m[(size_t)y * m_pitch + x] = score[r][c];
+        }
 }
 
 // Batched form for the matrix-fed streaming kernel: one matrix row per stream position of a
@@ -1179,18 +1218,26 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
 int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st)
 {
     if (L1 <= 0 || L2 <= 0) return 0;
-    dim3 b(32, 8), g((L2 + 31) / 32, (L1 + 7) / 8);
     int amax = 1;
     for (int i = 0; i < sets.n; i++) {
         if (sets.s[i].A > BS_MAXA) { pg_set_error("alphabet size %d above %d", sets.s[i].A, BS_MAXA); return 1; }
         if (sets.s[i].A > amax) amax = sets.s[i].A;
     }
-    const size_t sm = sizeof(float) * (amax * amax + 40 * amax) + 40 * amax + 4 + sizeof(int) * 40;
-    k_build_scores<<<g, b, sm, st>>>(sets, L1, L2, m, m_pitch);
+    const char* ev = getenv("PGPU_K1_BIG");
+    const bool big = ev ? atoi(ev) != 0 : (size_t)L1 * L2 >= (size_t)1 << 21;   // measured: 7.7 -> 5.7 ms at 20k x 20k
+    const int nr = big ? 16 : 8, nc = big ? 64 : 32;
+    const size_t sm = sizeof(float) * (amax * amax + 2 * (nr + nc) * amax) + sizeof(int) * (nr + nc) + (size_t)(nr + nc) * amax + 32;
+    dim3 b(32, 8), g((L2 + nc - 1) / nc, (L1 + nr - 1) / nr);
+    if (big) {
+        auto kern = k_build_scores<2, 2>;
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<g, b, sm, st>>>(sets, L1, L2, m, m_pitch);
+    } else {
+        k_build_scores<1, 1><<<g, b, sm, st>>>(sets, L1, L2, m, m_pitch);
+    }
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }
-
 int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const PgRowBlock* blocks,
                          int n_blocks, int width, int transposed, float padv, float* mwave, cudaStream_t st)
 {
