@@ -194,6 +194,21 @@ int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, 
                     const uint8_t* z, int L1, int L2);
 
 /*
+ * Guide-tree clustering.  Replaces HierarchicalClusteringAlgorithm.merge_order
+ * (praline/util/cluster.py:27-57) and its linkages (:60-111): dist_dev is the [n][n] f32
+ * distance matrix GuideTreeBuilder forms (component/tree.py:142-147), linkage 0 = single,
+ * 1 = complete, 2 = average.  merges_dev receives the n-1 (merge_one_id, merge_two_id) pairs in
+ * the reference's order (first minimum in row-major order over the clusters in ascending id;
+ * `two` is merged into `one`).  workspace_dev: pgpu_cluster_workspace_bytes(n) bytes.
+ */
+#define PGPU_LINKAGE_SINGLE 0
+#define PGPU_LINKAGE_COMPLETE 1
+#define PGPU_LINKAGE_AVERAGE 2
+int64_t pgpu_cluster_workspace_bytes(int n);
+int pgpu_cluster_merge_order(int n, int linkage, const float* dist_dev, void* workspace_dev, int32_t* merges_dev,
+                             void* stream);
+
+/*
  * Pipe-rate micro-benchmarks used for the DP roofline denominator: returns in out[0..n) the
  * measured warp-instructions per NANOSECOND per SM (wall clock, CUDA events) for (0) FADD, (1) FMNMX, (2) FMNMX3,
  * (3) the 4 FADD : 3 FMNMX mix of the score-only recurrence, (4) VIADDMNMX.S32,

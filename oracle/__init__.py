@@ -243,3 +243,40 @@ def ref_build_scores(P1s, P2s, Ss):
     m = np.zeros((P1s[0].shape[0], P2s[0].shape[0]), np.float32)
     cx.cext_build_scores(P1s, P2s, [nzmat(p) for p in P1s], [nzmat(p) for p in P2s], Ss, m)
     return m
+
+
+# ---- guide-tree clustering (reference: praline/util/cluster.py:27-111) ---------------------------
+def cluster_merge_order(dist, linkage="average"):
+    """Restatement of HierarchicalClusteringAlgorithm.merge_order (cluster.py:27-57): every
+    round rebuilds the float64 inter-cluster matrix `a` over the clusters in ascending id
+    (dict insertion order, :34), diagonal 2**32 (:12, :40), takes the first minimum in row-major
+    order (:49) and merges cluster `two` into `one` (:55-56).  Linkages (:60-111): min, max, or
+    float64 mean of the f32 member distances.  Pinned against the reference class itself
+    (tests/golden/cluster.json, made by tests/golden/make_cluster_golden.py)."""
+    dist = np.asarray(dist)
+    fun = {"single": np.min, "complete": np.max, "average": np.mean}[linkage]
+    clusters = {i: [i] for i in range(dist.shape[0])}
+    out = []
+    while len(clusters) > 1:
+        ids = list(clusters)
+        a = np.full((len(ids), len(ids)), float(2 ** 32), dtype=float)
+        for i, ci in enumerate(ids):
+            for j, cj in enumerate(ids):
+                if i != j:
+                    a[i, j] = fun(dist[np.ix_(clusters[ci], clusters[cj])].astype(float))
+        i, j = np.unravel_index(a.argmin(), a.shape)
+        one, two = ids[i], ids[j]
+        clusters[one] = clusters[one] + clusters[two]
+        del clusters[two]
+        out.append((int(one), int(two)))
+    return out
+
+
+def tree_distance_matrix(scores_condensed, n):
+    """GuideTreeBuilder's distance matrix (component/tree.py:92-147): d f32 [n x n] with 0 on the
+    diagonal and the pair scores elsewhere, dist = (-d) + d.max() in f32."""
+    d = np.zeros((n, n), np.float32)
+    iu = np.triu_indices(n, k=1)
+    d[iu] = np.asarray(scores_condensed, np.float32)
+    d[(iu[1], iu[0])] = d[iu]
+    return (-d) + d.max()

@@ -43,6 +43,8 @@ _SIGNATURES = {
                                    c_void_p, c_void_p]),
     "pgpu_fill_debug": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "pgpu_microbench": (c_int, [c_void_p, c_int]),
+    "pgpu_cluster_workspace_bytes": (c_int64, [c_int]),
+    "pgpu_cluster_merge_order": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -259,4 +259,14 @@ int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, 
     return rc;
 }
 
+// Guide-tree clustering (cluster.cu): the merge order of praline/util/cluster.py:27-57.
+int64_t pgpu_cluster_workspace_bytes(int n) { return n < 1 ? 0 : (int64_t)pg_cluster_workspace_bytes(n); }
+
+int pgpu_cluster_merge_order(int n, int linkage, const float* dist_dev, void* workspace_dev, int32_t* merges_dev,
+                             void* stream)
+{
+    if (!dist_dev || !workspace_dev || (n > 1 && !merges_dev)) { pg_set_error("cluster: null buffer"); return 1; }
+    return pg_launch_cluster(n, linkage, dist_dev, workspace_dev, merges_dev, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -723,6 +723,39 @@ class Engine(object):
                                             vp(zc) if zc is not None else None, L1, L2))
         return o, t
 
+    # -- guide-tree clustering ---------------------------------------------------------------------
+    LINKAGES = {"single": 0, "complete": 1, "average": 2}
+
+    def tree_distance(self, scores, n):
+        """Condensed pair scores (np.triu_indices order; device tensor or array) -> the f32 distance
+        matrix of GuideTreeBuilder on the device (component/tree.py:92-147): d has 0 on the diagonal,
+        dist = (-d) + d.max(), all in f32 like the reference's numpy expression."""
+        cond = scores if isinstance(scores, torch.Tensor) else self.dev(np.ascontiguousarray(scores, np.float32))
+        d = torch.zeros((n, n), dtype=torch.float32, device=self.device)
+        iu = torch.triu_indices(n, n, offset=1, device=self.device)
+        d[iu[0], iu[1]] = cond
+        d[iu[1], iu[0]] = cond
+        return (-d) + d.max()
+
+    def cluster_merge_order(self, dist, linkage="average"):
+        """HierarchicalClusteringAlgorithm(dist).merge_order(linkage) (util/cluster.py:27-57) on the
+        device; dist is an [n x n] f32 array or device tensor.  Returns a list of (one, two) tuples."""
+        if linkage not in self.LINKAGES:
+            raise ValueError("unknown linkage method '%s'" % linkage)
+        dd = dist if isinstance(dist, torch.Tensor) else self.dev(np.ascontiguousarray(dist, np.float32))
+        dd = dd.to(torch.float32).contiguous()
+        n = int(dd.shape[0])
+        if dd.dim() != 2 or int(dd.shape[1]) != n:
+            raise ValueError("distance matrix must be square")
+        if n < 2:
+            return []
+        ws = torch.empty(int(self.lib.pgpu_cluster_workspace_bytes(n)), dtype=torch.uint8, device=self.device)
+        merges = torch.empty((n - 1, 2), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.pgpu_cluster_merge_order(n, self.LINKAGES[linkage], self.ptr(dd), self.ptr(ws),
+                                                     self.ptr(merges), self.stream()))
+        self.launches += 2
+        return [(int(a), int(b)) for a, b in merges.cpu().numpy().tolist()]
+
     def microbench(self):
         out = (ctypes.c_double * 13)()
         _lib.check(self.lib.pgpu_microbench(out, 13))

@@ -31,9 +31,9 @@ def allgather_condensed(out, slot_cuts, group=None):
 
 
 def scores_to_distance(cond, n):
-    """Condensed scores -> the distance matrix of GuideTreeBuilder (tree.py:98-147):
-    d[i][j] = d[j][i] = score, diagonal MINUS_INFINITY = -(2**32), dist = -d + d.max()."""
-    d = torch.full((n, n), float(-(2 ** 32)), dtype=torch.float32, device=cond.device)
+    """Condensed scores -> the distance matrix of GuideTreeBuilder (tree.py:92-147):
+    d[i][j] = d[j][i] = score, d[i][i] = 0.0 (tree.py:132-133), dist = (-d) + d.max() in f32."""
+    d = torch.zeros((n, n), dtype=torch.float32, device=cond.device)
     iu = torch.triu_indices(n, n, offset=1, device=cond.device)
     d[iu[0], iu[1]] = cond
     d[iu[1], iu[0]] = cond

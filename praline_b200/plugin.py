@@ -27,7 +27,7 @@ from praline.core import (Component, Port, Environment, Execution, Manager, T, B
                           ProgressMessage, LogMessage, ComponentError, DataError, LogBundle, ROOT_LOG_NAME,
                           path_to_url)
 from praline.container import (Sequence, Alignment, ScoreMatrix, PlainTrack, ProfileTrack, MatchScoreModel,
-                               GapScoreModel)
+                               GapScoreModel, SequenceTree)
 from praline.util import compress_path
 
 from . import _lib
@@ -37,6 +37,7 @@ PAIRWISE_TID = "praline.component.PairwiseAligner"
 RAW_TID = "praline.component.RawPairwiseAligner"
 GLOBAL_MS_TID = "praline.component.GlobalMasterSlaveAligner"
 PROFILE_BUILDER_TID = "praline.component.ProfileBuilder"
+GUIDE_TREE_TID = "praline.component.GuideTreeBuilder"
 
 
 def _path_container(mode, path):
@@ -346,10 +347,101 @@ class GpuRawPairwiseAligner(Component):
         yield CompleteMessage(outputs=outputs)
 
 
-def register(index):
-    """Replace the CPU aligners of a TypeIndex (manager.py:49-57) by the GPU ones."""
+class GpuGuideTreeBuilder(Component):
+    """GPU drop-in for praline.component.GuideTreeBuilder (component/tree.py:18-172): same type
+    id, ports, options and defaults.  The reference queues one PairwiseAligner task per unordered
+    pair (:97-131), fills the score matrix (:141-145), forms dist = -d + d.max() (:147) and runs
+    the pure-Python clustering (util/cluster.py:27-57).  Here the N(N-1)/2 scores come from ONE
+    all-vs-all launch (sequence tracks: the packed/f32 streaming kernel; profile tracks: the
+    matrix-fed batch in the reference's evaluation order), the distance matrix stays on the
+    device and the merge order comes from the clustering kernel (csrc/cluster.cu).  Anything the
+    batched path does not cover (several track sets, semiglobal_auto, debug logging, a different
+    aligner, over-long sequences) runs the reference's own component unchanged."""
+    tid = GUIDE_TREE_TID
+
+    inputs = {'sequences': Port([Sequence.tid]),
+              'track_id_sets': Port([[str]]),
+              'score_matrices': Port([ScoreMatrix.tid])}
+    outputs = {'guide_tree': Port(SequenceTree.tid)}
+
+    options = {'gap_series': [float], 'aligner': str,
+               'aligner_env': Environment.tid,
+               'linkage_method': str, 'squash_profiles': bool,
+               'dist_mode': str, 'debug': int}
+    defaults = {'gap_series': [-11.0, -1.0],
+                'aligner': PAIRWISE_TID, 'aligner_env': Environment({}),
+                'linkage_method': 'average', 'squash_profiles': False,
+                'dist_mode': 'global', 'debug': 0}
+
+    def _pair_scores(self, seqs, track_id_sets, score_matrices, mode):
+        """Condensed scores of all pairs i < j (sequence_one = i, sequence_two = j, the order of
+        tree.py:97-131) or None when the batched path does not apply."""
+        env = self.environment
+        if env['aligner'] != PAIRWISE_TID or self.manager.index.resolve(PAIRWISE_TID) is not GpuPairwiseAligner:
+            return None
+        if env['debug'] != 0 or len(track_id_sets) != 1 or len(seqs) < 2:
+            return None
+        sub_env = Environment(keys=env['aligner_env'].keys, component=GpuPairwiseAligner, parent=env)
+        if sub_env['debug'] != 0:
+            return None
+        eng = get_engine()
+        n = len(seqs)
+        try:    # the checks of PairwiseAligner.execute on every sequence (against its neighbour)
+            tracks = []
+            for i in range(n):
+                sets, gaps = _prepare(seqs[i], seqs[(i + 1) % n], track_id_sets, track_id_sets, score_matrices,
+                                      sub_env['gap_series'])
+                tracks.append(sets[0][0])
+            sm = sets[0][2]
+        except (ComponentError, DataError):
+            return None     # the reference path raises it the reference's way
+        S = sm.matrix.astype(np.float32)
+        longest = max(len(t) for t in tracks)
+        if min(len(t) for t in tracks) < 1 or eng.k_for(longest) is None:
+            return None
+        arrs = [_seq_like(t) for t in tracks]
+        if all(a is not None for a in arrs) and eng.integer_exact(S, gaps[0], gaps[1], longest):
+            batch = eng.batch(arrs)
+            cond, _, _ = eng.allpairs_scores(batch, eng.dev(S), S.shape[0], gaps, mode=mode, S_host=S)
+            return cond
+        pi, pj = np.triu_indices(n, k=1)
+        pb = eng.profile_batch([_profile_of(t) for t in tracks])
+        import os
+        fast = os.environ.get("PGPU_FAST_PROFILES", "") not in ("", "0")
+        return eng.align_profile_pairs(pb, pi, pj, S, gaps, mode=mode, fast=fast)
+
+    def execute(self, sequences, track_id_sets, score_matrices):
+        linkage_method = self.environment['linkage_method']
+        dist_mode = self.environment['dist_mode']
+        if linkage_method not in {'single', 'complete', 'average'}:
+            raise ComponentError("unknown linkage method '{0}'".format(linkage_method))
+        if dist_mode not in {'semiglobal', 'global', 'semiglobal_auto'}:
+            raise ComponentError("unknown alignment mode '{0}'".format(dist_mode))
+        cond = None
+        if dist_mode != 'semiglobal_auto':
+            mode = "semiglobal_both" if dist_mode == "semiglobal" else "global"
+            cond = self._pair_scores(sequences, track_id_sets, score_matrices, mode)
+        if cond is None:
+            from praline.component import GuideTreeBuilder as _ReferenceGuideTreeBuilder
+            ref = _ReferenceGuideTreeBuilder(self.manager, self.environment, self.tag)
+            for msg in ref.execute(sequences, track_id_sets, score_matrices):
+                yield msg
+            return
+        eng = get_engine()
+        n = len(sequences)
+        yield ProgressMessage(1.0)
+        dist = eng.tree_distance(cond, n)
+        merges = eng.cluster_merge_order(dist, linkage_method)
+        yield CompleteMessage({'guide_tree': SequenceTree(sequences, merges)})
+
+
+def register(index, tree=True):
+    """Replace the CPU aligners and (tree=True) the guide-tree builder of a TypeIndex
+    (manager.py:49-57) by the GPU ones."""
     index.register(GpuPairwiseAligner)
     index.register(GpuRawPairwiseAligner)
+    if tree:
+        index.register(GpuGuideTreeBuilder)
     return index
 
 
@@ -447,8 +539,8 @@ class GpuBatchManager(Manager):
     """Manager whose execute_many aligns all PairwiseAligner requests of an Execution in one
     batched launch per (mode, matrix, gaps) group (manager.py:154-170)."""
 
-    def __init__(self, index, register_gpu=True):
-        super(GpuBatchManager, self).__init__(register(index) if register_gpu else index)
+    def __init__(self, index, register_gpu=True, gpu_tree=True):
+        super(GpuBatchManager, self).__init__(register(index, tree=gpu_tree) if register_gpu else index)
         self.batched_requests = 0
 
     def execute_many(self, requests, parent_tag):

@@ -420,3 +420,73 @@ def test_length_boundaries(eng):
     r = eng.align_seq_pair_general(lb, 0, 1, S, [-11.0, -1.0], "global")
     ws, wp = oracle.align_seqs("global", long_seqs[0], long_seqs[1], S, [-11.0, -1.0])
     assert r["score"] == ws and np.array_equal(r["path"], wp)
+
+
+# ---- guide-tree clustering (csrc/cluster.cu vs util/cluster.py) ---------------------------------
+def test_cluster_kernel_vs_reference_golden(eng):
+    import json, os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "cluster.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        got = eng.cluster_merge_order(np.asarray(c["dist"], np.float32), c["linkage"])
+        assert [list(x) for x in got] == c["order"], (c["n"], c["kind"], c["linkage"])
+
+
+@pytest.mark.parametrize("linkage", ["single", "complete", "average"])
+def test_cluster_kernel_vs_oracle_ties(eng, linkage):
+    """Tie-heavy integer distances (what sequence scores give): the order is exact."""
+    rng = np.random.default_rng(41)
+    for n, hi in ((37, 4), (70, 12)):
+        s = np.triu(rng.integers(0, hi, (n, n)), 1).astype(np.float32)
+        dist = s + s.T
+        assert eng.cluster_merge_order(dist, linkage) == oracle.cluster_merge_order(dist, linkage)
+
+
+def _cluster_numpy_fast(dist, linkage):
+    """Independent O(n^3 / vectorised) check for large n: float64 sum / min / max matrix updated in
+    place, argmin over the live sub-matrix in ascending-id order."""
+    n = dist.shape[0]
+    S = dist.astype(np.float64)
+    cnt = np.ones(n)
+    ids = list(range(n))
+    out = []
+    while len(ids) > 1:
+        sub = S[np.ix_(ids, ids)]
+        a = sub / np.outer(cnt[ids], cnt[ids]) if linkage == "average" else sub.copy()
+        np.fill_diagonal(a, float(2 ** 32))
+        i, j = np.unravel_index(a.argmin(), a.shape)
+        one, two = ids[i], ids[j]
+        if linkage == "average":
+            S[one, :] += S[two, :]
+        elif linkage == "single":
+            S[one, :] = np.minimum(S[one, :], S[two, :])
+        else:
+            S[one, :] = np.maximum(S[one, :], S[two, :])
+        S[:, one] = S[one, :]
+        cnt[one] += cnt[two]
+        ids.pop(j)
+        out.append((one, two))
+    return out
+
+
+def test_cluster_kernel_large_from_real_scores(eng):
+    """600 sequences: all-vs-all scores -> distance matrix on the device -> clustering kernel,
+    against the vectorised restatement (integer scores: exact) and structural properties."""
+    S = matrices.blosum62()
+    seqs = synth.family(9, 600, 60)
+    n = len(seqs)
+    batch = eng.batch(seqs)
+    cond, _, _ = eng.allpairs_scores(batch, eng.dev(S), 27, [-11.0, -1.0], mode="global", S_host=S)
+    dist = eng.tree_distance(cond, n)
+    want_dist = oracle.tree_distance_matrix(cond.cpu().numpy(), n)
+    assert np.array_equal(dist.cpu().numpy(), want_dist)
+    for linkage in ("average", "single", "complete"):
+        got = eng.cluster_merge_order(dist, linkage)
+        assert got == _cluster_numpy_fast(want_dist, linkage), linkage
+        twos = [b for _, b in got]
+        assert len(got) == n - 1 and len(set(twos)) == n - 1       # every cluster is merged away once
+        gone = set()
+        for a, b in got:
+            assert a not in gone and b not in gone and a != b
+            gone.add(b)

@@ -5,12 +5,14 @@
 (2) the reference's own compiled extension, oracle/_ref/cext*.so, on fresh random
     inputs (cell-exact o, t and m) -- skipped only if oracle/_ref was never built.
 """
+import os
+
 import numpy as np
 import pytest
 
 import oracle
 from praline_b200 import matrices, synth
-from conftest import MODES
+from conftest import MODES, GOLDEN
 
 
 def _S(case, mats):
@@ -127,3 +129,25 @@ def test_build_scores_bit_exact_vs_reference_extension():
             m = oracle.build_scores([p1], [p2], [S])
             r = oracle.ref_build_scores([p1], [p2], [S])
         assert np.array_equal(m, r)
+
+
+def test_cluster_oracle_vs_reference_golden():
+    """oracle.cluster_merge_order against merge orders produced by the reference's own
+    HierarchicalClusteringAlgorithm (tests/golden/make_cluster_golden.py)."""
+    import json
+    with open(os.path.join(GOLDEN, "cluster.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 30
+    for c in cases:
+        got = oracle.cluster_merge_order(np.asarray(c["dist"], np.float32), c["linkage"])
+        assert [list(x) for x in got] == c["order"], (c["n"], c["kind"], c["linkage"])
+
+
+def test_tree_distance_matrix_matches_reference_expression():
+    rng = np.random.default_rng(3)
+    n = 9
+    sc = rng.integers(-300, -10, n * (n - 1) // 2).astype(np.float32)     # all negative: d.max() is the diagonal 0
+    dist = oracle.tree_distance_matrix(sc, n)
+    assert dist.dtype == np.float32 and (np.diag(dist) == 0).all() and dist.min() == 0
+    iu = np.triu_indices(n, k=1)
+    assert np.array_equal(dist[iu], -sc) and np.array_equal(dist, dist.T)

@@ -158,11 +158,49 @@ def test_guide_tree_through_batch_manager():
         env = {'gap_series': [-11.0, -1.0], 'linkage_method': 'average', 'dist_mode': dist,
                'aligner': pc.PairwiseAligner.tid}
         want, _ = R.run_task(Manager(R.reference_index()), pc.GuideTreeBuilder, env, **kw)
-        mgr = plugin.GpuBatchManager(R.reference_index())
+        # the reference's GuideTreeBuilder on the batching manager: one batched launch for its tasks
+        mgr = plugin.GpuBatchManager(R.reference_index(), gpu_tree=False)
         got, msgs = R.run_task(mgr, pc.GuideTreeBuilder, env, **kw)
         assert got['guide_tree'].merge_orders == want['guide_tree'].merge_orders
         assert mgr.batched_requests == 14 * 13 // 2
         assert sum(1 for m in msgs if m.kind == "complete") >= 14 * 13 // 2
+        # the GPU GuideTreeBuilder (all-vs-all launch + clustering kernel) under the same type id
+        mgr = plugin.GpuBatchManager(R.reference_index())
+        got, msgs = R.run_task(mgr, pc.GuideTreeBuilder, env, **kw)
+        assert got['guide_tree'].merge_orders == want['guide_tree'].merge_orders
+        assert all(isinstance(a, int) and isinstance(b, int) for a, b in got['guide_tree'].merge_orders)
+        assert mgr.batched_requests == (0 if dist != "semiglobal_auto" else 14 * 13 // 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("linkage", ["single", "complete", "average"])
+def test_gpu_guide_tree_on_profile_tracks(linkage):
+    """The tree stage of the MSA workflow runs on preprofile tracks (workflow.py:164-181): f32
+    profile x profile scores, clustered on the device, same merge order as the reference."""
+    sm = _blosum()
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i in range(11):
+        L = int(rng.integers(40, 70))
+        counts = np.zeros((L, ALPHABET_AA.size), np.int64)
+        for _ in range(int(rng.integers(1, 6))):
+            counts[np.arange(L), rng.integers(0, 20, L)] += 1
+        seqs.append(Sequence("p%d" % i, [(TRACK_ID_PREPROFILE, ProfileTrack(counts, ALPHABET_AA))]))
+    kw = dict(sequences=seqs, track_id_sets=[[TRACK_ID_PREPROFILE]], score_matrices=[sm])
+    env = {'gap_series': [-11.0, -1.0], 'linkage_method': linkage, 'dist_mode': 'global',
+           'aligner': pc.PairwiseAligner.tid}
+    want, _ = R.run_task(Manager(R.reference_index()), pc.GuideTreeBuilder, env, **kw)
+    got, _ = R.run_task(plugin.GpuBatchManager(R.reference_index()), pc.GuideTreeBuilder, env, **kw)
+    assert got['guide_tree'].merge_orders == want['guide_tree'].merge_orders
+
+
+def test_guide_tree_component_mirrors_reference():
+    ref, gpu = pc.GuideTreeBuilder, plugin.GpuGuideTreeBuilder
+    assert gpu.tid == ref.tid
+    assert set(gpu.inputs) == set(ref.inputs) and set(gpu.outputs) == set(ref.outputs)
+    assert gpu.options == ref.options
+    assert {k: v for k, v in gpu.defaults.items() if k != 'aligner_env'} == \
+           {k: v for k, v in ref.defaults.items() if k != 'aligner_env'}
 
 
 @pytest.mark.gpu
