@@ -88,6 +88,10 @@ class _PreprofileBatch(object):
         self.masters.append(master_idx)
         self.slaves.append(slave_idx)
 
+    def add_many(self, master_idx, slave_idxs):
+        self.masters.extend([master_idx] * len(slave_idxs))
+        self.slaves.extend(slave_idxs)
+
     def counts(self, master_idx):
         if self.result is None:
             g = self.group
@@ -97,6 +101,19 @@ class _PreprofileBatch(object):
         off, length = where[int(master_idx)]
         A = self.group.S.shape[0]
         return cnt[off:off + length * A].reshape(length, A).copy()
+
+
+class _RangePicks(object):
+    """(group, pair number) of every slave of one master: pairs k0 .. k0+n-1 of the group."""
+
+    def __init__(self, group, k0, n):
+        self.group, self.k0, self.n = group, k0, n
+
+    def __iter__(self):
+        return iter((self.group, k) for k in range(self.k0, self.k0 + self.n))
+
+    def __len__(self):
+        return self.n
 
 
 class LazyMasterSlaveAlignment(Alignment):
@@ -453,9 +470,9 @@ class _Group(object):
         self.seq_index = {}
         self.seqs = []
         self.pi, self.pj = [], []
-        self.scores = None
+        self._scores = None
         self.paths = None
-        self.batch = None
+        self._batch = None
 
     def add_seq(self, track, arr):
         k = id(track)
@@ -469,9 +486,28 @@ class _Group(object):
         self.pj.append(self.add_seq(t2, b))
         return len(self.pi) - 1
 
+    def add_pairs(self, one_idx, two_idxs):
+        """Bulk form: sequence one against many sequences two; returns the first pair number."""
+        k0 = len(self.pi)
+        self.pi.extend([one_idx] * len(two_idxs))
+        self.pj.extend(two_idxs)
+        return k0
+
+    @property
+    def batch(self):
+        if self._batch is None:
+            self._batch = get_engine().batch(self.seqs)
+        return self._batch
+
+    @property
+    def scores(self):
+        """Score per pair, computed by one score-only launch on first use."""
+        if self._scores is None:
+            self._scores, _ = get_engine().align_pairs(self.batch, self.pi, self.pj, self.S, self.gaps, mode=self.mode)
+        return self._scores
+
     def run_scores(self, eng):
-        self.batch = eng.batch(self.seqs)
-        self.scores, _ = eng.align_pairs(self.batch, self.pi, self.pj, self.S, self.gaps, mode=self.mode)
+        self.scores
 
     def path(self, k):
         if self.paths is None:   # first access traces the whole group at once
@@ -651,7 +687,91 @@ class GpuBatchManager(Manager):
             self.batched_requests += 1
 
     # -- GlobalMasterSlaveAligner requests (preprofile.py:67-156) --------------------------------
+    def _bulk_master_slave(self, requests, idxs, parent_tag, handled):
+        """The common shape of the preprofile stage (workflow.py:139-161): N requests over ONE set of
+        plain-track sequences, one track set, one matrix, one aligner environment.  Every sequence
+        is validated once (the per-pair checks of PairwiseAligner.execute, component/align.py:114-189,
+        are per-sequence properties) and the N(N-1) ordered pairs are filed with list operations
+        only -- no per-pair Python.  Returns False when the requests do not have that shape."""
+        eng = get_engine()
+        if self.index.resolve(PAIRWISE_TID) is not GpuPairwiseAligner:
+            return False
+        first = requests[idxs[0]][1]
+        track_ids, mats = first['track_id_sets'], first['score_matrices']
+        if len(track_ids) != 1 or len(track_ids[0]) != 1 or len(mats) < 1:
+            return False
+        tid0 = track_ids[0][0]
+        comp = self.index.resolve(GLOBAL_MS_TID)
+        envs = []
+        key0 = None
+        for n in idxs:
+            _, inputs, _, env0 = requests[n]
+            if inputs['track_id_sets'] != track_ids or len(inputs['score_matrices']) != len(mats) or \
+                    any(a is not b for a, b in zip(inputs['score_matrices'], mats)):
+                return False
+            env = Environment(keys=env0.keys, component=comp)
+            if env['aligner'] != PAIRWISE_TID:
+                return False
+            sub_env = Environment(keys=env['aligner_env'].keys, component=GpuPairwiseAligner, parent=env)
+            key = (tuple(sub_env['gap_series']), sub_env['debug'], env['score_threshold'])
+            if key0 is None:
+                key0 = key
+            if key != key0 or sub_env['debug'] != 0:
+                return False
+            envs.append(env)
+        gap_series, _, threshold = key0
+        # one validation per distinct sequence
+        seq_idx, tracks = {}, []
+        try:
+            for n in idxs:
+                inputs = requests[n][1]
+                for seq in [inputs['master_sequence']] + list(inputs['slave_sequences']):
+                    if id(seq) not in seq_idx:
+                        sets, gaps = _prepare(seq, seq, track_ids, track_ids, mats, list(gap_series))
+                        if sets[0][0].tid != PlainTrack.tid:
+                            return False
+                        seq_idx[id(seq)] = len(tracks)
+                        tracks.append(sets[0][0])
+        except (ComponentError, DataError):
+            return False        # the per-request path reports it the reference's way
+        arrs = [np.asarray(t.values) for t in tracks]
+        S = mats[0].matrix.astype(np.float32)
+        longest = max(len(a) for a in arrs)
+        if min(len(a) for a in arrs) < 1 or eng.k_for(longest) is None or \
+                not eng.integer_exact(S, gaps[0], gaps[1], longest):
+            return False
+        g = _Group("global", S, gaps)
+        for t, a in zip(tracks, arrs):
+            g.add_seq(t, a)
+        pre = _PreprofileBatch(g, threshold)
+        self._bulk_out = []
+        for n, env in zip(idxs, envs):
+            _, inputs, tag, _ = requests[n]
+            master, slaves = inputs['master_sequence'], inputs['slave_sequences']
+            midx = seq_idx[id(master)]
+            sidx = [seq_idx[id(s_)] for s_ in slaves]
+            k0 = g.add_pairs(midx, sidx)
+            pre.add_many(midx, sidx)
+            alignment = LazyMasterSlaveAlignment(master, slaves, _RangePicks(g, k0, len(sidx)), threshold, tid0, pre, midx)
+            self._bulk_out.append((n, tag, alignment, len(sidx)))
+        return True
+
     def _batched_master_slave(self, requests, idxs, parent_tag, handled):
+        if len(idxs) > 1 and self._bulk_master_slave(requests, idxs, parent_tag, handled):
+            for n, tag, alignment, npairs in self._bulk_out:
+                begin = BeginMessage(parent_tag)
+                begin.tag = tag
+                yield begin
+                prog = ProgressMessage(1.0)
+                prog.tag = tag
+                yield prog
+                done = CompleteMessage({'alignment': alignment})
+                done.tag = tag
+                yield done
+                handled.add(n)
+                self.batched_requests += npairs
+            self._bulk_out = []
+            return
         eng = get_engine()
         groups, plans = {}, {}
         for n in idxs:

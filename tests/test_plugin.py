@@ -257,3 +257,45 @@ def test_long_sequences_fall_back_to_general_kernels():
     want, _ = R.run_task(Manager(R.reference_index()), pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
     got, _ = R.run_task(plugin.GpuBatchManager(R.reference_index()), pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
     _same_alignment(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threshold", [None, 250.0])
+def test_bulk_master_slave_matches_reference(threshold):
+    """N GlobalMasterSlaveAligner requests in one Execution (workflow.py:139-161) take the bulk
+    path: the lazily built alignments and the device count tables (ProfileBuilder) equal the
+    reference's, with and without a score threshold (preprofile.py:145)."""
+    from praline.core import Execution
+    sm = _blosum()
+    fam = synth.family(31, 9, 70)
+    outs, profs = [], []
+    for mk_mgr in (lambda: Manager(R.reference_index()), lambda: plugin.GpuBatchManager(R.reference_index())):
+        mgr = mk_mgr()
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+        ex = Execution(mgr, R.ROOT_TAG)
+        for i, master in enumerate(seqs):
+            t = ex.add_task(pc.GlobalMasterSlaveAligner)
+            t.environment(Environment(keys={'gap_series': [-11.0, -1.0], 'score_threshold': threshold,
+                                            'aligner': pc.PairwiseAligner.tid}))
+            t.inputs(master_sequence=master, slave_sequences=[s for j, s in enumerate(seqs) if j != i],
+                     track_id_sets=[[TRACK_ID_INPUT]], score_matrices=[sm])
+        for _ in ex.run():
+            pass
+        alns = [o['alignment'] for o in ex.outputs]
+        # ProfileBuilder on every alignment (the device count tables on the GPU manager) ...
+        ex2 = Execution(mgr, R.ROOT_TAG)
+        for a in alns:
+            t = ex2.add_task(pc.ProfileBuilder)
+            t.environment(Environment(keys={}))
+            t.inputs(alignment=a, track_id=TRACK_ID_INPUT)
+        for _ in ex2.run():
+            pass
+        profs.append([o['profile_track'].counts for o in ex2.outputs])
+        # ... and the alignments themselves (lazy on the GPU manager)
+        outs.append([(np.asarray(a.path), [it.name for it in a.items]) for a in alns])
+        if isinstance(mgr, plugin.GpuBatchManager):
+            assert mgr.batched_requests == 9 * 8
+    for (p0, n0), (p1, n1) in zip(*outs):
+        assert n0 == n1 and np.array_equal(p0, p1)
+    for c0, c1 in zip(*profs):
+        assert np.array_equal(c0, c1)

@@ -8,7 +8,7 @@ from praline.container import Sequence, PlainTrack, ALPHABET_AA, TRACK_ID_INPUT
 pre, msa = sys.argv[1], sys.argv[2]
 with praline.open_builtin('matrices/blosum62') as f:
     sm = praline.load_score_matrix(f, alphabet=ALPHABET_AA)
-fam = synth.family(1, 50, 300)
+fam = synth.family(1, int(sys.argv[3]) if len(sys.argv) > 3 else 50, 300)
 mk = lambda: [Sequence("s%d" % i, [(TRACK_ID_INPUT, PlainTrack(None, ALPHABET_AA, raw_indices=s))]) for i, s in enumerate(fam)]
 mgr = plugin.GpuBatchManager(R.reference_index())
 R.workflow_fasta(mgr, mk()[:4], sm, pre, msa)
