@@ -1019,39 +1019,82 @@ __global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int 
 // consecutive too): PgRowBlock = {first matrix row, profile row of that matrix row, rows,
 // resident sequence, first row is the region's dummy row}.  Same evaluation order as
 // k_build_scores; `transposed` says the resident is sequence one.
+//
+// Both operands are compacted to their NONZERO entries first (ascending symbol, the order of
+// build_nonzero_matrix, component/align.py:449-458): the 32 streamed rows once per block by
+// ballot, the thread's own resident row into a [entry][thread] table.  A cell then costs
+// nnz1 x nnz2 terms of {LDS.64 (value, S offset), LDS S, FMUL, FMUL, FADD}; S is padded to an odd
+// row stride so that threads on different symbols hit different banks.
 __global__ void __launch_bounds__(128) k_build_rows(const float* __restrict__ prof, const int64_t* __restrict__ rowoff,
                                                     int A, const float* __restrict__ S,
                                                     const PgRowBlock* __restrict__ blocks, int width,
                                                     int transposed, float padv, float* __restrict__ mwave)
 {
-    extern __shared__ float sh[];   // S [A*A] then the streamed profile rows [32][A]
+    extern __shared__ __align__(16) float sh[];
+    const int AS = (A <= 32) ? 33 : (A | 1);
+    float* sS = sh;                                             // [A][AS]
+    float2* sstr = reinterpret_cast<float2*>(sS + ((A * AS + 1) & ~1));   // [32][A] (value, S offset) of streamed rows
+    float* rval = reinterpret_cast<float*>(sstr + 32 * A);      // [A][128] resident values
+    int* roff = reinterpret_cast<int*>(rval + A * 128);         // [A][128] resident S offsets
+    __shared__ int scnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int xblocks = (width + 127) / 128;
     const PgRowBlock blk = blocks[blockIdx.x / xblocks];
-    const int x = (int)(blockIdx.x % xblocks) * 128 + threadIdx.x;
-    float* srows = sh + A * A;
-    for (int i = threadIdx.x; i < A * A; i += 128) sh[i] = S[i];
-    for (int i = threadIdx.x; i < blk.rows * A; i += 128) {
-        const int rr = i / A, c = i % A;
-        srows[i] = (blk.dummy && rr == 0) ? 0.f : prof[(size_t)(blk.src0 + rr) * A + c];
+    const int x = (int)(blockIdx.x % xblocks) * 128 + tid;
+    for (int i = tid; i < A * A; i += 128) sS[(i / A) * AS + (i % A)] = S[i];
+    // streamed rows: the streamed sequence is sequence one when the resident is sequence two
+    // (row of S = its symbol, offset i*AS) and sequence two otherwise (column, offset j)
+    for (int r = warp; r < blk.rows; r += 4) {
+        int c = 0;
+        if (!(blk.dummy && r == 0)) {
+            const float* src = prof + (size_t)(blk.src0 + r) * A;
+            for (int base = 0; base < A; base += 32) {
+                const int i = base + lane;
+                const float p = i < A ? src[i] : 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, p != 0.f);
+                if (p != 0.f) sstr[r * A + c + __popc(m & ((1u << lane) - 1u))] = make_float2(p, __int_as_float(transposed ? i : i * AS));
+                c += __popc(m);
+            }
+        }
+        if (lane == 0) scnt[r] = c;
+    }
+    const int64_t q0 = rowoff[blk.res];
+    const int Lr = (int)(rowoff[blk.res + 1] - q0);
+    int nres = 0;
+    if (x < width && x < Lr) {
+        const float* rr_ = prof + (size_t)(q0 + x) * A;   // resident profile row
+        for (int i = 0; i < A; i++) {
+            const float p = rr_[i];
+            if (p != 0.f) { rval[nres * 128 + tid] = p; roff[nres * 128 + tid] = transposed ? i * AS : i; nres++; }
+        }
     }
     __syncthreads();
     if (x >= width) return;
-    const int64_t q0 = rowoff[blk.res];
-    const int Lr = (int)(rowoff[blk.res + 1] - q0);
-    const float* rr_ = prof + (size_t)(q0 + x) * A;   // resident profile row (x < Lr)
     for (int r = 0; r < blk.rows; r++) {
         float v = padv;
         if (blk.dummy && r == 0) v = 0.f;
         else if (x < Lr) {
-            const float* sr = srows + r * A;
+            const float2* sr = sstr + r * A;
+            const int ns = scnt[r];
             float acc = 0.f;
-            for (int i = 0; i < A; i++) {
-                const float p1 = transposed ? rr_[i] : sr[i];
-                if (p1 == 0.f) continue;
-                for (int j = 0; j < A; j++) {
-                    const float p2 = transposed ? sr[j] : rr_[j];
-                    if (p2 == 0.f) continue;
-                    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p2, sh[i * A + j]), p1));
+            if (transposed) {       // resident = sequence one: outer loop over MY entries, inner over the streamed row's
+                for (int a = 0; a < nres; a++) {
+                    const float p1 = rval[a * 128 + tid];
+                    const float* srow = sS + roff[a * 128 + tid];
+#pragma unroll 4
+                    for (int b = 0; b < ns; b++) {
+                        const float2 e = sr[b];
+                        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(e.x, srow[__float_as_int(e.y)]), p1));
+                    }
+                }
+            } else {                // resident = sequence two: outer loop over the streamed row, inner over MY entries
+                for (int a = 0; a < ns; a++) {
+                    const float2 e = sr[a];
+                    const float p1 = e.x;
+                    const float* srow = sS + __float_as_int(e.y);
+#pragma unroll 4
+                    for (int b = 0; b < nres; b++)
+                        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(rval[b * 128 + tid], srow[roff[b * 128 + tid]]), p1));
                 }
             }
             v = __fadd_rn(0.f, acc);
@@ -1244,8 +1287,10 @@ int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const 
     if (n_blocks <= 0) return 0;
     const int64_t nb = (int64_t)n_blocks * ((width + 127) / 128);
     if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
-    k_build_rows<<<(unsigned)nb, 128, sizeof(float) * (A * A + 32 * A), st>>>(prof, rowoff, A, S, blocks, width, transposed,
-                                                                              padv, mwave);
+    const int AS = (A <= 32) ? 33 : (A | 1);
+    const size_t sm = sizeof(float) * (size_t)(((A * AS + 1) & ~1) + 2 * 32 * A + 2 * 128 * A) + 16;
+    PG_CUDA_OK(cudaFuncSetAttribute(k_build_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_build_rows<<<(unsigned)nb, 128, sm, st>>>(prof, rowoff, A, S, blocks, width, transposed, padv, mwave);
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }

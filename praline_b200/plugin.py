@@ -28,7 +28,8 @@ from praline.core import (Component, Port, Environment, Execution, Manager, T, B
                           path_to_url)
 from praline.container import (Sequence, Alignment, ScoreMatrix, PlainTrack, ProfileTrack, MatchScoreModel,
                                GapScoreModel, SequenceTree)
-from praline.util import compress_path
+from praline.util import compress_path, auto_align_mode
+from praline.container import TRACK_ID_INPUT
 
 from . import _lib
 from .engine import get_engine, MODES
@@ -38,6 +39,7 @@ RAW_TID = "praline.component.RawPairwiseAligner"
 GLOBAL_MS_TID = "praline.component.GlobalMasterSlaveAligner"
 PROFILE_BUILDER_TID = "praline.component.ProfileBuilder"
 GUIDE_TREE_TID = "praline.component.GuideTreeBuilder"
+TREE_MSA_TID = "praline.component.TreeMultipleSequenceAligner"
 
 
 def _path_container(mode, path):
@@ -452,6 +454,118 @@ class GpuGuideTreeBuilder(Component):
         yield CompleteMessage({'guide_tree': SequenceTree(sequences, merges)})
 
 
+def merge_profile_counts(counts_one, counts_two, path):
+    """ProfileTrack.merge (container/sequence.py:205-239) without the per-column Python loop:
+    column i of the merged profile is the sum of the count rows the path step i -> i+1 consumes
+    (row path[i+1, 0] - 1 of profile one if index 0 advances, likewise for profile two).  The
+    reference accumulates in f32 and ProfileTrack casts to int (sequence.py:184); the same here."""
+    path = np.asarray(path)
+    step = (path[1:] - path[:-1]) > 0
+    merged = np.zeros((path.shape[0] - 1, counts_one.shape[1]), dtype=np.float32)
+    r1 = np.flatnonzero(step[:, 0])
+    merged[r1] += counts_one[path[r1 + 1, 0] - 1]
+    r2 = np.flatnonzero(step[:, 1])
+    merged[r2] += counts_two[path[r2 + 1, 1] - 1]
+    return merged
+
+
+def merge_alignment_paths(path_one, path_two, path):
+    """The path of Alignment.merge (container/align.py:30-61): row i of the merged path is row
+    path[i, 0] of alignment one next to row path[i, 1] of alignment two (-1 rows stay -1)."""
+    path = np.asarray(path)
+    one = np.where((path[:, 0] >= 0)[:, None], np.asarray(path_one)[np.maximum(path[:, 0], 0)], -1)
+    two = np.where((path[:, 1] >= 0)[:, None], np.asarray(path_two)[np.maximum(path[:, 1], 0)], -1)
+    return np.hstack([one, two]).astype(int)
+
+
+class GpuTreeMultipleSequenceAligner(Component):
+    """Drop-in for praline.component.TreeMultipleSequenceAligner (component/msa.py:22-247): same
+    type id, ports, options and defaults.  The progressive merge is a dependency chain of
+    profile x profile alignments (one per guide-tree node, msa.py:124-237), so it stays on one
+    GPU; every alignment still goes through the manager as a PairwiseAligner task (the general
+    K1 + K3 path), but the host glue between two launches -- ProfileTrack.merge and
+    Alignment.merge, per-column Python loops in the reference -- is vectorised
+    (merge_profile_counts, merge_alignment_paths).  Debug logging runs the reference component."""
+    tid = TREE_MSA_TID
+
+    inputs = {'sequences': Port([Sequence.tid]),
+              'guide_tree': Port(SequenceTree.tid),
+              'track_id_sets': Port([[str]]),
+              'score_matrices': Port([ScoreMatrix.tid])}
+    outputs = {'alignment': Port(Alignment.tid)}
+
+    options = {'gap_series': [float], 'aligner': str,
+               'aligner_env': Environment.tid, 'merge_mode': str,
+               'debug': int, 'log_track_ids': [str]}
+    defaults = {'gap_series': [-11.0, -1.0], 'aligner': PAIRWISE_TID,
+                'aligner_env': Environment({}), 'merge_mode': 'semiglobal',
+                'debug': 0, 'log_track_ids': [TRACK_ID_INPUT]}
+
+    def execute(self, sequences, guide_tree, track_id_sets, score_matrices):
+        merge_mode = self.environment['merge_mode']
+        if self.environment['debug'] > 0:
+            from praline.component import TreeMultipleSequenceAligner as _Reference
+            ref = _Reference(self.manager, self.environment, self.tag)
+            for msg in ref.execute(sequences, guide_tree, track_id_sets, score_matrices):
+                yield msg
+            return
+        if merge_mode not in {"global", "semiglobal", "semiglobal_auto"}:
+            raise ComponentError("unknown merge mode '{0}'".format(merge_mode))
+        track_ids = []
+        for id_set in track_id_sets:
+            for track_id in id_set:
+                if track_id not in track_ids:
+                    track_ids.append(track_id)
+        # per cluster: the count profile of every track (msa.py:71-97) and the alignment path
+        clusters, paths, members = {}, {}, {}
+        for i, seq in enumerate(sequences):
+            cluster = Sequence("Cluster #{0}".format(i), [])
+            for track_id in track_ids:
+                track = seq.get_track(track_id)
+                if track.tid == PlainTrack.tid:
+                    counts = np.zeros((len(track), track.alphabet.size), dtype=np.int32)
+                    counts[np.arange(len(track)), np.asarray(track.values)] = 1
+                    cluster.add_track(track_id, ProfileTrack(counts, track.alphabet))
+                elif track.tid == ProfileTrack.tid:
+                    cluster.add_track(track_id, ProfileTrack(np.array(track.counts, dtype=np.int32), track.alphabet))
+            clusters[i] = cluster
+            paths[i] = np.arange(len(seq) + 1).reshape(len(seq) + 1, 1)
+            members[i] = [seq]
+        index = self.manager.index
+        total = len(guide_tree.merge_orders)
+        for step, (i, j) in enumerate(guide_tree.merge_orders):
+            one, two = clusters[i], clusters[j]
+            if merge_mode == "semiglobal":
+                mode = "semiglobal_both"
+            elif merge_mode == "global":
+                mode = "global"
+            else:
+                mode = auto_align_mode(one, two)
+            execution = Execution(self.manager, self.tag)
+            task = execution.add_task(index.resolve(self.environment['aligner']))
+            task.environment(self.environment, self.environment['aligner_env'])
+            task.inputs(mode=mode, sequence_one=one, sequence_two=two, track_id_sets_one=track_id_sets,
+                        track_id_sets_two=track_id_sets, score_matrices=score_matrices)
+            for msg in execution.run():
+                yield msg
+            path = np.array(execution.outputs[0]['alignment'].path)
+            merged = []
+            for track_id in track_ids:
+                t1, t2 = one.get_track(track_id), two.get_track(track_id)
+                if t2.tid != t1.tid:
+                    raise DataError("can not merge with non-profile track {0}".format(t2.tid))
+                merged.append((track_id, ProfileTrack(merge_profile_counts(t1.counts, t2.counts, path), t1.alphabet)))
+                one.del_track(track_id)
+            for track_id, track in merged:
+                one.add_track(track_id, track)
+            paths[i] = merge_alignment_paths(paths[i], paths[j], path)
+            members[i] = members[i] + members[j]
+            del clusters[j], paths[j], members[j]
+            yield ProgressMessage(progress=(step + 1) / total)
+        first = next(iter(paths))
+        yield CompleteMessage(outputs={'alignment': Alignment(members[first], paths[first])})
+
+
 def register(index, tree=True):
     """Replace the CPU aligners and (tree=True) the guide-tree builder of a TypeIndex
     (manager.py:49-57) by the GPU ones."""
@@ -459,6 +573,7 @@ def register(index, tree=True):
     index.register(GpuRawPairwiseAligner)
     if tree:
         index.register(GpuGuideTreeBuilder)
+        index.register(GpuTreeMultipleSequenceAligner)
     return index
 
 

@@ -299,3 +299,61 @@ def test_bulk_master_slave_matches_reference(threshold):
         assert n0 == n1 and np.array_equal(p0, p1)
     for c0, c1 in zip(*profs):
         assert np.array_equal(c0, c1)
+
+
+def test_vectorised_merges_equal_reference_loops():
+    """merge_profile_counts / merge_alignment_paths against ProfileTrack.merge
+    (container/sequence.py:205-239) and Alignment.merge (container/align.py:30-61) on random
+    monotone paths."""
+    from praline.container import Alignment
+    rng = np.random.default_rng(1)
+    for trial in range(100):
+        L1, L2 = (int(v) for v in rng.integers(1, 30, 2))
+        y = x = 0
+        rows = [(0, 0)]
+        while (y, x) != (L1, L2):
+            opts = [(1, 1)] * (y < L1 and x < L2) + [(1, 0)] * (y < L1) + [(0, 1)] * (x < L2)
+            dy, dx = opts[int(rng.integers(len(opts)))]
+            y, x = y + dy, x + dx
+            rows.append((y, x))
+        path = np.array(rows)
+        t1 = ProfileTrack(rng.integers(0, 5, (L1, 27)), ALPHABET_AA)
+        t2 = ProfileTrack(rng.integers(0, 5, (L2, 27)), ALPHABET_AA)
+        want = t1.merge(t2, path).counts
+        got = ProfileTrack(plugin.merge_profile_counts(t1.counts, t2.counts, path), ALPHABET_AA).counts
+        assert np.array_equal(got, want)
+        n1, n2 = (int(v) for v in rng.integers(1, 4, 2))
+        p1, p2 = rng.integers(-1, 9, (L1 + 1, n1)), rng.integers(-1, 9, (L2 + 1, n2))
+        want = Alignment(list(range(n1)), p1).merge(Alignment(list(range(n2)), p2), path).path
+        got = plugin.merge_alignment_paths(p1, p2, path)
+        assert np.array_equal(got, want) and got.dtype == want.dtype
+
+
+def test_tree_msa_component_mirrors_reference():
+    ref, gpu = pc.TreeMultipleSequenceAligner, plugin.GpuTreeMultipleSequenceAligner
+    assert gpu.tid == ref.tid
+    assert set(gpu.inputs) == set(ref.inputs) and set(gpu.outputs) == set(ref.outputs)
+    assert gpu.options == ref.options
+    assert {k: v for k, v in gpu.defaults.items() if k != 'aligner_env'} == \
+           {k: v for k, v in ref.defaults.items() if k != 'aligner_env'}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("merge_mode", ["global", "semiglobal", "semiglobal_auto"])
+def test_tree_msa_component_matches_reference(merge_mode):
+    """TreeMultipleSequenceAligner on a fixed guide tree: the GPU component (vectorised merges,
+    K1 + K3 alignments) returns the reference's alignment path and item order."""
+    sm = _blosum()
+    fam = synth.family(61, 10, 55)
+    from praline.container import SequenceTree
+    tree_orders = [(0, 3), (1, 2), (4, 9), (0, 1), (5, 6), (7, 8), (0, 4), (5, 7), (0, 5)]
+    outs = []
+    for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+        env = {'gap_series': [-11.0, -1.0], 'merge_mode': merge_mode, 'aligner': pc.PairwiseAligner.tid}
+        out, _ = R.run_task(mgr, pc.TreeMultipleSequenceAligner, env, sequences=seqs,
+                            guide_tree=SequenceTree(seqs, tree_orders), track_id_sets=[[TRACK_ID_INPUT]],
+                            score_matrices=[sm])
+        outs.append(out['alignment'])
+    assert [s.name for s in outs[0].items] == [s.name for s in outs[1].items]
+    assert np.array_equal(np.asarray(outs[0].path), np.asarray(outs[1].path))
