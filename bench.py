@@ -356,15 +356,21 @@ def main():
         roof = {"bound": "cuda_core_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                # (profiles/r01_kstream_v2_raw.csv): 443 KB read, 0 B written (the 2 MB of scores stay in L2);
-                # algorithmic bytes per launch: 0.3 MB sequences + 0.1 MB tiles in, 2.0 MB scores out
-                "traffic": 443392,
+                # (profiles/r01_kstream16r_raw.csv: 427,520 B read, 0 B written -- the 2 MB of scores stay in
+                # L2; f32 kernel, profiles/r01_kstream_v2_raw.csv: 443,392 B); algorithmic bytes per launch:
+                # 0.3 MB sequences + 0.1 MB tiles in, 2.0 MB scores out
+                "traffic": 427520 if plan[5] else 443392,
                 "note": "DP-cell roofline (SURVEY 8d): algorithmic 11 f32 add/max per cell (the kernel issues 7); "
                         "peak = measured f32 add issue rate (%.2f warp-instr/ns/SM, wall clock) x 32 lanes x %d SMs "
                         "(of measured; SM clock %.0f MHz during the run); f32 max / compare / shift / integer ops "
                         "issue at half that rate on this part (pipe_rates, warp-instr/ns/SM); HBM is not the "
                         "bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
                 "issue_bound_frac": (my_cells / (kms * 1e-3)) * (2.5 if plan[5] else 7.0) / 32.0 / (mb["fadd"] * sms * 1e9),
+                # fraction of the speed of the BARE recurrence (no loads, shuffles or loop) measured on this
+                # box with the same instructions: 5 packed instructions per 2 cells (cell_mix16) or the
+                # 7-instruction f32 cell (cell_mix), warp-instructions/ns/SM
+                "recurrence_frac": (my_cells / (kms * 1e-3)) / ((mb["cell_mix16"] / 2.5 if plan[5] else mb["cell_mix"] / 7.0)
+                                                               * 32.0 * sms * 1e9),
                 "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence at the "
                                     "measured full issue rate: 5 packed DPX/add instructions per 2 cells (int16 "
                                     "kernel) or 7 per cell (f32 kernel); the DPX and max instructions themselves "
@@ -385,6 +391,17 @@ def main():
         torch.cuda.synchronize(dev)
         roof["traced_gcups"] = tcells / (ta.elapsed_time(tb_) * 1e-3) / 1e9
         roof["traced_note"] = "120000 pairs, fill with 4-bit traceback + per-pair path walk, device time incl. plan upload"
+        # the caller of the scores: distance matrix + clustering kernel on the device
+        ga, gb, gc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        eng.cluster_merge_order(eng.tree_distance(out, n), "average")
+        ga.record()
+        dmat = eng.tree_distance(out, n)
+        gb.record()
+        merges = eng.cluster_merge_order(dmat, "average")
+        gc.record()
+        torch.cuda.synchronize(dev)
+        roof["guide_tree"] = {"distance_ms": ga.elapsed_time(gb), "cluster_ms_incl_d2h": gb.elapsed_time(gc),
+                              "merges": len(merges), "note": "average linkage, merge order of util/cluster.py on %d sequences" % n}
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_port(seqs, S)
             roof["msa_e2e"] = msa_e2e()

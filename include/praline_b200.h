@@ -213,7 +213,8 @@ int pgpu_cluster_merge_order(int n, int linkage, const float* dist_dev, void* wo
  * measured warp-instructions per NANOSECOND per SM (wall clock, CUDA events) for (0) FADD, (1) FMNMX, (2) FMNMX3,
  * (3) the 4 FADD : 3 FMNMX mix of the score-only recurrence, (4) VIADDMNMX.S32,
  * (5) VIADDMNMX.S16x2, (6) SHFL, (7) LDS.128, out[8] = SM clock in MHz held during a burst,
- * (9) SHF, (10) IMAD, (11) LOP3, (12) IADD3.  n must be >= 13.
+ * (9) SHF, (10) IMAD, (11) LOP3, (12) IADD3, (13) the packed s16x2 recurrence of the int16 kernels
+ * (2 VIADD.16x2, 2 VIADDMNMX.S16x2, 1 VIMNMX3.S16x2 per two cells).  n must be >= 14.
  */
 int pgpu_microbench(double* out, int n);
 

@@ -757,10 +757,10 @@ class Engine(object):
         return [(int(a), int(b)) for a, b in merges.cpu().numpy().tolist()]
 
     def microbench(self):
-        out = (ctypes.c_double * 13)()
-        _lib.check(self.lib.pgpu_microbench(out, 13))
+        out = (ctypes.c_double * 14)()
+        _lib.check(self.lib.pgpu_microbench(out, 14))
         names = ["fadd", "fmnmx", "fmnmx3", "cell_mix", "viaddmnmx_s32", "viaddmnmx_s16x2", "shfl", "lds128", "sm_mhz",
-                 "shf", "imad", "lop3", "iadd3"]
+                 "shf", "imad", "lop3", "iadd3", "cell_mix16"]
         return dict(zip(names, [float(v) for v in out]))
 
 
