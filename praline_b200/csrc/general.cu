@@ -1103,6 +1103,136 @@ __global__ void __launch_bounds__(128) k_build_rows(const float* __restrict__ pr
     }
 }
 
+// k_build_rows for a resident that is SEQUENCE ONE (transposed launches), the orientation the
+// engine prefers for exact profile batches.  The first rounded product of a term,
+// fl(p2[x][j] * S[i][j]), depends only on the streamed row x and the symbol pair (i, j): the block
+// tabulates it once per streamed row, T[r][i][b] for the row's nonzero entries b (zero padded to a
+// multiple of four, rows of T at an odd multiple of 16 bytes so that threads on different symbols
+// i load from different banks).  A cell is then, per nonzero entry (i, p1) of the thread's own
+// resident row, ceil(nnz2 / 4) x {LDS.128, 4 FMUL, 4 FADD} in the reference's order -- 2.25
+// instructions per term instead of ~7, with the same two roundings per term.  A padded entry adds
+// fl(0 * p1) = 0, which leaves every partial sum unchanged.
+// one cell: for every nonzero entry (value p1, byte offset of row i of T) of the thread's resident row,
+// N4 quads of tabulated first products, in order (N4 is uniform for the streamed row -> no tail loop)
+template <int N4>
+__device__ __forceinline__ float rows_t_cell(uint32_t tr_s, uint32_t ent_s, int nres)
+{
+    float acc = 0.f;
+    for (int a = 0; a < nres; a++) {
+        float p1;
+        uint32_t off;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(p1), "=r"(off) : "r"(ent_s + (uint32_t)a * 1024u));
+        const uint32_t row = tr_s + off;
+        float4 t[N4];
+#pragma unroll
+        for (int b = 0; b < N4; b++)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t[b].x), "=f"(t[b].y), "=f"(t[b].z), "=f"(t[b].w) : "r"(row + (uint32_t)b * 16u));
+#pragma unroll
+        for (int b = 0; b < N4; b++) {
+            acc = __fadd_rn(acc, __fmul_rn(t[b].x, p1));
+            acc = __fadd_rn(acc, __fmul_rn(t[b].y, p1));
+            acc = __fadd_rn(acc, __fmul_rn(t[b].z, p1));
+            acc = __fadd_rn(acc, __fmul_rn(t[b].w, p1));
+        }
+    }
+    return acc;
+}
+
+template <int RB>
+__global__ void __launch_bounds__(128) k_build_rows_t(const float* __restrict__ prof, const int64_t* __restrict__ rowoff,
+                                                      int A, int ST, const float* __restrict__ S,
+                                                      const PgRowBlock* __restrict__ blocks, int width,
+                                                      float padv, float* __restrict__ mwave)
+{
+    extern __shared__ __align__(16) float sh[];
+    float* T = sh;                                              // [RB][A][ST]
+    float* sS = T + RB * A * ST;                                // [A][A]
+    float2* rent = reinterpret_cast<float2*>(sS + ((A * A + 3) & ~3));   // [A][128] my resident row: (value, byte offset i * ST * 4)
+    float* sval = reinterpret_cast<float*>(rent + A * 128);     // [RB][A] streamed rows: values
+    int* sj = reinterpret_cast<int*>(sval + RB * A);            // [RB][A] ... and symbols j
+    __shared__ int scnt[RB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int xblocks = (width + 127) / 128;
+    const PgRowBlock blk = blocks[blockIdx.x / xblocks];
+    const int x = (int)(blockIdx.x % xblocks) * 128 + tid;
+    for (int i = tid; i < A * A; i += 128) sS[i] = S[i];
+    const int64_t q0 = rowoff[blk.res];
+    const int Lr = (int)(rowoff[blk.res + 1] - q0);
+    const bool mine = x < width && x < Lr;
+    int nres = 0;
+    if (mine) {
+        const float* rr_ = prof + (size_t)(q0 + x) * A;
+        for (int i = 0; i < A; i++) {
+            const float p = rr_[i];
+            if (p != 0.f) { rent[nres * 128 + tid] = make_float2(p, __int_as_float(i * ST * 4)); nres++; }
+        }
+    }
+    const uint32_t ent_s = (uint32_t)__cvta_generic_to_shared(rent + tid);
+    const uint32_t T_s = (uint32_t)__cvta_generic_to_shared(T);
+    for (int r0 = 0; r0 < blk.rows; r0 += RB) {
+        const int nr = min(RB, blk.rows - r0);
+        __syncthreads();                                        // the previous pass is done with T
+        for (int r = warp; r < nr; r += 4) {                    // compact the streamed rows (ascending symbol)
+            int c = 0;
+            if (!(blk.dummy && r0 + r == 0)) {
+                const float* src = prof + (size_t)(blk.src0 + r0 + r) * A;
+                for (int base = 0; base < A; base += 32) {
+                    const int j = base + lane;
+                    const float p = j < A ? src[j] : 0.f;
+                    const unsigned m = __ballot_sync(0xffffffffu, p != 0.f);
+                    if (p != 0.f) { const int at = r * A + c + __popc(m & ((1u << lane) - 1u)); sval[at] = p; sj[at] = j; }
+                    c += __popc(m);
+                }
+            }
+            if (lane == 0) scnt[r] = c;
+        }
+        __syncthreads();
+        for (int e = tid; e < nr * A * ST; e += 128) {          // T[r][i][b] = fl(p2_b * S[i][j_b]), zero padded
+            const int b = e % ST, i = (e / ST) % A, r = e / (ST * A);
+            T[e] = b < scnt[r] ? __fmul_rn(sval[r * A + b], sS[i * A + sj[r * A + b]]) : 0.f;
+        }
+        __syncthreads();
+        if (x < width) {
+            for (int r = 0; r < nr; r++) {
+                float v = padv;
+                if (blk.dummy && r0 + r == 0) v = 0.f;
+                else if (mine) {
+                    const uint32_t tr_s = T_s + (uint32_t)(r * A * ST) * 4u;
+                    const int n4 = (scnt[r] + 3) >> 2;
+                    float acc;
+                    switch (n4) {       // uniform per streamed row
+                        case 0: acc = 0.f; break;
+                        case 1: acc = rows_t_cell<1>(tr_s, ent_s, nres); break;
+                        case 2: acc = rows_t_cell<2>(tr_s, ent_s, nres); break;
+                        case 3: acc = rows_t_cell<3>(tr_s, ent_s, nres); break;
+                        case 4: acc = rows_t_cell<4>(tr_s, ent_s, nres); break;
+                        case 5: acc = rows_t_cell<5>(tr_s, ent_s, nres); break;
+                        case 6: acc = rows_t_cell<6>(tr_s, ent_s, nres); break;
+                        case 7: acc = rows_t_cell<7>(tr_s, ent_s, nres); break;
+                        default: {      // alphabets beyond 28 symbols per row
+                            acc = 0.f;
+                            for (int a = 0; a < nres; a++) {
+                                const float2 e = rent[a * 128 + tid];
+                                const float4* row = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(T + r * A * ST) + __float_as_int(e.y));
+                                for (int b = 0; b < n4; b++) {
+                                    const float4 t = row[b];
+                                    acc = __fadd_rn(acc, __fmul_rn(t.x, e.x));
+                                    acc = __fadd_rn(acc, __fmul_rn(t.y, e.x));
+                                    acc = __fadd_rn(acc, __fmul_rn(t.z, e.x));
+                                    acc = __fadd_rn(acc, __fmul_rn(t.w, e.x));
+                                }
+                            }
+                        }
+                    }
+                    v = __fadd_rn(0.f, acc);
+                }
+                mwave[(size_t)(blk.row0 + r0 + r) * width + x] = v;
+            }
+        }
+    }
+}
+
 // Tolerance-mode variant of k_build_rows for score-only profile batches (guide tree on deep
 // preprofiles): the contraction P1 . S . P2^T is factored through W = P_resident . S^T (or . S),
 // precomputed per sequence, so a cell costs A fused multiply-adds instead of nnz1 x nnz2
@@ -1287,6 +1417,27 @@ int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const 
     if (n_blocks <= 0) return 0;
     const int64_t nb = (int64_t)n_blocks * ((width + 127) / 128);
     if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
+    if (transposed && getenv("PGPU_NO_ROWS_T") == nullptr) {
+        // resident = sequence one: tabulated first products (k_build_rows_t) when the tables fit
+        int st4 = (A + 3) / 4;
+        if (!(st4 & 1)) st4++;
+        const int ST = 4 * st4;
+        auto need = [&](int rb) {
+            return sizeof(float) * ((size_t)rb * A * ST + ((A * A + 3) & ~3) + 2 * (size_t)128 * A + 2 * (size_t)rb * A) + 16;
+        };
+#define PG_ROWS_T(RBV)                                                                                   \
+    do {                                                                                                 \
+        auto kern = k_build_rows_t<RBV>;                                                                 \
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(RBV))); \
+        kern<<<(unsigned)nb, 128, need(RBV), st>>>(prof, rowoff, A, ST, S, blocks, width, padv, mwave);  \
+        PG_CUDA_OK(cudaGetLastError());                                                                  \
+        return 0;                                                                                        \
+    } while (0)
+        if (need(8) <= 72 * 1024) PG_ROWS_T(8);
+        if (need(4) <= 72 * 1024) PG_ROWS_T(4);
+        if (need(2) <= 100 * 1024) PG_ROWS_T(2);
+#undef PG_ROWS_T
+    }
     const int AS = (A <= 32) ? 33 : (A | 1);
     const size_t sm = sizeof(float) * (size_t)(((A * AS + 1) & ~1) + 2 * 32 * A + 2 * 128 * A) + 16;
     PG_CUDA_OK(cudaFuncSetAttribute(k_build_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -473,7 +473,9 @@ class Engine(object):
         if n == 0:
             return np.zeros(0, np.float32)
         if resident is None:
-            resident = "one" if len(np.unique(pi)) < len(np.unique(pj)) else "two"
+            # exact score rows are cheapest with sequence one resident (k_build_rows_t tabulates the
+            # first product of every term per streamed row); tolerance mode does not care
+            resident = "one" if (not fast or len(np.unique(pi)) < len(np.unique(pj))) else "two"
         transposed = resident == "one"
         res, strm = (pi, pj) if transposed else (pj, pi)
         kcls = np.asarray([self.k_for(int(l)) or -1 for l in pbatch.lens])
