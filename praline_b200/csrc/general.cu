@@ -1188,9 +1188,17 @@ __global__ void __launch_bounds__(128) k_build_rows_t(const float* __restrict__ 
             if (lane == 0) scnt[r] = c;
         }
         __syncthreads();
-        for (int e = tid; e < nr * A * ST; e += 128) {          // T[r][i][b] = fl(p2_b * S[i][j_b]), zero padded
-            const int b = e % ST, i = (e / ST) % A, r = e / (ST * A);
-            T[e] = b < scnt[r] ? __fmul_rn(sval[r * A + b], sS[i * A + sj[r * A + b]]) : 0.f;
+        // T[r][i][b] = fl(p2_b * S[i][j_b]), zero padded: a warp per streamed row, a lane per entry b
+        // (no index divisions: they cost more than the table's multiplies)
+        for (int r = warp; r < nr; r += 4) {
+            const int ns = scnt[r];
+            for (int b = lane; b < ST; b += 32) {
+                const bool on = b < ns;
+                const float p2 = on ? sval[r * A + b] : 0.f;
+                const float* scol = sS + (on ? sj[r * A + b] : 0);
+                float* dst = T + (size_t)r * A * ST + b;
+                for (int i = 0; i < A; i++) dst[i * ST] = on ? __fmul_rn(p2, scol[i * A]) : 0.f;
+            }
         }
         __syncthreads();
         if (x < width) {

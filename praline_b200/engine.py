@@ -59,7 +59,7 @@ class SeqBatch(object):
     """A set of index sequences resident on the device (uint8 symbols + int64 offsets)."""
 
     def __init__(self, engine, seqs):
-        self.lens = np.asarray([len(s) for s in seqs], np.int64)
+        self.lens = np.fromiter((len(s) for s in seqs), np.int64, len(seqs))
         if len(seqs) == 0 or (self.lens <= 0).any():
             raise ValueError("empty sequences cannot be aligned")
         flat = np.concatenate([np.asarray(s) for s in seqs])
@@ -179,6 +179,12 @@ class Engine(object):
             if 32 * k >= length:
                 return k
         return None
+
+    def k_classes(self, lens):
+        """k_for over an array of lengths: columns-per-lane class per sequence, -1 beyond the limit."""
+        ks = np.asarray(self.k_set, np.int64)
+        pos = np.searchsorted(32 * ks, np.asarray(lens, np.int64), side="left")
+        return np.where(pos < len(ks), ks[np.minimum(pos, len(ks) - 1)], -1)
 
     def batch(self, seqs):
         return SeqBatch(self, seqs)
@@ -375,7 +381,7 @@ class Engine(object):
             resident = "one" if len(np.unique(pi)) < len(np.unique(pj)) else "two"
         transposed = resident == "one"
         res, strm = (pi, pj) if transposed else (pj, pi)
-        kcls = np.asarray([self.k_for(int(l)) or -1 for l in batch.lens])
+        kcls = self.k_classes(batch.lens)
         if (kcls[res] < 0).any():
             raise _lib.PralineGpuError("resident sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
         order = np.lexsort((np.arange(n), res, kcls[res]))
@@ -478,7 +484,7 @@ class Engine(object):
             resident = "one" if (not fast or len(np.unique(pi)) < len(np.unique(pj))) else "two"
         transposed = resident == "one"
         res, strm = (pi, pj) if transposed else (pj, pi)
-        kcls = np.asarray([self.k_for(int(l)) or -1 for l in pbatch.lens])
+        kcls = self.k_classes(pbatch.lens)
         if (kcls[res] < 0).any():
             raise _lib.PralineGpuError("resident profile longer than %d: use the general kernel" % (32 * self.k_set[-1]))
         order = np.lexsort((np.arange(n), res, kcls[res]))
@@ -548,7 +554,7 @@ class Engine(object):
         lens = batch.lens
         cs = np.zeros(n + 1, np.int64)
         np.cumsum(lens, out=cs[1:])
-        kcls = np.asarray([self.k_for(int(l)) or -1 for l in lens])
+        kcls = self.k_classes(lens)
         if (kcls[:max(n - 1, 1)] < 0).any():
             raise _lib.PralineGpuError("sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
         cond = lambda i, j: i * n - i * (i + 1) // 2 + (j - i - 1)
