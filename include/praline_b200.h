@@ -105,6 +105,18 @@ int pgpu_align_tiles16(int K, int paired, int transposed, const uint8_t* seqs_de
                        int A, int gap_open, int gap_extend, int neg, const float* topD_dev, int left0,
                        int left1, int border_len, float* scores_dev, void* stream);
 
+/* Traced form of pgpu_align_tiles16 (two streamed sequences per warp, any pair list): global mode,
+ * integer scores, every DP value within +-16000.  Writes the score per slot and the packed
+ * traceback words (4 rows x 2 register halves per 32-bit word, 0.5 B per cell), to be walked by
+ * pgpu_traceback_tiles with tb_fmt = 1 (tb_fmt = 0 is the f32 kernel's layout); emit_t carries the
+ * register half of a slot in bit 30.  Replaces the same reference chain as pgpu_align_tiles with
+ * traceback (cext.c:308-455, :99-306; component/align.py:357-431). */
+int pgpu_align_tiles16_traced(int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
+                              const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, const float* S_dev,
+                              int A, int gap_open, int gap_extend, int neg, const float* topD_dev, int left0, int left1,
+                              int border_len, float* scores_dev, uint32_t* tb_dev, const int64_t* tb_base_dev,
+                              int32_t* emit_t_dev, int64_t* pair_tb_dev, void* stream);
+
 /*
  * Traceback of an inter-task batch (K4).  Replaces get_paths (util/align.py:144-185), the
  * semiglobal end-cell scan (component/align.py:405-426) and extend_path_semiglobal
@@ -125,7 +137,7 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs_de
                          const int64_t* path_off_dev, int32_t* path_buf_dev, int32_t* path_start_dev,
                          int32_t* path_len_dev, const uint8_t* seqs_dev, int32_t* counts_dev,
                          const int64_t* cnt_off_dev, int A, const float* scores_dev, int use_threshold,
-                         float threshold, void* stream);
+                         float threshold, int tb_fmt, void* stream);
 
 /*
  * Match-score matrix (K1).  Replaces cext_build_scores (cext.c:308-455): m[y][x] = sum over

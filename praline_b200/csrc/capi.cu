@@ -97,15 +97,38 @@ int pgpu_align_tiles16(int K, int paired, int transposed, const uint8_t* seqs, c
     return pg_launch_stream16(a, n_tiles, K, paired, (cudaStream_t)stream);
 }
 
+// Traced form of pgpu_align_tiles16 (two streamed sequences per warp): global mode, integer scores,
+// every value within +-16000.  Traceback words in the packed layout (tb_fmt = 1 of
+// pgpu_traceback_tiles); emit_t carries the register half of the slot in bit 30.
+int pgpu_align_tiles16_traced(int K, int transposed, const uint8_t* seqs, const int64_t* offs, const int32_t* stream_ids,
+                              const void* tiles, int n_tiles, const float* S, int A, int gap_open, int gap_extend,
+                              int neg, const float* topD, int left0, int left1, int border_len, float* scores,
+                              uint32_t* tb, const int64_t* tb_base, int32_t* emit_t, int64_t* pair_tb, void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    if (border_len < 32 * K + 1) { pg_set_error("border array too short for K=%d", K); return 1; }
+    if (neg > -1 || neg < -16000) { pg_set_error("sentinel %d outside the traced int16 working range", neg); return 1; }
+    if (!tb || !tb_base || !emit_t || !pair_tb) { pg_set_error("traced launch needs the traceback buffers"); return 1; }
+    StreamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seqs = seqs; a.offs = offs; a.stream_ids = stream_ids; a.tiles = (const PgTile*)tiles;
+    a.S = S; a.A = A; a.transposed = transposed; a.topD = topD; a.border_len = border_len; a.scores = scores;
+    a.go16 = gap_open; a.ge16 = gap_extend; a.neg16 = neg; a.left0_16 = left0; a.left1_16 = left1;
+    a.tb = tb; a.tb_base = tb_base; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    return pg_launch_stream16(a, n_tiles, K, 0, (cudaStream_t)stream);
+}
+
 int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, const int32_t* slot_resident,
                          const int32_t* slot_stream, int64_t n_slots, const uint64_t* keys,
                          const uint32_t* tb, const int32_t* emit_t, const int64_t* pair_tb, int code00,
                          int top_ramp, int left_ramp, const int64_t* path_off, int32_t* path_buf,
                          int32_t* path_start, int32_t* path_len, const uint8_t* seqs, int32_t* counts,
-                         const int64_t* cnt_off, int A, const float* scores, int use_thr, float thr, void* stream)
+                         const int64_t* cnt_off, int A, const float* scores, int use_thr, float thr, int tb_fmt,
+                         void* stream)
 {
     TraceArgs a;
     memset(&a, 0, sizeof(a));
+    a.tb_fmt = tb_fmt;
     a.n_slots = n_slots; a.mode = mode; a.K = K; a.transposed = transposed; a.offs = offs;
     a.slot_resident = slot_resident; a.slot_stream = slot_stream; a.tb = tb; a.emit_t = emit_t;
     a.pair_tb = pair_tb;

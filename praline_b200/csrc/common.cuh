@@ -85,6 +85,7 @@ struct TraceArgs {
     const float* scores;            // per slot, for the score threshold
     int use_thr;
     float thr;
+    int tb_fmt;                     // 0: f32 kernel's nibbles, 8 rows per word; 1: packed int16 kernel's words (4 rows x 2 halves)
 };
 
 // Arguments of the general single-alignment path (general.cu).

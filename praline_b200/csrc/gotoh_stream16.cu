@@ -17,6 +17,15 @@
 // sentinel NEG, chosen by the host below every reachable value minus the largest score, and
 // the host only routes a launch here when |go| + (|ge| + max|S|) * (L1 + L2) and the sentinel
 // arithmetic fit (Engine.fits_s16).  Otherwise the f32 kernel runs.
+//
+// Traced variant (TB).  The four tie tests of a cell compare a value with a maximum it took part
+// in (a <= b always), so "a == b" is the sign of  b + ~a = b - a - 1  per 16-bit half: packed adds
+// of complements, no packed subtract or compare exists.  Two PRMTs with sign replication turn the
+// eight sign bits of a column step (4 tests x 2 halves) into byte masks, two LOP3s keep one bit
+// per test, and one IMAD shifts them into the column's word: four rows of both halves per 32-bit
+// word, stored [step/4][k][lane] (coalesced 128-byte lines, 0.5 B per cell like the f32 kernel).
+// 18 instructions per TWO cells against 16 per cell in f32.  The host routes a traced global
+// batch here only when all values stay within +-16000 (the tests need b - a - 1 inside int16).
 #include "common.cuh"
 
 #define FLAG_LAST 0x80000000u
@@ -24,6 +33,13 @@
 #define FULL 0xffffffffu
 
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)(v & 0xffff)) | ((uint32_t)v << 16); }
+// generic PRMT: a selector nibble with bit 3 set replicates the sign of the selected byte
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 template <int K>
 __device__ __forceinline__ uint32_t pick_u(const uint32_t (&v)[K], int k)
@@ -34,10 +50,11 @@ __device__ __forceinline__ uint32_t pick_u(const uint32_t (&v)[K], int k)
     return r;
 }
 
-template <int K, int NW>
+// TB: write packed traceback words.  TR: tie order of a transposed (resident = sequence one) launch.
+template <int K, int NW, bool TB, bool TR>
 __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
 {
-    constexpr int UNR = 4;
+    constexpr int UNR = 4;                  // = the four rows of one traceback word
     constexpr int NCH = (K + 7) / 8;        // 16-byte chunks of 8 int16 columns per lane
     constexpr int ROWB = NCH * 512;
     constexpr int KP = (K + 3) & ~3;        // top-border table, words per lane
@@ -106,8 +123,14 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
     const uint32_t* mytop = top2 + lane * (KP + 4);
 
     uint32_t Mo[K], U[K], D[K];
+    uint32_t nMo[TB ? K : 1], acc[TB ? K : 1];     // traced: ~Mo of the previous row, flag word per column
 #pragma unroll
     for (int k = 0; k < K; k++) { Mo[k] = 0u; U[k] = 0u; D[k] = 0u; }
+    if (TB) {
+#pragma unroll
+        for (int k = 0; k < K; k++) { nMo[k] = ~0u; acc[k] = 0u; }
+    }
+    const int64_t tbw0 = TB ? a.tb_base[(int64_t)blockIdx.x * NW + warp] : 0;
     uint32_t Mo_last = 0u, L_last = 0u, D_last = 0u, Dleft_prev = 0u, bord = 0u;
     int qA = sb, qB = mid;
     int psA = sb - 1, ppA = 0, psB = mid - 1, ppB = 0;   // producer cursors (element, offset)
@@ -178,6 +201,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
                 bord = __vadd2(bord, left1_2);
                 uint32_t diag = Dleft_prev;
                 Dleft_prev = Dn;
+                uint32_t nMl = ~Ml;
 
 #pragma unroll
                 for (int k = 0; k < K; k++) {
@@ -190,6 +214,21 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
                     diag = D[k];
                     const uint32_t d = __vimax3_s16x2(m, u, l);
                     const uint32_t mo = __vadd2(m, go2);
+                    if (TB) {
+                        // sign per half = "equal": M is the maximum | the first-priority gap state is |
+                        // U was opened | L was opened (ties keep the reference's priority)
+                        const uint32_t nmo = ~mo;
+                        const uint32_t t1 = __vadd2(d, ~m);
+                        const uint32_t t2 = __vadd2(d, ~(TR ? l : u));
+                        const uint32_t t3 = __vadd2(u, nMo[k]);
+                        const uint32_t t4 = __vadd2(l, nMl);
+                        const uint32_t p12 = prmt(t1, t2, 0xBF9Du);     // bytes: t1.B t2.B t1.A t2.A as 0x00 / 0xff
+                        const uint32_t p34 = prmt(t3, t4, 0xBF9Du);
+                        const uint32_t q = (p12 & 0x02020202u) | (p34 & 0x01010101u);
+                        acc[k] = (i == 0) ? q : acc[k] * 4u + q;
+                        nMo[k] = nmo;
+                        nMl = nmo;
+                    }
                     Mo[k] = mo;
                     U[k] = u;
                     D[k] = d;
@@ -199,13 +238,26 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
                 Mo_last = Ml;
                 L_last = Ll;
                 D_last = D[K - 1];
+                if (TB && i == UNR - 1) {
+                    uint32_t* dst = a.tb + tbw0 + (int64_t)((t0 + g) >> 2) * (K * 32) + lane;
+#pragma unroll
+                    for (int k = 0; k < K; k++) dst[k * 32] = acc[k];
+                }
 
                 if ((int)(wA | wB) < 0) {   // a LAST row in one of the two streams
                     const bool lastA = (int)wA < 0, lastB = (int)wB < 0;
                     if (lane == lr) {
                         const uint32_t dv = pick_u<K>(D, klast);
-                        if (lastA && (wA & FLAG_EMIT)) a.scores[tile.out_base + (qA - tile.stream_begin)] = (float)(int)(int16_t)(dv & 0xffffu);
-                        if (lastB && (wB & FLAG_EMIT)) a.scores[tile.out_base + (qB - tile.stream_begin)] = (float)(int)(int16_t)(dv >> 16);
+                        if (lastA && (wA & FLAG_EMIT)) {
+                            const int64_t slot = tile.out_base + (qA - tile.stream_begin);
+                            a.scores[slot] = (float)(int)(int16_t)(dv & 0xffffu);
+                            if (TB) { a.emit_t[slot] = t0 + g + i; a.pair_tb[slot] = tbw0; }
+                        }
+                        if (lastB && (wB & FLAG_EMIT)) {
+                            const int64_t slot = tile.out_base + (qB - tile.stream_begin);
+                            a.scores[slot] = (float)(int)(int16_t)(dv >> 16);
+                            if (TB) { a.emit_t[slot] = (t0 + g + i) | (1 << 30); a.pair_tb[slot] = tbw0; }   // bit 30: high half
+                        }
                     }
                     if (lastA && (wA & FLAG_EMIT)) qA++;
                     if (lastB && (wB & FLAG_EMIT)) qB++;
@@ -220,6 +272,10 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
                     }
                     Dleft_prev = __byte_perm(Dleft_prev, mytop[KP], sel);
                     bord = __byte_perm(bord, left0_2, sel);
+                    if (TB) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) nMo[k] = ~Mo[k];
+                    }
                 }
             }
         }
@@ -428,9 +484,16 @@ static int launch16(const StreamArgs& a, int n_tiles, int paired, cudaStream_t s
     } else {
         constexpr int NCH = (K + 7) / 8;
         const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16 * 256 * sizeof(uint32_t);
-        auto kern = k_stream16<K, kNW16>;
-        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<n_tiles, kNW16 * 32, smem, st>>>(a);
+#define PG_S16(TBV, TRV)                                                                              \
+    do {                                                                                              \
+        auto kern = k_stream16<K, kNW16, TBV, TRV>;                                                   \
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<n_tiles, kNW16 * 32, smem, st>>>(a);                                                   \
+    } while (0)
+        if (!a.tb) PG_S16(false, false);
+        else if (a.transposed) PG_S16(true, true);
+        else PG_S16(true, false);
+#undef PG_S16
     }
     PG_CUDA_OK(cudaGetLastError());
     return 0;

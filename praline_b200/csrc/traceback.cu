@@ -45,7 +45,8 @@ __global__ void k_traceback(const TraceArgs a)
     const int Lr = (int)(a.offs[rid + 1] - a.offs[rid]);   // kernel columns
     const int Ls = (int)(a.offs[sid + 1] - a.offs[sid]);   // kernel rows
     const int K = a.K, lr = (Lr - 1) / K;
-    const int emit = a.emit_t[slot];
+    const int emit = a.emit_t[slot] & 0x3fffffff;
+    const int half = (a.emit_t[slot] >> 30) & 1;            // packed kernel: register half that carried this pair
     const uint32_t* tbw = a.tb + a.pair_tb[slot];
     const bool TR = a.transposed != 0;
     const int L1 = TR ? Lr : Ls, L2 = TR ? Ls : Lr;        // reference lengths
@@ -53,6 +54,14 @@ __global__ void k_traceback(const TraceArgs a)
     auto nib_at = [&](int yk, int xk) -> uint32_t {
         const int lane = (xk - 1) / K, k = (xk - 1) - lane * K;
         const int step = emit - (Ls - yk) - (lr - lane);
+        if (a.tb_fmt == 1) {
+            // packed kernel (gotoh_stream16.cu): 4 rows per word, row r at bits 2*(3-r) of every byte;
+            // byte 2h+1 = (M is max, U opened), byte 2h = (first gap state is max, L opened); 1 = yes
+            const uint32_t w = tbw[(int64_t)(step >> 2) * (K * 32) + k * 32 + lane];
+            const int sh = 2 * (3 - (step & 3));
+            const uint32_t e13 = (w >> (8 * (2 * half + 1) + sh)) & 3u, e24 = (w >> (8 * (2 * half) + sh)) & 3u;
+            return ((e13 >> 1) ^ 1u) | (((e24 >> 1) ^ 1u) << 1) | (((e13 & 1u) ^ 1u) << 2) | (((e24 & 1u) ^ 1u) << 3);
+        }
         const uint32_t w = tbw[(int64_t)(step >> 3) * (K * 32) + k * 32 + lane];
         return (w >> (4 * (7 - (step & 7)))) & 15u;
     };

@@ -225,6 +225,21 @@ class Engine(object):
         T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
         return (T // 8) * (K * 32)
 
+    def _tb_words16(self, tiles, K, cs):
+        """Traceback words per (tile, warp) of the packed traced kernel: a warp cuts its slice into two
+        halves that run in lock step, four steps per word."""
+        nw = self.nw
+        tb_, te_ = tiles["stream_begin"].astype(np.int64), tiles["stream_end"].astype(np.int64)
+        per = (te_ - tb_ + nw - 1) // nw
+        w = np.arange(nw)[None, :]
+        sb = tb_[:, None] + w * per[:, None]
+        se = np.minimum(sb + per[:, None], te_[:, None])
+        sb = np.minimum(sb, se)
+        mid = sb + (se - sb + 1) // 2
+        rows = np.maximum(cs[mid] - cs[sb], cs[se] - cs[mid])
+        T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
+        return (T // 4) * (K * 32)
+
     def _pick_tile(self, n_pairs):
         # enough tiles to fill 148 SMs several times over, but streams of >= 2 sequences per warp
         if os.environ.get("PGPU_TILE"):
@@ -273,7 +288,11 @@ class Engine(object):
             self.launches += 1 + int(semi)
             return out
         # traced: waves bounded by the traceback budget; tiles are in slot order
-        words = self._tb_words(tiles, K, cs)
+        neg16 = self.fits_s16(S_host, go, ge, batch.lens, limit=16000) if (
+            md == 0 and mwave_dev is None and self.use_s16) else None
+        fmt = 1 if neg16 is not None else 0
+        self.last_traced_fmt = fmt      # 1: packed int16 traced kernel, 0: f32 (tests look at it)
+        words = self._tb_words16(tiles, K, cs) if fmt else self._tb_words(tiles, K, cs)
         per_tile = words.sum(axis=1)
         lo = 0
         while lo < len(tiles):
@@ -291,13 +310,21 @@ class Engine(object):
             pair_tb = torch.empty(ns, dtype=torch.int64, device=self.device)
             keys = torch.empty(2 * ns, dtype=torch.int64, device=self.device) if semi else None
             sc = scores_dev[s_lo:s_hi]
-            _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
-                                            self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(wt), ns,
-                                            self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
-                                            self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1, self.ptr(sc),
-                                            self.ptr(keys),
-                                            self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
-                                            None, None, self.stream()))
+            if fmt:     # packed int16 traced kernel (global mode, integer scores inside +-16000)
+                _lib.check(lib.pgpu_align_tiles16_traced(K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
+                                                         self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(wt),
+                                                         self.ptr(S_dev), A, int(go), int(ge), neg16, self.ptr(top_dev),
+                                                         int(B["left0"]), int(B["left1"]), maxlen + 1, self.ptr(sc),
+                                                         self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t),
+                                                         self.ptr(pair_tb), self.stream()))
+            else:
+                _lib.check(lib.pgpu_align_tiles(md, K, int(transposed), self.ptr(batch.flat_dev), self.ptr(batch.offs_dev),
+                                                self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(wt), ns,
+                                                self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
+                                                self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1, self.ptr(sc),
+                                                self.ptr(keys),
+                                                self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
+                                                None, None, self.stream()))
             if counts is not None:
                 # preprofile mode: the walk adds into the masters' count tables, no path leaves the device
                 cnt_dev, cnt_off_dev, thr = counts
@@ -308,7 +335,7 @@ class Engine(object):
                                                     self.ptr(batch.flat_dev), self.ptr(cnt_dev),
                                                     self.ptr(cnt_off_dev[s_lo:s_hi]), A, self.ptr(sc),
                                                     int(thr is not None), float(thr if thr is not None else 0.0),
-                                                    self.stream()))
+                                                    fmt, self.stream()))
                 self.launches += 2 + int(semi)
                 lo = hi
                 continue
@@ -324,15 +351,16 @@ class Engine(object):
                                                 ns, self.ptr(keys), self.ptr(tb), self.ptr(emit_t), self.ptr(pair_tb),
                                                 B["code00"], B["top_ramp"], B["left_ramp"], self.ptr(poff_dev),
                                                 self.ptr(pbuf), self.ptr(pstart), self.ptr(plen),
-                                                None, None, None, A, None, 0, 0.0, self.stream()))
+                                                None, None, None, A, None, 0, 0.0, fmt, self.stream()))
             self.launches += 2 + int(semi)
             out.append((s_lo, s_hi, poff, pbuf, pstart, plen))
             lo = hi
         return out
 
-    def fits_s16(self, S, go, ge, lens):
+    def fits_s16(self, S, go, ge, lens, limit=32000):
         """Sentinel for the packed int16 kernel, or None when the batch must stay in f32: integer
-        scores, and |go| + (|ge| + max|S|) * (L1 + L2) plus the sentinel arithmetic inside int16."""
+        scores, and |go| + (|ge| + max|S|) * (L1 + L2) plus the sentinel arithmetic inside int16
+        (limit 32000), or inside +-16000 for the traced variant whose tie tests subtract two values."""
         if S is None:
             return None
         vals = np.concatenate([S.ravel().astype(np.float64), [float(go), float(ge)]])
@@ -342,7 +370,7 @@ class Engine(object):
         lmax = int(np.max(lens))
         v = abs(float(go)) + (abs(float(ge)) + smax) * 2 * lmax
         neg = -(v + smax + 1)
-        if neg - abs(float(go)) - 2 * abs(float(ge)) - smax < -32000 or smax * lmax > 32000:
+        if neg - abs(float(go)) - 2 * abs(float(ge)) - smax < -limit or smax * lmax > limit:
             return None
         return int(neg)
 

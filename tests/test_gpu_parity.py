@@ -490,3 +490,36 @@ def test_cluster_kernel_large_from_real_scores(eng):
         for a, b in got:
             assert a not in gone and b not in gone and a != b
             gone.add(b)
+
+
+@pytest.mark.parametrize("resident", ["one", "two"])
+def test_packed_traced_kernel_paths_and_counts(eng, resident):
+    """Global traced batches with integer scores inside +-16000 run the packed int16 traced kernel
+    (tb_fmt 1): paths equal the oracle's and the f32 traced kernel's, for both orientations, mixed
+    lengths across K classes, self pairs and both pair orders."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(77)
+    seqs = synth.family(71, 14, 180) + synth.family(72, 9, 75) + [rng.integers(0, 20, n).astype(np.int32) for n in (1, 2, 33, 64, 250, 400)]
+    pi, pj = synth.all_pairs(len(seqs))
+    pi, pj = np.concatenate([pi, pj[:60], np.arange(6)]), np.concatenate([pj, pi[:60], np.arange(6)])
+    flat, offs = synth.pack(seqs)
+    batch = eng.batch(seqs)
+    for gaps in ([-11.0, -1.0], [-3.0], [-2.0, -2.0]):
+        want, wpaths = oracle.align_batch("global", flat, offs, pi, pj, S, gaps, want_paths=True)
+        eng.use_s16 = True
+        got, paths = eng.align_pairs(batch, pi, pj, S, gaps, mode="global", want_paths=True, resident=resident)
+        assert eng.last_traced_fmt == 1
+        assert np.array_equal(got, want)
+        assert all(np.array_equal(a, b) for a, b in zip(paths, wpaths)), gaps
+        eng.use_s16 = False
+        try:
+            got32, paths32 = eng.align_pairs(batch, pi, pj, S, gaps, mode="global", want_paths=True, resident=resident)
+            assert eng.last_traced_fmt == 0
+        finally:
+            eng.use_s16 = True
+        assert np.array_equal(got32, want) and all(np.array_equal(a, b) for a, b in zip(paths32, wpaths))
+    # beyond the +-16000 working range the f32 kernel takes over
+    long_seqs = synth.family(73, 4, 900)
+    lb = eng.batch(long_seqs)
+    eng.align_pairs(lb, [0, 1], [2, 3], S, [-11.0, -1.0], mode="global", want_paths=True, resident=resident)
+    assert eng.last_traced_fmt == 0
