@@ -51,19 +51,44 @@ __global__ void k_traceback(const TraceArgs a)
     const bool TR = a.transposed != 0;
     const int L1 = TR ? Lr : Ls, L2 = TR ? Ls : Lr;        // reference lengths
 
-    auto nib_at = [&](int yk, int xk) -> uint32_t {
+    // word holding the flags of interior cell (yk, xk), and the nibble inside it
+    auto word_index = [&](int yk, int xk) -> int64_t {
         const int lane = (xk - 1) / K, k = (xk - 1) - lane * K;
+        const int step = emit - (Ls - yk) - (lr - lane);
+        return (int64_t)(step >> (a.tb_fmt == 1 ? 2 : 3)) * (K * 32) + k * 32 + lane;
+    };
+    auto nib_of = [&](uint32_t w, int yk, int xk) -> uint32_t {
+        const int lane = (xk - 1) / K;
         const int step = emit - (Ls - yk) - (lr - lane);
         if (a.tb_fmt == 1) {
             // packed kernel (gotoh_stream16.cu): 4 rows per word, row r at bits 2*(3-r) of every byte;
             // byte 2h+1 = (M is max, U opened), byte 2h = (first gap state is max, L opened); 1 = yes
-            const uint32_t w = tbw[(int64_t)(step >> 2) * (K * 32) + k * 32 + lane];
             const int sh = 2 * (3 - (step & 3));
             const uint32_t e13 = (w >> (8 * (2 * half + 1) + sh)) & 3u, e24 = (w >> (8 * (2 * half) + sh)) & 3u;
             return ((e13 >> 1) ^ 1u) | (((e24 >> 1) ^ 1u) << 1) | (((e13 & 1u) ^ 1u) << 2) | (((e24 & 1u) ^ 1u) << 3);
         }
-        const uint32_t w = tbw[(int64_t)(step >> 3) * (K * 32) + k * 32 + lane];
         return (w >> (4 * (7 - (step & 7)))) & 15u;
+    };
+    // The walk is a chain of dependent loads.  Alignments of related sequences move diagonally most
+    // of the time and the addresses of diagonal predecessors need no data, so the words of the next
+    // three diagonal cells are kept in flight (p1..p3 belong to (py - j, px - j), j = 0, 1, 2); any
+    // other request reloads directly.
+    int py = -1, px = -1;
+    uint32_t p1 = 0, p2 = 0, p3 = 0;
+    auto fetch = [&](int yk, int xk) -> uint32_t { return (yk >= 1 && xk >= 1) ? __ldg(tbw + word_index(yk, xk)) : 0u; };
+    auto nib_at = [&](int yk, int xk) -> uint32_t {
+        uint32_t w;
+        if (yk == py && xk == px) {
+            w = p1;
+        } else if (yk == py - 1 && xk == px - 1) {      // one step down the diagonal: shift the window
+            w = p2; p1 = p2; p2 = p3; py = yk; px = xk;
+            p3 = fetch(yk - 2, xk - 2);
+        } else {                                         // off the diagonal: prime the window here
+            py = yk; px = xk;
+            p1 = fetch(yk, xk); p2 = fetch(yk - 1, xk - 1); p3 = fetch(yk - 2, xk - 2);
+            w = p1;
+        }
+        return nib_of(w, yk, xk);
     };
     auto code_at = [&](int yk, int xk) -> int {
         if (yk == 0 && xk == 0) return a.code00;

@@ -155,7 +155,8 @@ class Engine(object):
         self.nw = self.lib.pgpu_warps_per_tile()
         self.k_set = [k for k in range(1, 65) if self.lib.pgpu_supported_k(k)]
         self.launches = 0          # kernels of ours launched (bench.py reports it)
-        self.tb_budget_words = 1 << 30
+        # traceback words per wave: 16 GiB of the 180 GB (more pairs per wave = more walkers in flight in K4)
+        self.tb_budget_words = int(float(os.environ.get("PGPU_TB_GIB", "16")) * (1 << 28))
         self._borders = {}
         self.use_s16 = os.environ.get("PGPU_NO_S16", "") == ""
         self.m_budget_floats = 1 << 31     # 8 GiB of match scores per wave of a profile batch
