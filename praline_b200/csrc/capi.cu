@@ -115,6 +115,7 @@ int pgpu_align_tiles16_traced(int K, int transposed, const uint8_t* seqs, const 
     a.S = S; a.A = A; a.transposed = transposed; a.topD = topD; a.border_len = border_len; a.scores = scores;
     a.go16 = gap_open; a.ge16 = gap_extend; a.neg16 = neg; a.left0_16 = left0; a.left1_16 = left1;
     a.tb = tb; a.tb_base = tb_base; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    a.all_ones = -1;
     return pg_launch_stream16(a, n_tiles, K, 0, (cudaStream_t)stream);
 }
 

@@ -56,6 +56,7 @@ struct StreamArgs {
     int32_t* emit_t;             // per slot: step at which the owning lane saw the last row
     int64_t* pair_tb;            // per slot: word offset of its warp's traceback region
     int go16, ge16, neg16, left0_16, left1_16;   // packed s16x2 variant (gotoh_stream16.cu)
+    int all_ones;                // -1, opaque to ptxas: ~x = x * all_ones + all_ones stays an IMAD (FMA pipe)
     const float* mwave;          // profile batches: match scores [row][32*K], rows in stream order
     const int64_t* mrow_base;    // first matrix row per (tile, warp); row 0 of a region is the dummy row
 };

@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
         for (int k = 0; k < K; k++) { nMo[k] = ~0u; acc[k] = 0u; }
     }
     const int64_t tbw0 = TB ? a.tb_base[(int64_t)blockIdx.x * NW + warp] : 0;
+    // the ALU pipe (DPX, PRMT, LOP3) is the traced kernel's binding unit: complements are taken as
+    // x * (-1) + (-1) with the -1 from a kernel argument, which keeps them on the FMA pipe as IMADs
+    const uint32_t ones = (uint32_t)a.all_ones;
+    auto inv = [&](uint32_t x) -> uint32_t { return x * ones + ones; };
     uint32_t Mo_last = 0u, L_last = 0u, D_last = 0u, Dleft_prev = 0u, bord = 0u;
     int qA = sb, qB = mid;
     int psA = sb - 1, ppA = 0, psB = mid - 1, ppB = 0;   // producer cursors (element, offset)
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
                 bord = __vadd2(bord, left1_2);
                 uint32_t diag = Dleft_prev;
                 Dleft_prev = Dn;
-                uint32_t nMl = ~Ml;
+                uint32_t nMl = TB ? inv(Ml) : 0u;
 
 #pragma unroll
                 for (int k = 0; k < K; k++) {
@@ -217,9 +221,9 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
                     if (TB) {
                         // sign per half = "equal": M is the maximum | the first-priority gap state is |
                         // U was opened | L was opened (ties keep the reference's priority)
-                        const uint32_t nmo = ~mo;
-                        const uint32_t t1 = __vadd2(d, ~m);
-                        const uint32_t t2 = __vadd2(d, ~(TR ? l : u));
+                        const uint32_t nmo = inv(mo);
+                        const uint32_t t1 = __vadd2(d, inv(m));
+                        const uint32_t t2 = __vadd2(d, inv(TR ? l : u));
                         const uint32_t t3 = __vadd2(u, nMo[k]);
                         const uint32_t t4 = __vadd2(l, nMl);
                         const uint32_t p12 = prmt(t1, t2, 0xBF9Du);     // bytes: t1.B t2.B t1.A t2.A as 0x00 / 0xff
