@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpraline_b200.so")
+LIB_PATH = os.environ.get("PGPU_LIB") or os.path.join(_HERE, "libpraline_b200.so")   # PGPU_LIB: experiment builds
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 

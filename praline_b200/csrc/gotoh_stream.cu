@@ -57,7 +57,7 @@ __device__ __forceinline__ float pick(const float (&v)[K], int k)
 template <int K, int KM, bool TB, bool TR, bool MS, int NW>
 __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
 {
-    constexpr int UNR = TB ? 8 : 4;   // steps unrolled per inner iteration (8 = one traceback word)
+    constexpr int UNR = 8;            // steps unrolled per inner iteration (8 = one traceback word)
     constexpr int NCH = (K + 3) / 4;
     constexpr int ROWB = NCH * 512;
     extern __shared__ __align__(16) unsigned char smem[];

@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t pick_u(const uint32_t (&v)[K], int k)
 template <int K, int NW, bool TB, bool TR>
 __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
 {
-    constexpr int UNR = 4;                  // = the four rows of one traceback word
+    constexpr int UNR = TB ? 4 : 8;         // traced: the four rows of one traceback word
     constexpr int NCH = (K + 7) / 8;        // 16-byte chunks of 8 int16 columns per lane
     constexpr int ROWB = NCH * 512;
     constexpr int KP = (K + 3) & ~3;        // top-border table, words per lane
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
 template <int K, int NW>
 __global__ void __launch_bounds__(NW * 32) k_stream16r(const StreamArgs a)
 {
-    constexpr int UNR = 4;
+    constexpr int UNR = 8;                  // measured: 4 -> 8 steps per inner iteration, 7.97 -> 7.16 ms on the bench (16: slower)
     constexpr int NCH = (K + 3) / 4;        // 16-byte chunks of 4 packed columns per lane
     constexpr int ROWB = NCH * 512;
     constexpr int KP = (K + 3) & ~3;

@@ -1,8 +1,9 @@
 """BASELINE config 3 at full size on this rank's GPUs: 10,000 synthetic 400-aa proteins.
 (a) guide-tree stage on sequence tracks: all 49,995,000 unordered pairs, global, score per pair;
-(b) preprofile stage: a sample of masters against ALL other sequences, traced on the device into
-    count tables (the full 10^8 ordered pairs are (a)'s cells x2; reported extrapolated).
-Prints JSON lines.  Single process per GPU (torchrun for N > 1 shards (a) and all-gathers)."""
+(b) preprofile stage: a sample of masters (40 per rank) against ALL other sequences, traced on the
+    device into count tables, masters sharded by rank and the tables all-gathered (the full 10^8
+    ordered pairs are (a)'s cells x2; reported extrapolated).
+Prints JSON lines.  Single process per GPU (torchrun for N > 1 shards both stages)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -43,16 +44,38 @@ if rank == 0:
     print(json.dumps({"stage": "C3 guide-tree all-vs-all (score only)", "n_seqs": n, "pairs": n * (n - 1) // 2, "cells": cells,
                       "n_gpus": world, "ms": float(t.item()), "gcups": cells / float(t.item()) / 1e6, "plan_s": t_plan, "gen_s": t_gen,
                       "checksum_first_1000": chk}))
-if rank == 0 and world == 1:
-    nm = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    masters = np.repeat(np.arange(nm), n - 1)
-    slaves = np.concatenate([np.r_[0:i, i + 1:n] for i in range(nm)])
-    eng.preprofile_counts(batch, masters[:1000], slaves[:1000], S, [-11.0, -1.0])
+# (b) preprofile stage on a sample of masters, sharded BY MASTER over the ranks: every rank
+# traces its masters against all other sequences into its own count tables, one padded all-gather
+# hands every rank all tables.
+nm = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+nm = max(nm, world) * (1 if world == 1 else 1)
+all_masters = np.arange(nm * world if world > 1 else nm)
+mine, cuts = parallel.shard_masters(all_masters, lens, rank, world)
+masters = np.repeat(mine, n - 1)
+slaves = np.concatenate([np.r_[0:i, i + 1:n] for i in mine]) if len(mine) else np.zeros(0, np.int64)
+eng.preprofile_counts(batch, masters[:1000], slaves[:1000], S, [-11.0, -1.0])
+for rep in range(2):
+    if world > 1: dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     cnt, where, sc = eng.preprofile_counts(batch, masters, slaves, S, [-11.0, -1.0])
+    if world > 1:
+        local = torch.from_numpy(cnt).to(eng.device)
+        sizes = [int(lens[all_masters[cuts[r]:cuts[r + 1]]].sum()) * 27 for r in range(world)]
+        allc = parallel.allgather_counts(local, sizes)
+        total_counts = int(allc.sum().item())
+    else:
+        total_counts = int(cnt.sum())
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    pc = int((lens[masters] * lens[slaves]).sum())
-    print(json.dumps({"stage": "C3 preprofile (traced -> count tables on device)", "masters": nm, "pairs": len(masters), "cells": pc,
-                      "wall_s": dt, "gcups": pc / dt / 1e9, "full_stage_extrapolated_s": dt * n / nm, "counts_sum": int(cnt.sum())}))
+td = torch.tensor([dt], dtype=torch.float64, device=eng.device)
+pc = torch.tensor([float((lens[masters] * lens[slaves]).sum())], dtype=torch.float64, device=eng.device)
+if world > 1:
+    dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    dist.all_reduce(pc, op=dist.ReduceOp.SUM)
+if rank == 0:
+    dt, cells_pre = float(td.item()), float(pc.item())
+    print(json.dumps({"stage": "C3 preprofile (traced -> count tables on device, masters sharded by rank, tables all-gathered)",
+                      "n_gpus": world, "masters": int(len(all_masters)), "pairs": int(len(all_masters)) * (n - 1), "cells": cells_pre,
+                      "wall_s": dt, "gcups": cells_pre / dt / 1e9, "full_stage_extrapolated_s": dt * n / len(all_masters),
+                      "counts_sum": total_counts}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
