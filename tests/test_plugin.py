@@ -357,3 +357,23 @@ def test_tree_msa_component_matches_reference(merge_mode):
         outs.append(out['alignment'])
     assert [s.name for s in outs[0].items] == [s.name for s in outs[1].items]
     assert np.array_equal(np.asarray(outs[0].path), np.asarray(outs[1].path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_gpu_guide_tree_tiny_inputs(n):
+    """One, two and three sequences through the GPU GuideTreeBuilder and the tree MSA."""
+    sm = _blosum()
+    fam = synth.family(91, 3, 40)[:n]
+    outs = []
+    for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+        env = {'gap_series': [-11.0, -1.0], 'linkage_method': 'average', 'dist_mode': 'global',
+               'aligner': pc.PairwiseAligner.tid, 'merge_mode': 'global'}
+        tree, _ = R.run_task(mgr, pc.GuideTreeBuilder, env, sequences=seqs, track_id_sets=[[TRACK_ID_INPUT]],
+                             score_matrices=[sm])
+        msa, _ = R.run_task(mgr, pc.TreeMultipleSequenceAligner, env, sequences=seqs, guide_tree=tree['guide_tree'],
+                            track_id_sets=[[TRACK_ID_INPUT]], score_matrices=[sm])
+        outs.append((tree['guide_tree'].merge_orders, np.asarray(msa['alignment'].path)))
+    assert list(map(tuple, outs[0][0])) == list(map(tuple, outs[1][0]))
+    assert np.array_equal(outs[0][1], outs[1][1])
