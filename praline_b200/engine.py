@@ -143,6 +143,39 @@ class ProfileBatch(object):
         self.max_sym = self.A - 1
 
 
+class GrowingProfileBatch(ProfileBatch):
+    """ProfileBatch with room to append: the ad-hoc MSA adds one merged profile per round and
+    never needs the old ones moved (dead profiles simply stay behind)."""
+
+    def __init__(self, engine, profiles, cap_rows=0):
+        ProfileBatch.__init__(self, engine, profiles)
+        self._engine = engine
+        rows = int(self.offs[-1])
+        cap = max(int(cap_rows), rows)
+        self._store = torch.empty((cap, self.A), dtype=torch.float32, device=engine.device)
+        self._store[:rows].copy_(self.prof_dev)
+        self.prof_dev = self._store[:rows]
+
+    def append(self, profile):
+        """Adds one [L x A] f32 profile; returns its index."""
+        p = np.ascontiguousarray(profile, np.float32)
+        if p.ndim != 2 or p.shape[1] != self.A or p.shape[0] < 1:
+            raise ValueError("profile does not fit this batch")
+        r0 = int(self.offs[-1])
+        r1 = r0 + p.shape[0]
+        if r1 > self._store.shape[0]:
+            bigger = torch.empty((max(2 * self._store.shape[0], r1), self.A), dtype=torch.float32, device=self._store.device)
+            bigger[:r0].copy_(self._store[:r0])
+            self._store = bigger
+        self._store[r0:r1].copy_(torch.from_numpy(p), non_blocking=False)
+        self.prof_dev = self._store[:r1]
+        self.lens = np.append(self.lens, p.shape[0])
+        self.offs = np.append(self.offs, r1)
+        self.offs_dev = self._engine.dev(self.offs)
+        self.n += 1
+        return self.n - 1
+
+
 class Engine(object):
     def __init__(self, device=0, pin=True):
         self.lib = _lib.load()
@@ -190,7 +223,10 @@ class Engine(object):
     def batch(self, seqs):
         return SeqBatch(self, seqs)
 
-    def profile_batch(self, profiles):
+    def profile_batch(self, profiles, cap_rows=None):
+        """cap_rows: build a batch that profiles can be appended to (GrowingProfileBatch)."""
+        if cap_rows is not None:
+            return GrowingProfileBatch(self, profiles, cap_rows)
         return ProfileBatch(self, profiles)
 
     # -- inter-task batch ----------------------------------------------------------------------
@@ -413,8 +449,13 @@ class Engine(object):
         kcls = self.k_classes(batch.lens)
         if (kcls[res] < 0).any():
             raise _lib.PralineGpuError("resident sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
-        order = np.lexsort((np.arange(n), res, kcls[res]))
-        res_s, str_s = res[order], strm[order]
+        kres = kcls[res]
+        if n < 2 or ((res[1:] >= res[:-1]).all() and (kres[1:] >= kres[:-1]).all()):
+            order = np.arange(n)            # already grouped (master-slave lists are): no sort
+            res_s, str_s = res, strm
+        else:
+            order = np.lexsort((np.arange(n), res, kres))
+            res_s, str_s = res[order], strm[order]
         S_dev = self.dev(S)
         stream_ids_dev = self.dev(str_s.astype(np.int32))
         scores_dev = torch.empty(n, dtype=torch.float32, device=self.device)

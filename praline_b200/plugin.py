@@ -40,6 +40,7 @@ GLOBAL_MS_TID = "praline.component.GlobalMasterSlaveAligner"
 PROFILE_BUILDER_TID = "praline.component.ProfileBuilder"
 GUIDE_TREE_TID = "praline.component.GuideTreeBuilder"
 TREE_MSA_TID = "praline.component.TreeMultipleSequenceAligner"
+ADHOC_MSA_TID = "praline.component.AdHocMultipleSequenceAligner"
 
 
 def _path_container(mode, path):
@@ -517,20 +518,9 @@ class GpuTreeMultipleSequenceAligner(Component):
                 if track_id not in track_ids:
                     track_ids.append(track_id)
         # per cluster: the count profile of every track (msa.py:71-97) and the alignment path
-        clusters, paths, members = {}, {}, {}
-        for i, seq in enumerate(sequences):
-            cluster = Sequence("Cluster #{0}".format(i), [])
-            for track_id in track_ids:
-                track = seq.get_track(track_id)
-                if track.tid == PlainTrack.tid:
-                    counts = np.zeros((len(track), track.alphabet.size), dtype=np.int32)
-                    counts[np.arange(len(track)), np.asarray(track.values)] = 1
-                    cluster.add_track(track_id, ProfileTrack(counts, track.alphabet))
-                elif track.tid == ProfileTrack.tid:
-                    cluster.add_track(track_id, ProfileTrack(np.array(track.counts, dtype=np.int32), track.alphabet))
-            clusters[i] = cluster
-            paths[i] = np.arange(len(seq) + 1).reshape(len(seq) + 1, 1)
-            members[i] = [seq]
+        clusters = _cluster_tracks(sequences, track_ids)
+        paths = {i: np.arange(len(seq) + 1).reshape(len(seq) + 1, 1) for i, seq in enumerate(sequences)}
+        members = {i: [seq] for i, seq in enumerate(sequences)}
         index = self.manager.index
         total = len(guide_tree.merge_orders)
         for step, (i, j) in enumerate(guide_tree.merge_orders):
@@ -566,6 +556,173 @@ class GpuTreeMultipleSequenceAligner(Component):
         yield CompleteMessage(outputs={'alignment': Alignment(members[first], paths[first])})
 
 
+def _cluster_tracks(sequences, track_ids):
+    """Initial clusters of the MSA components (msa.py:71-97, :313-339): every track as a count
+    profile (one-hot for plain tracks)."""
+    clusters = {}
+    for i, seq in enumerate(sequences):
+        cluster = Sequence("Cluster #{0}".format(i), [])
+        for track_id in track_ids:
+            track = seq.get_track(track_id)
+            if track.tid == PlainTrack.tid:
+                counts = np.zeros((len(track), track.alphabet.size), dtype=np.int32)
+                counts[np.arange(len(track)), np.asarray(track.values)] = 1
+                cluster.add_track(track_id, ProfileTrack(counts, track.alphabet))
+            elif track.tid == ProfileTrack.tid:
+                cluster.add_track(track_id, ProfileTrack(np.array(track.counts, dtype=np.int32), track.alphabet))
+        clusters[i] = cluster
+    return clusters
+
+
+class GpuAdHocMultipleSequenceAligner(Component):
+    """Drop-in for praline.component.AdHocMultipleSequenceAligner (component/msa.py:249-560), the
+    default MSA mode of the CLI (cmd.py:82-85): same type id, ports, options and defaults.
+
+    The reference scores every pair of current clusters each round, reusing the scores that do
+    not involve the cluster merged last (`_merge_indices`, msa.py:488-558), merges the first
+    maximum of the score matrix in row-major order and repeats.  Here the score matrix lives in
+    one array indexed by the original cluster ids (clusters keep their dict order, so list order
+    is id order), the first round is ONE all-vs-all launch, every later round one batch of
+    (merged cluster x every other cluster) profile alignments in the reference's orientation
+    (sequence one = the cluster earlier in the list) against profiles that stay on the device
+    (GrowingProfileBatch), and the merge itself is the vectorised glue of the tree aligner.  One
+    track set, `dist_mode` global / semiglobal, the GPU PairwiseAligner and no debug logging;
+    anything else runs the reference component."""
+    tid = ADHOC_MSA_TID
+
+    inputs = {'sequences': Port([Sequence.tid]),
+              'track_id_sets': Port([[str]]),
+              'score_matrices': Port([ScoreMatrix.tid])}
+    outputs = {'alignment': Port(Alignment.tid)}
+
+    options = {'gap_series': [float], 'aligner': str,
+               'aligner_env': Environment.tid, 'merge_mode': str,
+               'dist_mode': str, 'debug': int, 'log_track_ids': [str]}
+    defaults = {'gap_series': [-11.0, -1.0], 'aligner': PAIRWISE_TID,
+                'aligner_env': Environment({}), 'merge_mode': 'semiglobal',
+                'dist_mode': 'global', 'debug': 0,
+                'log_track_ids': [TRACK_ID_INPUT]}
+
+    def _reference(self, sequences, track_id_sets, score_matrices):
+        from praline.component import AdHocMultipleSequenceAligner as _Reference
+        ref = _Reference(self.manager, self.environment, self.tag)
+        for msg in ref.execute(sequences, track_id_sets, score_matrices):
+            yield msg
+
+    def execute(self, sequences, track_id_sets, score_matrices):
+        env = self.environment
+        merge_mode, dist_mode = env['merge_mode'], env['dist_mode']
+        if merge_mode not in {'global', 'semiglobal', 'semiglobal_auto'}:
+            raise ComponentError("unknown merge mode '{0}'".format(merge_mode))
+        if dist_mode not in {'global', 'semiglobal', 'semiglobal_auto'}:
+            raise ComponentError("unknown distance mode '{0}'".format(dist_mode))
+        eng = get_engine()
+        ok = (env['debug'] == 0 and dist_mode != 'semiglobal_auto' and len(track_id_sets) == 1 and
+              len(track_id_sets[0]) == 1 and len(sequences) >= 2 and env['aligner'] == PAIRWISE_TID and
+              self.manager.index.resolve(PAIRWISE_TID) is GpuPairwiseAligner)
+        sub_env = gaps = S = None
+        if ok:
+            sub_env = Environment(keys=env['aligner_env'].keys, component=GpuPairwiseAligner, parent=env)
+            ok = sub_env['debug'] == 0
+        track_id = track_id_sets[0][0] if ok else None
+        if ok:
+            try:    # the per-pair checks of PairwiseAligner.execute are per-sequence properties
+                for seq in sequences:
+                    sets, gaps = _prepare(seq, seq, track_id_sets, track_id_sets, score_matrices, sub_env['gap_series'])
+                S = sets[0][2].matrix.astype(np.float32)
+            except (ComponentError, DataError):
+                ok = False
+        if ok:
+            lens = [len(seq.get_track(track_id)) for seq in sequences]
+            ok = min(lens) >= 1 and eng.k_for(max(lens)) is not None
+        if not ok:
+            for msg in self._reference(sequences, track_id_sets, score_matrices):
+                yield msg
+            return
+
+        dmode = "semiglobal_both" if dist_mode == "semiglobal" else "global"
+        n = len(sequences)
+        clusters = _cluster_tracks(sequences, [track_id])
+        paths = {i: np.arange(len(seq) + 1).reshape(len(seq) + 1, 1) for i, seq in enumerate(sequences)}
+        members = {i: [seq] for i, seq in enumerate(sequences)}
+        import os
+        fast = os.environ.get("PGPU_FAST_PROFILES", "") not in ("", "0")
+        # score matrix over the original ids, upper triangle; dead or unset entries are -inf, so its
+        # first row-major maximum is the reference's (msa.py:549: first maximum of the symmetric s)
+        sc = np.full((n, n), -np.inf, dtype=np.float32)
+        tracks = [clusters[i].get_track(track_id) for i in range(n)]
+        arrs = [_seq_like(t) for t in tracks]
+        iu = np.triu_indices(n, k=1)
+        pb = eng.profile_batch([_profile_of(t) for t in tracks], cap_rows=3 * sum(lens))
+        pidx = {i: i for i in range(n)}             # cluster id -> its current profile in the batch
+        if all(a is not None for a in arrs) and eng.integer_exact(S, gaps[0], gaps[1], max(lens)) and \
+                eng.k_for(max(lens)) is not None:
+            batch = eng.batch(arrs)
+            cond, _, _ = eng.allpairs_scores(batch, eng.dev(S), S.shape[0], gaps, mode=dmode, S_host=S)
+            sc[iu] = cond.cpu().numpy()
+        else:
+            sc[iu] = eng.align_profile_pairs(pb, iu[0], iu[1], S, gaps, mode=dmode, fast=fast)
+        alive = list(range(n))
+        index = self.manager.index
+        total = n - 1
+        for step in range(total):
+            i, j = np.unravel_index(sc.argmax(), sc.shape)
+            i, j = int(i), int(j)
+            one, two = clusters[i], clusters[j]
+            if merge_mode == "semiglobal":
+                mode = "semiglobal_both"
+            elif merge_mode == "global":
+                mode = "global"
+            else:
+                mode = auto_align_mode(one, two)
+            execution = Execution(self.manager, self.tag)
+            task = execution.add_task(index.resolve(env['aligner']))
+            task.environment(env, env['aligner_env'])
+            task.inputs(mode=mode, sequence_one=one, sequence_two=two, track_id_sets_one=track_id_sets,
+                        track_id_sets_two=track_id_sets, score_matrices=score_matrices)
+            for msg in execution.run():
+                yield msg
+            path = np.array(execution.outputs[0]['alignment'].path)
+            t1, t2 = one.get_track(track_id), two.get_track(track_id)
+            merged = ProfileTrack(merge_profile_counts(t1.counts, t2.counts, path), t1.alphabet)
+            one.del_track(track_id)
+            one.add_track(track_id, merged)
+            paths[i] = merge_alignment_paths(paths[i], paths[j], path)
+            members[i] = members[i] + members[j]
+            del clusters[j], paths[j], members[j]
+            alive.remove(j)
+            sc[j, :] = -np.inf
+            sc[:, j] = -np.inf
+            yield ProgressMessage(progress=(step + 1) / total)
+            if len(alive) < 2:
+                break
+            # the merged cluster against every other one, sequence one = the earlier cluster
+            pidx[i] = pb.append(_profile_of(merged))
+            before = [k for k in alive if k < i]
+            after = [k for k in alive if k > i]
+            if eng.k_for(len(merged)) is None:
+                # a cluster wider than the inter-task kernels: its pairs go through the general path
+                prof = {k: _profile_of(clusters[k].get_track(track_id)) for k in alive}
+                for a_, b_ in [(i, k) for k in after] + [(k, i) for k in before]:
+                    m = eng.build_scores([prof[a_]], [prof[b_]], [S])
+                    g1 = np.empty((prof[a_].shape[0], 2), np.float32)
+                    g2 = np.empty((prof[b_].shape[0], 2), np.float32)
+                    g1[:] = gaps
+                    g2[:] = gaps
+                    sc[a_, b_] = eng.align_general(dmode, m, g1, g2, want_path=False)["score"]
+                continue
+            if after:       # (i, k): the merged cluster is sequence one and the resident of all its pairs
+                got = eng.align_profile_pairs(pb, [pidx[i]] * len(after), [pidx[k] for k in after], S, gaps,
+                                              mode=dmode, resident="one", fast=fast)
+                sc[i, after] = got
+            if before:      # (k, i): the merged cluster is sequence two, still the shared resident
+                got = eng.align_profile_pairs(pb, [pidx[k] for k in before], [pidx[i]] * len(before), S, gaps,
+                                              mode=dmode, resident="two", fast=fast)
+                sc[before, i] = got
+        first = next(iter(paths))
+        yield CompleteMessage(outputs={'alignment': Alignment(members[first], paths[first])})
+
+
 def register(index, tree=True):
     """Replace the CPU aligners and (tree=True) the guide-tree builder of a TypeIndex
     (manager.py:49-57) by the GPU ones."""
@@ -574,6 +731,7 @@ def register(index, tree=True):
     if tree:
         index.register(GpuGuideTreeBuilder)
         index.register(GpuTreeMultipleSequenceAligner)
+        index.register(GpuAdHocMultipleSequenceAligner)
     return index
 
 

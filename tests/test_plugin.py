@@ -377,3 +377,59 @@ def test_gpu_guide_tree_tiny_inputs(n):
         outs.append((tree['guide_tree'].merge_orders, np.asarray(msa['alignment'].path)))
     assert list(map(tuple, outs[0][0])) == list(map(tuple, outs[1][0]))
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_adhoc_msa_component_mirrors_reference():
+    ref, gpu = pc.AdHocMultipleSequenceAligner, plugin.GpuAdHocMultipleSequenceAligner
+    assert gpu.tid == ref.tid
+    assert set(gpu.inputs) == set(ref.inputs) and set(gpu.outputs) == set(ref.outputs)
+    assert gpu.options == ref.options
+    assert {k: v for k, v in gpu.defaults.items() if k != 'aligner_env'} == \
+           {k: v for k, v in ref.defaults.items() if k != 'aligner_env'}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dist_mode,merge_mode", [("global", "semiglobal"), ("semiglobal", "global"),
+                                                  ("global", "semiglobal_auto")])
+def test_adhoc_msa_component_matches_reference(dist_mode, merge_mode):
+    """AdHocMultipleSequenceAligner (the CLI's default MSA mode): the GPU component (score matrix
+    cache on ids, batched rounds, vectorised merges) returns the reference's alignment."""
+    sm = _blosum()
+    fam = synth.family(62, 13, 48)
+    outs = []
+    for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+        env = {'gap_series': [-11.0, -1.0], 'merge_mode': merge_mode, 'dist_mode': dist_mode,
+               'aligner': pc.PairwiseAligner.tid}
+        out, _ = R.run_task(mgr, pc.AdHocMultipleSequenceAligner, env, sequences=seqs,
+                            track_id_sets=[[TRACK_ID_INPUT]], score_matrices=[sm])
+        outs.append(out['alignment'])
+    assert [s.name for s in outs[0].items] == [s.name for s in outs[1].items]
+    assert np.array_equal(np.asarray(outs[0].path), np.asarray(outs[1].path))
+
+
+@pytest.mark.gpu
+def test_adhoc_msa_on_profile_tracks_matches_reference():
+    """Ad-hoc MSA on preprofile tracks (what --preprofile-global feeds it): f32 profile scores in the
+    reference's evaluation order decide every merge."""
+    sm = _blosum()
+    rng = np.random.default_rng(8)
+    def mk():
+        r = np.random.default_rng(8)
+        seqs = []
+        for i in range(9):
+            L = int(r.integers(30, 50))
+            counts = np.zeros((L, ALPHABET_AA.size), np.int64)
+            for _ in range(int(r.integers(1, 5))):
+                counts[np.arange(L), r.integers(0, 20, L)] += 1
+            seqs.append(Sequence("p%d" % i, [(TRACK_ID_PREPROFILE, ProfileTrack(counts, ALPHABET_AA))]))
+        return seqs
+    outs = []
+    for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+        env = {'gap_series': [-11.0, -1.0], 'merge_mode': 'semiglobal', 'dist_mode': 'global',
+               'aligner': pc.PairwiseAligner.tid}
+        out, _ = R.run_task(mgr, pc.AdHocMultipleSequenceAligner, env, sequences=mk(),
+                            track_id_sets=[[TRACK_ID_PREPROFILE]], score_matrices=[sm])
+        outs.append(out['alignment'])
+    assert [s.name for s in outs[0].items] == [s.name for s in outs[1].items]
+    assert np.array_equal(np.asarray(outs[0].path), np.asarray(outs[1].path))
