@@ -204,7 +204,7 @@ def cpu_baseline_port(seqs, S, seconds=12.0):
                       % (n, dt)}
 
 
-def msa_e2e(n=50, length=300):
+def msa_e2e(n=50, length=300, preprofile="global", msa="tree"):
     """Second half of the BASELINE metric: wall time of the reference's MSA workflow
     (`praline --preprofile-global --msa-tree`, 50 x 300 aa, BASELINE configs[0] scale) on the
     GPU manager and on the reference's own single-process Manager; outputs must be identical.
@@ -214,7 +214,7 @@ def msa_e2e(n=50, length=300):
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "praline")):
         return None
     try:
-        out = subprocess.run([sys.executable, tool, str(n), str(length), "global", "tree"], capture_output=True,
+        out = subprocess.run([sys.executable, tool, str(n), str(length), preprofile, msa], capture_output=True,
                              text=True, timeout=600)
         return json.loads(out.stdout.strip().splitlines()[-1])
     except Exception as e:   # the DP numbers above stand on their own
@@ -405,6 +405,7 @@ def main():
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_port(seqs, S)
             roof["msa_e2e"] = msa_e2e()
+            roof["msa_e2e_cli_default"] = msa_e2e(preprofile="dummy", msa="ad_hoc")   # praline in.fa out.aln
 
     if rank == 0:
         line = {"metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS", "n_gpus": world,
