@@ -191,3 +191,46 @@ def test_profile_wave_blocks_cover_rows():
                     assert src[r] == offs[str_s[el]] + y and res[r] == res_s[el]
                     r += 1
     assert (src != -9).all()
+
+
+def test_tb_words16_formula():
+    """Traceback words of the packed traced kernel: a warp's slice runs as two halves in lock step
+    (gotoh_stream16.cu: mid = sb + (se - sb + 1) / 2), four steps per word."""
+    eng = _FakeEngine()
+    rng = np.random.default_rng(4)
+    lens = rng.integers(1, 60, 37).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(lens)])
+    tiles = np.zeros(2, E.TILE_DTYPE)
+    tiles["stream_begin"], tiles["stream_end"] = [0, 20], [20, 37]
+    w = eng._tb_words16(tiles, 5, cs)
+    for ti, (b, e) in enumerate([(0, 20), (20, 37)]):
+        per = (e - b + 7) // 8
+        for k in range(8):
+            sb, se = min(b + k * per, e), min(b + k * per + per, e)
+            mid = sb + (se - sb + 1) // 2
+            rows = max(lens[sb:mid].sum(), lens[mid:se].sum())
+            T = (rows + 1 + 31 + 31) // 32 * 32 if se > sb else 0
+            assert w[ti, k] == T // 4 * 5 * 32
+
+
+def test_k_classes_match_k_for():
+    eng = _FakeEngine()
+    lens = np.asarray([1, 31, 32, 33, 64, 65, 150, 319, 320, 321, 400, 416, 417, 1000, 1024, 1025, 5000])
+    got = eng.k_classes(lens)
+    want = [eng.k_for(int(l)) or -1 for l in lens]
+    assert got.tolist() == want
+
+
+def test_fits_s16_ranges():
+    """The traced packed kernel needs every DP value inside +-16000 (its tie tests subtract two
+    values), the score-only one inside +-32000; non-integer scores never qualify."""
+    from praline_b200 import matrices
+    eng = _FakeEngine()
+    S = matrices.blosum62()
+    assert eng.fits_s16(S, -11.0, -1.0, np.asarray([300, 300])) is not None
+    assert eng.fits_s16(S, -11.0, -1.0, np.asarray([300, 400]), limit=16000) is not None
+    assert eng.fits_s16(S, -11.0, -1.0, np.asarray([900]), limit=16000) is None
+    assert eng.fits_s16(S, -11.0, -1.0, np.asarray([900])) is not None
+    assert eng.fits_s16(S, -11.0, -1.0, np.asarray([2000])) is None
+    assert eng.fits_s16(S, -11.5, -1.0, np.asarray([100])) is None
+    assert eng.fits_s16(S * 0.5, -11.0, -1.0, np.asarray([100])) is None
