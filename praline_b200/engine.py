@@ -734,8 +734,8 @@ class Engine(object):
         z_dev = None
         if zero_idxs is not None and len(zero_idxs):
             z = np.zeros((L1 + 1, L2 + 1), np.uint8)
-            for idx in zero_idxs:
-                z[tuple(idx)] = 1
+            zi = np.asarray(zero_idxs, np.int64).reshape(-1, 2)     # Waterman-Eggert boxes: tens of thousands of cells
+            z[zi[:, 0], zi[:, 1]] = 1
             z_dev = self.dev(z)
         ws = torch.empty(int(self.lib.pgpu_general_workspace_bytes(L1, L2)), dtype=torch.uint8, device=self.device)
         # one int32 buffer: [score | cell y x k | path start | path len | pad 2] + path rows
