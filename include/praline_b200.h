@@ -140,6 +140,38 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs_de
                          float threshold, int tb_fmt, void* stream);
 
 /*
+ * Local traced batch and its walk: the inner loop of LocalMasterSlaveAligner (component/
+ * preprofile.py:227-267) -- PairwiseAligner in mode "local" (cext.c:203-243 with MODE_LOCAL, end
+ * cell = first row-major maximum, component/align.py:401-403) with zero_idxs = the bounding boxes of
+ * the alignments found in earlier Waterman-Eggert iterations (preprofile.py:252-259; masked cells
+ * keep M = U = L = 0 and no flags, cext.c:143-148).  Reference orientation only (resident =
+ * sequence two), gap penalties <= 0, integer-valued scores.
+ *
+ *   boxes      NULL, or [n_slots][PGPU_NBOX][4] int32 (ylo, yhi, xlo, xhi), inclusive, y over sequence
+ *              one; (1, 0, 1, 0) = empty
+ *   box_out    [n_slots][PGPU_NBOX][4]: the walk writes the bounding box of its path into box number
+ *              box_slot (may alias boxes: iteration n reads boxes 0..n-2 and writes box n-1)
+ *   counts     local preprofile mode: compress_path + extend_path_local + Alignment.merge +
+ *              get_frequencies (util/align.py:187-266) as atomic adds into the master's table
+ * Paths are NOT extended (the reference extends after compress_path, preprofile.py:262-263).
+ */
+#define PGPU_NBOX 3
+int pgpu_align_tiles_local(int K, const uint8_t* seqs_dev, const int64_t* offs_dev, const int32_t* stream_ids_dev,
+                           const void* tiles_dev, int n_tiles, int64_t n_slots, const float* S_dev, int A,
+                           float gap_open, float gap_extend, const float* topD_dev, float left0, float left1,
+                           int border_len, float* scores_dev, uint64_t* keys_dev, uint32_t* tb_dev,
+                           const int64_t* tb_base_dev, int32_t* emit_t_dev, int64_t* pair_tb_dev,
+                           const int32_t* boxes_dev, void* stream);
+int pgpu_traceback_tiles_local(int K, const int64_t* offs_dev, const int32_t* slot_resident_dev,
+                               const int32_t* slot_stream_dev, int64_t n_slots, const uint64_t* keys_dev,
+                               const uint32_t* tb_dev, const int32_t* emit_t_dev, const int64_t* pair_tb_dev,
+                               int code00, const int64_t* path_off_dev, int32_t* path_buf_dev,
+                               int32_t* path_start_dev, int32_t* path_len_dev, const uint8_t* seqs_dev,
+                               int32_t* counts_dev, const int64_t* cnt_off_dev, int A, const float* scores_dev,
+                               int use_threshold, float threshold, const int32_t* boxes_dev, int32_t* box_out_dev,
+                               int box_slot, void* stream);
+
+/*
  * Match-score matrix (K1).  Replaces cext_build_scores (cext.c:308-455): m[y][x] = sum over
  * track sets of P1[y] . S . P2[x]^T, evaluated in the reference's order.  P1/P2/S are HOST
  * arrays of DEVICE pointers (one per set), A the alphabet size per set.

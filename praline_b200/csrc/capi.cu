@@ -144,6 +144,59 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, c
     return pg_launch_traceback(a, (cudaStream_t)stream);
 }
 
+// Local traced batch (K2 local instantiations) and its walk (K4 local mode): the inner loop of
+// LocalMasterSlaveAligner (preprofile.py:227-267), boxes = Waterman-Eggert masks per slot.
+int pgpu_align_tiles_local(int K, const uint8_t* seqs, const int64_t* offs, const int32_t* stream_ids,
+                           const void* tiles, int n_tiles, int64_t n_slots, const float* S, int A,
+                           float gap_open, float gap_extend, const float* topD, float left0, float left1,
+                           int border_len, float* scores, uint64_t* keys, uint32_t* tb, const int64_t* tb_base,
+                           int32_t* emit_t, int64_t* pair_tb, const int32_t* boxes, void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    if (border_len < 32 * K + 1) { pg_set_error("border arrays too short for K=%d", K); return 1; }
+    if (!keys || !tb || !tb_base || !emit_t || !pair_tb) { pg_set_error("local traced launch needs keys and the traceback buffers"); return 1; }
+    if (gap_open > 0.f || gap_extend > 0.f) { pg_set_error("local traced batches need gap penalties <= 0"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    StreamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seqs = seqs; a.offs = offs; a.stream_ids = stream_ids; a.tiles = (const PgTile*)tiles;
+    a.S = S; a.A = A; a.transposed = 0; a.go = gap_open; a.ge = gap_extend;
+    a.topD = topD; a.border_len = border_len; a.left0 = left0; a.left1 = left1;
+    a.scores = scores;
+    a.rowkey = (unsigned long long*)keys;
+    a.colkey = (unsigned long long*)keys + n_slots;
+    a.tb = tb; a.tb_base = tb_base; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    a.boxes = (const int4*)boxes;
+    PG_CUDA_OK(cudaMemsetAsync(keys, 0, sizeof(uint64_t) * 2 * (size_t)n_slots, st));
+    int rc = pg_launch_stream_local(a, n_tiles, K, boxes != nullptr, st);
+    if (rc) return rc;
+    return pg_launch_semi_scores(n_slots, a.rowkey, a.colkey, PG_LOCAL, 0, scores, st);
+}
+
+int pgpu_traceback_tiles_local(int K, const int64_t* offs, const int32_t* slot_resident, const int32_t* slot_stream,
+                               int64_t n_slots, const uint64_t* keys, const uint32_t* tb, const int32_t* emit_t,
+                               const int64_t* pair_tb, int code00, const int64_t* path_off, int32_t* path_buf,
+                               int32_t* path_start, int32_t* path_len, const uint8_t* seqs, int32_t* counts,
+                               const int64_t* cnt_off, int A, const float* scores, int use_thr, float thr,
+                               const int32_t* boxes, int32_t* box_out, int box_slot, void* stream)
+{
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_slots = n_slots; a.mode = PG_LOCAL; a.K = K; a.transposed = 0; a.offs = offs;
+    a.slot_resident = slot_resident; a.slot_stream = slot_stream; a.tb = tb; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    a.rowkey = (const unsigned long long*)keys;
+    a.colkey = keys ? (const unsigned long long*)keys + n_slots : nullptr;
+    a.code00 = code00; a.top_ramp = 1; a.left_ramp = 1;    // local borders are the gap ramps (align.py:370-385)
+    a.path_off = path_off; a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
+    a.seqs = seqs; a.counts = counts; a.cnt_off = cnt_off; a.A = A; a.scores = scores; a.use_thr = use_thr; a.thr = thr;
+    a.boxes = boxes; a.box_out = box_out; a.box_slot = box_slot;
+    if (!keys) { pg_set_error("local walks start from the keys of pgpu_align_tiles_local"); return 1; }
+    if (counts && (!seqs || !cnt_off || (use_thr && !scores))) { pg_set_error("preprofile mode needs seqs, cnt_off and scores"); return 1; }
+    if (!counts && !path_buf && !box_out) { pg_set_error("nothing to produce: neither paths, counts nor boxes requested"); return 1; }
+    if (box_out && (box_slot < 0 || box_slot >= PG_NBOX)) { pg_set_error("box_slot %d outside 0..%d", box_slot, PG_NBOX - 1); return 1; }
+    return pg_launch_traceback(a, (cudaStream_t)stream);
+}
+
 int pgpu_build_scores(int n_sets, const float* const* P1, const float* const* P2, const float* const* S,
                       const int* A, int L1, int L2, float* m, int m_pitch, void* stream)
 {

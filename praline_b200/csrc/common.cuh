@@ -13,6 +13,12 @@ enum { PG_GLOBAL = 0, PG_LOCAL = 1, PG_SG_BOTH = 2, PG_SG_ONE = 3, PG_SG_TWO = 4
 enum { TB_MM = 1 << 1, TB_MU = 1 << 2, TB_ML = 1 << 3, TB_UO = 1 << 4, TB_UE = 1 << 5,
        TB_LO = 1 << 6, TB_LE = 1 << 7 };
 
+// Waterman-Eggert boxes per pair (local master-slave alignments, reference preprofile.py:227-267):
+// iteration n masks the bounding boxes of the n - 1 alignments before it; PG_NBOX + 1 iterations
+// are served by the batched path.  A box is (ylo, yhi, xlo, xhi), inclusive, reference orientation;
+// (1, 0, 1, 0) is empty.
+#define PG_NBOX 3
+
 // One unit of work of the inter-task kernel: a resident sequence (laid across the lanes of
 // every warp of the CTA) against a contiguous run of streamed sequences.
 struct PgTile {
@@ -57,6 +63,7 @@ struct StreamArgs {
     int64_t* pair_tb;            // per slot: word offset of its warp's traceback region
     int go16, ge16, neg16, left0_16, left1_16;   // packed s16x2 variant (gotoh_stream16.cu)
     int all_ones;                // -1, opaque to ptxas: ~x = x * all_ones + all_ones stays an IMAD (FMA pipe)
+    const int4* boxes;           // local traced + masks: [slot][PG_NBOX] boxes
     const float* mwave;          // profile batches: match scores [row][32*K], rows in stream order
     const int64_t* mrow_base;    // first matrix row per (tile, warp); row 0 of a region is the dummy row
 };
@@ -86,6 +93,9 @@ struct TraceArgs {
     const float* scores;            // per slot, for the score threshold
     int use_thr;
     float thr;
+    const int32_t* boxes;           // local mode: [slot][PG_NBOX][4] masked boxes (may be NULL)
+    int32_t* box_out;               // local mode: [slot][PG_NBOX][4], the walk writes the bounding box of its path
+    int box_slot;                   //             into box number box_slot (may alias `boxes`)
     int tb_fmt;                     // 0: f32 kernel's nibbles, 8 rows per word; 1: packed int16 kernel's words (4 rows x 2 halves)
 };
 
@@ -142,6 +152,7 @@ int pg_stream_supported_k(int k);
 int pg_launch_cluster(int n, int linkage, const float* dist, void* work, int32_t* merges, cudaStream_t st);
 size_t pg_cluster_workspace_bytes(int n);
 int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb, cudaStream_t st);
+int pg_launch_stream_local(const StreamArgs& a, int n_tiles, int K, bool masked, cudaStream_t st);
 int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, int paired, cudaStream_t st);
 int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,
                           int mode, int transposed, float* scores, cudaStream_t st);

@@ -27,6 +27,17 @@
 // master index is y.  Counts are order-independent sums, so pairs add with atomics straight
 // into the master's [L x A] table and no path ever leaves the device.  Pairs below the score
 // threshold are skipped (preprofile.py:144-145).
+//
+// Local mode (K2's local traced launches, reference orientation only).  The walk starts in state M
+// at the first row-major maximum (key of K2; (0,0) when nothing is positive, np.argmax over the
+// zero-initialised `o`, align.py:401-403) and stops (a) where an M cell carries the stop code
+// (bit 0 clear, bit 1 set: its three sums are all negative, no flag in the reference), (b) at any
+// interior cell inside a Waterman-Eggert box (masked cells keep t = 0, cext.c:143-148), (c) at
+// (0,0) after the border chain.  The path is not extended.  Every walk writes the bounding box of
+// its path (preprofile.py:252-259) for the next iteration.  Local preprofile counts: the same
+// "first row per master index" rule, plus what extend_path_local's -1 padding does to
+// get_frequencies (util/align.py:205-211, :234-266): the step from -1 to x0 at master row y0 >= 1
+// counts slave[x0 - 1] (Python indexing: x0 = 0 is the LAST residue) against master position y0.
 #include "common.cuh"
 
 __device__ __forceinline__ float tkey_value(unsigned long long k)
@@ -40,7 +51,9 @@ __global__ void k_traceback(const TraceArgs a)
 {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.n_slots) return;
-    if (a.counts && a.use_thr && !(a.scores[slot] >= a.thr)) return;
+    const bool local = a.mode == PG_LOCAL;
+    const bool below = a.counts && a.use_thr && !(a.scores[slot] >= a.thr);
+    if (below && !(local && a.box_out)) return;   // a Waterman-Eggert box is due even below the threshold
     const int rid = a.slot_resident[slot], sid = a.slot_stream[slot];
     const int Lr = (int)(a.offs[rid + 1] - a.offs[rid]);   // kernel columns
     const int Ls = (int)(a.offs[sid + 1] - a.offs[sid]);   // kernel rows
@@ -102,7 +115,19 @@ __global__ void k_traceback(const TraceArgs a)
 
     // ---- start cell (kernel coordinates) ----------------------------------------------------
     int yk = Ls, xk = Lr;
-    if (a.mode != PG_GLOBAL) {
+    int bx[PG_NBOX][4];
+#pragma unroll
+    for (int b = 0; b < PG_NBOX; b++) {
+        const bool have = local && a.boxes;
+#pragma unroll
+        for (int c = 0; c < 4; c++) bx[b][c] = have ? a.boxes[slot * (PG_NBOX * 4) + 4 * b + c] : ((c & 1) ? 0 : 1);
+    }
+    if (local) {
+        const unsigned long long rk = a.rowkey[slot];
+        const uint32_t idx = ~(uint32_t)rk;
+        if (tkey_value(rk) > 0.f) { yk = (int)(idx >> 11); xk = (int)(idx & 2047u); }
+        else { yk = 0; xk = 0; }
+    } else if (a.mode != PG_GLOBAL) {
         const unsigned long long rk = a.rowkey[slot], ck = a.colkey[slot];
         const float rv = tkey_value(rk), cv = tkey_value(ck);
         const int rx = (int)(uint32_t)rk, cy = (int)(uint32_t)ck;
@@ -113,7 +138,8 @@ __global__ void k_traceback(const TraceArgs a)
         else     take_kernel_row = !((cv > rv) && from_row);
         if (take_kernel_row) { yk = Ls; xk = rx; } else { yk = cy; xk = Lr; }
     }
-    int s = code_at(yk, xk);
+    int s = local ? 0 : code_at(yk, xk);
+    const int end_y = yk, end_x = xk;
 
     const int64_t base = a.path_buf ? a.path_off[slot] : 0;
     const int cap = Lr + Ls + 2;
@@ -127,7 +153,7 @@ __global__ void k_traceback(const TraceArgs a)
         }
     };
     // preprofile mode: sequence one is the master, sequence two the slave
-    int* cnt = a.counts ? a.counts + a.cnt_off[slot] : nullptr;
+    int* cnt = (a.counts && !below) ? a.counts + a.cnt_off[slot] : nullptr;
     const uint8_t* slave = a.seqs ? a.seqs + a.offs[TR ? sid : rid] : nullptr;
     int pend_y = -1, pend_x = 0;
     auto kept = [&](int yr, int xr) {   // (yr, xr) is the first path row with master index yr
@@ -136,7 +162,7 @@ __global__ void k_traceback(const TraceArgs a)
         pend_x = xr;
     };
 
-    if (a.mode != PG_GLOBAL) {  // extend_path_semiglobal, trailing part (util/align.py:283-295)
+    if (a.mode != PG_GLOBAL && !local) {  // extend_path_semiglobal, trailing part (util/align.py:283-295)
         const int ye = TR ? xk : yk, xe = TR ? yk : xk;
         if (ye != L1) { for (int v = L1; v > ye; v--) push(v, xe); }
         else if (xe != L2) { for (int v = L2; v > xe; v--) push(ye, v); }
@@ -147,7 +173,13 @@ __global__ void k_traceback(const TraceArgs a)
         push(cy, cx);
         int ny = yk, nx = xk;
         bool moved = true;
-        if (yk == 0 && xk == 0) moved = false;
+        bool halt = false;
+        if (local && yk >= 1 && xk >= 1) {
+#pragma unroll
+            for (int b = 0; b < PG_NBOX; b++) halt |= (yk >= bx[b][0] && yk <= bx[b][1] && xk >= bx[b][2] && xk <= bx[b][3]);
+            if (!halt && s == 0) halt = (nib_at(yk, xk) & 3u) == 2u;
+        }
+        if (halt || (yk == 0 && xk == 0)) moved = false;
         else if (xk == 0) {
             if (s == 1 && a.left_ramp) ny--; else moved = false;
         } else if (yk == 0) {
@@ -165,7 +197,13 @@ __global__ void k_traceback(const TraceArgs a)
         yk = ny; xk = nx;
     }
 
-    if (a.mode != PG_GLOBAL) {  // leading part (util/align.py:270-279): rows first, then columns
+    if (local) {
+        if (cnt && yk >= 1) atomicAdd(cnt + (int64_t)(yk - 1) * a.A + slave[xk >= 1 ? xk - 1 : Lr - 1], 1);
+        if (a.box_out) {
+            int32_t* bo = a.box_out + slot * (PG_NBOX * 4) + 4 * a.box_slot;
+            bo[0] = yk; bo[1] = end_y; bo[2] = xk; bo[3] = end_x;
+        }
+    } else if (a.mode != PG_GLOBAL) {  // leading part (util/align.py:270-279): rows first, then columns
         const int y0 = TR ? xk : yk, x0 = TR ? yk : xk;
         if (y0 != 0) { for (int v = y0 - 1; v >= 0; v--) push(v, 0); }
         else if (x0 != 0) { for (int v = x0 - 1; v >= 0; v--) push(0, v); }
@@ -179,7 +217,10 @@ __global__ void k_traceback(const TraceArgs a)
 int pg_launch_traceback(const TraceArgs& a, cudaStream_t st)
 {
     if (a.n_slots <= 0) return 0;
-    if (a.mode == PG_LOCAL) { pg_set_error("batched traceback does not cover local mode"); return 1; }
+    if (a.mode == PG_LOCAL && (a.transposed || a.tb_fmt != 0)) {
+        pg_set_error("local walks need the f32 kernel's layout in the reference orientation");
+        return 1;
+    }
     k_traceback<<<(unsigned)((a.n_slots + 127) / 128), 128, 0, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
     return 0;

@@ -530,6 +530,167 @@ class Engine(object):
         scores[order] = scores_dev.cpu().numpy()
         return cnt.cpu().numpy().astype(np.int64), {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, scores
 
+    NBOX = 3    # PGPU_NBOX: boxes per pair -> up to NBOX + 1 Waterman-Eggert iterations on the device
+
+    def local_batchable(self, S, gap_series, lens):
+        """Local traced batches (pgpu_align_tiles_local): integer-exact scores, gap penalties <= 0,
+        residents within the K classes, streamed sequences below 2^20 rows (end-cell key)."""
+        go, ge = _gaps(gap_series)
+        lens = np.asarray(lens, np.int64)
+        return bool(go <= 0 and ge <= 0 and len(lens) and lens.min() >= 1 and lens.max() < (1 << 20)
+                    and self.k_for(int(lens.max())) is not None
+                    and self.integer_exact(S, go, ge, int(lens.max())))
+
+    def local_pairs(self, batch, pi, pj, S, gap_series, iterations=1, want_paths=False, counts=None):
+        """Local alignments of pairs (sequence_one = pi[k], sequence_two = pj[k]) with Waterman-Eggert
+        iterations, the inner loop of LocalMasterSlaveAligner (preprofile.py:227-267): iteration n is a
+        local alignment whose zero_idxs are the bounding boxes of iterations 0 .. n-1 of the same pair.
+
+        Returns (scores f32 [iterations x n], paths or None, boxes int32 [n x NBOX x 4]); paths is a
+        list per iteration of int32 [rows, 2] arrays (not extended).  counts = (count tables on the
+        device, table offset per pair, threshold): local preprofile mode of the walk."""
+        if not 1 <= iterations <= self.NBOX + 1:
+            raise _lib.PralineGpuError("1..%d Waterman-Eggert iterations are batched" % (self.NBOX + 1))
+        go, ge = _gaps(gap_series)
+        pi = np.asarray(pi, np.int64)
+        pj = np.asarray(pj, np.int64)
+        n = len(pi)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        if batch.max_sym >= A:
+            raise ValueError("sequence symbol outside the score matrix")
+        if not self.local_batchable(S, gap_series, batch.lens):
+            raise _lib.PralineGpuError("local batch outside the batched path: use align_general")
+        if n == 0:
+            return np.zeros((iterations, 0), np.float32), ([[] for _ in range(iterations)] if want_paths else None), \
+                np.zeros((0, self.NBOX, 4), np.int32)
+        res, strm = pj, pi                      # reference orientation: sequence two lies across the lanes
+        kcls = self.k_classes(batch.lens)
+        kres = kcls[res]
+        if n < 2 or ((res[1:] >= res[:-1]).all() and (kres[1:] >= kres[:-1]).all()):
+            order = np.arange(n)
+        else:
+            order = np.lexsort((np.arange(n), res, kres))
+        res_s, str_s = res[order], strm[order]
+        S_dev = self.dev(S)
+        stream_ids_dev = self.dev(str_s.astype(np.int32))
+        slot_res_dev = self.dev(res_s.astype(np.int32))
+        scores_dev = torch.empty((iterations, n), dtype=torch.float32, device=self.device)
+        empty = np.tile(np.array([1, 0, 1, 0], np.int32), (n, self.NBOX, 1))
+        boxes_dev = self.dev(empty)
+        cs = np.zeros(n + 1, np.int64)
+        np.cumsum(batch.lens[str_s], out=cs[1:])
+        caps = (batch.lens[res_s] + batch.lens[str_s] + 2).astype(np.int64)
+        cnt_dev = cnt_off_dev = thr = None
+        if counts is not None:
+            cnt_dev, cnt_off, thr = counts
+            cnt_off_dev = self.dev(np.asarray(cnt_off, np.int64)[order])
+        maxlen = max(32 * self.k_set[-1], int(batch.lens.max())) + 2
+        bkey = (1, float(go), float(ge), maxlen, False)
+        if bkey not in self._borders:
+            B = borders(1, go, ge, maxlen, False)
+            self._borders[bkey] = (B, self.dev(B["topD"]), self.dev(B["leftD"]))
+        B, top_dev, _ = self._borders[bkey]
+        kk = kcls[res_s]
+        bounds = np.flatnonzero(np.diff(kk)) + 1
+        tile = self._pick_tile(n)
+        pending = []
+        for a, b in zip(np.concatenate([[0], bounds]), np.concatenate([bounds, [n]])):
+            K = int(kk[a])
+            tiles = self._make_tiles(res_s[a:b], b - a, tile)
+            for f in ("stream_begin", "stream_end", "out_base"):
+                tiles[f] += a
+            words = self._tb_words(tiles, K, cs)
+            per_tile = words.sum(axis=1)
+            lo = 0
+            while lo < len(tiles):
+                acc = np.cumsum(per_tile[lo:])
+                hi = lo + max(1, int(np.searchsorted(acc, self.tb_budget_words, side="right")))
+                wt = tiles[lo:hi].copy()
+                s_lo, s_hi = int(wt["stream_begin"][0]), int(wt["stream_end"][-1])
+                ns = s_hi - s_lo
+                wt["out_base"] -= s_lo
+                wbase = np.zeros(words[lo:hi].size, np.int64)
+                np.cumsum(words[lo:hi].ravel()[:-1], out=wbase[1:])
+                tb = torch.empty(int(words[lo:hi].sum()), dtype=torch.int32, device=self.device)
+                tiles_dev, wbase_dev = self.dev(wt.view(np.uint8)), self.dev(wbase)
+                emit_t = torch.empty(ns, dtype=torch.int32, device=self.device)
+                pair_tb = torch.empty(ns, dtype=torch.int64, device=self.device)
+                keys = torch.empty(2 * ns, dtype=torch.int64, device=self.device)
+                wboxes = boxes_dev[s_lo:s_hi]
+                poff = poff_dev = None
+                if want_paths:
+                    cap = caps[s_lo:s_hi]
+                    poff = np.zeros(ns, np.int64)
+                    np.cumsum(cap[:-1], out=poff[1:])
+                    poff_dev = self.dev(poff)
+                for it in range(iterations):
+                    sc = scores_dev[it, s_lo:s_hi]
+                    _lib.check(self.lib.pgpu_align_tiles_local(
+                        K, self.ptr(batch.flat_dev), self.ptr(batch.offs_dev), self.ptr(stream_ids_dev), self.ptr(tiles_dev),
+                        len(wt), ns, self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev), B["left0"], B["left1"],
+                        maxlen + 1, self.ptr(sc), self.ptr(keys), self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t),
+                        self.ptr(pair_tb), self.ptr(wboxes) if it > 0 else None, self.stream()))
+                    pbuf = pstart = plen = None
+                    if want_paths:
+                        pbuf = torch.empty((int(cap.sum()), 2), dtype=torch.int32, device=self.device)
+                        pstart = torch.empty(ns, dtype=torch.int32, device=self.device)
+                        plen = torch.empty(ns, dtype=torch.int32, device=self.device)
+                    _lib.check(self.lib.pgpu_traceback_tiles_local(
+                        K, self.ptr(batch.offs_dev), self.ptr(slot_res_dev[s_lo:s_hi]), self.ptr(stream_ids_dev[s_lo:s_hi]),
+                        ns, self.ptr(keys), self.ptr(tb), self.ptr(emit_t), self.ptr(pair_tb), B["code00"],
+                        self.ptr(poff_dev), self.ptr(pbuf), self.ptr(pstart), self.ptr(plen),
+                        self.ptr(batch.flat_dev), self.ptr(cnt_dev), self.ptr(cnt_off_dev[s_lo:s_hi]) if cnt_dev is not None else None,
+                        A, self.ptr(sc), int(thr is not None), float(thr if thr is not None else 0.0),
+                        self.ptr(wboxes) if it > 0 else None, self.ptr(wboxes) if it < self.NBOX else None,
+                        min(it, self.NBOX - 1), self.stream()))
+                    self.launches += 3
+                    if want_paths:
+                        pending.append((it, s_lo, s_hi, poff, pbuf, pstart, plen))
+                lo = hi
+        scores = np.empty((iterations, n), np.float32)
+        scores[:, order] = scores_dev.cpu().numpy()
+        boxes = np.empty((n, self.NBOX, 4), np.int32)
+        boxes[order] = boxes_dev.cpu().numpy()
+        paths = None
+        if want_paths:
+            paths = [[None] * n for _ in range(iterations)]
+            for (it, s_lo, s_hi, poff, pbuf, pstart, plen) in pending:
+                pb, ps, pl = pbuf.cpu().numpy(), pstart.cpu().numpy(), plen.cpu().numpy()
+                for k in range(s_hi - s_lo):
+                    o = poff[k] + ps[k]
+                    paths[it][order[s_lo + k]] = pb[o:o + pl[k]]
+        return scores, paths, boxes
+
+    def local_preprofile_counts(self, batch, masters, slaves, S, gap_series, iterations=2, threshold=None):
+        """Count tables of local master-slave preprofiles (LocalMasterSlaveAligner, preprofile.py:160-
+        267, followed by ProfileBuilder, profile.py:56), entirely on the device.  Same return value as
+        preprofile_counts; scores are [iterations x pairs]."""
+        masters = np.asarray(masters, np.int64)
+        slaves = np.asarray(slaves, np.int64)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        cnt, off, uniq, lens, slot_of = self._own_counts(batch, masters, A)
+        scores, _, _ = self.local_pairs(batch, masters, slaves, S, gap_series, iterations=iterations,
+                                        counts=(cnt, off[slot_of[masters]], threshold))
+        return cnt.cpu().numpy().astype(np.int64), {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, scores
+
+    def _own_counts(self, batch, masters, A):
+        """Zeroed count tables of the distinct masters with every master's own residues counted once
+        (the master occupies every column of its own alignment, util/align.py:205-211)."""
+        uniq = np.unique(masters)
+        lens = batch.lens[uniq]
+        off = np.zeros(len(uniq) + 1, np.int64)
+        np.cumsum(lens * A, out=off[1:])
+        slot_of = np.full(batch.n, -1, np.int64)
+        slot_of[uniq] = np.arange(len(uniq))
+        cnt = torch.zeros(int(off[-1]), dtype=torch.int32, device=self.device)
+        rows = np.concatenate([np.arange(l) for l in lens]) if len(lens) else np.zeros(0, np.int64)
+        base = np.repeat(off[:-1], lens)
+        syms = np.concatenate([batch.flat_host.numpy()[batch.offs[u]:batch.offs[u + 1]] for u in uniq]).astype(np.int64)
+        cnt[self.dev(base + rows * A + syms)] = 1
+        return cnt, off, uniq, lens, slot_of
+
     def align_profile_pairs(self, pbatch, pi, pj, S, gap_series, mode="global", resident=None, fast=False):
         """Scores of profile x profile pairs (sequence_one = pi[k], sequence_two = pj[k]), one track
         set, constant gaps: K1 rows in the reference's evaluation order feed the streaming kernel.

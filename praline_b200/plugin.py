@@ -28,7 +28,7 @@ from praline.core import (Component, Port, Environment, Execution, Manager, T, B
                           path_to_url)
 from praline.container import (Sequence, Alignment, ScoreMatrix, PlainTrack, ProfileTrack, MatchScoreModel,
                                GapScoreModel, SequenceTree)
-from praline.util import compress_path, auto_align_mode
+from praline.util import compress_path, extend_path_local, auto_align_mode
 from praline.container import TRACK_ID_INPUT
 
 from . import _lib
@@ -37,6 +37,7 @@ from .engine import get_engine, MODES
 PAIRWISE_TID = "praline.component.PairwiseAligner"
 RAW_TID = "praline.component.RawPairwiseAligner"
 GLOBAL_MS_TID = "praline.component.GlobalMasterSlaveAligner"
+LOCAL_MS_TID = "praline.component.LocalMasterSlaveAligner"
 PROFILE_BUILDER_TID = "praline.component.ProfileBuilder"
 GUIDE_TREE_TID = "praline.component.GuideTreeBuilder"
 TREE_MSA_TID = "praline.component.TreeMultipleSequenceAligner"
@@ -82,10 +83,12 @@ class _PreprofileBatch(object):
     """All master-slave pairs of one execute_many call that share a (matrix, gaps, threshold)
     class.  The count tables of every master are produced by ONE device pass on first use."""
 
-    def __init__(self, group, threshold):
+    def __init__(self, group, threshold, iterations=None):
         self.group, self.threshold = group, threshold
+        self.iterations = iterations      # None: global master-slave; n: local with n Waterman-Eggert iterations
         self.masters, self.slaves = [], []
         self.result = None
+        self._local = None
 
     def add(self, master_idx, slave_idx):
         self.masters.append(master_idx)
@@ -98,12 +101,26 @@ class _PreprofileBatch(object):
     def counts(self, master_idx):
         if self.result is None:
             g = self.group
-            self.result = get_engine().preprofile_counts(g.batch, self.masters, self.slaves, g.S, g.gaps,
-                                                         self.threshold)
+            if self.iterations is None:
+                self.result = get_engine().preprofile_counts(g.batch, self.masters, self.slaves, g.S, g.gaps,
+                                                             self.threshold)
+            else:
+                self.result = get_engine().local_preprofile_counts(g.batch, self.masters, self.slaves, g.S, g.gaps,
+                                                                   iterations=self.iterations, threshold=self.threshold)
         cnt, where, _ = self.result
         off, length = where[int(master_idx)]
         A = self.group.S.shape[0]
         return cnt[off:off + length * A].reshape(length, A).copy()
+
+
+    def local_alignments(self):
+        """(scores [iterations x pairs], paths per iteration) of the local batch, traced on first use."""
+        if self._local is None:
+            g = self.group
+            scores, paths, _ = get_engine().local_pairs(g.batch, self.masters, self.slaves, g.S, g.gaps,
+                                                        iterations=self.iterations, want_paths=True)
+            self._local = (scores, paths)
+        return self._local
 
 
 class _RangePicks(object):
@@ -137,6 +154,17 @@ class LazyMasterSlaveAlignment(Alignment):
             master = self._master
             path = np.arange(len(master) + 1).reshape(len(master) + 1, 1)
             alignment = Alignment([master], path)
+            if self._batch is not None and self._batch.iterations is not None:    # preprofile.py:227-265
+                scores, paths = self._batch.local_alignments()
+                for slave, (g, k) in zip(self._slaves, self._picks):
+                    for n in range(self._batch.iterations):
+                        if self._threshold is None or float(scores[n][k]) >= self._threshold:
+                            p = compress_path(np.array(paths[n][k], dtype=int), 0)
+                            p = extend_path_local(p, len(master), 0)
+                            merge_path = np.arange(len(slave) + 1).reshape(len(slave) + 1, 1)
+                            alignment = alignment.merge(Alignment([slave], merge_path), p)
+                self._built = alignment
+                return self._built
             for slave, (g, k) in zip(self._slaves, self._picks):     # preprofile.py:144-152
                 score = float(g.scores[k])
                 if self._threshold is None or score >= self._threshold:
@@ -857,18 +885,23 @@ class GpuBatchManager(Manager):
             from praline.core import PralineError
             raise PralineError("manager has been closed")
         requests = list(requests)
-        plain, ms = [], []
+        plain, ms, lms = [], [], []
         for n, (tid, inputs, tag, env) in enumerate(requests):
             if tid == PAIRWISE_TID and self.index.resolve(tid) is GpuPairwiseAligner:
                 plain.append(n)
             elif tid == GLOBAL_MS_TID and len(requests) > 0:
                 ms.append(n)
+            elif tid == LOCAL_MS_TID:
+                lms.append(n)
         handled = set()
         if plain:
             for msg in self._batched_pairwise(requests, plain, parent_tag, handled):
                 yield msg
         if ms:
             for msg in self._batched_master_slave(requests, ms, parent_tag, handled):
+                yield msg
+        if lms and self._bulk_master_slave(requests, lms, parent_tag, handled, ms_tid=LOCAL_MS_TID):
+            for msg in self._bulk_messages(parent_tag, handled):
                 yield msg
         for n, (tid, inputs, tag, env) in enumerate(requests):
             if n in handled:
@@ -960,12 +993,32 @@ class GpuBatchManager(Manager):
             self.batched_requests += 1
 
     # -- GlobalMasterSlaveAligner requests (preprofile.py:67-156) --------------------------------
-    def _bulk_master_slave(self, requests, idxs, parent_tag, handled):
+    def _bulk_messages(self, parent_tag, handled):
+        for n, tag, alignment, npairs in self._bulk_out:
+            begin = BeginMessage(parent_tag)
+            begin.tag = tag
+            yield begin
+            prog = ProgressMessage(1.0)
+            prog.tag = tag
+            yield prog
+            done = CompleteMessage({'alignment': alignment})
+            done.tag = tag
+            yield done
+            handled.add(n)
+            self.batched_requests += npairs
+        self._bulk_out = []
+
+    def _bulk_master_slave(self, requests, idxs, parent_tag, handled, ms_tid=GLOBAL_MS_TID):
         """The common shape of the preprofile stage (workflow.py:139-161): N requests over ONE set of
         plain-track sequences, one track set, one matrix, one aligner environment.  Every sequence
         is validated once (the per-pair checks of PairwiseAligner.execute, component/align.py:114-189,
         are per-sequence properties) and the N(N-1) ordered pairs are filed with list operations
-        only -- no per-pair Python.  Returns False when the requests do not have that shape."""
+        only -- no per-pair Python.  Returns False when the requests do not have that shape.
+
+        ms_tid = LOCAL_MS_TID: the same for LocalMasterSlaveAligner (preprofile.py:160-267): local
+        alignments with Waterman-Eggert iterations, whose bounding-box masks stay on the device
+        (Engine.local_pairs); every (pair, iteration) above the threshold adds into the master's table."""
+        local = ms_tid == LOCAL_MS_TID
         eng = get_engine()
         if self.index.resolve(PAIRWISE_TID) is not GpuPairwiseAligner:
             return False
@@ -974,7 +1027,7 @@ class GpuBatchManager(Manager):
         if len(track_ids) != 1 or len(track_ids[0]) != 1 or len(mats) < 1:
             return False
         tid0 = track_ids[0][0]
-        comp = self.index.resolve(GLOBAL_MS_TID)
+        comp = self.index.resolve(ms_tid)
         envs = []
         key0 = None
         for n in idxs:
@@ -986,13 +1039,16 @@ class GpuBatchManager(Manager):
             if env['aligner'] != PAIRWISE_TID:
                 return False
             sub_env = Environment(keys=env['aligner_env'].keys, component=GpuPairwiseAligner, parent=env)
-            key = (tuple(sub_env['gap_series']), sub_env['debug'], env['score_threshold'])
+            key = (tuple(sub_env['gap_series']), sub_env['debug'], env['score_threshold'],
+                   env['waterman_eggert_iterations'] if local else None)
             if key0 is None:
                 key0 = key
             if key != key0 or sub_env['debug'] != 0:
                 return False
             envs.append(env)
-        gap_series, _, threshold = key0
+        gap_series, _, threshold, iterations = key0
+        if local and not 1 <= iterations <= eng.NBOX + 1:
+            return False
         # one validation per distinct sequence
         seq_idx, tracks = {}, []
         try:
@@ -1013,10 +1069,12 @@ class GpuBatchManager(Manager):
         if min(len(a) for a in arrs) < 1 or eng.k_for(longest) is None or \
                 not eng.integer_exact(S, gaps[0], gaps[1], longest):
             return False
-        g = _Group("global", S, gaps)
+        if local and not eng.local_batchable(S, gaps, [len(a) for a in arrs]):
+            return False
+        g = _Group("local" if local else "global", S, gaps)
         for t, a in zip(tracks, arrs):
             g.add_seq(t, a)
-        pre = _PreprofileBatch(g, threshold)
+        pre = _PreprofileBatch(g, threshold, iterations if local else None)
         self._bulk_out = []
         for n, env in zip(idxs, envs):
             _, inputs, tag, _ = requests[n]
@@ -1026,24 +1084,13 @@ class GpuBatchManager(Manager):
             k0 = g.add_pairs(midx, sidx)
             pre.add_many(midx, sidx)
             alignment = LazyMasterSlaveAlignment(master, slaves, _RangePicks(g, k0, len(sidx)), threshold, tid0, pre, midx)
-            self._bulk_out.append((n, tag, alignment, len(sidx)))
+            self._bulk_out.append((n, tag, alignment, len(sidx) * (iterations if local else 1)))
         return True
 
     def _batched_master_slave(self, requests, idxs, parent_tag, handled):
         if len(idxs) > 1 and self._bulk_master_slave(requests, idxs, parent_tag, handled):
-            for n, tag, alignment, npairs in self._bulk_out:
-                begin = BeginMessage(parent_tag)
-                begin.tag = tag
-                yield begin
-                prog = ProgressMessage(1.0)
-                prog.tag = tag
-                yield prog
-                done = CompleteMessage({'alignment': alignment})
-                done.tag = tag
-                yield done
-                handled.add(n)
-                self.batched_requests += npairs
-            self._bulk_out = []
+            for msg in self._bulk_messages(parent_tag, handled):
+                yield msg
             return
         eng = get_engine()
         groups, plans = {}, {}

@@ -523,3 +523,119 @@ def test_packed_traced_kernel_paths_and_counts(eng, resident):
     lb = eng.batch(long_seqs)
     eng.align_pairs(lb, [0, 1], [2, 3], S, [-11.0, -1.0], mode="global", want_paths=True, resident=resident)
     assert eng.last_traced_fmt == 0
+
+
+def _we_family():
+    rng = np.random.default_rng(5)
+    fam = [np.asarray(s) for s in synth.family(17, 6, 90)] + [rng.integers(0, 20, 15).astype(np.int32)]
+    fam += [np.asarray(s) for s in synth.family(19, 3, 150)]
+    w = 17   # tryptophan: S[W][W] = 11 ties a gap opening of -11 against the local zero
+    fam.append(np.array([w, 3, w, w, 5, w, 2, w, w], np.int32))
+    fam.append(np.array([w, w, 4, w, 6, 6, w, w, 1, w], np.int32))
+    return fam
+
+
+@pytest.mark.parametrize("gaps", [[-11.0, -1.0], [-3.0], [-11.0, 0.0]])
+def test_local_waterman_eggert_batches_vs_oracle(eng, gaps):
+    """Batched local alignments with Waterman-Eggert iterations (pgpu_align_tiles_local +
+    pgpu_traceback_tiles_local): score, path and bounding box of every (pair, iteration) equal the
+    reference's LocalMasterSlaveAligner inner loop restated on the oracle (tests/we_model.py)."""
+    import we_model
+    S = matrices.blosum62()
+    fam = _we_family()
+    n = len(fam)
+    batch = eng.batch(fam)
+    pi = np.repeat(np.arange(n), n - 1)
+    pj = np.concatenate([[j for j in range(n) if j != i] for i in range(n)])
+    for iterations in (1, 4):
+        scores, paths, boxes = eng.local_pairs(batch, pi, pj, S, gaps, iterations=iterations, want_paths=True)
+        for k, (i, j) in enumerate(zip(pi, pj)):
+            want = we_model.we_alignments(fam[i], fam[j], S, gaps, iterations)
+            for it, (score, path, _) in enumerate(want):
+                assert scores[it][k] == score, (gaps, i, j, it)
+                assert np.array_equal(paths[it][k], path), (gaps, i, j, it)
+            wb = we_model.boxes_of([p for _, p, _ in want])
+            for it in range(min(iterations, 3)):
+                assert tuple(boxes[k, it]) == wb[it], (gaps, i, j, it)
+
+
+def test_local_batches_vs_reference_golden(eng):
+    """The same against what the reference itself produced (tests/golden/local_ms.json)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    S = matrices.blosum62()
+    with open(os.path.join(GOLDEN, "local_ms.json")) as f:
+        cases = json.load(f)
+    for case in cases:
+        seqs = [np.asarray(s, np.int32) for s in case["seqs"]]
+        n = len(seqs)
+        batch = eng.batch(seqs)
+        masters = np.repeat(np.arange(n), n - 1)
+        slaves = np.concatenate([[j for j in range(n) if j != i] for i in range(n)])
+        scores, paths, _ = eng.local_pairs(batch, masters, slaves, S, case["gaps"], iterations=case["iterations"],
+                                           want_paths=True)
+        cnt, where, sc2 = eng.local_preprofile_counts(batch, masters, slaves, S, case["gaps"],
+                                                      iterations=case["iterations"], threshold=case["threshold"])
+        assert np.array_equal(scores, sc2)
+        k = 0
+        for i, gm in enumerate(case["masters"]):
+            calls = iter(gm["calls"])
+            for j in range(n):
+                if j == i:
+                    continue
+                for it in range(case["iterations"]):
+                    c = next(calls)
+                    assert c["score"] == scores[it][k]
+                    assert np.array_equal(np.asarray(c["path"]), paths[it][k])
+                k += 1
+            off, length = where[i]
+            assert np.array_equal(cnt[off:off + length * 27].reshape(length, 27), np.asarray(gm["counts"])), (case["seed"], i)
+
+
+@pytest.mark.parametrize("thr", [None, 35.0])
+def test_local_preprofile_counts_on_device(eng, thr):
+    """Count tables of local master-slave preprofiles from the device equal the reference's host
+    pipeline compress_path -> extend_path_local -> Alignment.merge -> get_frequencies."""
+    import we_model
+    S = matrices.blosum62()
+    fam = _we_family()
+    n = len(fam)
+    batch = eng.batch(fam)
+    masters = np.repeat(np.arange(n), n - 1)
+    slaves = np.concatenate([[j for j in range(n) if j != i] for i in range(n)])
+    cnt, where, scores = eng.local_preprofile_counts(batch, masters, slaves, S, [-11.0, -1.0], iterations=2, threshold=thr)
+    for i in range(n):
+        want, _, _ = we_model.local_master_counts(fam, i, S, [-11.0, -1.0], 2, thr, 27)
+        off, length = where[i]
+        assert np.array_equal(cnt[off:off + length * 27].reshape(length, 27), want), (thr, i)
+
+
+def test_local_batch_full_size_properties(eng):
+    """At a size the oracle does not finish quickly: iteration 1 of the local batch scores what the
+    score-only local kernel scores, every
+    path lies inside its own box and outside the boxes of earlier iterations (first cell excepted:
+    a walk may END on a masked cell), and the count tables hold one count per (pair, iteration,
+    aligned master position) at most."""
+    S = matrices.blosum62()
+    seqs = synth.family(23, 120, 300)
+    n = len(seqs)
+    batch = eng.batch(seqs)
+    pi = np.repeat(np.arange(n), n - 1)
+    pj = np.concatenate([[j for j in range(n) if j != i] for i in range(n)])
+    scores, paths, boxes = eng.local_pairs(batch, pi, pj, S, [-11.0, -1.0], iterations=3, want_paths=True)
+    plain, _ = eng.align_pairs(batch, pi, pj, S, [-11.0, -1.0], mode="local")
+    assert np.array_equal(scores[0], plain)
+    assert (scores >= 0).all()
+    rng = np.random.default_rng(0)
+    for k in rng.integers(0, len(pi), 400):
+        for it in range(3):
+            p = paths[it][k]
+            ylo, yhi, xlo, xhi = boxes[k, it]
+            assert (p[0] == (ylo, xlo)).all() and (p[-1] == (yhi, xhi)).all()
+            d = np.diff(p, axis=0)
+            assert ((d >= 0) & (d <= 1)).all() and (d.sum(axis=1) >= 1).all()
+            for e in range(it):
+                b = boxes[k, e]
+                inside = (p[1:, 0] >= max(b[0], 1)) & (p[1:, 0] <= b[1]) & (p[1:, 1] >= max(b[2], 1)) & (p[1:, 1] <= b[3])
+                assert not inside.any()

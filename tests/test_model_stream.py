@@ -92,3 +92,39 @@ def test_model_local_scores_match_oracle(transposed):
         one, two = (fam[0], s) if transposed else (s, fam[0])
         want, _ = oracle.align_seqs("local", one, two, S, [-11.0, -1.0])
         assert float(o["score"]) == want
+
+
+def test_local_model_matches_oracle_with_boxes():
+    """The local traced encoding (tests/model_local.py = what gotoh_stream.cuh / traceback.cu do in
+    local mode) gives the oracle's scores, paths, boxes and preprofile counts over Waterman-Eggert
+    iterations, ties on W-W = -gap_open and linear gaps included."""
+    import model_local
+    import we_model
+    from praline_b200 import matrices, synth
+    S = matrices.blosum62()
+    rng = np.random.default_rng(5)
+    fam = [np.asarray(s) for s in synth.family(17, 4, 36)] + [rng.integers(0, 20, 15).astype(np.int32)]
+    w = 17   # tryptophan: S[W][W] = 11 ties a gap opening of -11 against the local zero
+    fam.append(np.array([w, 3, w, w, 5, w, 2, w, w], np.int32))
+    fam.append(np.array([w, w, 4, w, 6, 6, w, w, 1, w], np.int32))
+    for gaps in ([-11.0, -1.0], [-3.0], [-11.0, 0.0]):
+        go, ge = (gaps[0], gaps[-1])
+        for i, a in enumerate(fam):
+            want_counts, _, _ = we_model.local_master_counts(fam, i, S, gaps, 3, None, 27)
+            counts = np.zeros_like(want_counts)
+            counts[np.arange(len(a)), a] += 1
+            for j, b in enumerate(fam):
+                if i == j:
+                    continue
+                boxes = []
+                for K in (1, 3):
+                    boxes = []
+                    for score, path, _ in we_model.we_alignments(a, b, S, gaps, 3):
+                        nib, key = model_local.fill(a, b, S, go, ge, boxes, K=K)
+                        got = model_local.walk(nib, key, boxes)
+                        assert key[0] == score, (gaps, i, j)
+                        assert np.array_equal(got, path), (gaps, i, j, len(boxes))
+                        boxes.append(we_model.boxes_of([path])[0])
+                        if K == 3:
+                            model_local.counts_from_path(got, b, len(a), 27, counts)
+            assert np.array_equal(counts, want_counts), (gaps, i)

@@ -151,3 +151,34 @@ def test_tree_distance_matrix_matches_reference_expression():
     assert dist.dtype == np.float32 and (np.diag(dist) == 0).all() and dist.min() == 0
     iu = np.triu_indices(n, k=1)
     assert np.array_equal(dist[iu], -sc) and np.array_equal(dist, dist.T)
+
+
+def test_local_master_slave_restatement_against_reference_golden():
+    """oracle.align_raw(mode='local', zero_idxs=boxes) and the host restatement of compress_path /
+    extend_path_local / Alignment.merge / get_frequencies (tests/we_model.py) reproduce what the
+    reference's LocalMasterSlaveAligner + ProfileBuilder produced (tests/golden/local_ms.json)."""
+    import json
+    import os
+    import we_model
+    from conftest import GOLDEN
+    from praline_b200 import matrices
+    S = matrices.blosum62()
+    with open(os.path.join(GOLDEN, "local_ms.json")) as f:
+        cases = json.load(f)
+    for case in cases:
+        seqs = [np.asarray(s, np.int32) for s in case["seqs"]]
+        for i, gm in enumerate(case["masters"]):
+            calls = iter(gm["calls"])
+            for j in range(len(seqs)):
+                if j == i:
+                    continue
+                for score, path, n_zero in we_model.we_alignments(seqs[i], seqs[j], S, case["gaps"], case["iterations"]):
+                    c = next(calls)
+                    assert c["slave"] == "s%d" % j and c["n_zero"] == n_zero
+                    assert c["score"] == score
+                    assert np.array_equal(np.asarray(c["path"]), path)
+            counts, path, names = we_model.local_master_counts(seqs, i, S, case["gaps"], case["iterations"],
+                                                               case["threshold"], 27)
+            assert np.array_equal(counts, np.asarray(gm["counts"]))
+            assert np.array_equal(path, np.asarray(gm["path"]).reshape(len(seqs[i]) + 1, -1))
+            assert ["s%d" % k for k in names] == gm["items"]

@@ -229,7 +229,8 @@ def test_lazy_alignment_paths_from_batch():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("preprofile,msa", [("global", "tree"), ("dummy", "tree"), ("global", "ad_hoc")])
+@pytest.mark.parametrize("preprofile,msa", [("global", "tree"), ("dummy", "tree"), ("global", "ad_hoc"),
+                                            ("local", "tree")])
 def test_msa_workflow_identical_to_reference(preprofile, msa):
     sm = _blosum()
     seqs = praline.load_sequence_fasta(R.ROOT + "/tests/golden/BBA0184.tfa", ALPHABET_AA)
@@ -295,6 +296,47 @@ def test_bulk_master_slave_matches_reference(threshold):
         outs.append([(np.asarray(a.path), [it.name for it in a.items]) for a in alns])
         if isinstance(mgr, plugin.GpuBatchManager):
             assert mgr.batched_requests == 9 * 8
+    for (p0, n0), (p1, n1) in zip(*outs):
+        assert n0 == n1 and np.array_equal(p0, p1)
+    for c0, c1 in zip(*profs):
+        assert np.array_equal(c0, c1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threshold,iterations", [(None, 2), (60.0, 3), (None, 1)])
+def test_bulk_local_master_slave_matches_reference(threshold, iterations):
+    """N LocalMasterSlaveAligner requests in one Execution (workflow.py:139-161, preprofile_mode
+    'local') take the bulk path: Waterman-Eggert iterations with their box masks on the device;
+    the lazily built alignments and the device count tables equal the reference's."""
+    from praline.core import Execution
+    sm = _blosum()
+    fam = synth.family(33, 7, 60) + [np.random.default_rng(3).integers(0, 20, 21)]
+    outs, profs = [], []
+    for mk_mgr in (lambda: Manager(R.reference_index()), lambda: plugin.GpuBatchManager(R.reference_index())):
+        mgr = mk_mgr()
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+        ex = Execution(mgr, R.ROOT_TAG)
+        for i, master in enumerate(seqs):
+            t = ex.add_task(pc.LocalMasterSlaveAligner)
+            t.environment(Environment(keys={'gap_series': [-11.0, -1.0], 'score_threshold': threshold,
+                                            'aligner': pc.PairwiseAligner.tid,
+                                            'waterman_eggert_iterations': iterations}))
+            t.inputs(master_sequence=master, slave_sequences=[s for j, s in enumerate(seqs) if j != i],
+                     track_id_sets=[[TRACK_ID_INPUT]], score_matrices=[sm])
+        for _ in ex.run():
+            pass
+        alns = [o['alignment'] for o in ex.outputs]
+        ex2 = Execution(mgr, R.ROOT_TAG)
+        for a in alns:
+            t = ex2.add_task(pc.ProfileBuilder)
+            t.environment(Environment(keys={}))
+            t.inputs(alignment=a, track_id=TRACK_ID_INPUT)
+        for _ in ex2.run():
+            pass
+        profs.append([o['profile_track'].counts for o in ex2.outputs])
+        outs.append([(np.asarray(a.path), [it.name for it in a.items]) for a in alns])
+        if isinstance(mgr, plugin.GpuBatchManager):
+            assert mgr.batched_requests == 8 * 7 * iterations
     for (p0, n0), (p1, n1) in zip(*outs):
         assert n0 == n1 and np.array_equal(p0, p1)
     for c0, c1 in zip(*profs):
