@@ -188,6 +188,8 @@ class Engine(object):
         self.nw = self.lib.pgpu_warps_per_tile()
         self.k_set = [k for k in range(1, 65) if self.lib.pgpu_supported_k(k)]
         self.launches = 0          # kernels of ours launched (bench.py reports it)
+        self.trace_on = os.environ.get("PGPU_TRACE", "") not in ("", "0")
+        self._traces = []
         # traceback words per wave: 16 GiB of the 180 GB (more pairs per wave = more walkers in flight in K4)
         self.tb_budget_words = int(float(os.environ.get("PGPU_TB_GIB", "16")) * (1 << 28))
         self._borders = {}
@@ -195,6 +197,26 @@ class Engine(object):
         self.m_budget_floats = 1 << 31     # 8 GiB of match scores per wave of a profile batch
 
     # -- helpers -------------------------------------------------------------------------------
+    def _trace_event(self, name, chain=None):
+        """PGPU_TRACE=1: CUDA events between the C-ABI calls of a pass; dump_trace() prints the device
+        time of every section.  A no-op otherwise."""
+        if not self.trace_on:
+            return None
+        chain = chain if chain is not None else []
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        chain.append((name, e))
+        if name is None:
+            self._traces.append(chain)
+        return chain
+
+    def dump_trace(self):
+        torch.cuda.synchronize()
+        for chain in self._traces:
+            for (n0, e0), (_, e1) in zip(chain[:-1], chain[1:]):
+                print("  [trace] %-40s %8.3f ms" % (n0, e0.elapsed_time(e1)))
+        self._traces = []
+
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -626,11 +648,13 @@ class Engine(object):
                     poff_dev = self.dev(poff)
                 for it in range(iterations):
                     sc = scores_dev[it, s_lo:s_hi]
+                    ev = self._trace_event("local fill it%d K%d (%d slots)" % (it, K, ns))
                     _lib.check(self.lib.pgpu_align_tiles_local(
                         K, self.ptr(batch.flat_dev), self.ptr(batch.offs_dev), self.ptr(stream_ids_dev), self.ptr(tiles_dev),
                         len(wt), ns, self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev), B["left0"], B["left1"],
                         maxlen + 1, self.ptr(sc), self.ptr(keys), self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t),
                         self.ptr(pair_tb), self.ptr(wboxes) if it > 0 else None, self.stream()))
+                    self._trace_event("local walk it%d" % it, ev)
                     pbuf = pstart = plen = None
                     if want_paths:
                         pbuf = torch.empty((int(cap.sum()), 2), dtype=torch.int32, device=self.device)
@@ -645,6 +669,7 @@ class Engine(object):
                         self.ptr(wboxes) if it > 0 else None, self.ptr(wboxes) if it < self.NBOX else None,
                         min(it, self.NBOX - 1), self.stream()))
                     self.launches += 3
+                    self._trace_event(None, ev)
                     if want_paths:
                         pending.append((it, s_lo, s_hi, poff, pbuf, pstart, plen))
                 lo = hi
