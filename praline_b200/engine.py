@@ -532,25 +532,49 @@ class Engine(object):
         slaves = np.asarray(slaves, np.int64)
         S = np.ascontiguousarray(S, np.float32)
         A = S.shape[0]
-        uniq = np.unique(masters)
-        lens = batch.lens[uniq]
-        off = np.zeros(len(uniq) + 1, np.int64)
-        np.cumsum(lens * A, out=off[1:])
-        slot_of = np.full(batch.n, -1, np.int64)
-        slot_of[uniq] = np.arange(len(uniq))
-        cnt = torch.zeros(int(off[-1]), dtype=torch.int32, device=self.device)
-        # the master itself occupies every column of its own alignment (util/align.py:205-211)
-        rows = np.concatenate([np.arange(l) for l in lens]) if len(lens) else np.zeros(0, np.int64)
-        base = np.repeat(off[:-1], lens)
-        syms = np.concatenate([batch.flat_host.numpy()[batch.offs[u]:batch.offs[u + 1]] for u in uniq]).astype(np.int64)
-        own = self.dev(base + rows * A + syms)
-        cnt[own] = 1
+        cnt, off, uniq, lens, slot_of = self._own_counts(batch, masters, A)
         scores_dev, order, _ = self.align_pairs(batch, masters, slaves, S, gap_series, mode="global", want_paths=True,
                                                 resident="one", device_only=True,
                                                 counts=(cnt, off[slot_of[masters]], threshold))
         scores = np.empty(len(masters), np.float32)
         scores[order] = scores_dev.cpu().numpy()
         return cnt.cpu().numpy().astype(np.int64), {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, scores
+
+    def preprofile_stage(self, batch, S, gap_series, threshold=None, masters=None, mode="global", iterations=2,
+                         chunk_pairs=1 << 20):
+        """The whole preprofile stage of the workflow (workflow.py:139-161 + :211-224): every master
+        against ALL other sequences of the batch, count tables on the device.  Masters are processed in
+        chunks of about chunk_pairs pairs; nothing synchronises between chunks, so the host plans
+        chunk c + 1 while the device traces chunk c.  mode: "global" (GlobalMasterSlaveAligner) or
+        "local" (LocalMasterSlaveAligner with `iterations` Waterman-Eggert iterations).
+
+        Returns (count tables as ONE int32 device tensor, {master id: (offset, length)}, DP cells)."""
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        n = batch.n
+        masters = np.arange(n, dtype=np.int64) if masters is None else np.unique(np.asarray(masters, np.int64))
+        cnt, off, uniq, lens, slot_of = self._own_counts(batch, masters, A)
+        per = max(1, int(chunk_pairs) // max(n - 1, 1))
+        everyone = np.arange(n, dtype=np.int64)
+        cells = 0
+        total_len = int(batch.lens.sum())
+        for c0 in range(0, len(masters), per):
+            chunk = masters[c0:c0 + per]
+            grid = np.broadcast_to(everyone, (len(chunk), n))
+            s_arr = grid[grid != chunk[:, None]]              # row-major: each master's slaves in id order
+            m_arr = np.repeat(chunk, n - 1)
+            cells += int((batch.lens[chunk] * (total_len - batch.lens[chunk])).sum())
+            ctx = (cnt, off[slot_of[m_arr]], threshold)
+            if mode == "global":
+                self.align_pairs(batch, m_arr, s_arr, S, gap_series, mode="global", want_paths=True, resident="one",
+                                 device_only=True, counts=ctx)
+            elif mode == "local":
+                self.local_pairs(batch, m_arr, s_arr, S, gap_series, iterations=iterations, counts=ctx, device_only=True)
+            else:
+                raise ValueError("preprofile mode must be 'global' or 'local'")
+        if mode == "local":
+            cells *= iterations
+        return cnt, {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, cells
 
     NBOX = 3    # PGPU_NBOX: boxes per pair -> up to NBOX + 1 Waterman-Eggert iterations on the device
 
@@ -563,7 +587,7 @@ class Engine(object):
                     and self.k_for(int(lens.max())) is not None
                     and self.integer_exact(S, go, ge, int(lens.max())))
 
-    def local_pairs(self, batch, pi, pj, S, gap_series, iterations=1, want_paths=False, counts=None):
+    def local_pairs(self, batch, pi, pj, S, gap_series, iterations=1, want_paths=False, counts=None, device_only=False):
         """Local alignments of pairs (sequence_one = pi[k], sequence_two = pj[k]) with Waterman-Eggert
         iterations, the inner loop of LocalMasterSlaveAligner (preprofile.py:227-267): iteration n is a
         local alignment whose zero_idxs are the bounding boxes of iterations 0 .. n-1 of the same pair.
@@ -673,6 +697,8 @@ class Engine(object):
                     if want_paths:
                         pending.append((it, s_lo, s_hi, poff, pbuf, pstart, plen))
                 lo = hi
+        if device_only:        # nothing read back: the caller keeps queueing work
+            return scores_dev, order, boxes_dev
         scores = np.empty((iterations, n), np.float32)
         scores[:, order] = scores_dev.cpu().numpy()
         boxes = np.empty((n, self.NBOX, 4), np.int32)

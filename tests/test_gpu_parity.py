@@ -639,3 +639,25 @@ def test_local_batch_full_size_properties(eng):
                 b = boxes[k, e]
                 inside = (p[1:, 0] >= max(b[0], 1)) & (p[1:, 0] <= b[1]) & (p[1:, 1] >= max(b[2], 1)) & (p[1:, 1] <= b[3])
                 assert not inside.any()
+
+
+@pytest.mark.parametrize("mode", ["global", "local"])
+def test_preprofile_stage_chunks_equal_one_batch(eng, mode):
+    """Engine.preprofile_stage (masters in chunks, nothing read back between chunks) gives the count
+    tables of the one-batch entry points, for both master-slave aligners."""
+    S = matrices.blosum62()
+    seqs = synth.family(29, 23, 80) + [np.random.default_rng(1).integers(0, 20, 40).astype(np.int32)]
+    n = len(seqs)
+    batch = eng.batch(seqs)
+    masters = np.repeat(np.arange(n), n - 1)
+    slaves = np.concatenate([[j for j in range(n) if j != i] for i in range(n)])
+    if mode == "global":
+        want, where, _ = eng.preprofile_counts(batch, masters, slaves, S, [-11.0, -1.0], threshold=50.0)
+    else:
+        want, where, _ = eng.local_preprofile_counts(batch, masters, slaves, S, [-11.0, -1.0], iterations=2, threshold=50.0)
+    cnt, where2, cells = eng.preprofile_stage(batch, S, [-11.0, -1.0], threshold=50.0, mode=mode, iterations=2,
+                                              chunk_pairs=5 * (n - 1))
+    assert where == where2
+    assert np.array_equal(cnt.cpu().numpy(), want)
+    lens = batch.lens
+    assert cells == int((lens.sum() ** 2 - (lens ** 2).sum())) * (2 if mode == "local" else 1)

@@ -77,5 +77,34 @@ if rank == 0:
                       "n_gpus": world, "masters": int(len(all_masters)), "pairs": int(len(all_masters)) * (n - 1), "cells": cells_pre,
                       "wall_s": dt, "gcups": cells_pre / dt / 1e9, "full_stage_extrapolated_s": dt * n / len(all_masters),
                       "counts_sum": total_counts}))
+# (c) the WHOLE preprofile stage, measured (argv[3] = "full" or "full-local"): all n masters sharded by rank,
+# every master against all other sequences, chunked with nothing read back between chunks
+# (Engine.preprofile_stage); count tables all-gathered at the end.
+if len(sys.argv) > 3 and sys.argv[3].startswith("full"):
+    pmode = "local" if sys.argv[3] == "full-local" else "global"
+    nfull = int(sys.argv[4]) if len(sys.argv) > 4 else n          # masters taking part (default: all)
+    allm = np.arange(nfull)
+    mine, cuts = parallel.shard_masters(allm, lens, rank, world)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    cnt_dev, where, cells_mine = eng.preprofile_stage(batch, S, [-11.0, -1.0], masters=mine, mode=pmode, iterations=2)
+    t_host = time.perf_counter() - t0
+    if world > 1:
+        sizes = [int(lens[allm[cuts[r]:cuts[r + 1]]].sum()) * 27 for r in range(world)]
+        allc = parallel.allgather_counts(cnt_dev, sizes)
+    else:
+        allc = cnt_dev
+    total_counts = int(allc.sum(dtype=torch.int64).item())
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    td = torch.tensor([dt], dtype=torch.float64, device=eng.device)
+    pc = torch.tensor([float(cells_mine)], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pc, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"stage": "C3 preprofile stage, FULL (%s master-slave, count tables on device, all-gathered)" % pmode,
+                          "n_gpus": world, "masters": int(nfull), "pairs": int(nfull) * (n - 1), "cells": float(pc.item()),
+                          "wall_s": float(td.item()), "gcups": float(pc.item()) / float(td.item()) / 1e9,
+                          "host_planning_s_rank0": t_host, "counts_sum": total_counts}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
