@@ -353,8 +353,24 @@ def main():
         torch.cuda.synchronize(dev)
         kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
         achieved = my_cells * W_FLOPS_PER_CELL / (kms * 1e-3)
-        roof = {"bound": "cuda_core_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
-                "frac": achieved / peak,
+        # The roofline of this kernel is the CUDA-core pipe its recurrence runs on (not HBM, not
+        # tensor).  peak = the BARE recurrence (same instructions, no loads / shuffles / loop) measured on
+        # this box by pgpu_microbench: 5 packed DPX/add instructions per 2 cells (cell_mix16) or the
+        # 7-instruction f32 cell (cell_mix); achieved = the same instruction count at the kernel's cell rate.
+        ipc_cell = 2.5 if plan[5] else 7.0
+        mix = mb["cell_mix16"] if plan[5] else mb["cell_mix"]
+        ach_ops = my_cells / (kms * 1e-3) * ipc_cell
+        peak_ops = mix * 32.0 * sms * 1e9
+        roof = {"bound": "cuda_core_issue", "achieved": ach_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
+                "frac": ach_ops / peak_ops,
+                "frac_note": "of measured: recurrence lane-instructions per second of this kernel (%.1f per cell) / the rate "
+                             "of the bare recurrence instruction mix on this box (pgpu_microbench, %.2f warp-instr/ns/SM)"
+                             % (ipc_cell, mix),
+                # SURVEY 8d's DP-cell roofline (the figure BASELINE's '>= 50 %% of the DP-cell roofline' refers to):
+                # algorithmic W = 11 f32 add/max per cell against the measured f32 add issue rate; above 1 for the
+                # packed kernel because one DPX instruction does two cells
+                "dp_cell_roofline": {"w_ops_per_cell": W_FLOPS_PER_CELL, "achieved": achieved / 1e12, "peak": peak / 1e12,
+                                     "unit": "Tlane-op/s", "frac": achieved / peak},
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
                 # (profiles/r01_kstream16r_raw.csv: 427,520 B read, 0 B written -- the 2 MB of scores stay in
                 # L2; f32 kernel, profiles/r01_kstream_v2_raw.csv: 443,392 B); algorithmic bytes per launch:
@@ -366,11 +382,6 @@ def main():
                         "issue at half that rate on this part (pipe_rates, warp-instr/ns/SM); HBM is not the "
                         "bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
                 "issue_bound_frac": (my_cells / (kms * 1e-3)) * (2.5 if plan[5] else 7.0) / 32.0 / (mb["fadd"] * sms * 1e9),
-                # fraction of the speed of the BARE recurrence (no loads, shuffles or loop) measured on this
-                # box with the same instructions: 5 packed instructions per 2 cells (cell_mix16) or the
-                # 7-instruction f32 cell (cell_mix), warp-instructions/ns/SM
-                "recurrence_frac": (my_cells / (kms * 1e-3)) / ((mb["cell_mix16"] / 2.5 if plan[5] else mb["cell_mix"] / 7.0)
-                                                               * 32.0 * sms * 1e9),
                 "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence at the "
                                     "measured full issue rate: 5 packed DPX/add instructions per 2 cells (int16 "
                                     "kernel) or 7 per cell (f32 kernel); the DPX and max instructions themselves "

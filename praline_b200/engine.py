@@ -188,6 +188,7 @@ class Engine(object):
         self.nw = self.lib.pgpu_warps_per_tile()
         self.k_set = [k for k in range(1, 65) if self.lib.pgpu_supported_k(k)]
         self.launches = 0          # kernels of ours launched (bench.py reports it)
+        self._stage = None
         self.trace_on = os.environ.get("PGPU_TRACE", "") not in ("", "0")
         self._traces = []
         # traceback words per wave: 16 GiB of the 180 GB (more pairs per wave = more walkers in flight in K4)
@@ -220,11 +221,39 @@ class Engine(object):
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    STAGE_TIERS = ((1 << 20, 6), (32 << 20, 4))     # (slot bytes, slots): small and large staging rings
+
     def dev(self, arr):
-        t = torch.from_numpy(np.ascontiguousarray(arr))
-        if self.pin and t.numel() * t.element_size() >= (1 << 20):
-            t = t.pin_memory()
-        return t.to(self.device, non_blocking=True)
+        """Host array -> device tensor, asynchronously on the current stream.  Arrays between 16 KB and
+        32 MB go through rings of persistent pinned staging buffers (a fresh pin_memory() costs
+        milliseconds per call, a pageable copy makes the host wait for the stream); slots are pinned on
+        first use and reused only after the copy that read them has completed."""
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a)
+        nbytes = a.nbytes
+        if not self.pin or nbytes < (1 << 14):
+            return t.to(self.device, non_blocking=True)
+        tier = next((k for k, (size, _) in enumerate(self.STAGE_TIERS) if nbytes <= size), None)
+        if tier is None:
+            return t.pin_memory().to(self.device, non_blocking=True)
+        if self._stage is None:
+            self._stage = [[[None, None] for _ in range(slots)] for _, slots in self.STAGE_TIERS]
+            self._stage_next = [0] * len(self.STAGE_TIERS)
+        ring = self._stage[tier]
+        slot = ring[self._stage_next[tier]]
+        self._stage_next[tier] = (self._stage_next[tier] + 1) % len(ring)
+        if slot[0] is None:
+            slot[0] = torch.empty(self.STAGE_TIERS[tier][0], dtype=torch.uint8).pin_memory()
+        if slot[1] is not None:
+            slot[1].synchronize()
+        src = slot[0][:nbytes]
+        src.numpy()[:] = a.reshape(-1).view(np.uint8)
+        out = torch.empty(a.shape, dtype=t.dtype, device=self.device)
+        out.view(torch.uint8).reshape(-1).copy_(src, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+        return out
 
     @staticmethod
     def ptr(t):
