@@ -62,6 +62,37 @@ int pgpu_supported_k(int k);
 int pgpu_warps_per_tile(void);
 
 /*
+ * The two self-contained entry points.  Everything the tile-level functions below
+ * expect from their caller -- grouping pairs by resident sequence, tiles, traceback waves, border
+ * arrays, workspaces -- is done inside the library (C++ host code, stream-ordered temporaries).
+ *
+ * pgpu_align_batch: n_pairs sequence-sequence alignments, pair k = (sequence_one = pair_i[k],
+ * sequence_two = pair_j[k]), one PairwiseAligner.execute each in the reference (component/
+ * align.py:88-251: cext_build_scores + border init + cext_align_<mode> + end cell + get_paths +
+ * extend_path_semiglobal).  All five modes; linear gaps: gap_extend = gap_open.  scores_out [n_pairs].
+ * want_paths: integer-valued scores only (else code 4: use pgpu_align_profiles pair by pair);
+ * path_buf is [sum_k (L1_k + L2_k + 2)][2] int32, the region of pair k starts at the prefix sum of
+ * those capacities and its path ((y, x) rows, reference orientation) occupies the LAST
+ * path_len_out[k] rows of the region.  Sequence two must be <= 1024 long (code 4 otherwise).
+ * Synchronises the stream once while planning (pair ids and offsets are read back).
+ *
+ * pgpu_align_profiles: one profile-profile alignment over n_sets track sets, m = sum_sets
+ * P1 . S . P2^T in the reference's evaluation order (cext.c:308-455) followed by
+ * RawPairwiseAligner (component/align.py:302-447) with per-position gap arrays g1 [L1][2],
+ * g2 [L2][2] and an optional mask zmask [(L1+1)][(L2+1)] (zero_idxs).  P1/P2/S are HOST arrays of
+ * DEVICE pointers.  score_out [1]; path_out [L1+L2+2][2] (may be NULL together with path_len_out),
+ * the path occupies the LAST path_len_out[0] rows.  Fully asynchronous on the stream.
+ */
+int pgpu_align_batch(int mode, int64_t n_pairs, const uint8_t* seqs_dev, const int64_t* seq_offsets_dev,
+                     const int32_t* pair_i_dev, const int32_t* pair_j_dev, const float* S_dev, int A,
+                     float gap_open, float gap_extend, int want_paths, float* scores_out_dev,
+                     int32_t* path_buf_dev, int32_t* path_len_out_dev, void* stream);
+int pgpu_align_profiles(int mode, int n_sets, const float* const* P1_dev, const float* const* P2_dev,
+                        const float* const* S_dev, const int* A, int L1, int L2, const float* g1_dev,
+                        const float* g2_dev, const uint8_t* zmask_dev_or_null, float* score_out_dev,
+                        int32_t* path_out_dev, int32_t* path_len_out_dev, void* stream);
+
+/*
  * Inter-task batch (K2): sequence-sequence alignments with constant gap penalties.
  * Replaces, per pair, cext_build_scores + cext_align_<mode> + the end-cell choice
  * (cext.c:308-455, :99-306; component/align.py:401-431), i.e. one PairwiseAligner.execute

@@ -18,6 +18,10 @@ _SIGNATURES = {
     "pgpu_last_error": (ctypes.c_char_p, []),
     "pgpu_supported_k": (c_int, [c_int]),
     "pgpu_warps_per_tile": (c_int, []),
+    "pgpu_align_batch": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgpu_align_profiles": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgpu_align_tiles": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
                                  c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_float, c_float, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
