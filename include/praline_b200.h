@@ -238,6 +238,12 @@ int pgpu_profile_times_matrix(const float* prof_dev, const float* S_dev, int A, 
 int pgpu_build_rows_fast(const float* prof_dev, const float* wres_dev, const int64_t* rowoff_dev, int A,
                          const void* blocks_dev, int n_blocks, int width, int local_mode, float* mwave_dev,
                          void* stream);
+/* Tensor-core form of pgpu_build_rows_fast (tcgen05.mma kind::tf32 with an FP32-accurate hi/lo split,
+ * accumulators in TMEM): same inputs and output; quads_dev is an int32 [n_quads][2] array of (first row
+ * block, number of row blocks <= 4), every quad's blocks sharing one resident.  A <= 32, width % 32 == 0. */
+int pgpu_build_rows_tc(const float* prof_dev, const float* wres_dev, const int64_t* rowoff_dev, int A,
+                       const void* blocks_dev, const void* quads_dev, int n_quads, int width, int local_mode,
+                       float* mwave_dev, void* stream);
 int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
                           int L2, float* m_dev, int m_pitch, void* stream);
 

@@ -1,0 +1,212 @@
+// score_rows_tc.cu -- K1t, the tolerance-mode profile score rows on the 5th-generation tensor cores.
+//
+// What it replaces: cext_build_scores (praline/util/cext.c:308-455) for score-only batches of
+// profile x profile pairs, m[y][x] = P1[y] . S . P2[x]^T, in the factored form of the fast path
+// (k_build_rows_fast, general.cu): W = P_res . S^T per resident profile once, then a dense
+// contraction  m[row][x] = sum_a P[row][a] * W[x][a]  over the alphabet (A <= 32).  Not the
+// reference's evaluation order: scores agree to ~1e-6 relative (stated bound 1e-5), opt-in.
+//
+// Shape.  One CTA = one 128-row x NC-column tile: 4 row blocks of <= 32 matrix rows that share a
+// resident (the wave's row blocks, engine.plan_profile_wave) x one column chunk of the resident
+// (NC <= 256, a multiple of 16).  The contraction runs as tcgen05.mma kind::tf32 with an FP32-accurate
+// split: every f32 operand is hi + lo with hi = tf32(x), lo = x - hi, and
+//     m = P_hi.W_hi + P_lo.W_hi + P_hi.W_lo           (the lo.lo term is below 2^-22 relative)
+// accumulated in one TMEM accumulator: 3 terms x 4 MMAs of K = 8 (alphabet padded to 32).
+//   * operands are staged by the CTA's own threads straight into the canonical no-swizzle K-major
+//     layout (8 x 16 B core matrices; SBO = 1024 B between 8-row groups, LBO = 128 B between the two
+//     16-byte K chunks of an instruction) -- the rows are gathered from the profile store, so TMA has
+//     nothing contiguous to fetch; fence.proxy.async hands them to the tensor core;
+//   * one elected thread issues the 12 MMAs and commits them to an mbarrier;
+//   * warp w owns TMEM lanes 32w .. 32w+31 = the rows of row block w: tcgen05.ld 32x32b.x16, then
+//     128-bit stores of its row (pad columns, dummy rows and short blocks handled here).
+// Bound: HBM writes, 4 B per cell (the same matrix the matrix-fed K2 streams back in); the tensor
+// pipe needs 192 tf32 flop per cell and idles.  Two CTAs per SM (<= 96 KB smem, <= 256 TMEM columns
+// each) so that one tile's stores overlap the other's staging + MMA.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// canonical K-major, no swizzle: byte offset of element (row r, k) of an [R x 32] tf32 operand
+__device__ __forceinline__ uint32_t core_off(int r, int k)
+{
+    return (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1 [46,48),
+    // base offset 0, lbo mode 0, layout type 0 (no swizzle) [61,64)
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo)
+{
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    lo = v - hi;
+}
+
+}  // namespace
+
+struct RowsTcArgs {
+    const float* prof;          // [rows x A] profile store (streamed side)
+    const float* wres;          // [rows x A] W = P . S^T (or P . S) of the same store (resident side)
+    const int64_t* rowoff;      // first row per sequence
+    const PgRowBlock* blocks;
+    const int2* quads;          // (first row block, number of row blocks <= 4): one resident per quad
+    int A, width, n_chunks, chunk;
+    float padv;
+    float* mwave;
+};
+
+__global__ void __launch_bounds__(128) k_build_rows_tc(const RowsTcArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_slot;
+    // operands: A_hi | A_lo (16 KB each), B_hi | B_lo (chunk x 128 B each)
+    unsigned char* sm = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* A_hi = sm;
+    unsigned char* A_lo = sm + 16384;
+    unsigned char* B_hi = sm + 32768;
+    unsigned char* B_lo = B_hi + (size_t)a.chunk * 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int2 quad = a.quads[blockIdx.x / a.n_chunks];
+    const int c0 = (int)(blockIdx.x % a.n_chunks) * a.chunk;
+    const int NC = min(a.chunk, a.width - c0);                 // columns of this tile, a multiple of 16
+    const PgRowBlock blk0 = a.blocks[quad.x];
+    const int64_t q0 = a.rowoff[blk0.res];
+    const int Lr = (int)(a.rowoff[blk0.res + 1] - q0);
+
+    // ---- TMEM accumulator: NC fp32 columns (power of two >= 32) ---------------------------------
+    uint32_t ncols = 32;
+    while ((int)ncols < NC) ncols <<= 1;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+
+    // ---- stage the operands, split into tf32 hi / lo ---------------------------------------------
+    for (int idx = tid; idx < 128 * 32; idx += 128) {
+        const int r = idx >> 5, k = idx & 31, b = r >> 5, rr = r & 31;
+        float v = 0.f;
+        if (b < quad.y && k < a.A) {
+            const PgRowBlock blk = a.blocks[quad.x + b];
+            if (rr < blk.rows && !(blk.dummy && rr == 0)) v = a.prof[(size_t)(blk.src0 + rr) * a.A + k];
+        }
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        const uint32_t o = core_off(r, k);
+        *reinterpret_cast<float*>(A_hi + o) = hi;
+        *reinterpret_cast<float*>(A_lo + o) = lo;
+    }
+    for (int idx = tid; idx < NC * 32; idx += 128) {
+        const int n = idx >> 5, k = idx & 31, x = c0 + n;
+        const float v = (x < Lr && k < a.A) ? a.wres[(size_t)(q0 + x) * a.A + k] : 0.f;
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        const uint32_t o = core_off(n, k);
+        *reinterpret_cast<float*>(B_hi + o) = hi;
+        *reinterpret_cast<float*>(B_lo + o) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    // ---- 3 terms x 4 K-steps of tcgen05.mma kind::tf32, M = 128, N = NC -----------------------------
+    if (warp == 0 && lane == 0) {
+        // cute::UMMA::InstrDescriptor: D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t sa[3] = {smem_u32(A_hi), smem_u32(A_lo), smem_u32(A_hi)};
+        const uint32_t sb[3] = {smem_u32(B_hi), smem_u32(B_hi), smem_u32(B_lo)};
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint64_t da = make_desc(sa[t] + s * 256), db = make_desc(sb[t] + s * 256);
+                const uint32_t acc = (t | s) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    {   // everybody waits for the accumulator (phase 0 of the barrier)
+        uint32_t done = 0;
+        const uint32_t addr = smem_u32(&mbar);
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(addr), "r"(0u) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: TMEM lane = matrix row; warp w writes the rows of row block w ---------------------
+    if (warp < quad.y) {
+        const PgRowBlock blk = a.blocks[quad.x + warp];
+        const bool live = lane < blk.rows;
+        const bool dummy = blk.dummy && lane == 0;
+        float* dst = a.mwave + (size_t)(blk.row0 + lane) * a.width + c0;
+        for (int c = 0; c < NC; c += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 o;
+                    float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int x = c0 + c + j + e;
+                        of[e] = dummy ? 0.f : (x < Lr ? __uint_as_float(v[j + e]) : a.padv);
+                    }
+                    *reinterpret_cast<float4*>(dst + c + j) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
+}
+
+int pg_launch_build_rows_tc(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
+                            const int2* quads, int n_quads, int width, float padv, float* mwave, cudaStream_t st)
+{
+    if (n_quads <= 0) return 0;
+    if (A < 1 || A > 32) { pg_set_error("tensor-core score rows: alphabet size %d above 32", A); return 1; }
+    if (width < 32 || width % 32) { pg_set_error("tensor-core score rows: width %d is not a multiple of 32", width); return 1; }
+    if (reinterpret_cast<uintptr_t>(mwave) & 15) { pg_set_error("tensor-core score rows: matrix not 16-byte aligned"); return 1; }
+    RowsTcArgs a;
+    a.prof = prof; a.wres = wres; a.rowoff = rowoff; a.blocks = blocks; a.quads = quads;
+    a.A = A; a.width = width; a.padv = padv; a.mwave = mwave;
+    a.n_chunks = (width + 255) / 256;
+    a.chunk = ((width + a.n_chunks - 1) / a.n_chunks + 15) / 16 * 16;
+    const int64_t nb = (int64_t)n_quads * a.n_chunks;
+    if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
+    const size_t smem = 1024 + 32768 + 2 * (size_t)a.chunk * 128;
+    PG_CUDA_OK(cudaFuncSetAttribute(k_build_rows_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_build_rows_tc<<<(unsigned)nb, 128, smem, st>>>(a);
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}

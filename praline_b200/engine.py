@@ -122,6 +122,21 @@ def plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, offs, rows_per_block=32)
     return mrow_base, blocks, n_rows
 
 
+def row_block_quads(blocks):
+    """Groups of <= 4 consecutive row blocks with one resident: the 128-row tiles of the tensor-core
+    score-row kernel.  Returns int32 [n_quads x 2] = (first block, number of blocks)."""
+    res = np.asarray(blocks["res"])
+    n = len(res)
+    if n == 0:
+        return np.zeros((0, 2), np.int32)
+    new_run = np.ones(n, bool)
+    new_run[1:] = res[1:] != res[:-1]
+    run_start = np.maximum.accumulate(np.where(new_run, np.arange(n), 0))
+    first = np.flatnonzero((np.arange(n) - run_start) % 4 == 0)
+    count = np.diff(np.append(first, n))
+    return np.stack([first, count], axis=1).astype(np.int32)
+
+
 class ProfileBatch(object):
     """A set of f32 profiles [L x A] resident on the device: one [rows x A] array plus int64 row
     offsets (the analogue of SeqBatch for ProfileTrack inputs, component/align.py:171-172)."""
@@ -196,6 +211,8 @@ class Engine(object):
         self._borders = {}
         self.use_s16 = os.environ.get("PGPU_NO_S16", "") == ""
         self.m_budget_floats = 1 << 31     # 8 GiB of match scores per wave of a profile batch
+        self.keep_mwave = False
+        self.fast_tc = os.environ.get("PGPU_FAST_TC", "1") not in ("", "0")   # tolerance-mode score rows on tcgen05
 
     # -- helpers -------------------------------------------------------------------------------
     def _trace_event(self, name, chain=None):
@@ -834,7 +851,14 @@ class Engine(object):
                 # keep every device temporary referenced until the launches that read it are queued:
                 # a tensor freed right after data_ptr() is handed to the next allocation
                 blocks_dev = self.dev(blocks.view(np.uint8))
-                if fast:
+                if fast and self.fast_tc and A <= 32:
+                    # tensor-core score rows (tcgen05 tf32 with a hi/lo split): 128-row tiles = quads of
+                    # consecutive row blocks that share a resident
+                    quads_dev = self.dev(row_block_quads(blocks))
+                    _lib.check(self.lib.pgpu_build_rows_tc(self.ptr(pbatch.prof_dev), self.ptr(wres), self.ptr(pbatch.offs_dev),
+                                                           A, self.ptr(blocks_dev), self.ptr(quads_dev), int(quads_dev.shape[0]),
+                                                           width, int(md == 1), self.ptr(mwave), self.stream()))
+                elif fast:
                     _lib.check(self.lib.pgpu_build_rows_fast(self.ptr(pbatch.prof_dev), self.ptr(wres), self.ptr(pbatch.offs_dev),
                                                              A, self.ptr(blocks_dev), len(blocks), width, int(md == 1),
                                                              self.ptr(mwave), self.stream()))
@@ -843,6 +867,8 @@ class Engine(object):
                                                         self.ptr(S_dev), self.ptr(blocks_dev), len(blocks), width,
                                                         int(transposed), int(md == 1), self.ptr(mwave), self.stream()))
                 self.launches += 1
+                if self.keep_mwave:      # tests compare the score rows of the three builders element by element
+                    self.last_mwave = mwave
                 self.run_tiles(md, K, transposed, pbatch, stream_ids_dev, wt, n, S_dev, A, go, ge, scores_dev,
                                mwave_dev=mwave, mrow_base_dev=self.dev(mrow_base))
                 lo = hi

@@ -661,3 +661,37 @@ def test_preprofile_stage_chunks_equal_one_batch(eng, mode):
     assert np.array_equal(cnt.cpu().numpy(), want)
     lens = batch.lens
     assert cells == int((lens.sum() ** 2 - (lens ** 2).sum())) * (2 if mode == "local" else 1)
+
+
+@pytest.mark.parametrize("resident", ["one", "two"])
+@pytest.mark.parametrize("mode", ["global", "local"])
+def test_tensor_core_score_rows(eng, resident, mode):
+    """k_build_rows_tc (tcgen05 tf32, hi/lo split) against the exact score rows and the CUDA-core
+    tolerance kernel, element by element over a whole wave, then the alignment scores against the
+    oracle within the stated 1e-5: several K classes (column chunks 32 .. 2 x 208), short row
+    blocks, residents shorter than the tile, an asymmetric matrix."""
+    rng = np.random.default_rng(8)
+    S = matrices.blosum62().copy()
+    S[3, 7] += 2.0                      # asymmetric: P.S and P.S^T differ
+    lens = [31, 64, 65, 150, 300, 301, 410, 97, 5]
+    profs = [synth.profile_from_counts(synth.count_profile(60 + k, L, 7 + k, 20, 27)) for k, L in enumerate(lens)]
+    pb = eng.profile_batch(profs)
+    pi, pj = synth.all_pairs(len(profs))
+    rows = {}
+    try:
+        eng.keep_mwave = True
+        for name, kw, tc in (("exact", dict(fast=False), True), ("fma", dict(fast=True), False), ("tc", dict(fast=True), True)):
+            eng.fast_tc = tc
+            sc = eng.align_profile_pairs(pb, pi, pj, S, [-11.0, -1.0], mode=mode, resident=resident, **kw)
+            rows[name] = (eng.last_mwave.cpu().numpy().copy(), sc)
+    finally:
+        eng.keep_mwave, eng.fast_tc = False, True
+    m_exact, s_exact = rows["exact"]
+    m_tc, s_tc = rows["tc"]
+    m_fma, _ = rows["fma"]
+    fin = np.isfinite(m_exact)
+    assert np.array_equal(np.isfinite(m_tc), fin) and np.array_equal(m_tc[~fin], m_exact[~fin])
+    scale = np.abs(m_exact[fin]).max()
+    assert np.abs(m_tc[fin] - m_exact[fin]).max() <= 4e-6 * scale
+    assert np.abs(m_tc[fin] - m_fma[fin]).max() <= 4e-6 * scale
+    assert np.allclose(s_tc, s_exact, rtol=1e-5, atol=1e-4)

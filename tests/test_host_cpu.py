@@ -234,3 +234,21 @@ def test_fits_s16_ranges():
     assert eng.fits_s16(S, -11.0, -1.0, np.asarray([2000])) is None
     assert eng.fits_s16(S, -11.5, -1.0, np.asarray([100])) is None
     assert eng.fits_s16(S * 0.5, -11.0, -1.0, np.asarray([100])) is None
+
+
+def test_row_block_quads():
+    """128-row tiles of the tensor-core score rows: <= 4 consecutive row blocks of one resident."""
+    from praline_b200.engine import row_block_quads, ROWBLOCK_DTYPE
+    b = np.zeros(11, ROWBLOCK_DTYPE)
+    b["res"] = [5, 5, 5, 5, 5, 5, 7, 7, 9, 9, 9]
+    assert row_block_quads(b).tolist() == [[0, 4], [4, 2], [6, 2], [8, 3]]
+    assert row_block_quads(b[:0]).shape == (0, 2)
+    rng = np.random.default_rng(0)
+    res = np.repeat(rng.integers(0, 50, 300), rng.integers(1, 12, 300))
+    b = np.zeros(len(res), ROWBLOCK_DTYPE)
+    b["res"] = res
+    q = row_block_quads(b)
+    assert q[:, 1].sum() == len(res) and (q[:, 1] >= 1).all() and (q[:, 1] <= 4).all()
+    assert (q[1:, 0] == q[:-1, 0] + q[:-1, 1]).all()
+    for f, c in q:
+        assert len(set(res[f:f + c])) == 1
