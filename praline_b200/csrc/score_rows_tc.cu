@@ -17,8 +17,12 @@
 //     16-byte K chunks of an instruction) -- the rows are gathered from the profile store, so TMA has
 //     nothing contiguous to fetch; fence.proxy.async hands them to the tensor core;
 //   * one elected thread issues the 12 MMAs and commits them to an mbarrier;
-//   * warp w owns TMEM lanes 32w .. 32w+31 = the rows of row block w: tcgen05.ld 32x32b.x16, then
-//     128-bit stores of its row (pad columns, dummy rows and short blocks handled here).
+//   * warps w and w + 4 own TMEM lanes 32w .. 32w+31 = the rows of row block w (even / odd 32-column
+//     chunks): tcgen05.ld 32x32b.x32 hands a thread 32 columns of ITS row, so the chunk is transposed
+//     through shared memory (the operand tiles are dead once the MMAs have committed; 16-byte pieces
+//     XOR-swizzled by row, conflict-free both ways) and leaves as 128-bit stores in which a warp
+//     writes four whole 128-byte row segments per instruction; pad columns, dummy rows and short
+//     blocks are handled here.
 // Bound: HBM writes, 4 B per cell (the same matrix the matrix-fed K2 streams back in); the tensor
 // pipe needs 192 tf32 flop per cell and idles.  Two CTAs per SM (<= 96 KB smem, <= 256 TMEM columns
 // each) so that one tile's stores overlap the other's staging + MMA.
@@ -63,7 +67,9 @@ struct RowsTcArgs {
     float* mwave;
 };
 
-__global__ void __launch_bounds__(128) k_build_rows_tc(const RowsTcArgs a)
+constexpr int kTcThreads = 256;
+
+__global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -96,27 +102,38 @@ __global__ void __launch_bounds__(128) k_build_rows_tc(const RowsTcArgs a)
     }
 
     // ---- stage the operands, split into tf32 hi / lo ---------------------------------------------
-    for (int idx = tid; idx < 128 * 32; idx += 128) {
-        const int r = idx >> 5, k = idx & 31, b = r >> 5, rr = r & 31;
-        float v = 0.f;
-        if (b < quad.y && k < a.A) {
-            const PgRowBlock blk = a.blocks[quad.x + b];
-            if (rr < blk.rows && !(blk.dummy && rr == 0)) v = a.prof[(size_t)(blk.src0 + rr) * a.A + k];
+    // One operand row per thread: its <= 32 alphabet entries are independent loads (all in flight at
+    // once), and the row's eight 16-byte K chunks go out as 128-bit shared stores -- a quarter warp
+    // writes 8 consecutive rows of one core matrix = 128 contiguous bytes, conflict-free.
+    auto stage_row = [&](const float* src, int r, unsigned char* hi_base, unsigned char* lo_base) {
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = (src != nullptr && k < a.A) ? __ldg(src + k) : 0.f;
+        const uint32_t o = core_off(r, 0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float4 h, l;
+            split_tf32(v[4 * j], h.x, l.x);
+            split_tf32(v[4 * j + 1], h.y, l.y);
+            split_tf32(v[4 * j + 2], h.z, l.z);
+            split_tf32(v[4 * j + 3], h.w, l.w);
+            *reinterpret_cast<float4*>(hi_base + o + j * 128) = h;
+            *reinterpret_cast<float4*>(lo_base + o + j * 128) = l;
         }
-        float hi, lo;
-        split_tf32(v, hi, lo);
-        const uint32_t o = core_off(r, k);
-        *reinterpret_cast<float*>(A_hi + o) = hi;
-        *reinterpret_cast<float*>(A_lo + o) = lo;
-    }
-    for (int idx = tid; idx < NC * 32; idx += 128) {
-        const int n = idx >> 5, k = idx & 31, x = c0 + n;
-        const float v = (x < Lr && k < a.A) ? a.wres[(size_t)(q0 + x) * a.A + k] : 0.f;
-        float hi, lo;
-        split_tf32(v, hi, lo);
-        const uint32_t o = core_off(n, k);
-        *reinterpret_cast<float*>(B_hi + o) = hi;
-        *reinterpret_cast<float*>(B_lo + o) = lo;
+    };
+    for (int row = tid; row < 128 + NC; row += kTcThreads) {
+        if (row < 128) {
+            const int b = row >> 5, rr = row & 31;
+            const float* src = nullptr;
+            if (b < quad.y) {
+                const PgRowBlock blk = a.blocks[quad.x + b];
+                if (rr < blk.rows && !(blk.dummy && rr == 0)) src = a.prof + (size_t)(blk.src0 + rr) * a.A;
+            }
+            stage_row(src, row, A_hi, A_lo);
+        } else {
+            const int n = row - 128, x = c0 + n;
+            stage_row(x < Lr ? a.wres + (size_t)(q0 + x) * a.A : nullptr, n, B_hi, B_lo);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor core reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -155,34 +172,45 @@ __global__ void __launch_bounds__(128) k_build_rows_tc(const RowsTcArgs a)
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: TMEM lane = matrix row; warp w writes the rows of row block w ---------------------
-    if (warp < quad.y) {
-        const PgRowBlock blk = a.blocks[quad.x + warp];
-        const bool live = lane < blk.rows;
-        const bool dummy = blk.dummy && lane == 0;
-        float* dst = a.mwave + (size_t)(blk.row0 + lane) * a.width + c0;
-        for (int c = 0; c < NC; c += 16) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+    // ---- epilogue: TMEM lane = matrix row; warps q and q + 4 write the rows of row block q -----------
+    const int q = warp & 3, half = warp >> 2;
+    if (q < quad.y) {
+        const PgRowBlock blk = a.blocks[quad.x + q];
+        unsigned char* tbuf = sm + warp * 4096;          // 32 rows x 128 B, inside the dead A tiles
+        const uint32_t tb_s = smem_u32(tbuf);
+        for (int c = half * 32; c < NC; c += 64) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (live) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float4 o;
+            for (int j = 0; j < 8; j++)      // my row, 16-byte piece j, swizzled by the row
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tb_s + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                             "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+            __syncwarp();
+            const int j = lane & 7, x = c0 + c + 4 * j;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {    // four rows per instruction, 128 contiguous bytes each
+                const int rr = 4 * i + (lane >> 3);
+                float4 o;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                             : "r"(tb_s + rr * 128 + ((j ^ (rr & 7)) << 4)) : "memory");
+                if (rr < blk.rows && c + 4 * j < NC) {
+                    const bool dummy = blk.dummy && rr == 0;
                     float* of = reinterpret_cast<float*>(&o);
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int x = c0 + c + j + e;
-                        of[e] = dummy ? 0.f : (x < Lr ? __uint_as_float(v[j + e]) : a.padv);
-                    }
-                    *reinterpret_cast<float4*>(dst + c + j) = o;
+                    for (int e = 0; e < 4; e++) of[e] = dummy ? 0.f : (x + e < Lr ? of[e] : a.padv);
+                    *reinterpret_cast<float4*>(a.mwave + (size_t)(blk.row0 + rr) * a.width + x) = o;
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -206,7 +234,7 @@ int pg_launch_build_rows_tc(const float* prof, const float* wres, const int64_t*
     if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
     const size_t smem = 1024 + 32768 + 2 * (size_t)a.chunk * 128;
     PG_CUDA_OK(cudaFuncSetAttribute(k_build_rows_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_build_rows_tc<<<(unsigned)nb, 128, smem, st>>>(a);
+    k_build_rows_tc<<<(unsigned)nb, kTcThreads, smem, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }

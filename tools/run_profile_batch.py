@@ -13,13 +13,19 @@ pb = eng.profile_batch(profs)
 pi, pj = synth.all_pairs(n)
 cells = float((pb.lens[pi] * pb.lens[pj]).sum())
 res = {}
-for fast in (True, False):
+only = sys.argv[4] if len(sys.argv) > 4 else ""          # "tc": just the tensor-core pass (for ncu)
+for name, fast, tc in (("fast_tc", True, True), ("fast_fma", True, False), ("exact", False, True)):
+    if only and not name.endswith(only):
+        continue
+    eng.fast_tc = tc
     eng.align_profile_pairs(pb, pi[:2000], pj[:2000], S, [-11.0, -1.0], mode="global", fast=fast)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     sc = eng.align_profile_pairs(pb, pi, pj, S, [-11.0, -1.0], mode="global", fast=fast)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    res["fast" if fast else "exact"] = sc
-    print(json.dumps({"mode": "fast" if fast else "exact", "n": n, "L": L, "depth": depth, "pairs": len(pi), "cells": cells,
+    res[name] = sc
+    print(json.dumps({"mode": name, "n": n, "L": L, "depth": depth, "pairs": len(pi), "cells": cells,
                       "wall_s": dt, "gcups": cells / dt / 1e9}))
-rel = np.abs(res["fast"] - res["exact"]) / np.maximum(1.0, np.abs(res["exact"]))
-print(json.dumps({"max_rel_diff_fast_vs_exact": float(rel.max())}))
+for name in ("fast_tc", "fast_fma"):
+    if name in res and "exact" in res:
+        rel = np.abs(res[name] - res["exact"]) / np.maximum(1.0, np.abs(res["exact"]))
+        print(json.dumps({"max_rel_diff_%s_vs_exact" % name: float(rel.max())}))
