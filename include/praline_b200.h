@@ -239,11 +239,20 @@ int pgpu_build_rows_fast(const float* prof_dev, const float* wres_dev, const int
                          const void* blocks_dev, int n_blocks, int width, int local_mode, float* mwave_dev,
                          void* stream);
 /* Tensor-core form of pgpu_build_rows_fast (tcgen05.mma kind::tf32 with an FP32-accurate hi/lo split,
- * accumulators in TMEM): same inputs and output; quads_dev is an int32 [n_quads][2] array of (first row
- * block, number of row blocks <= 4), every quad's blocks sharing one resident.  A <= 32, width % 32 == 0. */
-int pgpu_build_rows_tc(const float* prof_dev, const float* wres_dev, const int64_t* rowoff_dev, int A,
-                       const void* blocks_dev, const void* quads_dev, int n_quads, int width, int local_mode,
-                       float* mwave_dev, void* stream);
+ * accumulators in TMEM): same output.  One pgpu_quad per 128-row tile: <= 4 row blocks (<= 32 matrix rows
+ * each) that share a resident, with the resident's first profile row and length.  A <= 32, width % 32 == 0. */
+typedef struct pgpu_quad {
+    int64_t q0;          /* first profile row of the resident */
+    int32_t Lr;          /* resident length */
+    int32_t nblk;        /* row blocks in this tile (1..4) */
+    int64_t row0[4];     /* first matrix row per block */
+    int64_t src0[4];     /* profile row feeding matrix row row0 (row0 + r is fed by src0 + r) */
+    int32_t rows[4];
+    int32_t dummy[4];    /* matrix row row0 is the region's dummy row */
+    int64_t reserved[2];
+} pgpu_quad;
+int pgpu_build_rows_tc(const float* prof_dev, const float* wres_dev, int A, const void* quads_dev, int n_quads,
+                       int width, int local_mode, float* mwave_dev, void* stream);
 int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
                           int L2, float* m_dev, int m_pitch, void* stream);
 

@@ -222,11 +222,11 @@ int pgpu_build_rows_fast(const float* prof, const float* wres, const int64_t* ro
                                      local_mode ? -INFINITY : 0.f, mwave, (cudaStream_t)stream);
 }
 
-int pgpu_build_rows_tc(const float* prof, const float* wres, const int64_t* rowoff, int A, const void* blocks,
-                       const void* quads, int n_quads, int width, int local_mode, float* mwave, void* stream)
+int pgpu_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
+                       int local_mode, float* mwave, void* stream)
 {
-    return pg_launch_build_rows_tc(prof, wres, rowoff, A, (const PgRowBlock*)blocks, (const int2*)quads, n_quads, width,
-                                   local_mode ? -INFINITY : 0.f, mwave, (cudaStream_t)stream);
+    return pg_launch_build_rows_tc(prof, wres, A, quads, n_quads, width, local_mode ? -INFINITY : 0.f, mwave,
+                                   (cudaStream_t)stream);
 }
 
 int pgpu_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,

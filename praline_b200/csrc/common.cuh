@@ -144,8 +144,8 @@ int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const 
                          int n_blocks, int width, int transposed, float padv, float* mwave, cudaStream_t st);
 int pg_launch_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
                               int n_blocks, int width, float padv, float* mwave, cudaStream_t st);
-int pg_launch_build_rows_tc(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
-                            const int2* quads, int n_quads, int width, float padv, float* mwave, cudaStream_t st);
+int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
+                            float padv, float* mwave, cudaStream_t st);
 int pg_launch_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,
                                    cudaStream_t st);
 int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* S, int A, int L1, int L2,

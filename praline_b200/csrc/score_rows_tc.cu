@@ -27,6 +27,7 @@
 // pipe needs 192 tf32 flop per cell and idles.  Two CTAs per SM (<= 96 KB smem, <= 256 TMEM columns
 // each) so that one tile's stores overlap the other's staging + MMA.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -56,12 +57,24 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo)
 
 }  // namespace
 
+// One 128-row tile: <= 4 row blocks of one resident, everything the CTA needs in ONE 128-byte line
+// (the row-block list -> resident -> row offset chain would be three dependent round trips).
+struct PgQuad {
+    int64_t q0;                 // first profile row of the resident
+    int32_t Lr;                 // resident length
+    int32_t nblk;               // row blocks in this tile
+    int64_t row0[4];            // first matrix row per block
+    int64_t src0[4];            // profile row feeding it
+    int32_t rows[4];
+    int32_t dummy[4];
+    int64_t _pad[2];
+};
+static_assert(sizeof(PgQuad) == 128, "PgQuad is one cache line");
+
 struct RowsTcArgs {
     const float* prof;          // [rows x A] profile store (streamed side)
     const float* wres;          // [rows x A] W = P . S^T (or P . S) of the same store (resident side)
-    const int64_t* rowoff;      // first row per sequence
-    const PgRowBlock* blocks;
-    const int2* quads;          // (first row block, number of row blocks <= 4): one resident per quad
+    const PgQuad* quads;
     int A, width, n_chunks, chunk;
     float padv;
     float* mwave;
@@ -81,13 +94,11 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
     unsigned char* B_hi = sm + 32768;
     unsigned char* B_lo = B_hi + (size_t)a.chunk * 128;
 
+    __shared__ PgQuad quad;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int2 quad = a.quads[blockIdx.x / a.n_chunks];
+    if (tid < 8) reinterpret_cast<int4*>(&quad)[tid] = __ldg(reinterpret_cast<const int4*>(a.quads + blockIdx.x / a.n_chunks) + tid);
     const int c0 = (int)(blockIdx.x % a.n_chunks) * a.chunk;
     const int NC = min(a.chunk, a.width - c0);                 // columns of this tile, a multiple of 16
-    const PgRowBlock blk0 = a.blocks[quad.x];
-    const int64_t q0 = a.rowoff[blk0.res];
-    const int Lr = (int)(a.rowoff[blk0.res + 1] - q0);
 
     // ---- TMEM accumulator: NC fp32 columns (power of two >= 32) ---------------------------------
     uint32_t ncols = 32;
@@ -100,6 +111,9 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
+    __syncthreads();
+    const int64_t q0 = quad.q0;
+    const int Lr = quad.Lr;
 
     // ---- stage the operands, split into tf32 hi / lo ---------------------------------------------
     // One operand row per thread: its <= 32 alphabet entries are independent loads (all in flight at
@@ -125,10 +139,8 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
         if (row < 128) {
             const int b = row >> 5, rr = row & 31;
             const float* src = nullptr;
-            if (b < quad.y) {
-                const PgRowBlock blk = a.blocks[quad.x + b];
-                if (rr < blk.rows && !(blk.dummy && rr == 0)) src = a.prof + (size_t)(blk.src0 + rr) * a.A;
-            }
+            if (b < quad.nblk && rr < quad.rows[b] && !(quad.dummy[b] && rr == 0))
+                src = a.prof + (size_t)(quad.src0[b] + rr) * a.A;
             stage_row(src, row, A_hi, A_lo);
         } else {
             const int n = row - 128, x = c0 + n;
@@ -174,8 +186,10 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
 
     // ---- epilogue: TMEM lane = matrix row; warps q and q + 4 write the rows of row block q -----------
     const int q = warp & 3, half = warp >> 2;
-    if (q < quad.y) {
-        const PgRowBlock blk = a.blocks[quad.x + q];
+    if (q < quad.nblk) {
+        const int brows = quad.rows[q];
+        const bool bdummy = quad.dummy[q] != 0;
+        const int64_t brow0 = quad.row0[q];
         unsigned char* tbuf = sm + warp * 4096;          // 32 rows x 128 B, inside the dead A tiles
         const uint32_t tb_s = smem_u32(tbuf);
         for (int c = half * 32; c < NC; c += 64) {
@@ -202,12 +216,12 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
                 float4 o;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                              : "r"(tb_s + rr * 128 + ((j ^ (rr & 7)) << 4)) : "memory");
-                if (rr < blk.rows && c + 4 * j < NC) {
-                    const bool dummy = blk.dummy && rr == 0;
+                if (rr < brows && c + 4 * j < NC) {
+                    const bool dummy = bdummy && rr == 0;
                     float* of = reinterpret_cast<float*>(&o);
 #pragma unroll
                     for (int e = 0; e < 4; e++) of[e] = dummy ? 0.f : (x + e < Lr ? of[e] : a.padv);
-                    *reinterpret_cast<float4*>(a.mwave + (size_t)(blk.row0 + rr) * a.width + x) = o;
+                    *reinterpret_cast<float4*>(a.mwave + (size_t)(brow0 + rr) * a.width + x) = o;
                 }
             }
             __syncwarp();
@@ -218,17 +232,20 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
 }
 
-int pg_launch_build_rows_tc(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
-                            const int2* quads, int n_quads, int width, float padv, float* mwave, cudaStream_t st)
+int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
+                            float padv, float* mwave, cudaStream_t st)
 {
     if (n_quads <= 0) return 0;
     if (A < 1 || A > 32) { pg_set_error("tensor-core score rows: alphabet size %d above 32", A); return 1; }
     if (width < 32 || width % 32) { pg_set_error("tensor-core score rows: width %d is not a multiple of 32", width); return 1; }
     if (reinterpret_cast<uintptr_t>(mwave) & 15) { pg_set_error("tensor-core score rows: matrix not 16-byte aligned"); return 1; }
     RowsTcArgs a;
-    a.prof = prof; a.wres = wres; a.rowoff = rowoff; a.blocks = blocks; a.quads = quads;
+    a.prof = prof; a.wres = wres; a.quads = (const PgQuad*)quads;
     a.A = A; a.width = width; a.padv = padv; a.mwave = mwave;
-    a.n_chunks = (width + 255) / 256;
+    // column chunks of <= 128: A + B tiles fit 64 KB, three CTAs per SM (PGPU_TC_CHUNK overrides for experiments)
+    int max_chunk = 128;
+    if (const char* e = getenv("PGPU_TC_CHUNK")) { const int v = atoi(e); if (v >= 16 && v <= 256) max_chunk = v / 16 * 16; }
+    a.n_chunks = (width + max_chunk - 1) / max_chunk;
     a.chunk = ((width + a.n_chunks - 1) / a.n_chunks + 15) / 16 * 16;
     const int64_t nb = (int64_t)n_quads * a.n_chunks;
     if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }

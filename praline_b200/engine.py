@@ -122,19 +122,38 @@ def plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, offs, rows_per_block=32)
     return mrow_base, blocks, n_rows
 
 
-def row_block_quads(blocks):
-    """Groups of <= 4 consecutive row blocks with one resident: the 128-row tiles of the tensor-core
-    score-row kernel.  Returns int32 [n_quads x 2] = (first block, number of blocks)."""
+QUAD_DTYPE = np.dtype([("q0", np.int64), ("Lr", np.int32), ("nblk", np.int32), ("row0", np.int64, 4), ("src0", np.int64, 4),
+                       ("rows", np.int32, 4), ("dummy", np.int32, 4), ("reserved", np.int64, 2)])
+
+
+def row_block_quads(blocks, offs=None):
+    """128-row tiles of the tensor-core score-row kernel (pgpu_quad): groups of <= 4 consecutive row
+    blocks with one resident, each with the resident's first profile row and length.  Without `offs`
+    returns just int32 [n_quads x 2] = (first block, number of blocks)."""
     res = np.asarray(blocks["res"])
     n = len(res)
     if n == 0:
-        return np.zeros((0, 2), np.int32)
+        return np.zeros((0, 2), np.int32) if offs is None else np.zeros(0, QUAD_DTYPE)
     new_run = np.ones(n, bool)
     new_run[1:] = res[1:] != res[:-1]
     run_start = np.maximum.accumulate(np.where(new_run, np.arange(n), 0))
     first = np.flatnonzero((np.arange(n) - run_start) % 4 == 0)
     count = np.diff(np.append(first, n))
-    return np.stack([first, count], axis=1).astype(np.int32)
+    if offs is None:
+        return np.stack([first, count], axis=1).astype(np.int32)
+    q = np.zeros(len(first), QUAD_DTYPE)
+    r = res[first]
+    q["q0"] = offs[r]
+    q["Lr"] = offs[r + 1] - offs[r]
+    q["nblk"] = count
+    for j in range(4):
+        idx = np.minimum(first + j, n - 1)
+        ok = j < count
+        q["row0"][:, j] = np.where(ok, blocks["row0"][idx], 0)
+        q["src0"][:, j] = np.where(ok, blocks["src0"][idx], 0)
+        q["rows"][:, j] = np.where(ok, blocks["rows"][idx], 0)
+        q["dummy"][:, j] = np.where(ok, blocks["dummy"][idx], 0)
+    return q
 
 
 class ProfileBatch(object):
@@ -854,10 +873,10 @@ class Engine(object):
                 if fast and self.fast_tc and A <= 32:
                     # tensor-core score rows (tcgen05 tf32 with a hi/lo split): 128-row tiles = quads of
                     # consecutive row blocks that share a resident
-                    quads_dev = self.dev(row_block_quads(blocks))
-                    _lib.check(self.lib.pgpu_build_rows_tc(self.ptr(pbatch.prof_dev), self.ptr(wres), self.ptr(pbatch.offs_dev),
-                                                           A, self.ptr(blocks_dev), self.ptr(quads_dev), int(quads_dev.shape[0]),
-                                                           width, int(md == 1), self.ptr(mwave), self.stream()))
+                    quads = row_block_quads(blocks, pbatch.offs)
+                    quads_dev = self.dev(quads.view(np.uint8))
+                    _lib.check(self.lib.pgpu_build_rows_tc(self.ptr(pbatch.prof_dev), self.ptr(wres), A, self.ptr(quads_dev),
+                                                           len(quads), width, int(md == 1), self.ptr(mwave), self.stream()))
                 elif fast:
                     _lib.check(self.lib.pgpu_build_rows_fast(self.ptr(pbatch.prof_dev), self.ptr(wres), self.ptr(pbatch.offs_dev),
                                                              A, self.ptr(blocks_dev), len(blocks), width, int(md == 1),

@@ -252,3 +252,23 @@ def test_row_block_quads():
     assert (q[1:, 0] == q[:-1, 0] + q[:-1, 1]).all()
     for f, c in q:
         assert len(set(res[f:f + c])) == 1
+
+
+def test_row_block_quad_descriptors():
+    """pgpu_quad records: one 128-byte line per tile with the resident's rows and every block's fields."""
+    from praline_b200.engine import row_block_quads, ROWBLOCK_DTYPE, QUAD_DTYPE
+    assert QUAD_DTYPE.itemsize == 128
+    b = np.zeros(7, ROWBLOCK_DTYPE)
+    b["res"] = [2, 2, 2, 2, 2, 0, 0]
+    b["row0"] = [0, 32, 64, 96, 128, 160, 170]
+    b["src0"] = [99, 131, 163, 195, 227, 5, 15]
+    b["rows"] = [32, 32, 32, 32, 7, 10, 3]
+    b["dummy"] = [1, 0, 0, 0, 0, 1, 0]
+    offs = np.array([0, 40, 100, 400], np.int64)
+    q = row_block_quads(b, offs)
+    assert q["nblk"].tolist() == [4, 1, 2] and q["q0"].tolist() == [100, 100, 0] and q["Lr"].tolist() == [300, 300, 40]
+    assert q["row0"].tolist() == [[0, 32, 64, 96], [128, 0, 0, 0], [160, 170, 0, 0]]
+    assert q["src0"].tolist() == [[99, 131, 163, 195], [227, 0, 0, 0], [5, 15, 0, 0]]
+    assert q["rows"].tolist() == [[32, 32, 32, 32], [7, 0, 0, 0], [10, 3, 0, 0]]
+    assert q["dummy"].tolist() == [[1, 0, 0, 0], [0, 0, 0, 0], [1, 0, 0, 0]]
+    assert len(row_block_quads(b[:0], offs)) == 0
