@@ -123,6 +123,44 @@ class _PreprofileBatch(object):
         return self._local
 
 
+class _StagePreprofile(object):
+    """The whole preprofile stage of a workflow (workflow.py:66-73: every sequence is a master, its
+    slaves are all the others in input order): no pair list is ever built on the host -- the count
+    tables come from Engine.preprofile_stage (masters in chunks, nothing read back in between), and a
+    master's alignments are traced on demand for the rare caller that wants the alignment itself."""
+    complete = True
+
+    def __init__(self, group, threshold, iterations=None):
+        self.group, self.threshold, self.iterations = group, threshold, iterations
+        self.result = None
+
+    def counts(self, master_idx):
+        if self.result is None:
+            g = self.group
+            cnt, where, _ = get_engine().preprofile_stage(g.batch, g.S, g.gaps, threshold=self.threshold,
+                                                          mode="global" if self.iterations is None else "local",
+                                                          iterations=self.iterations or 1)
+            self.result = (cnt.cpu().numpy(), where)
+        cnt, where = self.result
+        off, length = where[int(master_idx)]
+        A = self.group.S.shape[0]
+        return cnt[off:off + length * A].reshape(length, A).astype(np.int64)
+
+    def alignments_of(self, master_idx):
+        """(scores [iterations x n-1], paths [iterations][n-1]) of one master against all others."""
+        g = self.group
+        n = len(g.seqs)
+        sidx = np.r_[0:master_idx, master_idx + 1:n]
+        midx = np.full(n - 1, master_idx, np.int64)
+        if self.iterations is None:
+            scores, paths = get_engine().align_pairs(g.batch, midx, sidx, g.S, g.gaps, mode="global", want_paths=True,
+                                                     resident="one")
+            return scores[None, :], [paths]
+        scores, paths, _ = get_engine().local_pairs(g.batch, midx, sidx, g.S, g.gaps, iterations=self.iterations,
+                                                    want_paths=True)
+        return scores, paths
+
+
 class _RangePicks(object):
     """(group, pair number) of every slave of one master: pairs k0 .. k0+n-1 of the group."""
 
@@ -154,6 +192,19 @@ class LazyMasterSlaveAlignment(Alignment):
             master = self._master
             path = np.arange(len(master) + 1).reshape(len(master) + 1, 1)
             alignment = Alignment([master], path)
+            if getattr(self._batch, "complete", False):     # preprofile.py:127-154 / :227-265, this master only
+                scores, paths = self._batch.alignments_of(self._master_idx)
+                local = self._batch.iterations is not None
+                for k, slave in enumerate(self._slaves):
+                    for n in range(len(paths)):
+                        if self._threshold is None or float(scores[n][k]) >= self._threshold:
+                            p = compress_path(np.array(paths[n][k], dtype=int), 0)
+                            if local:
+                                p = extend_path_local(p, len(master), 0)
+                            merge_path = np.arange(len(slave) + 1).reshape(len(slave) + 1, 1)
+                            alignment = alignment.merge(Alignment([slave], merge_path), p)
+                self._built = alignment
+                return self._built
             if self._batch is not None and self._batch.iterations is not None:    # preprofile.py:227-265
                 scores, paths = self._batch.local_alignments()
                 for slave, (g, k) in zip(self._slaves, self._picks):
@@ -1051,16 +1102,31 @@ class GpuBatchManager(Manager):
             return False
         # one validation per distinct sequence
         seq_idx, tracks = {}, []
+        gaps = None
+
+        def visit(seq):
+            if id(seq) in seq_idx:
+                return True
+            sets, g_ = _prepare(seq, seq, track_ids, track_ids, mats, list(gap_series))
+            if sets[0][0].tid != PlainTrack.tid:
+                return False
+            seq_idx[id(seq)] = len(tracks)
+            tracks.append(sets[0][0])
+            return True
+
+        # the workflow's own shape (workflow.py:66-73): request i's master is sequence i, its slaves are
+        # all the others in order -- checked with C-speed list comparisons, no per-pair Python at all
+        everyone = [requests[n][1]['master_sequence'] for n in idxs]
         try:
-            for n in idxs:
-                inputs = requests[n][1]
-                for seq in [inputs['master_sequence']] + list(inputs['slave_sequences']):
-                    if id(seq) not in seq_idx:
-                        sets, gaps = _prepare(seq, seq, track_ids, track_ids, mats, list(gap_series))
-                        if sets[0][0].tid != PlainTrack.tid:
-                            return False
-                        seq_idx[id(seq)] = len(tracks)
-                        tracks.append(sets[0][0])
+            _, gaps = _prepare(everyone[0], everyone[0], track_ids, track_ids, mats, list(gap_series))
+            if not all(visit(seq) for seq in everyone):
+                return False
+            complete = len(tracks) == len(everyone) > 1 and \
+                all(requests[n][1]['slave_sequences'] == everyone[:i] + everyone[i + 1:] for i, n in enumerate(idxs))
+            if not complete:
+                for n in idxs:
+                    if not all(visit(seq) for seq in requests[n][1]['slave_sequences']):
+                        return False
         except (ComponentError, DataError):
             return False        # the per-request path reports it the reference's way
         arrs = [np.asarray(t.values) for t in tracks]
@@ -1074,8 +1140,15 @@ class GpuBatchManager(Manager):
         g = _Group("local" if local else "global", S, gaps)
         for t, a in zip(tracks, arrs):
             g.add_seq(t, a)
-        pre = _PreprofileBatch(g, threshold, iterations if local else None)
         self._bulk_out = []
+        if complete:
+            pre = _StagePreprofile(g, threshold, iterations if local else None)
+            for i, n in enumerate(idxs):
+                _, inputs, tag, _ = requests[n]
+                alignment = LazyMasterSlaveAlignment(everyone[i], inputs['slave_sequences'], None, threshold, tid0, pre, i)
+                self._bulk_out.append((n, tag, alignment, (len(everyone) - 1) * (iterations if local else 1)))
+            return True
+        pre = _PreprofileBatch(g, threshold, iterations if local else None)
         for n, env in zip(idxs, envs):
             _, inputs, tag, _ = requests[n]
             master, slaves = inputs['master_sequence'], inputs['slave_sequences']
