@@ -204,6 +204,15 @@ def cpu_baseline_port(seqs, S, seconds=12.0):
                       % (n, dt)}
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written: measured copy bandwidth and bf16 GEMM rate of this pool's B200s)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def msa_e2e(n=50, length=300, preprofile="global", msa="tree"):
     """Second half of the BASELINE metric: wall time of the reference's MSA workflow
     (`praline --preprofile-global --msa-tree`, 50 x 300 aa, BASELINE configs[0] scale) on the
@@ -413,6 +422,35 @@ def main():
         torch.cuda.synchronize(dev)
         roof["guide_tree"] = {"distance_ms": ga.elapsed_time(gb), "cluster_ms_incl_d2h": gb.elapsed_time(gc),
                               "merges": len(merges), "note": "average linkage, merge order of util/cluster.py on %d sequences" % n}
+        # the score-matrix kernel on tensor cores (north star (1)): HBM GB/s of k_build_rows_tc against the
+        # measured copy bandwidth, on one wave of 60 depth-50 profiles of length 400 (tolerance mode)
+        try:
+            profs = [synth.profile_from_counts(synth.count_profile(2000 + k, 400, 50, 20, 27)) for k in range(60)]
+            pbat = eng.profile_batch(profs)
+            ppi, ppj = synth.all_pairs(len(profs))
+            eng.align_profile_pairs(pbat, ppi, ppj, S, gaps, mode=mode, fast=True)
+            eng.take_trace()
+            eng.trace_on = True
+            eng.align_profile_pairs(pbat, ppi, ppj, S, gaps, mode=mode, fast=True)
+            eng.trace_on = False
+            tr = eng.take_trace()
+            tc = [(nm, ms) for nm, ms in tr if nm.startswith("score rows tc")]
+            fed = [ms for nm, ms in tr if nm == "matrix-fed stream"]
+            nbytes = sum(int(nm.split("(")[1].split(" ")[0]) for nm, _ in tc)
+            tc_ms = sum(ms for _, ms in tc)
+            hbm_meas = measured_peaks().get("hbm_gbs")
+            hbm_peak = hbm_meas or 6650.0     # B200_PROFILING.md's fallback when the driver's file is absent
+            pcells = float((pbat.lens[ppi] * pbat.lens[ppj]).sum())
+            roof["score_rows_tc"] = {"kernel": "k_build_rows_tc (tcgen05 kind::tf32, hi/lo split, TMEM accumulator)",
+                                     "bound": "hbm", "bytes_written": nbytes, "kernel_ms": tc_ms,
+                                     "achieved": nbytes / (tc_ms * 1e-3) / 1e9 if tc_ms else None,
+                                     "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": (nbytes / (tc_ms * 1e-3) / 1e9 / hbm_peak) if tc_ms and hbm_peak else None,
+                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_meas else "6650 GB/s (of fallback)",
+                                     "matrix_fed_stream_ms": sum(fed),
+                                     "profile_batch_gcups_device": pcells / ((tc_ms + sum(fed)) * 1e-3) / 1e9 if tc_ms else None}
+        except Exception as e:   # the headline numbers stand on their own
+            roof["score_rows_tc"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_port(seqs, S)
             roof["msa_e2e"] = msa_e2e()

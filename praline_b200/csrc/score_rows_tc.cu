@@ -242,8 +242,9 @@ int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const v
     RowsTcArgs a;
     a.prof = prof; a.wres = wres; a.quads = (const PgQuad*)quads;
     a.A = A; a.width = width; a.padv = padv; a.mwave = mwave;
-    // column chunks of <= 128: A + B tiles fit 64 KB, three CTAs per SM (PGPU_TC_CHUNK overrides for experiments)
-    int max_chunk = 128;
+    // column chunks of <= 256 (two CTAs per SM).  Measured per wave: 256 -> 1.67 ms, 160 -> 1.70, 128 -> 1.77 (three CTAs
+    // per SM, but the A tile is staged once per chunk), 64 -> 2.18; PGPU_TC_CHUNK overrides for experiments
+    int max_chunk = 256;
     if (const char* e = getenv("PGPU_TC_CHUNK")) { const int v = atoi(e); if (v >= 16 && v <= 256) max_chunk = v / 16 * 16; }
     a.n_chunks = (width + max_chunk - 1) / max_chunk;
     a.chunk = ((width + a.n_chunks - 1) / a.n_chunks + 15) / 16 * 16;

@@ -247,12 +247,17 @@ class Engine(object):
             self._traces.append(chain)
         return chain
 
-    def dump_trace(self):
+    def take_trace(self):
+        """[(section name, device ms)] of everything traced since the last call (PGPU_TRACE / trace_on)."""
         torch.cuda.synchronize()
-        for chain in self._traces:
-            for (n0, e0), (_, e1) in zip(chain[:-1], chain[1:]):
-                print("  [trace] %-40s %8.3f ms" % (n0, e0.elapsed_time(e1)))
+        out = [(n0, e0.elapsed_time(e1)) for chain in self._traces
+               for (n0, e0), (_, e1) in zip(chain[:-1], chain[1:])]
         self._traces = []
+        return out
+
+    def dump_trace(self):
+        for name, ms in self.take_trace():
+            print("  [trace] %-40s %8.3f ms" % (name, ms))
 
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -870,6 +875,8 @@ class Engine(object):
                 # keep every device temporary referenced until the launches that read it are queued:
                 # a tensor freed right after data_ptr() is handed to the next allocation
                 blocks_dev = self.dev(blocks.view(np.uint8))
+                ev = self._trace_event("score rows %s (%d B)" % ("tc" if fast and self.fast_tc and A <= 32 else
+                                                               "fma" if fast else "exact", n_rows * width * 4))
                 if fast and self.fast_tc and A <= 32:
                     # tensor-core score rows (tcgen05 tf32 with a hi/lo split): 128-row tiles = quads of
                     # consecutive row blocks that share a resident
@@ -886,10 +893,12 @@ class Engine(object):
                                                         self.ptr(S_dev), self.ptr(blocks_dev), len(blocks), width,
                                                         int(transposed), int(md == 1), self.ptr(mwave), self.stream()))
                 self.launches += 1
+                self._trace_event("matrix-fed stream", ev)
                 if self.keep_mwave:      # tests compare the score rows of the three builders element by element
                     self.last_mwave = mwave
                 self.run_tiles(md, K, transposed, pbatch, stream_ids_dev, wt, n, S_dev, A, go, ge, scores_dev,
                                mwave_dev=mwave, mrow_base_dev=self.dev(mrow_base))
+                self._trace_event(None, ev)
                 lo = hi
         out = np.empty(n, np.float32)
         out[order] = scores_dev.cpu().numpy()
