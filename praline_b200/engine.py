@@ -875,13 +875,15 @@ class Engine(object):
                 # keep every device temporary referenced until the launches that read it are queued:
                 # a tensor freed right after data_ptr() is handed to the next allocation
                 blocks_dev = self.dev(blocks.view(np.uint8))
-                ev = self._trace_event("score rows %s (%d B)" % ("tc" if fast and self.fast_tc and A <= 32 else
-                                                               "fma" if fast else "exact", n_rows * width * 4))
-                if fast and self.fast_tc and A <= 32:
+                use_tc = fast and self.fast_tc and A <= 32
+                if use_tc:
                     # tensor-core score rows (tcgen05 tf32 with a hi/lo split): 128-row tiles = quads of
                     # consecutive row blocks that share a resident
                     quads = row_block_quads(blocks, pbatch.offs)
                     quads_dev = self.dev(quads.view(np.uint8))
+                ev = self._trace_event("score rows %s (%d B)" % ("tc" if use_tc else "fma" if fast else "exact",
+                                                               n_rows * width * 4))
+                if use_tc:
                     _lib.check(self.lib.pgpu_build_rows_tc(self.ptr(pbatch.prof_dev), self.ptr(wres), A, self.ptr(quads_dev),
                                                            len(quads), width, int(md == 1), self.ptr(mwave), self.stream()))
                 elif fast:
