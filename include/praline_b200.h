@@ -249,10 +249,19 @@ typedef struct pgpu_quad {
     int64_t src0[4];     /* profile row feeding matrix row row0 (row0 + r is fed by src0 + r) */
     int32_t rows[4];
     int32_t dummy[4];    /* matrix row row0 is the region's dummy row */
-    int64_t reserved[2];
+    int64_t bcan;        /* first row of the resident in the pre-split store of pgpu_split_residents */
+    int64_t reserved;
 } pgpu_quad;
+/* whi_dev / wlo_dev: NULL, or the resident side pre-split by pgpu_split_residents -- the kernel then fetches its
+ * B tiles with TMA bulk copies (cp.async.bulk) instead of gathering rows. */
 int pgpu_build_rows_tc(const float* prof_dev, const float* wres_dev, int A, const void* quads_dev, int n_quads,
-                       int width, int local_mode, float* mwave_dev, void* stream);
+                       int width, int local_mode, float* mwave_dev, const void* whi_dev, const void* wlo_dev,
+                       void* stream);
+/* W rows [rows x A] -> tf32 hi / lo parts in the canonical K-major core-matrix layout (128 B per row, 8-row groups
+ * of 1024 B); sequence s occupies rows padoff[s] .. padoff[s+1] (multiples of 32, zero rows beyond its length).
+ * whi_dev / wlo_dev: padoff[n_seqs] * 128 bytes each. */
+int pgpu_split_residents(const float* wres_dev, const int64_t* rowoff_dev, const int64_t* padoff_dev, int n_seqs, int A,
+                         void* whi_dev, void* wlo_dev, void* stream);
 int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
                           int L2, float* m_dev, int m_pitch, void* stream);
 

@@ -223,10 +223,16 @@ int pgpu_build_rows_fast(const float* prof, const float* wres, const int64_t* ro
 }
 
 int pgpu_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
-                       int local_mode, float* mwave, void* stream)
+                       int local_mode, float* mwave, const void* whi, const void* wlo, void* stream)
 {
-    return pg_launch_build_rows_tc(prof, wres, A, quads, n_quads, width, local_mode ? -INFINITY : 0.f, mwave,
+    return pg_launch_build_rows_tc(prof, wres, A, quads, n_quads, width, local_mode ? -INFINITY : 0.f, mwave, whi, wlo,
                                    (cudaStream_t)stream);
+}
+
+int pgpu_split_residents(const float* wres, const int64_t* rowoff, const int64_t* padoff, int n_seqs, int A, void* whi,
+                         void* wlo, void* stream)
+{
+    return pg_launch_split_residents(wres, rowoff, padoff, n_seqs, A, whi, wlo, (cudaStream_t)stream);
 }
 
 int pgpu_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,

@@ -67,7 +67,8 @@ struct PgQuad {
     int64_t src0[4];            // profile row feeding it
     int32_t rows[4];
     int32_t dummy[4];
-    int64_t _pad[2];
+    int64_t bcan;               // first row of the resident in the pre-split canonical store (multiple of 8)
+    int64_t _pad;
 };
 static_assert(sizeof(PgQuad) == 128, "PgQuad is one cache line");
 
@@ -75,6 +76,8 @@ struct RowsTcArgs {
     const float* prof;          // [rows x A] profile store (streamed side)
     const float* wres;          // [rows x A] W = P . S^T (or P . S) of the same store (resident side)
     const PgQuad* quads;
+    const unsigned char* whi;   // residents pre-split into tf32 hi / lo in the canonical K-major layout (128 B per
+    const unsigned char* wlo;   // row, 8-row groups of 1024 B), rows beyond a resident's length zero; NULL: gather
     int A, width, n_chunks, chunk;
     float padv;
     float* mwave;
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ __align__(8) unsigned long long mbar_b;      // completion of the B tiles' bulk copies (TMA)
     __shared__ uint32_t tmem_slot;
     // operands: A_hi | A_lo (16 KB each), B_hi | B_lo (chunk x 128 B each)
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
     unsigned char* B_hi = sm + 32768;
     unsigned char* B_lo = B_hi + (size_t)a.chunk * 128;
 
-    __shared__ PgQuad quad;
+    __shared__ __align__(16) PgQuad quad;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 8) reinterpret_cast<int4*>(&quad)[tid] = __ldg(reinterpret_cast<const int4*>(a.quads + blockIdx.x / a.n_chunks) + tid);
     const int c0 = (int)(blockIdx.x % a.n_chunks) * a.chunk;
@@ -109,11 +113,25 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_b)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
     const int64_t q0 = quad.q0;
     const int Lr = quad.Lr;
+    const bool tma_b = a.whi != nullptr;
+    if (tma_b && tid == 0) {
+        // the resident's column chunk is ONE contiguous block of the pre-split store: two bulk copies
+        const uint32_t bytes = (uint32_t)NC * 128u;
+        const unsigned char* gh = a.whi + (size_t)(quad.bcan + c0) * 128;
+        const unsigned char* gl = a.wlo + (size_t)(quad.bcan + c0) * 128;
+        const uint32_t mb = smem_u32(&mbar_b);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(B_hi)), "l"(gh), "r"(bytes), "r"(mb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(B_lo)), "l"(gl), "r"(bytes), "r"(mb) : "memory");
+    }
 
     // ---- stage the operands, split into tf32 hi / lo ---------------------------------------------
     // One operand row per thread: its <= 32 alphabet entries are independent loads (all in flight at
@@ -135,7 +153,7 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
             *reinterpret_cast<float4*>(lo_base + o + j * 128) = l;
         }
     };
-    for (int row = tid; row < 128 + NC; row += kTcThreads) {
+    for (int row = tid; row < (tma_b ? 128 : 128 + NC); row += kTcThreads) {
         if (row < 128) {
             const int b = row >> 5, rr = row & 31;
             const float* src = nullptr;
@@ -155,6 +173,15 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
 
     // ---- 3 terms x 4 K-steps of tcgen05.mma kind::tf32, M = 128, N = NC -----------------------------
     if (warp == 0 && lane == 0) {
+        if (tma_b) {     // the B tiles have landed (async proxy writes, ordered by the barrier)
+            uint32_t done = 0;
+            const uint32_t addr = smem_u32(&mbar_b);
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(addr), "r"(0u) : "memory");
+            }
+        }
         // cute::UMMA::InstrDescriptor: D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t sa[3] = {smem_u32(A_hi), smem_u32(A_lo), smem_u32(A_hi)};
@@ -232,8 +259,44 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
 }
 
+// Pre-split the resident side once per batch: W rows -> tf32 hi / lo in the canonical K-major layout, every
+// sequence padded with zero rows to padoff[s + 1] - padoff[s] rows (a multiple of 32 covering its K class).
+__global__ void k_split_residents(const float* __restrict__ wres, const int64_t* __restrict__ rowoff,
+                                  const int64_t* __restrict__ padoff, int A, unsigned char* __restrict__ whi,
+                                  unsigned char* __restrict__ wlo)
+{
+    const int s = blockIdx.x;
+    const int64_t q0 = rowoff[s], p0 = padoff[s];
+    const int L = (int)(rowoff[s + 1] - q0), P = (int)(padoff[s + 1] - p0);
+    for (int idx = threadIdx.x; idx < P * 8; idx += blockDim.x) {
+        const int x = idx >> 3, j = idx & 7;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = (x < L && 4 * j + e < A) ? wres[(size_t)(q0 + x) * A + 4 * j + e] : 0.f;
+        float4 h, l;
+        split_tf32(v[0], h.x, l.x);
+        split_tf32(v[1], h.y, l.y);
+        split_tf32(v[2], h.z, l.z);
+        split_tf32(v[3], h.w, l.w);
+        const int64_t r = p0 + x;
+        const size_t o = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 16 + (size_t)j * 128;
+        *reinterpret_cast<float4*>(whi + o) = h;
+        *reinterpret_cast<float4*>(wlo + o) = l;
+    }
+}
+
+int pg_launch_split_residents(const float* wres, const int64_t* rowoff, const int64_t* padoff, int n_seqs, int A,
+                              void* whi, void* wlo, cudaStream_t st)
+{
+    if (n_seqs <= 0) return 0;
+    if (A < 1 || A > 32) { pg_set_error("tensor-core score rows: alphabet size %d above 32", A); return 1; }
+    k_split_residents<<<n_seqs, 256, 0, st>>>(wres, rowoff, padoff, A, (unsigned char*)whi, (unsigned char*)wlo);
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
-                            float padv, float* mwave, cudaStream_t st)
+                            float padv, float* mwave, const void* whi, const void* wlo, cudaStream_t st)
 {
     if (n_quads <= 0) return 0;
     if (A < 1 || A > 32) { pg_set_error("tensor-core score rows: alphabet size %d above 32", A); return 1; }
@@ -241,6 +304,8 @@ int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const v
     if (reinterpret_cast<uintptr_t>(mwave) & 15) { pg_set_error("tensor-core score rows: matrix not 16-byte aligned"); return 1; }
     RowsTcArgs a;
     a.prof = prof; a.wres = wres; a.quads = (const PgQuad*)quads;
+    a.whi = (const unsigned char*)whi; a.wlo = (const unsigned char*)wlo;
+    if ((whi == nullptr) != (wlo == nullptr)) { pg_set_error("tensor-core score rows: whi and wlo go together"); return 1; }
     a.A = A; a.width = width; a.padv = padv; a.mwave = mwave;
     // column chunks of <= 256 (two CTAs per SM).  Measured per wave: 256 -> 1.67 ms, 160 -> 1.70, 128 -> 1.77 (three CTAs
     // per SM, but the A tile is staged once per chunk), 64 -> 2.18; PGPU_TC_CHUNK overrides for experiments

@@ -123,10 +123,10 @@ def plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, offs, rows_per_block=32)
 
 
 QUAD_DTYPE = np.dtype([("q0", np.int64), ("Lr", np.int32), ("nblk", np.int32), ("row0", np.int64, 4), ("src0", np.int64, 4),
-                       ("rows", np.int32, 4), ("dummy", np.int32, 4), ("reserved", np.int64, 2)])
+                       ("rows", np.int32, 4), ("dummy", np.int32, 4), ("bcan", np.int64), ("reserved", np.int64)])
 
 
-def row_block_quads(blocks, offs=None):
+def row_block_quads(blocks, offs=None, padoff=None):
     """128-row tiles of the tensor-core score-row kernel (pgpu_quad): groups of <= 4 consecutive row
     blocks with one resident, each with the resident's first profile row and length.  Without `offs`
     returns just int32 [n_quads x 2] = (first block, number of blocks)."""
@@ -145,6 +145,8 @@ def row_block_quads(blocks, offs=None):
     r = res[first]
     q["q0"] = offs[r]
     q["Lr"] = offs[r + 1] - offs[r]
+    if padoff is not None:
+        q["bcan"] = padoff[r]
     q["nblk"] = count
     for j in range(4):
         idx = np.minimum(first + j, n - 1)
@@ -231,6 +233,7 @@ class Engine(object):
         self.use_s16 = os.environ.get("PGPU_NO_S16", "") == ""
         self.m_budget_floats = 1 << 31     # 8 GiB of match scores per wave of a profile batch
         self.keep_mwave = False
+        self.tc_tma = os.environ.get("PGPU_TC_TMA", "1") not in ("", "0")      # B tiles by TMA bulk copy
         self.fast_tc = os.environ.get("PGPU_FAST_TC", "1") not in ("", "0")   # tolerance-mode score rows on tcgen05
 
     # -- helpers -------------------------------------------------------------------------------
@@ -849,6 +852,19 @@ class Engine(object):
                                                           int(pbatch.prof_dev.shape[0]), int(transposed), self.ptr(wres),
                                                           self.stream()))
             self.launches += 1
+        whi = wlo = padoff = None
+        if fast and self.fast_tc and A <= 32 and self.tc_tma:
+            # resident side pre-split once per batch into the tensor core's operand layout: the score-row
+            # kernel then fetches its B tiles with TMA bulk copies
+            pad = np.where(kcls > 0, 32 * kcls, (pbatch.lens + 31) // 32 * 32).astype(np.int64)
+            padoff = np.zeros(pbatch.n + 1, np.int64)
+            np.cumsum(pad, out=padoff[1:])
+            whi = torch.empty(int(padoff[-1]) * 128, dtype=torch.uint8, device=self.device)
+            wlo = torch.empty_like(whi)
+            padoff_dev = self.dev(padoff)
+            _lib.check(self.lib.pgpu_split_residents(self.ptr(wres), self.ptr(pbatch.offs_dev), self.ptr(padoff_dev), pbatch.n, A,
+                                                     self.ptr(whi), self.ptr(wlo), self.stream()))
+            self.launches += 1
         stream_ids_dev = self.dev(str_s.astype(np.int32))
         scores_dev = torch.empty(n, dtype=torch.float32, device=self.device)
         lens_s = pbatch.lens[str_s]
@@ -879,13 +895,14 @@ class Engine(object):
                 if use_tc:
                     # tensor-core score rows (tcgen05 tf32 with a hi/lo split): 128-row tiles = quads of
                     # consecutive row blocks that share a resident
-                    quads = row_block_quads(blocks, pbatch.offs)
+                    quads = row_block_quads(blocks, pbatch.offs, padoff)
                     quads_dev = self.dev(quads.view(np.uint8))
                 ev = self._trace_event("score rows %s (%d B)" % ("tc" if use_tc else "fma" if fast else "exact",
                                                                n_rows * width * 4))
                 if use_tc:
                     _lib.check(self.lib.pgpu_build_rows_tc(self.ptr(pbatch.prof_dev), self.ptr(wres), A, self.ptr(quads_dev),
-                                                           len(quads), width, int(md == 1), self.ptr(mwave), self.stream()))
+                                                           len(quads), width, int(md == 1), self.ptr(mwave),
+                                                           self.ptr(whi), self.ptr(wlo), self.stream()))
                 elif fast:
                     _lib.check(self.lib.pgpu_build_rows_fast(self.ptr(pbatch.prof_dev), self.ptr(wres), self.ptr(pbatch.offs_dev),
                                                              A, self.ptr(blocks_dev), len(blocks), width, int(md == 1),
