@@ -18,11 +18,19 @@ for name, fast, tc in (("fast_tc", True, True), ("fast_fma", True, False), ("exa
     if only and not name.endswith(only):
         continue
     eng.fast_tc = tc
-    eng.align_profile_pairs(pb, pi[:2000], pj[:2000], S, [-11.0, -1.0], mode="global", fast=fast)
+    eng.align_profile_pairs(pb, pi, pj, S, [-11.0, -1.0], mode="global", fast=fast)     # warm-up at full size
+    eng.take_trace()
+    eng.trace_on = True
     torch.cuda.synchronize(); t0 = time.perf_counter()
     sc = eng.align_profile_pairs(pb, pi, pj, S, [-11.0, -1.0], mode="global", fast=fast)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     res[name] = sc
+    eng.trace_on = False
+    tr = eng.take_trace()
+    rows_ms = sum(ms for nm, ms in tr if nm.startswith("score rows"))
+    fed_ms = sum(ms for nm, ms in tr if nm == "matrix-fed stream")
+    print(json.dumps({"mode": name, "device_ms_score_rows": rows_ms, "device_ms_matrix_fed_stream": fed_ms,
+                      "gcups_device": cells / ((rows_ms + fed_ms) * 1e-3) / 1e9}))
     print(json.dumps({"mode": name, "n": n, "L": L, "depth": depth, "pairs": len(pi), "cells": cells,
                       "wall_s": dt, "gcups": cells / dt / 1e9}))
 for name in ("fast_tc", "fast_fma"):
