@@ -112,7 +112,9 @@ int pgpu_align_profiles(int mode, int n_sets, const float* const* P1_dev, const 
  *   mwave, mrow_base  NULL for sequence batches.  Profile x profile batches (score only): the
  *                match scores of the wave made by pgpu_build_rows, one row of 32*K floats per
  *                stream position, and the first row per (tile, warp); seqs_dev is then unused and
- *                offs_dev holds profile ROW offsets per sequence
+ *                offs_dev holds profile ROW offsets per sequence;
+ *                the buffer must be 16-byte aligned and carry 16 bytes of slack behind its last row (the
+ *                kernel reads whole aligned float4s around a lane's K scores)
  */
 int pgpu_align_tiles(int mode, int K, int transposed, const uint8_t* seqs_dev, const int64_t* offs_dev,
                      const int32_t* stream_ids_dev, const void* tiles_dev, int n_tiles, int64_t n_slots,

@@ -170,8 +170,26 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
                             sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
                         }
                     } else {
+                        // K floats at a 4-byte-aligned offset: aligned 128-bit loads that cover them for any
+                        // misalignment (0..3 floats, constant per lane), then a two-stage shift by selects --
+                        // NV requests per step instead of K scalar ones (the row pitch is a multiple of 16 B;
+                        // the buffer carries 16 B of slack behind its last row)
+                        constexpr int NV = (K + 3 + 3) / 4;
+                        const int mis = (lane * K) & 3;
+                        const float4* vb = reinterpret_cast<const float4*>(mr - mis);
+                        float buf[NV * 4 + 3];
 #pragma unroll
-                        for (int k = 0; k < K; k++) sc[k] = __ldg(mr + k);
+                        for (int j = 0; j < NV; j++) {
+                            const float4 v = __ldg(vb + j);
+                            buf[4 * j] = v.x; buf[4 * j + 1] = v.y; buf[4 * j + 2] = v.z; buf[4 * j + 3] = v.w;
+                        }
+                        buf[NV * 4] = buf[NV * 4 + 1] = buf[NV * 4 + 2] = 0.f;
+#pragma unroll
+                        for (int k = 0; k < NV * 4 - 1; k++) buf[k] = (mis & 1) ? buf[k + 1] : buf[k];
+#pragma unroll
+                        for (int k = 0; k < NV * 4 - 2; k++) buf[k] = (mis & 2) ? buf[k + 2] : buf[k];
+#pragma unroll
+                        for (int k = 0; k < K; k++) sc[k] = buf[k];
                     }
                 } else {
                     const uint32_t pa = (w & 0x00ffffffu) | lane16;

@@ -265,7 +265,8 @@ class Engine(object):
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    STAGE_TIERS = ((1 << 20, 6), (32 << 20, 4))     # (slot bytes, slots): small and large staging rings
+    # (slot bytes, slots) of the staging rings; pinning a slot costs about 0.3 ms per MB, once
+    STAGE_TIERS = ((256 << 10, 8), (2 << 20, 4), (8 << 20, 4), (32 << 20, 2))
 
     def dev(self, arr):
         """Host array -> device tensor, asynchronously on the current stream.  Arrays between 16 KB and
@@ -887,7 +888,8 @@ class Engine(object):
                 hi = lo + max(1, int(np.searchsorted(acc, self.m_budget_floats, side="right")))
                 wt = tiles[lo:hi]
                 mrow_base, blocks, n_rows = plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, pbatch.offs)
-                mwave = torch.empty(n_rows * width, dtype=torch.float32, device=self.device)
+                # + 4 floats: the matrix-fed kernel reads whole aligned float4s around a lane's K scores
+                mwave = torch.empty(n_rows * width + 4, dtype=torch.float32, device=self.device)[:n_rows * width]
                 # keep every device temporary referenced until the launches that read it are queued:
                 # a tensor freed right after data_ptr() is handed to the next allocation
                 blocks_dev = self.dev(blocks.view(np.uint8))
