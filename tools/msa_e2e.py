@@ -34,7 +34,11 @@ mgr = plugin.GpuBatchManager(R.reference_index())
 R.workflow_fasta(mgr, mk()[:4], sm, pre, msa)          # warm-up: CUDA context, kernels
 t0 = time.perf_counter()
 got = R.workflow_fasta(mgr, mk(), sm, pre, msa)
-res["gpu_s"] = time.perf_counter() - t0
+res["gpu_first_s"] = time.perf_counter() - t0      # first full-size run of the process: device allocator and pinned staging warm up
+t0 = time.perf_counter()
+got2 = R.workflow_fasta(mgr, mk(), sm, pre, msa)
+res["gpu_s"] = time.perf_counter() - t0            # steady state (same process, second run)
+assert got2 == got
 res["gpu_batched_requests"] = mgr.batched_requests
 if not skip_cpu:
     t0 = time.perf_counter()
@@ -42,4 +46,5 @@ if not skip_cpu:
     res["cpu_1core_s"] = time.perf_counter() - t0
     res["identical"] = bool(got == want)
     res["speedup"] = res["cpu_1core_s"] / res["gpu_s"]
+res["note"] = "gpu_s: steady state (second run in the process); gpu_first_s: first full-size run; speedup = cpu_1core_s / gpu_s"
 print(json.dumps(res))
