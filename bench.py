@@ -244,6 +244,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # NCCL prints its version banner on stdout at some debug levels: keep stdout for the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         if rank == 0:
             reference_arm(args)

@@ -20,4 +20,8 @@ for rep in range(3):
 pr = cProfile.Profile(); pr.enable()
 R.workflow_fasta(mgr, mk(), sm, pre, msa)
 pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+st = pstats.Stats(pr).sort_stats("tottime")
+st.print_stats(8)
+st.print_callers("torch.empty")
+import torch
+print(torch.cuda.memory_summary(abbreviated=True)[:1500])
