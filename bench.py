@@ -135,7 +135,7 @@ def _ref_worker(args):
     return cells, scores
 
 
-def reference_arm(args):
+def reference_arm(args, emit=None):
     """--impl reference: the reference's CPU implementation of the path on all host cores."""
     import multiprocessing as mp
     import oracle
@@ -179,7 +179,7 @@ def reference_arm(args):
                              "sample": "%d random pairs per step x %d steps, cext_build_scores + cext_align_global"
                                        % (per_step, args.steps)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    (emit or (lambda o: print(json.dumps(o))))(line)
 
 
 def cpu_baseline_port(seqs, S, seconds=12.0):
@@ -244,11 +244,24 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version
+    # banner, for one) goes to stderr instead; emit() restores the descriptor for the line itself
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj))
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
     # NCCL prints its version banner on stdout at some debug levels: keep stdout for the one JSON line
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         if rank == 0:
-            reference_arm(args)
+            reference_arm(args, emit)
         return
 
     import torch
@@ -470,7 +483,7 @@ def main():
                 "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
