@@ -253,12 +253,16 @@ typedef struct pgpu_quad {
     int32_t dummy[4];    /* matrix row row0 is the region's dummy row */
     int64_t bcan;        /* first row of the resident in the pre-split store of pgpu_split_residents */
     int64_t reserved;
+    int64_t can0[4];     /* per block: its first row in the pre-split store of the streamed side if the block
+                            starts on an 8-row group there (rows src0 .. src0+31 = 4096 contiguous bytes), else -1 */
 } pgpu_quad;
-/* whi_dev / wlo_dev: NULL, or the resident side pre-split by pgpu_split_residents -- the kernel then fetches its
- * B tiles with TMA bulk copies (cp.async.bulk) instead of gathering rows. */
+/* whi_dev / wlo_dev: NULL, or the resident side (W) pre-split by pgpu_split_residents -- the kernel then fetches its
+ * B tiles with TMA bulk copies (cp.async.bulk) instead of gathering rows.  phi_dev / plo_dev: NULL, or the streamed
+ * side (the profiles themselves) pre-split with the same row numbering, 32 rows of slack behind the last one: row
+ * blocks with can0 >= 0 then arrive by TMA as well. */
 int pgpu_build_rows_tc(const float* prof_dev, const float* wres_dev, int A, const void* quads_dev, int n_quads,
                        int width, int local_mode, float* mwave_dev, const void* whi_dev, const void* wlo_dev,
-                       void* stream);
+                       const void* phi_dev, const void* plo_dev, void* stream);
 /* W rows [rows x A] -> tf32 hi / lo parts in the canonical K-major core-matrix layout (128 B per row, 8-row groups
  * of 1024 B); sequence s occupies rows padoff[s] .. padoff[s+1] (multiples of 32, zero rows beyond its length).
  * whi_dev / wlo_dev: padoff[n_seqs] * 128 bytes each. */

@@ -50,7 +50,7 @@ _SIGNATURES = {
     "pgpu_build_rows_fast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                      c_void_p]),
     "pgpu_build_rows_tc": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p, c_void_p]),
     "pgpu_split_residents": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pgpu_build_scores_seq": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                       c_void_p]),

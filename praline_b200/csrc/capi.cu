@@ -223,10 +223,11 @@ int pgpu_build_rows_fast(const float* prof, const float* wres, const int64_t* ro
 }
 
 int pgpu_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
-                       int local_mode, float* mwave, const void* whi, const void* wlo, void* stream)
+                       int local_mode, float* mwave, const void* whi, const void* wlo, const void* phi, const void* plo,
+                       void* stream)
 {
     return pg_launch_build_rows_tc(prof, wres, A, quads, n_quads, width, local_mode ? -INFINITY : 0.f, mwave, whi, wlo,
-                                   (cudaStream_t)stream);
+                                   phi, plo, (cudaStream_t)stream);
 }
 
 int pgpu_split_residents(const float* wres, const int64_t* rowoff, const int64_t* padoff, int n_seqs, int A, void* whi,

@@ -145,7 +145,8 @@ int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const 
 int pg_launch_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
                               int n_blocks, int width, float padv, float* mwave, cudaStream_t st);
 int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
-                            float padv, float* mwave, const void* whi, const void* wlo, cudaStream_t st);
+                            float padv, float* mwave, const void* whi, const void* wlo, const void* phi, const void* plo,
+                            cudaStream_t st);
 int pg_launch_split_residents(const float* wres, const int64_t* rowoff, const int64_t* padoff, int n_seqs, int A,
                               void* whi, void* wlo, cudaStream_t st);
 int pg_launch_profile_times_matrix(const float* prof, const float* S, int A, int64_t n_rows, int transposed, float* out,

@@ -69,8 +69,10 @@ struct PgQuad {
     int32_t dummy[4];
     int64_t bcan;               // first row of the resident in the pre-split canonical store (multiple of 8)
     int64_t _pad;
+    int64_t can0[4];            // per block: its first row in the pre-split store of the STREAMED side when the
+                                // block starts on an 8-row group there (then it is 4096 contiguous bytes), else -1
 };
-static_assert(sizeof(PgQuad) == 128, "PgQuad is one cache line");
+static_assert(sizeof(PgQuad) == 160, "PgQuad is ten 16-byte pieces");
 
 struct RowsTcArgs {
     const float* prof;          // [rows x A] profile store (streamed side)
@@ -78,6 +80,8 @@ struct RowsTcArgs {
     const PgQuad* quads;
     const unsigned char* whi;   // residents pre-split into tf32 hi / lo in the canonical K-major layout (128 B per
     const unsigned char* wlo;   // row, 8-row groups of 1024 B), rows beyond a resident's length zero; NULL: gather
+    const unsigned char* phi;   // the streamed side pre-split the same way (same row numbering as whi / wlo)
+    const unsigned char* plo;
     int A, width, n_chunks, chunk;
     float padv;
     float* mwave;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
 
     __shared__ __align__(16) PgQuad quad;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 8) reinterpret_cast<int4*>(&quad)[tid] = __ldg(reinterpret_cast<const int4*>(a.quads + blockIdx.x / a.n_chunks) + tid);
+    if (tid < 10) reinterpret_cast<int4*>(&quad)[tid] = __ldg(reinterpret_cast<const int4*>(a.quads + blockIdx.x / a.n_chunks) + tid);
     const int c0 = (int)(blockIdx.x % a.n_chunks) * a.chunk;
     const int NC = min(a.chunk, a.width - c0);                 // columns of this tile, a multiple of 16
 
@@ -126,7 +130,22 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
         const unsigned char* gh = a.whi + (size_t)(quad.bcan + c0) * 128;
         const unsigned char* gl = a.wlo + (size_t)(quad.bcan + c0) * 128;
         const uint32_t mb = smem_u32(&mbar_b);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * bytes) : "memory");
+        uint32_t a_bytes = 0;
+        if (a.phi != nullptr)
+            for (int b = 0; b < quad.nblk; b++) a_bytes += quad.can0[b] >= 0 ? 8192u : 0u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * bytes + a_bytes) : "memory");
+        if (a.phi != nullptr) {
+            // a row block that starts on an 8-row group of the pre-split store is 32 rows x 128 B = 4096
+            // contiguous bytes there AND in the A tile (rows 32b .. 32b+31): one bulk copy per part
+            for (int b = 0; b < quad.nblk; b++) {
+                if (quad.can0[b] < 0) continue;
+                const size_t off = (size_t)quad.can0[b] * 128;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(A_hi + b * 4096)), "l"(a.phi + off), "r"(4096u), "r"(mb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(A_lo + b * 4096)), "l"(a.plo + off), "r"(4096u), "r"(mb) : "memory");
+            }
+        }
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(B_hi)), "l"(gh), "r"(bytes), "r"(mb) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -157,6 +176,7 @@ __global__ void __launch_bounds__(kTcThreads) k_build_rows_tc(const RowsTcArgs a
         if (row < 128) {
             const int b = row >> 5, rr = row & 31;
             const float* src = nullptr;
+            if (a.phi != nullptr && b < quad.nblk && quad.can0[b] >= 0) continue;     // this block arrives by TMA
             if (b < quad.nblk && rr < quad.rows[b] && !(quad.dummy[b] && rr == 0))
                 src = a.prof + (size_t)(quad.src0[b] + rr) * a.A;
             stage_row(src, row, A_hi, A_lo);
@@ -296,7 +316,8 @@ int pg_launch_split_residents(const float* wres, const int64_t* rowoff, const in
 }
 
 int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,
-                            float padv, float* mwave, const void* whi, const void* wlo, cudaStream_t st)
+                            float padv, float* mwave, const void* whi, const void* wlo, const void* phi, const void* plo,
+                            cudaStream_t st)
 {
     if (n_quads <= 0) return 0;
     if (A < 1 || A > 32) { pg_set_error("tensor-core score rows: alphabet size %d above 32", A); return 1; }
@@ -305,6 +326,11 @@ int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const v
     RowsTcArgs a;
     a.prof = prof; a.wres = wres; a.quads = (const PgQuad*)quads;
     a.whi = (const unsigned char*)whi; a.wlo = (const unsigned char*)wlo;
+    a.phi = (const unsigned char*)phi; a.plo = (const unsigned char*)plo;
+    if ((phi == nullptr) != (plo == nullptr) || (phi != nullptr && whi == nullptr)) {
+        pg_set_error("tensor-core score rows: phi / plo go together and need whi / wlo");
+        return 1;
+    }
     if ((whi == nullptr) != (wlo == nullptr)) { pg_set_error("tensor-core score rows: whi and wlo go together"); return 1; }
     a.A = A; a.width = width; a.padv = padv; a.mwave = mwave;
     // column chunks of <= 256 (two CTAs per SM).  Measured per wave: 256 -> 1.67 ms, 160 -> 1.70, 128 -> 1.77 (three CTAs

@@ -123,7 +123,8 @@ def plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, offs, rows_per_block=32)
 
 
 QUAD_DTYPE = np.dtype([("q0", np.int64), ("Lr", np.int32), ("nblk", np.int32), ("row0", np.int64, 4), ("src0", np.int64, 4),
-                       ("rows", np.int32, 4), ("dummy", np.int32, 4), ("bcan", np.int64), ("reserved", np.int64)])
+                       ("rows", np.int32, 4), ("dummy", np.int32, 4), ("bcan", np.int64), ("reserved", np.int64),
+                       ("can0", np.int64, 4)])
 
 
 def row_block_quads(blocks, offs=None, padoff=None):
@@ -145,8 +146,15 @@ def row_block_quads(blocks, offs=None, padoff=None):
     r = res[first]
     q["q0"] = offs[r]
     q["Lr"] = offs[r + 1] - offs[r]
+    q["can0"] = -1
     if padoff is not None:
         q["bcan"] = padoff[r]
+        # streamed side: a block whose first profile row sits on an 8-row group of its sequence's pre-split
+        # rows (every block but the ones that carry a region's dummy row in front) can be fetched by TMA
+        src0 = np.asarray(blocks["src0"], np.int64)
+        seq = np.clip(np.searchsorted(offs, src0, side="right") - 1, 0, len(offs) - 2)
+        rel = src0 - offs[seq]
+        can = np.where((np.asarray(blocks["dummy"]) == 0) & (rel >= 0) & (rel % 8 == 0), padoff[seq] + rel, -1)
     q["nblk"] = count
     for j in range(4):
         idx = np.minimum(first + j, n - 1)
@@ -155,6 +163,8 @@ def row_block_quads(blocks, offs=None, padoff=None):
         q["src0"][:, j] = np.where(ok, blocks["src0"][idx], 0)
         q["rows"][:, j] = np.where(ok, blocks["rows"][idx], 0)
         q["dummy"][:, j] = np.where(ok, blocks["dummy"][idx], 0)
+        if padoff is not None:
+            q["can0"][:, j] = np.where(ok, can[idx], -1)
     return q
 
 
@@ -853,7 +863,7 @@ class Engine(object):
                                                           int(pbatch.prof_dev.shape[0]), int(transposed), self.ptr(wres),
                                                           self.stream()))
             self.launches += 1
-        whi = wlo = padoff = None
+        whi = wlo = phi = plo = padoff = None
         if fast and self.fast_tc and A <= 32 and self.tc_tma:
             # resident side pre-split once per batch into the tensor core's operand layout: the score-row
             # kernel then fetches its B tiles with TMA bulk copies
@@ -865,7 +875,12 @@ class Engine(object):
             padoff_dev = self.dev(padoff)
             _lib.check(self.lib.pgpu_split_residents(self.ptr(wres), self.ptr(pbatch.offs_dev), self.ptr(padoff_dev), pbatch.n, A,
                                                      self.ptr(whi), self.ptr(wlo), self.stream()))
-            self.launches += 1
+            # ... and the streamed side (the profiles themselves), 32 rows of slack: a bulk copy always takes 32 rows
+            phi = torch.zeros((int(padoff[-1]) + 32) * 128, dtype=torch.uint8, device=self.device)
+            plo = torch.zeros_like(phi)
+            _lib.check(self.lib.pgpu_split_residents(self.ptr(pbatch.prof_dev), self.ptr(pbatch.offs_dev), self.ptr(padoff_dev),
+                                                     pbatch.n, A, self.ptr(phi), self.ptr(plo), self.stream()))
+            self.launches += 2
         stream_ids_dev = self.dev(str_s.astype(np.int32))
         scores_dev = torch.empty(n, dtype=torch.float32, device=self.device)
         lens_s = pbatch.lens[str_s]
@@ -904,7 +919,8 @@ class Engine(object):
                 if use_tc:
                     _lib.check(self.lib.pgpu_build_rows_tc(self.ptr(pbatch.prof_dev), self.ptr(wres), A, self.ptr(quads_dev),
                                                            len(quads), width, int(md == 1), self.ptr(mwave),
-                                                           self.ptr(whi), self.ptr(wlo), self.stream()))
+                                                           self.ptr(whi), self.ptr(wlo), self.ptr(phi), self.ptr(plo),
+                                                           self.stream()))
                 elif fast:
                     _lib.check(self.lib.pgpu_build_rows_fast(self.ptr(pbatch.prof_dev), self.ptr(wres), self.ptr(pbatch.offs_dev),
                                                              A, self.ptr(blocks_dev), len(blocks), width, int(md == 1),

@@ -257,7 +257,7 @@ def test_row_block_quads():
 def test_row_block_quad_descriptors():
     """pgpu_quad records: one 128-byte line per tile with the resident's rows and every block's fields."""
     from praline_b200.engine import row_block_quads, ROWBLOCK_DTYPE, QUAD_DTYPE
-    assert QUAD_DTYPE.itemsize == 128
+    assert QUAD_DTYPE.itemsize == 160
     b = np.zeros(7, ROWBLOCK_DTYPE)
     b["res"] = [2, 2, 2, 2, 2, 0, 0]
     b["row0"] = [0, 32, 64, 96, 128, 160, 170]
@@ -271,4 +271,11 @@ def test_row_block_quad_descriptors():
     assert q["src0"].tolist() == [[99, 131, 163, 195], [227, 0, 0, 0], [5, 15, 0, 0]]
     assert q["rows"].tolist() == [[32, 32, 32, 32], [7, 0, 0, 0], [10, 3, 0, 0]]
     assert q["dummy"].tolist() == [[1, 0, 0, 0], [0, 0, 0, 0], [1, 0, 0, 0]]
+    assert (q["can0"] == -1).all()                       # no pre-split store given
+    # with a pre-split store: blocks that start on an 8-row group of their streamed sequence get a TMA row
+    padoff = np.array([0, 64, 128, 448], np.int64)
+    b["src0"] = [39, 40, 72, 99, 100, 132, 5]           # seq 0 rows 39 (dummy in front of seq 1), seq 1 rows 0, 32, 59; seq 2 rows 0, 32; seq 0 row 5
+    q = row_block_quads(b, offs, padoff)
+    assert q["bcan"].tolist() == [128, 128, 0]
+    assert q["can0"].tolist() == [[-1, 64, 96, -1], [128, -1, -1, -1], [-1, -1, -1, -1]]
     assert len(row_block_quads(b[:0], offs)) == 0
