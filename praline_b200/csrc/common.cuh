@@ -157,6 +157,7 @@ int pg_stream_supported_k(int k);
 int pg_launch_cluster(int n, int linkage, const float* dist, void* work, int32_t* merges, cudaStream_t st);
 size_t pg_cluster_workspace_bytes(int n);
 int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb, cudaStream_t st);
+int pg_launch_stream_ms(const StreamArgs& a, int n_tiles, int K, int km, cudaStream_t st);
 int pg_launch_stream_local(const StreamArgs& a, int n_tiles, int K, bool masked, cudaStream_t st);
 int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, int paired, cudaStream_t st);
 int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,

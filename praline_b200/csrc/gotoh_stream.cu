@@ -68,12 +68,6 @@ static int launch_one(const StreamArgs& a, int n_tiles, cudaStream_t st)
 template <int K>
 static int launch_k(const StreamArgs& a, int n_tiles, int km, bool tb, cudaStream_t st)
 {
-    if (a.mwave) {   // profile batches: score only, scores read from the materialised matrix
-        if (tb) { pg_set_error("matrix-fed batches are score-only; traced profile alignments use the general kernel"); return 1; }
-        if (km == 0) return launch_one<K, 0, false, false, true>(a, n_tiles, st);
-        if (km == 1) return launch_one<K, 1, false, false, true>(a, n_tiles, st);
-        return launch_one<K, 2, false, false, true>(a, n_tiles, st);
-    }
     if (!tb) {
         if (km == 0) return launch_one<K, 0, false, false>(a, n_tiles, st);
         if (km == 1) return launch_one<K, 1, false, false>(a, n_tiles, st);
@@ -101,6 +95,10 @@ int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb,
 {
     const int km = (mode == PG_GLOBAL) ? 0 : (mode == PG_LOCAL ? 1 : 2);
     if (n_tiles <= 0) return 0;
+    if (a.mwave) {   // profile batches: score only, scores read from the materialised matrix (gotoh_stream_ms.cu)
+        if (tb) { pg_set_error("matrix-fed batches are score-only; traced profile alignments use the general kernel"); return 1; }
+        return pg_launch_stream_ms(a, n_tiles, K, km, st);
+    }
     switch (K) {
         case 1: return launch_k<1>(a, n_tiles, km, tb, st);
         case 2: return launch_k<2>(a, n_tiles, km, tb, st);
