@@ -130,3 +130,44 @@ def test_align_profiles_entry_point(lib, mode):
     assert float(score.item()) == want_score
     n = int(plen.item())
     assert np.array_equal(path.cpu().numpy()[L1 + L2 + 2 - n:], want_path)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PGPU_TEST_C_PROGRAM", "0") != "1",
+                    reason="set PGPU_TEST_C_PROGRAM=1 (builds examples/capi_demo.c with gcc)")
+def test_plain_c_program(lib, tmp_path):
+    """examples/capi_demo.c: the library driven from plain C (cudart only, no Python in the data path).
+    Built with gcc here, run as a subprocess; every printed score and path equals the oracle's."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "capi_demo")
+    libdir = os.path.join(ROOT, "praline_b200")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(ROOT, "examples", "capi_demo.c"), "-o", exe, "-L", libdir, "-lpraline_b200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + libdir], check=True)
+    S = matrices.blosum62().astype(np.float32)
+    mfile = str(tmp_path / "blosum62.f32")
+    S.tofile(mfile)
+    n, L = 12, 40
+    out = subprocess.run([exe, mfile, "27", str(n), str(L)], check=True, capture_output=True, text=True).stdout
+    # the program's LCG, restated
+    seed = [12345]
+
+    def lcg():
+        seed[0] = (seed[0] * 1664525 + 1013904223) & 0xffffffff
+        return seed[0] >> 8
+    lens = [L - 3 + lcg() % 7 for _ in range(n)]
+    seqs = [np.array([lcg() % 20 for _ in range(l)], np.int32) for l in lens]
+    lines = out.strip().splitlines()
+    assert len(lines) == n * (n - 1) // 2
+    for line in lines:
+        parts = line.split()
+        i, j, score = int(parts[0]), int(parts[1]), float(parts[2])
+        path = np.array([[int(v) for v in p.split(",")] for p in parts[3:]], np.int32)
+        want_score, want_path = oracle.align_seqs("global", seqs[i], seqs[j], S, [-11.0, -1.0])
+        assert score == want_score, (i, j)
+        assert np.array_equal(path, want_path), (i, j)
