@@ -132,8 +132,6 @@ def test_align_profiles_entry_point(lib, mode):
     assert np.array_equal(path.cpu().numpy()[L1 + L2 + 2 - n:], want_path)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PGPU_TEST_C_PROGRAM", "0") != "1",
-                    reason="set PGPU_TEST_C_PROGRAM=1 (builds examples/capi_demo.c with gcc)")
 def test_plain_c_program(lib, tmp_path):
     """examples/capi_demo.c: the library driven from plain C (cudart only, no Python in the data path).
     Built with gcc here, run as a subprocess; every printed score and path equals the oracle's."""
