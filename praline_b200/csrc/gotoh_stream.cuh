@@ -104,6 +104,21 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
     const uint32_t lane16 = (uint32_t)lane << 4;
     if (!MS && (prof_s & 511u)) __trap();   // row addresses are OR-ed with the lane offset below
 
+    // matrix-fed launches: the aligned 128-bit pieces that hold a lane's K scores of one step, fetched one step ahead
+    constexpr int NVX = MS ? ((K % 4 == 0) ? K / 4 : (K + 3 + 3) / 4) : 1;
+    // fetched one step ahead where the extra registers do not cost a resident CTA (measured: K = 13 1.64 -> 1.48 ms
+    // per wave; K = 10 would drop from three CTAs per SM to two, 1.22 -> 1.33 ms, and keeps the direct loads)
+    constexpr bool PF = MS && K >= 12;
+    float4 pre[NVX];
+#pragma unroll
+    for (int j = 0; j < NVX; j++) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ms_fetch = [&](uint32_t wv) {
+        const float* mr = mwarp + (size_t)(wv & 0x00ffffffu) * (32 * K) + lane * K;
+        const int mis = (K % 4 == 0) ? 0 : ((lane * K) & 3);
+        const float4* vb = reinterpret_cast<const float4*>(mr - mis);
+#pragma unroll
+        for (int j = 0; j < NVX; j++) pre[j] = __ldg(vb + j);
+    };
     float Mo[K], U[K], D[K];
     uint32_t acc[K];
 #pragma unroll
@@ -155,6 +170,11 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
 #pragma unroll 1
         for (int g = 0; g < 32; g += UNR) {
             const uint32_t rp = rp0 + (uint32_t)g * 4u;
+            if (PF && g == 0) {     // first step of a 32-step block: its ring entry has only just been decoded
+                uint32_t w0;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rp) : "memory");
+                ms_fetch(w0);
+            }
 #pragma unroll
             for (int i = 0; i < UNR; i++) {
                 const int t = t0 + g + i;
@@ -162,32 +182,38 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const StreamArgs a)
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)i * 4u) : "memory");
                 float sc[NCH * 4];
                 if (MS) {
-                    const float* mr = mwarp + (size_t)(w & 0x00ffffffu) * (32 * K) + lane * K;
+                    // this step's vectors were requested one step ago; request the next step's now (the ring
+                    // already holds its row) so that the HBM / L2 latency overlaps this step's cells
+                    if (!PF) ms_fetch(w);
+                    float4 cur[NVX];
+#pragma unroll
+                    for (int j = 0; j < NVX; j++) cur[j] = pre[j];
+                    if (PF && (i + 1 < UNR || g + UNR < 32)) {
+                        uint32_t wn;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wn) : "r"(rp + (uint32_t)(i + 1) * 4u) : "memory");
+                        ms_fetch(wn);
+                    }
                     if (K % 4 == 0) {
 #pragma unroll
                         for (int j = 0; j < K / 4; j++) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(mr) + j);
-                            sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
+                            sc[4 * j] = cur[j].x; sc[4 * j + 1] = cur[j].y; sc[4 * j + 2] = cur[j].z; sc[4 * j + 3] = cur[j].w;
                         }
                     } else {
                         // K floats at a 4-byte-aligned offset: aligned 128-bit loads that cover them for any
                         // misalignment (0..3 floats, constant per lane), then a two-stage shift by selects --
-                        // NV requests per step instead of K scalar ones (the row pitch is a multiple of 16 B;
+                        // NVX requests per step instead of K scalar ones (the row pitch is a multiple of 16 B;
                         // the buffer carries 16 B of slack behind its last row)
-                        constexpr int NV = (K + 3 + 3) / 4;
                         const int mis = (lane * K) & 3;
-                        const float4* vb = reinterpret_cast<const float4*>(mr - mis);
-                        float buf[NV * 4 + 3];
+                        float buf[NVX * 4 + 3];
 #pragma unroll
-                        for (int j = 0; j < NV; j++) {
-                            const float4 v = __ldg(vb + j);
-                            buf[4 * j] = v.x; buf[4 * j + 1] = v.y; buf[4 * j + 2] = v.z; buf[4 * j + 3] = v.w;
+                        for (int j = 0; j < NVX; j++) {
+                            buf[4 * j] = cur[j].x; buf[4 * j + 1] = cur[j].y; buf[4 * j + 2] = cur[j].z; buf[4 * j + 3] = cur[j].w;
                         }
-                        buf[NV * 4] = buf[NV * 4 + 1] = buf[NV * 4 + 2] = 0.f;
+                        buf[NVX * 4] = buf[NVX * 4 + 1] = buf[NVX * 4 + 2] = 0.f;
 #pragma unroll
-                        for (int k = 0; k < NV * 4 - 1; k++) buf[k] = (mis & 1) ? buf[k + 1] : buf[k];
+                        for (int k = 0; k < NVX * 4 - 1; k++) buf[k] = (mis & 1) ? buf[k + 1] : buf[k];
 #pragma unroll
-                        for (int k = 0; k < NV * 4 - 2; k++) buf[k] = (mis & 2) ? buf[k + 2] : buf[k];
+                        for (int k = 0; k < NVX * 4 - 2; k++) buf[k] = (mis & 2) ? buf[k + 2] : buf[k];
 #pragma unroll
                         for (int k = 0; k < K; k++) sc[k] = buf[k];
                     }
