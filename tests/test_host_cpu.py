@@ -279,3 +279,33 @@ def test_row_block_quad_descriptors():
     assert q["bcan"].tolist() == [128, 128, 0]
     assert q["can0"].tolist() == [[-1, 64, 96, -1], [128, -1, -1, -1], [-1, -1, -1, -1]]
     assert len(row_block_quads(b[:0], offs)) == 0
+
+
+def test_tf32_split_accuracy_model():
+    """Numerical model of K1t's FP32-accurate split (score_rows_tc.cu): hi = cvt.rna.tf32(x), lo = x - hi (exact in
+    f32), the tensor core reads the top 19 bits of every operand, products are exact and summed in f32.  The three
+    kept terms hi.hi + lo.hi + hi.lo stay within 2e-6 of sum |terms| of the exact contraction (stated bound 1e-5)."""
+    rng = np.random.default_rng(4)
+
+    def tf32_rna(x):        # round to nearest, ties away, 10 explicit mantissa bits
+        b = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+        b = (b + 0x1000) & 0xffffe000
+        return b.astype(np.uint32).view(np.float32)
+
+    def tf32_trunc(x):      # what the MMA does with a 32-bit operand register
+        return (x.astype(np.float32).view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+
+    A = 27
+    P = rng.dirichlet(np.ones(A) * 0.3, size=400).astype(np.float32)           # profile rows
+    S = rng.integers(-4, 12, (A, A)).astype(np.float32)
+    W = (rng.dirichlet(np.ones(A) * 0.3, size=300).astype(np.float32) @ S.T).astype(np.float32)
+    Ph, Wh = tf32_rna(P), tf32_rna(W)
+    Pl, Wl = tf32_trunc(P - Ph), tf32_trunc(W - Wh)
+    assert np.array_equal(Ph + (P - Ph), P) and np.array_equal(Wh + (W - Wh), W)      # the split itself is exact
+    got = (Ph.astype(np.float64) @ Wh.astype(np.float64).T + Pl.astype(np.float64) @ Wh.astype(np.float64).T
+           + Ph.astype(np.float64) @ Wl.astype(np.float64).T).astype(np.float32)
+    exact = P.astype(np.float64) @ W.astype(np.float64).T
+    scale = np.abs(P).astype(np.float64) @ np.abs(W).astype(np.float64).T
+    assert (np.abs(got - exact) <= 2e-6 * scale).all()
+    one_term = (Ph.astype(np.float64) @ Wh.astype(np.float64).T)
+    assert (np.abs(one_term - exact) > 1e-5 * scale).any()       # plain tf32 would NOT meet the bound
