@@ -314,6 +314,16 @@ int pgpu_cluster_merge_order(int n, int linkage, const float* dist_dev, void* wo
                              void* stream);
 
 /*
+ * Distance matrix of GuideTreeBuilder (praline/component/tree.py:92-147) from the condensed score
+ * vector of the all-vs-all stage (np.triu_indices order): d[i][j] = d[j][i] = score, d[i][i] = 0.0
+ * (tree.py:132-133), dist = (-d) + d.max() in f32 (tree.py:142-147).  dist_dev: [n][n] f32;
+ * scratch_dev: 4 bytes.  The vector may be in rank slices (the padded all-gather layout): slot s with
+ * cuts_dev[r] <= s < cuts_dev[r+1] is read at cond_dev[s + shift_dev[r]]; n_cuts = 0 for a plain vector.
+ */
+int pgpu_tree_distance(int n, const float* cond_dev, int n_cuts, const int64_t* cuts_dev, const int64_t* shift_dev,
+                       float* dist_dev, void* scratch_dev, void* stream);
+
+/*
  * Pipe-rate micro-benchmarks used for the DP roofline denominator: returns in out[0..n) the
  * measured warp-instructions per NANOSECOND per SM (wall clock, CUDA events) for (0) FADD, (1) FMNMX, (2) FMNMX3,
  * (3) the 4 FADD : 3 FMNMX mix of the score-only recurrence, (4) VIADDMNMX.S32,

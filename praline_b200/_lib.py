@@ -62,6 +62,7 @@ _SIGNATURES = {
     "pgpu_microbench": (c_int, [c_void_p, c_int]),
     "pgpu_cluster_workspace_bytes": (c_int64, [c_int]),
     "pgpu_cluster_merge_order": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgpu_tree_distance": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -360,4 +360,17 @@ int pgpu_cluster_merge_order(int n, int linkage, const float* dist_dev, void* wo
     return pg_launch_cluster(n, linkage, dist_dev, workspace_dev, merges_dev, (cudaStream_t)stream);
 }
 
+// Distance matrix of GuideTreeBuilder from the condensed score vector (cluster.cu).
+int pgpu_tree_distance(int n, const float* cond_dev, int n_cuts, const int64_t* cuts_dev, const int64_t* shift_dev,
+                       float* dist_dev, void* scratch_dev, void* stream)
+{
+    if (n < 1) return 0;
+    if (!dist_dev || !scratch_dev || (n > 1 && !cond_dev) || (n_cuts > 0 && (!cuts_dev || !shift_dev))) {
+        pg_set_error("tree_distance: null buffer");
+        return 1;
+    }
+    return pg_launch_tree_distance(n, cond_dev, n_cuts, cuts_dev, shift_dev, dist_dev, (unsigned*)scratch_dev,
+                                   (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) k_cluster_init(const ClusterArgs a)
 }
 
 struct ClPub { double v; int row, col; };
+#define CL_MAX_CTAS 256          // CTAs of the cooperative merge kernel (one per SM at most); sizes the pub records
 
 // block-wide (value, index) minimum, smaller index wins ties; result valid in every thread
 __device__ __forceinline__ void cl_block_min(double& v, int& i, double* sv, int* si)
@@ -265,8 +266,8 @@ int pg_launch_cluster(int n, int linkage, const float* dist, void* work, int32_t
     a.todo = (int*)w; w += up(sizeof(int) * n);
     ClPub* pub = (ClPub*)w;
     int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    PG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int blocks = (n + 7) / 8;
     if (blocks > sms * 8) blocks = sms * 8;
     k_cluster_init<<<blocks, 256, 0, st>>>(a);
@@ -275,6 +276,7 @@ int pg_launch_cluster(int n, int linkage, const float* dist, void* work, int32_t
     int G = n / 16;
     if (G < 1) G = 1;
     if (G > sms) G = sms;
+    if (G > CL_MAX_CTAS) G = CL_MAX_CTAS;      // pub holds 2 * CL_MAX_CTAS records (pg_cluster_workspace_bytes)
     const size_t per = (size_t)(n + G - 1) / G + 1;
     const size_t smem = sizeof(double) * per + sizeof(int) * ((size_t)n + 2 * per) + 16;
     if (smem > 200 * 1024) { pg_set_error("clustering: %d objects exceed the shared-memory state of the kernel", n); return 1; }
@@ -284,8 +286,98 @@ int pg_launch_cluster(int n, int linkage, const float* dist, void* work, int32_t
     return 0;
 }
 
+// ---- distance matrix of GuideTreeBuilder (component/tree.py:92-147) ----------------------------------
+// d[i][j] = d[j][i] = score of pair (i, j), d[i][i] = 0.0 (tree.py:132-133); dist = (-d) + d.max(), all f32.
+// The condensed vector may be laid out in rank slices (the padded all-gather buffer of parallel.py):
+// slot s of the np.triu_indices order lives at cond[s + shift[r]] for cuts[r] <= s < cuts[r+1]
+// (n_cuts = 0: plain vector).
+struct TreeDistArgs {
+    int n, n_cuts;
+    const float* cond;
+    const int64_t* cuts;      // [n_cuts + 1] first slot of every rank slice
+    const int64_t* shift;     // [n_cuts] element offset added to a slot of that slice
+    float* dist;              // [n][n]
+    unsigned* maxkey;         // ordered key of d.max(), seeded with the diagonal's 0.0
+};
+
+__device__ __forceinline__ unsigned td_key(float v)
+{
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float td_unkey(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ int64_t td_where(const TreeDistArgs& a, int64_t slot)
+{
+    for (int r = 0; r < a.n_cuts; r++)
+        if (slot < a.cuts[r + 1]) return slot + a.shift[r];
+    return slot;
+}
+
+__global__ void k_tree_max(const TreeDistArgs a, int64_t n_pairs)
+{
+    float m = 0.0f;   // the diagonal takes part in d.max()
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_pairs; s += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, a.cond[td_where(a, s)]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(a.maxkey, td_key(m));
+}
+
+// one 32 x 32 tile of the upper triangle per CTA: coalesced read of the condensed rows, coalesced
+// writes of the tile and of its mirror image (transposed through shared memory)
+__global__ void __launch_bounds__(256) k_tree_fill(const TreeDistArgs a)
+{
+    __shared__ float tile[32][33];
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    if (bi > bj) return;
+    const float mx = td_unkey(*a.maxkey);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t n = a.n;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = (int64_t)bi * 32 + r, j = (int64_t)bj * 32 + tx;
+        float d = 0.0f;
+        if (i < n && j < n && i != j) {
+            const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+            d = a.cond[td_where(a, lo * n - lo * (lo + 1) / 2 + (hi - lo - 1))];
+        }
+        const float v = (-d) + mx;
+        tile[r][tx] = v;
+        if (i < n && j < n) a.dist[i * n + j] = v;
+    }
+    if (bi == bj) return;      // the diagonal tile is symmetric in itself
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = (int64_t)bj * 32 + r, i = (int64_t)bi * 32 + tx;
+        if (i < n && j < n) a.dist[j * n + i] = tile[tx][r];
+    }
+}
+
+int pg_launch_tree_distance(int n, const float* cond, int n_cuts, const int64_t* cuts, const int64_t* shift,
+                            float* dist, unsigned* scratch, cudaStream_t st)
+{
+    if (n < 1) return 0;
+    TreeDistArgs a;
+    a.n = n; a.n_cuts = n_cuts; a.cond = cond; a.cuts = cuts; a.shift = shift; a.dist = dist; a.maxkey = scratch;
+    const unsigned zero_key = 0x80000000u;      // td_key(0.0f)
+    PG_CUDA_OK(cudaMemcpyAsync(scratch, &zero_key, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    const int64_t n_pairs = (int64_t)n * (n - 1) / 2;
+    if (n_pairs > 0) {
+        int64_t blocks = (n_pairs + 1023) / 1024;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_tree_max<<<(unsigned)blocks, 256, 0, st>>>(a, n_pairs);
+        PG_CUDA_OK(cudaGetLastError());
+    }
+    const unsigned t = (unsigned)((n + 31) / 32);
+    k_tree_fill<<<dim3(t, t), 256, 0, st>>>(a);
+    PG_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 size_t pg_cluster_workspace_bytes(int n)
 {
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return up(sizeof(double) * (size_t)n * n) + up(sizeof(double) * n) + 4 * up(sizeof(int) * n) + up(2 * 256 * 16);
+    return up(sizeof(double) * (size_t)n * n) + up(sizeof(double) * n) + 4 * up(sizeof(int) * n) + up(2 * CL_MAX_CTAS * sizeof(ClPub));
 }

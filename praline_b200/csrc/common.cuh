@@ -156,6 +156,8 @@ int pg_launch_build_scores_seq(const uint8_t* a, const uint8_t* b, const float* 
 int pg_stream_supported_k(int k);
 int pg_launch_cluster(int n, int linkage, const float* dist, void* work, int32_t* merges, cudaStream_t st);
 size_t pg_cluster_workspace_bytes(int n);
+int pg_launch_tree_distance(int n, const float* cond, int n_cuts, const int64_t* cuts, const int64_t* shift,
+                            float* dist, unsigned* scratch, cudaStream_t st);
 int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb, cudaStream_t st);
 int pg_launch_stream_ms(const StreamArgs& a, int n_tiles, int K, int km, cudaStream_t st);
 int pg_launch_stream_local(const StreamArgs& a, int n_tiles, int K, bool masked, cudaStream_t st);

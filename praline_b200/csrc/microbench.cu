@@ -92,12 +92,13 @@ static int run_rate(int sms, const float* fin, const int* iin, float* fout, long
     cudaEventRecord(e0);
     k_rate<OP><<<sms, 1024>>>(fin, iin, fout, cyc, nullptr, LONG_ITERS);
     cudaEventRecord(e1);
-    PG_CUDA_OK(cudaGetLastError());
-    PG_CUDA_OK(cudaDeviceSynchronize());
+    const cudaError_t launch_rc = cudaGetLastError(), sync_rc = cudaDeviceSynchronize();
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    if (launch_rc == cudaSuccess && sync_rc == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    PG_CUDA_OK(launch_rc);
+    PG_CUDA_OK(sync_rc);
     const double per_it = (OP == 3) ? 7.0 : (OP == 13 ? 5.0 : 1.0);
     *rate = 32.0 * CH * (double)LONG_ITERS * per_it / ((double)ms * 1e6);
     return 0;
@@ -112,13 +113,23 @@ extern "C" int pgpu_microbench(double* out, int n)
     PG_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
     float hf[2 + CH] = {0.25f, -0.5f, 1, 2, 3, 4, 5, 6, 7, 8};
     int hi[2 + CH] = {3, -7, 1, 2, 3, 4, 5, 6, 7, 8};
-    float *fin, *fout;
-    int* iin;
-    long long* cyc;
-    PG_CUDA_OK(cudaMalloc((void**)&fin, sizeof(hf)));
-    PG_CUDA_OK(cudaMalloc((void**)&iin, sizeof(hi)));
-    PG_CUDA_OK(cudaMalloc((void**)&fout, sizeof(float) * sms * 1024));
-    PG_CUDA_OK(cudaMalloc((void**)&cyc, sizeof(long long) * sms));
+    // every device buffer of the probe is owned by this holder, so an early PG_CUDA_OK return frees them too
+    struct Bufs {
+        float *fin = nullptr, *fout = nullptr;
+        int* iin = nullptr;
+        long long* cyc = nullptr;
+        unsigned long long* ns = nullptr;
+        ~Bufs() { cudaFree(fin); cudaFree(fout); cudaFree(iin); cudaFree(cyc); cudaFree(ns); }
+    } b;
+    PG_CUDA_OK(cudaMalloc((void**)&b.fin, sizeof(hf)));
+    PG_CUDA_OK(cudaMalloc((void**)&b.iin, sizeof(hi)));
+    PG_CUDA_OK(cudaMalloc((void**)&b.fout, sizeof(float) * sms * 1024));
+    PG_CUDA_OK(cudaMalloc((void**)&b.cyc, sizeof(long long) * sms));
+    PG_CUDA_OK(cudaMalloc((void**)&b.ns, sizeof(unsigned long long) * sms));
+    float *fin = b.fin, *fout = b.fout;
+    int* iin = b.iin;
+    long long* cyc = b.cyc;
+    unsigned long long* ns = b.ns;
     PG_CUDA_OK(cudaMemcpy(fin, hf, sizeof(hf), cudaMemcpyHostToDevice));
     PG_CUDA_OK(cudaMemcpy(iin, hi, sizeof(hi), cudaMemcpyHostToDevice));
     int rc = 0;
@@ -136,8 +147,6 @@ extern "C" int pgpu_microbench(double* out, int n)
     rc |= run_rate<12>(sms, fin, iin, fout, cyc, &out[12]);
     rc |= run_rate<13>(sms, fin, iin, fout, cyc, &out[13]);
     // SM clock held during a burst of the cell mix: SM cycles (clock64) over %globaltimer ns
-    unsigned long long* ns = nullptr;
-    PG_CUDA_OK(cudaMalloc((void**)&ns, sizeof(unsigned long long) * sms));
     for (int rep = 0; rep < 20; rep++) k_rate<3><<<sms, 1024>>>(fin, iin, fout, cyc, ns, ITERS);
     PG_CUDA_OK(cudaDeviceSynchronize());
     long long c0 = 0;
@@ -145,7 +154,5 @@ extern "C" int pgpu_microbench(double* out, int n)
     PG_CUDA_OK(cudaMemcpy(&c0, cyc, sizeof(long long), cudaMemcpyDeviceToHost));
     PG_CUDA_OK(cudaMemcpy(&n0, ns, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     out[8] = (n0 > 0) ? (double)c0 / (double)n0 * 1e3 : (double)khz / 1e3;   // MHz
-    cudaFree(ns);
-    cudaFree(fin); cudaFree(iin); cudaFree(fout); cudaFree(cyc);
     return rc;
 }

@@ -394,10 +394,13 @@ class Engine(object):
 
     def run_tiles(self, mode, K, transposed, batch, stream_ids_dev, tiles, n_slots, S_dev, A, go, ge,
                   scores_dev, cs=None, slot_res_dev=None, slot_str_dev=None, want_paths=False, caps=None,
-                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None, S_host=None, paired=False):
+                  tiles_dev=None, mwave_dev=None, mrow_base_dev=None, counts=None, S_host=None, paired=False,
+                  out_shift=0):
         """Launch K2 (+K4) for one K class.  Returns list of (slot_lo, slot_hi, path_off, path_buf,
-        path_start, path_len) per wave when want_paths."""
+        path_start, path_len) per wave when want_paths.  out_shift (score-only launches): slot s is
+        written at scores_dev[s + out_shift] (the rank slices of parallel.ShardedCondensed)."""
         lib = self.lib
+        scores_ptr = ctypes.c_void_p(scores_dev.data_ptr() + 4 * int(out_shift)) if out_shift else self.ptr(scores_dev)
         md = MODES[mode] if isinstance(mode, str) else mode
         maxlen = max(32 * K, int(batch.lens.max())) + 2
         bkey = (md, float(go), float(ge), maxlen, bool(transposed))
@@ -417,7 +420,7 @@ class Engine(object):
                                                   self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles),
                                                   self.ptr(S_dev), A, int(go), int(ge), neg, self.ptr(top_dev),
                                                   int(B["left0"]), int(B["left1"]), maxlen + 1,
-                                                  self.ptr(scores_dev), self.stream()))
+                                                  scores_ptr, self.stream()))
                 self.launches += 1
                 return out
             keys = torch.empty(2 * n_slots, dtype=torch.int64, device=self.device) if semi else None
@@ -425,7 +428,7 @@ class Engine(object):
                                             self.ptr(stream_ids_dev), self.ptr(tiles_dev), len(tiles), n_slots,
                                             self.ptr(S_dev), A, float(go), float(ge), self.ptr(top_dev),
                                             self.ptr(left_dev), B["left0"], B["left1"], maxlen + 1,
-                                            self.ptr(scores_dev), self.ptr(keys),
+                                            scores_ptr, self.ptr(keys),
                                             None, None, None, None, self.ptr(mwave_dev), self.ptr(mrow_base_dev),
                                             self.stream()))
             self.launches += 1 + int(semi)
@@ -997,14 +1000,34 @@ class Engine(object):
         by_k = {int(K): tiles[kk == K] for K in np.unique(kk)}
         return by_k, (slot_cuts[rank], slot_cuts[rank + 1]), int(cells[sel].sum()), slot_cuts, {}, bool(paired)
 
+    def allpairs_plan(self, batch, S_host, gap_series, mode="global", shard=(0, 1)):
+        """allpairs_tiles for this batch, cached in the engine per (sequence lengths, shard, kernel
+        choice): the plan depends on nothing else, so repeated all-vs-all calls over sequences of the
+        same lengths (every step of a job, a re-uploaded batch) plan once and reuse the tile records
+        already on the device.  The cache holds the last few plans."""
+        md = MODES[mode]
+        go, ge = _gaps(gap_series)
+        paired = self.wants_paired(S_host, go, ge, md, batch)
+        key = (hash(batch.lens.tobytes()), int(batch.n), int(shard[0]), int(shard[1]), bool(paired))
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        plan = cache.pop(key, None)
+        if plan is None:
+            plan = self.allpairs_tiles(batch, shard, paired=paired)
+            while len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+        cache[key] = plan          # most recently used last
+        return plan
+
     def allpairs_scores(self, batch, S_dev, A, gap_series, mode="global", shard=(0, 1), out=None, plan=None,
                         S_host=None):
-        """Condensed all-vs-all score vector on the device (this shard's slots filled)."""
+        """Condensed all-vs-all score vector on the device (this shard's slots filled).  out: a plain
+        condensed f32 tensor, or a parallel.ShardedCondensed built on the plan's slot cuts -- then this
+        rank's scores land directly in its slice of the all-gather buffer."""
         md = MODES[mode]
         go, ge = _gaps(gap_series)
         n_pairs = batch.n * (batch.n - 1) // 2
         if plan is None:
-            plan = self.allpairs_tiles(batch, shard, paired=self.wants_paired(S_host, go, ge, md, batch))
+            plan = self.allpairs_plan(batch, S_host, gap_series, mode, shard)
         by_k, rng, cells = plan[0], plan[1], plan[2]
         cache = plan[4] if len(plan) > 4 else {}
         paired = bool(plan[5]) if len(plan) > 5 else False
@@ -1012,11 +1035,16 @@ class Engine(object):
             raise _lib.PralineGpuError("a paired-resident plan needs the packed int16 kernel (global mode, integer scores)")
         if out is None:
             out = torch.empty(n_pairs, dtype=torch.float32, device=self.device)
+        out_dev, shift = out, 0
+        if hasattr(out, "layout_dev"):
+            if list(out.cuts) != [int(c) for c in plan[3]]:
+                raise _lib.PralineGpuError("the sharded score buffer was built on other slot cuts than this plan")
+            out_dev, shift = out.buf, out.shift[shard[0]]
         for K, tiles in by_k.items():
             if K not in cache:
                 cache[K] = self.dev(tiles.view(np.uint8))
-            self.run_tiles(md, K, True, batch, None, tiles, n_pairs, S_dev, A, go, ge, out, tiles_dev=cache[K],
-                           S_host=S_host, paired=paired)
+            self.run_tiles(md, K, True, batch, None, tiles, n_pairs, S_dev, A, go, ge, out_dev, tiles_dev=cache[K],
+                           S_host=S_host, paired=paired, out_shift=shift)
         return out, rng, cells
 
     def wants_paired(self, S_host, go, ge, md, batch):
@@ -1137,15 +1165,29 @@ class Engine(object):
     LINKAGES = {"single": 0, "complete": 1, "average": 2}
 
     def tree_distance(self, scores, n):
-        """Condensed pair scores (np.triu_indices order; device tensor or array) -> the f32 distance
-        matrix of GuideTreeBuilder on the device (component/tree.py:92-147): d has 0 on the diagonal,
-        dist = (-d) + d.max(), all in f32 like the reference's numpy expression."""
-        cond = scores if isinstance(scores, torch.Tensor) else self.dev(np.ascontiguousarray(scores, np.float32))
-        d = torch.zeros((n, n), dtype=torch.float32, device=self.device)
-        iu = torch.triu_indices(n, n, offset=1, device=self.device)
-        d[iu[0], iu[1]] = cond
-        d[iu[1], iu[0]] = cond
-        return (-d) + d.max()
+        """Condensed pair scores (np.triu_indices order; device tensor, array, or a
+        parallel.ShardedCondensed holding the rank slices) -> the f32 distance matrix of
+        GuideTreeBuilder on the device (component/tree.py:92-147): d has 0 on the diagonal,
+        dist = (-d) + d.max(), all in f32 like the reference's numpy expression
+        (pgpu_tree_distance: a max reduction and a tiled symmetric fill, cluster.cu)."""
+        cuts_dev = shift_dev = None
+        n_cuts = 0
+        if hasattr(scores, "layout_dev"):
+            if scores.world > 1:
+                cuts_dev, shift_dev = scores.layout_dev()
+                n_cuts = scores.world
+            cond = scores.buf
+        else:
+            cond = scores if isinstance(scores, torch.Tensor) else self.dev(np.ascontiguousarray(scores, np.float32))
+            cond = cond.to(torch.float32).contiguous()
+            if cond.numel() != n * (n - 1) // 2:
+                raise ValueError("condensed vector of %d sequences has %d entries" % (n, n * (n - 1) // 2))
+        d = torch.empty((n, n), dtype=torch.float32, device=self.device)
+        scratch = torch.empty(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.pgpu_tree_distance(n, self.ptr(cond), n_cuts, self.ptr(cuts_dev), self.ptr(shift_dev),
+                                               self.ptr(d), self.ptr(scratch), self.stream()))
+        self.launches += 2
+        return d
 
     def cluster_merge_order(self, dist, linkage="average"):
         """HierarchicalClusteringAlgorithm(dist).merge_order(linkage) (util/cluster.py:27-57) on the

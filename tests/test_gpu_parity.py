@@ -256,6 +256,78 @@ def test_packed_int16_kernel_matches_f32_kernel(eng):
         assert np.array_equal(acc, want2), n_odd
 
 
+def test_paired_resident_kernel_every_k_class(eng):
+    """The all-vs-all kernel of BASELINE config 3 (k_stream16r<13>: 400-aa residents, two residents
+    per register) and every wider instantiation (K = 14 ... 32) against the oracle
+    (reference: praline/util/cext.c:99-306 through oracle.align_batch), and against the f32 kernel.
+    Families sit just under a K class boundary, with ragged members that fall into lower classes,
+    so resident pairs of mixed classes, b_skip tiles and the 8-step blocks with and without
+    sequence ends are all exercised; sharded plans must assemble to the same vector."""
+    S = matrices.blosum62()
+    gaps = [-11.0, -1.0]
+    rng = np.random.default_rng(2026)
+    cases = [(13, synth.family(3, 44, 400))]                      # config 3's own family (seed 3, 400 aa)
+    for K in (13, 14, 16, 20, 24, 32):
+        top = 32 * K
+        fam = synth.family(500 + K, 7, top - 9)                  # 3 indels of <= 5: stays inside the class
+        fam = [s[:top] for s in fam]
+        fam += [rng.integers(0, 20, int(n)).astype(np.int32) for n in (top, top - 31, 1, 33, int(rng.integers(2, top)))]
+        cases.append((K, fam))
+    for K, seqs in cases:
+        batch = eng.batch(seqs)
+        assert eng.k_for(int(batch.lens.max())) == K
+        assert eng.wants_paired(S, gaps[0], gaps[1], 0, batch)
+        pi, pj = synth.all_pairs(len(seqs))
+        flat, offs = synth.pack(seqs)
+        want = oracle.align_batch("global", flat, offs, pi, pj, S, gaps)
+        out, _, cells = eng.allpairs_scores(batch, eng.dev(S), 27, gaps, mode="global", S_host=S)
+        assert cells == int((batch.lens[pi] * batch.lens[pj]).sum())
+        assert np.array_equal(out.cpu().numpy(), want), K
+        out32, _, _ = eng.allpairs_scores(batch, eng.dev(S), 27, gaps, mode="global")       # f32 kernel
+        assert np.array_equal(out32.cpu().numpy(), want), K
+        acc = np.full(len(pi), np.nan, np.float32)
+        for r in range(3):                                       # three shards, small tiles
+            plan = eng.allpairs_tiles(batch, (r, 3), tile=8, paired=True)
+            o, (lo, hi), _ = eng.allpairs_scores(batch, eng.dev(S), 27, gaps, mode="global", shard=(r, 3), plan=plan,
+                                                 S_host=S)
+            acc[lo:hi] = o.cpu().numpy()[lo:hi]
+        assert np.array_equal(acc, want), K
+
+
+def test_sharded_condensed_layout_and_tree_distance(eng):
+    """parallel.ShardedCondensed: every shard writes straight into its slice of the all-gather
+    buffer (out_shift); the assembled slices equal the plain condensed vector, and the
+    distance-matrix kernel reads the sliced layout (reference: component/tree.py:132-147)."""
+    from praline_b200 import parallel
+    S = matrices.blosum62()
+    gaps = [-11.0, -1.0]
+    seqs = synth.family(77, 37, 150)
+    n = len(seqs)
+    batch = eng.batch(seqs)
+    pi, pj = synth.all_pairs(n)
+    flat, offs = synth.pack(seqs)
+    want = oracle.align_batch("global", flat, offs, pi, pj, S, gaps)
+    for world in (1, 2, 4):
+        for s_host in (S, None):                                  # packed paired kernel / f32 kernel
+            plans = [eng.allpairs_plan(batch, s_host, gaps, "global", (r, world)) for r in range(world)]
+            sc = parallel.ShardedCondensed(plans[0][3], eng.device)
+            sc.buf.fill_(float("nan"))
+            for r in range(world):                               # what each rank does; the all-gather only moves slices
+                eng.allpairs_scores(batch, eng.dev(S), 27, gaps, mode="global", shard=(r, world), out=sc,
+                                    plan=plans[r], S_host=s_host)
+            assert np.array_equal(sc.condensed().cpu().numpy(), want), (world, s_host is None)
+            slots = np.arange(len(pi))
+            assert np.array_equal(sc.buf.cpu().numpy()[sc.where(slots)], want)
+            dist = eng.tree_distance(sc, n)
+            assert np.array_equal(dist.cpu().numpy(), oracle.tree_distance_matrix(want, n)), world
+    # plain vectors, sizes around the 32 x 32 tiles of the fill kernel, negative-only scores (d.max() is the diagonal's 0)
+    for n2 in (1, 2, 31, 32, 33, 65):
+        v = np.random.default_rng(n2).integers(-50, 50, n2 * (n2 - 1) // 2).astype(np.float32)
+        for vec in (v, -np.abs(v) - 1):
+            got = eng.tree_distance(vec, n2).cpu().numpy()
+            assert np.array_equal(got, oracle.tree_distance_matrix(vec, n2)), n2
+
+
 def test_fast_profile_batches_within_tolerance(eng):
     """Tolerance mode of the profile batch (W = P.S^T, A FMAs per cell): every score within the
     stated 1e-5 relative of the oracle, all modes, both orientations."""
