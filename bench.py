@@ -1,11 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- GCUPS of the all-vs-all affine-gap DP (BASELINE.json metric) on N B200s.
 
-A "step" is one pass of the hot path over the whole pair list of BASELINE config 2:
-1,000 synthetic 300-residue proteins (seed 2 family), all 499,500 unordered
-pairs, BLOSUM62, gaps [-11, -1], global mode, score per pair (what GuideTreeBuilder needs).
-With N > 1 the pair list is sharded by DP cells over the ranks and the condensed score vector
-is assembled with one NCCL all-gather per step.
+A "step" is one pass of the hot path over the whole pair list of BASELINE configs[2] (the Target
+of north_star): 10,000 synthetic 400-residue proteins (seed 3 family), all
+49,995,000 unordered pairs = 8.0e12 DP cells, BLOSUM62, gaps [-11, -1], global mode, score per
+pair -- the all-vs-all GuideTreeBuilder queues (reference: praline/component/tree.py:99-147).
+STRONG scaling: the pair list is fixed and sharded by DP cells over the N ranks; the condensed
+score vector is assembled by one in-place NCCL all-gather per step (praline_b200/parallel.py).
+Every line carries a parity check: rank 0 compares >= 256 random slots of EVERY rank's slice of
+the gathered vector with the oracle, every rank's copy must hash to rank 0's, and the integer
+checksums of the whole vector must equal the recorded 1-GPU values; a mismatch exits non-zero.
+
+Sub-records (under "configs"): BASELINE configs[1] (1,000 x 300 aa, packed int16 and f32
+kernels, N = 1), the f32 kernel on the Target, the preprofile stage of configs[2] (traced
+alignments -> count tables, sharded by master), configs[3] (progressive merge workflow, N = 1),
+configs[4] (20 kb x 20 kb DNA profiles, N = 1) and the MSA wall time of configs[0].
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python bench.py --impl reference ...    # the reference's own C path on the host cores
@@ -25,28 +34,27 @@ sys.path.insert(0, ROOT)
 
 from praline_b200 import matrices, synth  # noqa: E402
 
-WORKLOAD = dict(n_seqs=1000, length=300, seed=2, gaps=[-11.0, -1.0], mode="global")
+C3 = dict(name="c3", n_seqs=10000, length=400, seed=3, gaps=[-11.0, -1.0], mode="global")
+C2 = dict(name="c2", n_seqs=1000, length=300, seed=2, gaps=[-11.0, -1.0], mode="global")
 W_FLOPS_PER_CELL = 11.0   # 7 add + 4 max of the reference recurrence
+# Integer checksums of the C3 condensed score vector (scores are integers, so int64 sums are exact and
+# independent of the sharding): sum(score) and sum(score * (slot % 1000003)).  Recorded from the 1-GPU
+# run whose sample was oracle-checked (profiles/r02_bench_1gpu_a.json); every N must reproduce them.
+C3_CHECKSUMS = (42018717167, 21000152364599771)
 
 
-def n_seqs_for(world):
-    """Weak scaling: the pair count (the per-GPU work) stays that of configs[1] per rank, so the
-    sequence count grows with sqrt(world): 1000, 1414, 2000, 2828 at 1, 2, 4, 8 GPUs."""
-    return int(round(WORKLOAD["n_seqs"] * np.sqrt(world)))
+def workload(cfg):
+    return synth.family(cfg["seed"], cfg["n_seqs"], cfg["length"]), matrices.blosum62()
 
 
-def workload(world=1):
-    seqs = synth.family(WORKLOAD["seed"], n_seqs_for(world), WORKLOAD["length"])
-    return seqs, matrices.blosum62()
-
-
-def config_dict(extra=None, world=1):
-    n = n_seqs_for(world)
-    c = {"workload": "all-vs-all pairwise scoring, %d synthetic 300-aa proteins (%d pairs), "
-                     "BLOSUM62 affine [-11,-1], global, score per pair (BASELINE configs[1]%s)"
-                     % (n, n * (n - 1) // 2, "" if world == 1 else ", pair count scaled x%d" % world),
-         "n_seqs": n, "seq_len": WORKLOAD["length"], "pairs": n * (n - 1) // 2,
-         "l2": "256 MiB buffer written between timed steps (inputs are smaller than L2)"}
+def config_dict(cfg, world, extra=None):
+    n = cfg["n_seqs"]
+    c = {"workload": "all-vs-all pairwise scoring (guide tree), %d synthetic %d-aa proteins (%d pairs), BLOSUM62 affine "
+                     "[-11,-1], global, score per pair (BASELINE configs[%d]%s)"
+                     % (n, cfg["length"], n * (n - 1) // 2, 2 if cfg is C3 else 1,
+                        ", the Target of north_star" if cfg is C3 else ""),
+         "n_seqs": n, "seq_len": cfg["length"], "pairs": n * (n - 1) // 2,
+         "l2": "256 MiB buffer written between timed steps; the 200 MB score vector alone exceeds L2"}
     if extra:
         c.update(extra)
     return c
@@ -136,27 +144,36 @@ def _ref_worker(args):
 
 
 def reference_arm(args, emit=None):
-    """--impl reference: the reference's CPU implementation of the path on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, on the
+    same workload (the C3 family), each step a bounded random sample of its pairs."""
     import multiprocessing as mp
     import oracle
-    seqs, S = workload(max(args.gpus, 1))
-    pi, pj = synth.all_pairs(len(seqs))
+    seqs, S = workload(C3)
+    n = len(seqs)
     cores = os.cpu_count() or 1
     kind = "reference" if oracle.ref_cext() is not None else "port"
     rng = np.random.default_rng(0)
-    per_step = 250 * cores                      # bounded sample: ~3 s of work per core and step
+    per_step = 600 * cores                      # bounded sample: ~1.5 s of work per core and step
     flat, offs = synth.pack(seqs)
 
     def one_step(pool, k):
-        pick = rng.choice(len(pi), per_step, replace=False)
+        i, j = rng.integers(0, n, per_step), rng.integers(0, n, per_step)
+        j = np.where(i == j, (j + 1) % n, j)
+        pi, pj = np.minimum(i, j).astype(np.int32), np.maximum(i, j).astype(np.int32)
+        sub = []
+        if kind == "reference":
+            for c in np.array_split(np.arange(per_step), cores):        # ship only the sequences a worker needs
+                ids = np.unique(np.concatenate([pi[c], pj[c]]))
+                remap = {int(g): k2 for k2, g in enumerate(ids)}
+                sub.append(([seqs[g] for g in ids], S, [(remap[int(a)], remap[int(b)]) for a, b in zip(pi[c], pj[c])],
+                            C3["gaps"]))
         t0 = time.perf_counter()
         if kind == "reference":
-            chunks = np.array_split(pick, cores)
-            res = pool.map(_ref_worker, [(seqs, S, list(zip(pi[c], pj[c])), WORKLOAD["gaps"]) for c in chunks])
+            res = pool.map(_ref_worker, sub)
             cells = sum(r[0] for r in res)
         else:
-            oracle.align_batch("global", flat, offs, pi[pick], pj[pick], S, WORKLOAD["gaps"])
-            cells = int((offs[1:] - offs[:-1])[pi[pick]] @ (offs[1:] - offs[:-1])[pj[pick]])
+            oracle.align_batch("global", flat, offs, pi, pj, S, C3["gaps"])
+            cells = int((offs[1:] - offs[:-1])[pi] @ (offs[1:] - offs[:-1])[pj])
         return cells, time.perf_counter() - t0
 
     with mp.get_context("fork").Pool(cores) as pool:
@@ -171,37 +188,42 @@ def reference_arm(args, emit=None):
     used = cores if kind == "reference" else 1
     line = {"impl": "reference", "metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict({"sample": "%d random pairs of the workload per step" % per_step},
-                                  max(args.gpus, 1)),
+            "config": config_dict(C3, max(args.gpus, 1)),
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": kind,
-                             "sample": "%d random pairs per step x %d steps, cext_build_scores + cext_align_global"
-                                       % (per_step, args.steps)},
+                             "sample": "%d random pairs of the workload per step x %d steps, cext_build_scores + "
+                                       "cext_align_global per pair" % (per_step, args.steps)},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     (emit or (lambda o: print(json.dumps(o))))(line)
 
 
-def cpu_baseline_port(seqs, S, seconds=12.0):
+def cpu_baseline_port(seqs, S, gaps, seconds=12.0):
     """The oracle's scalar C loop on one core over a bounded sample of the same pairs."""
     import oracle
     flat, offs = synth.pack(seqs)
-    pi, pj = synth.all_pairs(len(seqs))
+    n = len(seqs)
     rng = np.random.default_rng(1)
-    pick = rng.choice(len(pi), 400, replace=False)
+
+    def draw(k):
+        i = rng.integers(0, n, k)
+        j = rng.integers(0, n, k)
+        keep = i != j
+        return np.minimum(i, j)[keep].astype(np.int32), np.maximum(i, j)[keep].astype(np.int32)
+
+    pi, pj = draw(200)
     t0 = time.perf_counter()
-    oracle.align_batch("global", flat, offs, pi[pick], pj[pick], S, WORKLOAD["gaps"])
+    oracle.align_batch("global", flat, offs, pi, pj, S, gaps)
     dt = time.perf_counter() - t0
-    n = int(min(len(pi), max(400, 400 * seconds / max(dt, 1e-3))))
-    pick = rng.choice(len(pi), n, replace=False)
+    pi, pj = draw(int(max(200, 200 * seconds / max(dt, 1e-3))))
     lens = offs[1:] - offs[:-1]
     t0 = time.perf_counter()
-    oracle.align_batch("global", flat, offs, pi[pick], pj[pick], S, WORKLOAD["gaps"])
+    oracle.align_batch("global", flat, offs, pi, pj, S, gaps)
     dt = time.perf_counter() - t0
-    cells = int((lens[pi[pick]] * lens[pj[pick]]).sum())
+    cells = int((lens[pi] * lens[pj]).sum())
     return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
             "sample": "%d random pairs of the workload (%.1f s), oracle/praline_oracle.c scalar loop incl. traceback"
-                      % (n, dt)}
+                      % (len(pi), dt)}
 
 
 def measured_peaks():
@@ -213,24 +235,127 @@ def measured_peaks():
         return {}
 
 
-def msa_e2e(n=50, length=300, preprofile="global", msa="tree"):
+def _tool(script, argv, timeout=900, env=None):
+    """Run a tools/ script in its own process and return the JSON lines it printed."""
+    try:
+        e = dict(os.environ)
+        e.update(env or {})
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            e.pop(k, None)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script)] + [str(a) for a in argv],
+                             capture_output=True, text=True, timeout=timeout, env=e)
+        lines = [json.loads(l) for l in out.stdout.strip().splitlines() if l.startswith("{")]
+        if not lines:
+            return [{"error": (out.stderr or "no output")[-300:]}]
+        return lines
+    except Exception as e:   # the DP numbers stand on their own
+        return [{"error": str(e)[:300]}]
+
+
+def msa_e2e(n=50, length=300, preprofile="global", msa="tree", arms=("gpu", "cpu1", "cpun")):
     """Second half of the BASELINE metric: wall time of the reference's MSA workflow
-    (`praline --preprofile-global --msa-tree`, 50 x 300 aa, BASELINE configs[0] scale) on the
-    GPU manager and on the reference's own single-process Manager; outputs must be identical.
-    Needs the reference package (baseline/_ref); returns None when it is absent."""
-    import subprocess
-    tool = os.path.join(ROOT, "tools", "msa_e2e.py")
+    (`praline --preprofile-global --msa-tree`) on the GPU manager, on the reference's stock Manager
+    (`-t 1`) and on its ParallelExecutionManager with all host cores (`-t $(nproc)`, cmd.py:41-44);
+    outputs must be byte-identical (SHA-256 of the FASTA).  Needs the reference package
+    (baseline/_ref); returns None when it is absent."""
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "praline")):
         return None
-    try:
-        out = subprocess.run([sys.executable, tool, str(n), str(length), preprofile, msa], capture_output=True,
-                             text=True, timeout=600)
-        return json.loads(out.stdout.strip().splitlines()[-1])
-    except Exception as e:   # the DP numbers above stand on their own
-        return {"error": str(e)[:200]}
+    res = {"n_seqs": n, "length": length, "preprofile": preprofile, "msa": msa}
+    shas = set()
+    for arm in arms:
+        r = _tool("msa_e2e.py", [n, length, preprofile, msa, arm])[-1]
+        if "error" in r:
+            res[arm] = r
+            continue
+        shas.add(r["sha256"])
+        res[arm] = {k: r[k] for k in ("wall_s", "first_s", "threads", "batched_requests") if k in r}
+        res["cores"] = r.get("cores")
+    res["identical"] = len(shas) == 1
+    g = res.get("gpu", {}).get("wall_s")
+    for arm in ("cpu1", "cpun"):
+        if g and res.get(arm, {}).get("wall_s"):
+            res["speedup_vs_" + arm] = res[arm]["wall_s"] / g
+    return res
 
 
 # ---- our arm ---------------------------------------------------------------------------------
+def timed_allpairs(eng, batch, S, S_dev, gaps, mode, rank, world, steps, warmup, s_host, flush, sync, sampler=None):
+    """W warm-up + K timed steps of the sharded all-vs-all with the in-place all-gather; CUDA events
+    per step on the launching stream, L2 flushed between steps.  Returns (ms per step of this rank,
+    score buffer, plan, launches)."""
+    import torch
+    from praline_b200 import parallel
+    plan = eng.allpairs_plan(batch, s_host, gaps, mode, (rank, world))
+    sc = parallel.ShardedCondensed(plan[3], eng.device)
+
+    def step():
+        eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=sc, plan=plan,
+                            S_host=s_host)
+        sc.allgather(rank)
+
+    for _ in range(max(warmup, 0)):
+        step()
+    sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    l0 = eng.launches
+
+    def run():
+        sync()
+        for k in range(steps):
+            flush.fill_(k & 0xff)            # L2 flush, outside the timed events
+            torch.cuda.synchronize(eng.device)
+            ev[k][0].record()
+            step()
+            ev[k][1].record()
+        sync()
+
+    if sampler is not None:
+        with sampler:
+            run()
+    else:
+        run()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / max(steps, 1)
+    return ms, sc, plan, eng.launches - l0
+
+
+def parity_check(eng, sc, seqs, S, gaps, rank, world, expect=None, per_rank=256):
+    """Rank 0 oracle-checks `per_rank` random slots of every rank's slice of the gathered vector;
+    every rank's copy must carry the same integer checksums (and `expect`, when recorded)."""
+    import torch
+    import torch.distributed as dist
+    n = len(seqs)
+    vec = sc.condensed()
+    iv = vec.to(torch.int64)
+    idx = torch.arange(vec.numel(), device=vec.device, dtype=torch.int64) % 1000003
+    sums = torch.stack([iv.sum(), (iv * idx).sum(), (vec != iv.to(torch.float32)).sum().to(torch.int64)])
+    allsums = [sums.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allsums, sums)
+    res = {"slots_checked": 0, "oracle_mismatches": 0, "ranks_identical": True, "checksums": None, "ok": True}
+    if rank == 0:
+        import oracle
+        ref = allsums[0].cpu().tolist()
+        res["ranks_identical"] = all(a.cpu().tolist() == ref for a in allsums)
+        res["checksums"] = ref[:2]
+        res["non_integer_scores"] = int(ref[2])
+        if expect is not None:
+            res["matches_recorded_1gpu_checksums"] = (list(expect) == ref[:2])
+        rng = np.random.default_rng(12345)
+        slots = np.concatenate([rng.integers(sc.cuts[r], max(sc.cuts[r + 1], sc.cuts[r] + 1), per_rank)
+                                for r in range(world) if sc.cuts[r + 1] > sc.cuts[r]])
+        # condensed slot -> (i, j), i < j (np.triu_indices order)
+        i = (n - 2 - np.floor(np.sqrt(-8.0 * slots + 4.0 * n * (n - 1) - 7) / 2.0 - 0.5)).astype(np.int64)
+        j = (slots + i + 1 - n * (n - 1) // 2 + (n - i) * ((n - i) - 1) // 2).astype(np.int64)
+        flat, offs = synth.pack(seqs)
+        want = oracle.align_batch("global", flat, offs, i.astype(np.int32), j.astype(np.int32), S, gaps)
+        got = sc.buf[torch.from_numpy(sc.where(slots)).to(sc.buf.device)].cpu().numpy()
+        res["slots_checked"] = int(len(slots))
+        res["oracle_mismatches"] = int((got != want).sum())
+        res["ok"] = bool(res["oracle_mismatches"] == 0 and res["ranks_identical"] and res["non_integer_scores"] == 0
+                         and res.get("matches_recorded_1gpu_checksums", True))
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,6 +363,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + roofline only (profiling runs)")
+    ap.add_argument("--full-msa", action="store_true", help="also time the MSA workflow at 500 sequences")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,7 +384,6 @@ def main():
         sys.stdout.flush()
         os.dup2(2, 1)
 
-    # NCCL prints its version banner on stdout at some debug levels: keep stdout for the one JSON line
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         if rank == 0:
@@ -274,8 +400,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = get_engine(local_rank)
     dev = eng.device
-    seqs, S = workload(world)
-    gaps, mode = WORKLOAD["gaps"], WORKLOAD["mode"]
+    seqs, S = workload(C3)
+    gaps, mode = C3["gaps"], C3["mode"]
     n = len(seqs)
     n_pairs = n * (n - 1) // 2
 
@@ -284,63 +410,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- resident-input arm: sequences, matrix and tile plan already in HBM ------------------
     batch = eng.batch(seqs)
     S_dev = eng.dev(S)
-    go_, ge_ = float(gaps[0]), float(gaps[-1])
-    plan = eng.allpairs_tiles(batch, (rank, world), paired=eng.wants_paired(S, go_, ge_, 0, batch))
-    slot_cuts = plan[3]
-    my_cells = plan[2]
-    out = torch.empty(n_pairs, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    total_cells = int(sum(len(seqs[i]) for i in range(n)) ** 2 - sum(len(s) ** 2 for s in seqs)) // 2
-
-    def step_resident():
-        eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan,
-                            S_host=S)
-        if world > 1:
-            parallel.allgather_condensed(out, slot_cuts)
-
-    for _ in range(max(args.warmup, 0)):
-        step_resident()
-    sync()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = eng.launches
-    with ClockSampler(local_rank) as clk:
-        sync()
-        for k in range(args.steps):
-            flush.fill_(k & 0xff)            # L2 flush, outside the timed events
-            torch.cuda.synchronize(dev)
-            ev[k][0].record()
-            step_resident()
-            ev[k][1].record()
-        sync()
-    launches = eng.launches - l0
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / max(args.steps, 1)
+    lens = batch.lens
+    total_cells = int((int(lens.sum()) ** 2 - int((lens ** 2).sum())) // 2)
+    clk = ClockSampler(local_rank)
+    ms_rank, sc, plan, launches = timed_allpairs(eng, batch, S, S_dev, gaps, mode, rank, world, args.steps, args.warmup,
+                                                 S, flush, sync, clk)
+    my_cells = plan[2]
+    ms_per_step = allmax(ms_rank)
     gcups = total_cells / (ms_per_step * 1e-3) / 1e9
+    check = parity_check(eng, sc, seqs, S, gaps, rank, world, expect=C3_CHECKSUMS)
 
     # ---- end-to-end arm: host buffers in, host scores out, every step --------------------------
-    host_out = torch.empty(n_pairs, dtype=torch.float32).pin_memory()
+    # The call a user of the library makes: sequences on the host -> Engine.batch (pinned H2D) ->
+    # allpairs_plan (cached per lengths/shard) -> kernels -> in-place all-gather -> every rank copies ITS
+    # slice of the vector into one pinned host vector shared by the ranks of the node (SharedHostVector).
+    host = parallel.SharedHostVector(n_pairs, rank, world)
     h2d = d2h = 0
 
     def step_e2e():
         nonlocal h2d, d2h
         b = eng.batch(seqs)                                  # pinned host -> device
         sd = eng.dev(S)
-        pl = eng.allpairs_tiles(b, (rank, world), paired=eng.wants_paired(S, go_, ge_, 0, b))
-        o, (lo, hi), _ = eng.allpairs_scores(b, sd, S.shape[0], gaps, mode=mode, shard=(rank, world), plan=pl,
+        pl = eng.allpairs_plan(b, S, gaps, mode, (rank, world))
+        tiles_new = 0 if pl[4] else sum(t.nbytes for t in pl[0].values())
+        o, (lo, hi), _ = eng.allpairs_scores(b, sd, S.shape[0], gaps, mode=mode, shard=(rank, world), out=sc, plan=pl,
                                              S_host=S)
-        if world > 1:
-            parallel.allgather_condensed(o, pl[3])
-            lo, hi = 0, n_pairs
-        host_out[lo:hi].copy_(o[lo:hi], non_blocking=True)   # device -> pinned host
+        host.tensor[lo:hi].copy_(sc.slice_of(rank), non_blocking=True)   # device -> shared pinned host, own slice
+        sc.allgather(rank)                                   # every rank also holds the full vector on its device
         torch.cuda.synchronize(dev)
-        h2d = b.h2d_bytes + S.nbytes + sum(t.nbytes for t in pl[0].values())
+        h2d = b.h2d_bytes + S.nbytes + tiles_new
         d2h = (hi - lo) * 4
 
     for _ in range(max(args.warmup, 1)):
@@ -350,93 +458,146 @@ def main():
     for _ in range(args.steps):
         step_e2e()
     sync()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_gcups = total_cells * args.steps / e2e_s / 1e9
+    tb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_gcups = total_cells * args.steps / float(te.item()) / 1e9
+        dist.all_reduce(tb)
+    h2d_all, d2h_all = int(tb[0].item()), int(tb[1].item())
+    if rank == 0:      # the host vector assembled from the ranks' slices is the same vector
+        pick = np.random.default_rng(5).integers(0, n_pairs, 100000)
+        dev_vals = sc.buf[torch.from_numpy(sc.where(pick)).to(dev)].cpu().numpy()
+        check["e2e_host_vector_matches"] = bool(np.array_equal(host.array[pick], dev_vals))
+        check["ok"] = bool(check["ok"] and check["e2e_host_vector_matches"])
 
-    # ---- roofline of the dominant kernel (k_stream), timed live with CUDA events ----------------
+    # ---- sub-records on every N: the f32 kernel on the Target, the preprofile stage of configs[2] ----
+    configs = {}
+    eng.use_s16 = False
+    f32_ms, sc32, plan32, _ = timed_allpairs(eng, batch, S, S_dev, gaps, mode, rank, world, 1, 1, None, flush, sync)
+    eng.use_s16 = True
+    f32_ms = allmax(f32_ms)
+    same32 = bool(torch.equal(sc32.condensed(), sc.condensed()))
+    configs["c3_f32_kernel"] = {"kernel": "k_stream<13,global,score-only> (f32, what non-integer inputs get)",
+                                "ms_per_step": f32_ms, "gcups": total_cells / (f32_ms * 1e-3) / 1e9,
+                                "identical_to_int16_vector": same32, "steps": 1, "warmup": 1}
+    del sc32
+    if not args.no_extras:
+        # the preprofile stage of configs[2]: every master against all other sequences, traced on the device into
+        # count tables (global master-slave alignments), masters sharded by rank, tables all-gathered
+        allm = np.arange(n)
+        mine, cuts = parallel.shard_masters(allm, lens, rank, world)
+        eng.preprofile_stage(batch, S, gaps, masters=mine[:40])          # warm-up
+        sync()
+        l0 = eng.launches
+        t0 = time.perf_counter()
+        cnt_dev, where, cells_mine = eng.preprofile_stage(batch, S, gaps, masters=mine)
+        if world > 1:
+            sizes = [int(lens[allm[cuts[r]:cuts[r + 1]]].sum()) * S.shape[0] for r in range(world)]
+            cnt_all = parallel.allgather_counts(cnt_dev, sizes)
+        else:
+            cnt_all = cnt_dev
+        counts_sum = int(cnt_all.sum(dtype=torch.int64).item())
+        sync()
+        pre_s = allmax(time.perf_counter() - t0)
+        pre_cells = float(lens.sum()) ** 2 - float((lens ** 2).sum())
+        configs["c3_preprofile"] = {"stage": "preprofile stage of BASELINE configs[2]: 99,990,000 traced global master-slave "
+                                             "alignments -> count tables on the device (preprofile.py:127-154, util/align.py:187-232)",
+                                    "wall_s": pre_s, "gcups": pre_cells / pre_s / 1e9, "cells": pre_cells,
+                                    "counts_sum": counts_sum, "counts_sum_expected": 39090321290,
+                                    "identical_counts_sum": counts_sum == 39090321290,
+                                    "gpu_launches_rank0": int(eng.launches - l0), "n_gpus": world}
+        check["ok"] = bool(check["ok"] and counts_sum == 39090321290)
+        del cnt_dev, cnt_all
+
+    # ---- roofline of the dominant kernel, timed live with CUDA events ---------------------------
     roof = None
     cpu = None
+    clk_sum = clk.summary()
     if rank == 0:
         mb = eng.microbench()
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        clk_sum = clk.summary()
-        mhz = clk_sum["sm_mhz"] or mb["sm_mhz"]
-        # peak f32 add/max lane-ops per second on this box: the measured
-        # full-rate f32 issue (FADD, warp-instructions / clk / SM) x 32 lanes x SMs x SM clock
-        # sampled during the timed region
-        peak = mb["fadd"] * 32 * sms * 1e9     # warp-instr/ns/SM x lanes x SMs -> lane-ops/s, wall clock
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
         for a, b in kev:
             a.record()
-            eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=out, plan=plan,
-                            S_host=S)
+            eng.allpairs_scores(batch, S_dev, S.shape[0], gaps, mode=mode, shard=(rank, world), out=sc, plan=plan, S_host=S)
             b.record()
         torch.cuda.synchronize(dev)
         kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-        achieved = my_cells * W_FLOPS_PER_CELL / (kms * 1e-3)
-        # The roofline of this kernel is the CUDA-core pipe its recurrence runs on (not HBM, not
-        # tensor).  peak = the BARE recurrence (same instructions, no loads / shuffles / loop) measured on
-        # this box by pgpu_microbench: 5 packed DPX/add instructions per 2 cells (cell_mix16) or the
-        # 7-instruction f32 cell (cell_mix); achieved = the same instruction count at the kernel's cell rate.
-        ipc_cell = 2.5 if plan[5] else 7.0
-        mix = mb["cell_mix16"] if plan[5] else mb["cell_mix"]
-        ach_ops = my_cells / (kms * 1e-3) * ipc_cell
-        peak_ops = mix * 32.0 * sms * 1e9
-        roof = {"bound": "cuda_core_issue", "achieved": ach_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
-                "frac": ach_ops / peak_ops,
-                "frac_note": "of measured: recurrence lane-instructions per second of this kernel (%.1f per cell) / the rate "
-                             "of the bare recurrence instruction mix on this box (pgpu_microbench, %.2f warp-instr/ns/SM)"
-                             % (ipc_cell, mix),
-                # SURVEY 8d's DP-cell roofline (the figure BASELINE's '>= 50 %% of the DP-cell roofline' refers to):
-                # algorithmic W = 11 f32 add/max per cell against the measured f32 add issue rate; above 1 for the
-                # packed kernel because one DPX instruction does two cells
-                "dp_cell_roofline": {"w_ops_per_cell": W_FLOPS_PER_CELL, "achieved": achieved / 1e12, "peak": peak / 1e12,
-                                     "unit": "Tlane-op/s", "frac": achieved / peak},
+        rate = my_cells / (kms * 1e-3)                     # cells per second of this rank's launch
+        # The binding unit of the packed kernel is the half-rate ALU pipe that executes the DPX instructions:
+        # 3 per TWO cells (2 VIADDMNMX.S16x2 + 1 VIMNMX3.S16x2).  peak = the measured VIADDMNMX.S16x2 rate of the
+        # box (pgpu_microbench, warp-instr/ns/SM) x 32 lanes x SMs; achieved = 1.5 lane-instructions per cell at
+        # the kernel's cell rate.  ncu's sm__inst_executed_pipe_alu of the same kernel adds the few non-DPX ALU
+        # instructions (profiles/r02_kstream16r_*).
+        alu_peak = mb["viaddmnmx_s16x2"] * 32.0 * sms * 1e9
+        alu_ach = rate * 1.5
+        mix_peak = mb["cell_mix16"] * 32.0 * sms * 1e9      # bare 5-instruction recurrence of two cells
+        issue_peak = mb["fadd"] * 32.0 * sms * 1e9          # full-rate issue (FADD)
+        roof = {"bound": "cuda_core_alu_pipe", "achieved": alu_ach / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s",
+                "frac": alu_ach / alu_peak,
+                "frac_note": "of measured: DPX lane-instructions per second of this kernel (1.5 per cell: 2 VIADDMNMX.S16x2 + "
+                             "1 VIMNMX3.S16x2 per two cells) / the VIADDMNMX.S16x2 rate of this box (pgpu_microbench, %.2f "
+                             "warp-instr/ns/SM) -- the share of the binding ALU pipe the recurrence itself uses; ncu's "
+                             "pipe_alu utilisation of the same launch is this plus the kernel's other ALU instructions"
+                             % mb["viaddmnmx_s16x2"],
+                "frac_of_bare_recurrence_mix": rate * 2.5 / mix_peak,
+                "frac_of_issue": rate * 2.5 / issue_peak,
+                "frac_notes": "bare mix: 2.5 lane-instructions per cell against the bare 5-instruction packed recurrence "
+                              "(no loads, shuffles or loop) measured on this box; issue: the same against the full FADD issue rate",
+                # SURVEY 8d's W = 11 f32 add/max per cell against the measured f32 add issue rate: a note only -- above 1
+                # for the packed kernel because one DPX instruction does two cells and fuses add+max
+                "survey_w11_note": {"w_ops_per_cell": W_FLOPS_PER_CELL, "achieved": rate * W_FLOPS_PER_CELL / 1e12,
+                                    "peak": issue_peak / 1e12, "frac": rate * W_FLOPS_PER_CELL / issue_peak},
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                # (profiles/r01_kstream16r_raw.csv: 427,520 B read, 0 B written -- the 2 MB of scores stay in
-                # L2; f32 kernel, profiles/r01_kstream_v2_raw.csv: 443,392 B); algorithmic bytes per launch:
-                # 0.3 MB sequences + 0.1 MB tiles in, 2.0 MB scores out
-                "traffic": 427520 if plan[5] else 443392,
-                "note": "DP-cell roofline (SURVEY 8d): algorithmic 11 f32 add/max per cell (the kernel issues 7); "
-                        "peak = measured f32 add issue rate (%.2f warp-instr/ns/SM, wall clock) x 32 lanes x %d SMs "
-                        "(of measured; SM clock %.0f MHz during the run); f32 max / compare / shift / integer ops "
-                        "issue at half that rate on this part (pipe_rates, warp-instr/ns/SM); HBM is not the "
-                        "bound: 4 B/pair out" % (mb["fadd"], sms, mhz),
-                "issue_bound_frac": (my_cells / (kms * 1e-3)) * (2.5 if plan[5] else 7.0) / 32.0 / (mb["fadd"] * sms * 1e9),
-                "issue_bound_note": "fraction of the instruction-issue bound of this kernel's own recurrence at the "
-                                    "measured full issue rate: 5 packed DPX/add instructions per 2 cells (int16 "
-                                    "kernel) or 7 per cell (f32 kernel); the DPX and max instructions themselves "
-                                    "issue at half rate (pipe_rates), which is the binding pipe",
-                "kernel": "k_stream16r<10> (packed s16x2, paired residents)" if plan[5] else "k_stream<10,global,score-only>", "kernel_ms": kms,
-                "gcups_kernel": my_cells / (kms * 1e-3) / 1e9, "pipe_rates": mb}
-        # traced variant (what the preprofile master-slave alignments need): K2 with packed traceback
-        # + K4 walk, device time only, on the first 120k pairs of the same workload
-        tpi, tpj = synth.all_pairs(n)
+                # (profiles/r02_kstream16r_k13_*): algorithmic bytes per launch = sequences + tiles in, 4 B per pair out
+                "traffic": None,
+                "algorithmic_bytes": int(batch.h2d_bytes + sum(t.nbytes for t in plan[0].values()) + 4 * (plan[1][1] - plan[1][0])),
+                "kernel": "k_stream16r<13> (packed s16x2 DPX, paired residents)", "kernel_ms": kms,
+                "gcups_kernel": rate / 1e9, "pipe_rates": mb,
+                "note": "HBM is not the bound (4 B per pair out, 8e4 cells per pair); tensor cores have nothing to contract"}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")) as f:
+                roof["traffic"] = json.load(f).get("k_stream16r_13_dram_bytes")
+        except Exception:
+            pass
+
+    if rank == 0 and not args.no_extras and world == 1:
+        # BASELINE configs[1]: 1,000 x 300 aa on one B200, packed int16 and f32 kernels
+        seqs2, _ = workload(C2)
+        b2 = eng.batch(seqs2)
+        cells2 = int((int(b2.lens.sum()) ** 2 - int((b2.lens ** 2).sum())) // 2)
+        nosync = lambda: torch.cuda.synchronize(dev)
+        ms16, sc16, _, _ = timed_allpairs(eng, b2, S, S_dev, gaps, mode, 0, 1, 5, 3, S, flush, nosync)
+        eng.use_s16 = False
+        ms32, sc32b, _, _ = timed_allpairs(eng, b2, S, S_dev, gaps, mode, 0, 1, 3, 2, None, flush, nosync)
+        eng.use_s16 = True
+        configs["c2"] = {"workload": config_dict(C2, 1)["workload"], "cells": cells2,
+                         "int16_kernel": {"ms_per_step": ms16, "gcups": cells2 / (ms16 * 1e-3) / 1e9, "kernel": "k_stream16r<10>"},
+                         "f32_kernel": {"ms_per_step": ms32, "gcups": cells2 / (ms32 * 1e-3) / 1e9, "kernel": "k_stream<10>"},
+                         "identical": bool(torch.equal(sc16.condensed(), sc32b.condensed()))}
+        # traced variant on the same workload (fill with packed traceback + K4 walk, device time)
+        tpi, tpj = synth.all_pairs(C2["n_seqs"])
         tpi, tpj = tpi[:120000], tpj[:120000]
-        tcells = int((batch.lens[tpi] * batch.lens[tpj]).sum())
-        eng.align_pairs(batch, tpi, tpj, S, gaps, mode=mode, want_paths=True, resident="one", device_only=True)
+        tcells = int((b2.lens[tpi] * b2.lens[tpj]).sum())
+        eng.align_pairs(b2, tpi, tpj, S, gaps, mode=mode, want_paths=True, resident="one", device_only=True)
         torch.cuda.synchronize(dev)
         ta, tb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ta.record()
-        eng.align_pairs(batch, tpi, tpj, S, gaps, mode=mode, want_paths=True, resident="one", device_only=True)
+        eng.align_pairs(b2, tpi, tpj, S, gaps, mode=mode, want_paths=True, resident="one", device_only=True)
         tb_.record()
         torch.cuda.synchronize(dev)
-        roof["traced_gcups"] = tcells / (ta.elapsed_time(tb_) * 1e-3) / 1e9
-        roof["traced_note"] = "120000 pairs, fill with 4-bit traceback + per-pair path walk, device time incl. plan upload"
-        # the caller of the scores: distance matrix + clustering kernel on the device
+        configs["c2"]["traced_gcups"] = tcells / (ta.elapsed_time(tb_) * 1e-3) / 1e9
+        # the caller of the scores: distance matrix + clustering kernel on the device, C3 size
         ga, gb, gc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        eng.cluster_merge_order(eng.tree_distance(out, n), "average")
         ga.record()
-        dmat = eng.tree_distance(out, n)
+        dmat = eng.tree_distance(sc, n)
         gb.record()
         merges = eng.cluster_merge_order(dmat, "average")
         gc.record()
         torch.cuda.synchronize(dev)
-        roof["guide_tree"] = {"distance_ms": ga.elapsed_time(gb), "cluster_ms_incl_d2h": gb.elapsed_time(gc),
-                              "merges": len(merges), "note": "average linkage, merge order of util/cluster.py on %d sequences" % n}
+        configs["c3_guide_tree"] = {"distance_ms": ga.elapsed_time(gb), "cluster_ms_incl_d2h": gb.elapsed_time(gc),
+                                    "merges": len(merges), "note": "average linkage, merge order of util/cluster.py on %d sequences" % n}
+        del dmat
         # the score-matrix kernel on tensor cores (north star (1)): HBM GB/s of k_build_rows_tc against the
         # measured copy bandwidth, on one wave of 60 depth-50 profiles of length 400 (tolerance mode)
         try:
@@ -466,27 +627,52 @@ def main():
                                      "profile_batch_gcups_device": pcells / ((tc_ms + sum(fed)) * 1e-3) / 1e9 if tc_ms else None}
         except Exception as e:   # the headline numbers stand on their own
             roof["score_rows_tc"] = {"error": str(e)[:200]}
+        # BASELINE configs[4]: 20 kb x 20 kb DNA profiles on the intra-task wavefront path (own process)
+        c5 = _tool("run_c5.py", [20000, 3], timeout=600)
+        configs["c5"] = {"workload": "long nucleotide profile x profile alignment, 20 kb x 20 kb, depth-8 count profiles (BASELINE configs[4])",
+                         "cases": c5}
         if not args.no_cpu_baseline:
-            cpu = cpu_baseline_port(seqs, S)
-            roof["msa_e2e"] = msa_e2e()
-            roof["msa_e2e_cli_default"] = msa_e2e(preprofile="dummy", msa="ad_hoc")   # praline in.fa out.aln
+            cpu = cpu_baseline_port(seqs, S, gaps)
+            # BASELINE configs[3]: progressive merge of 2,000 x 400 aa through the reference's workflow (own process)
+            configs["c4"] = {"workload": "progressive profile-profile merge, 2,000 x 400 aa, global preprofiles, guide tree, "
+                                         "merge_mode='semiglobal' (BASELINE configs[3]); whole workflow wall time on GpuBatchManager",
+                             "exact_profile_scores": _tool("run_c4.py", [2000, 400, 40], timeout=900)[-1],
+                             "tolerance_profile_scores": _tool("run_c4.py", [2000, 400, 0], timeout=900,
+                                                               env={"PGPU_FAST_PROFILES": "1"})[-1]}
+            # BASELINE configs[0] / second half of the metric: MSA wall time next to the host-CPU reference
+            configs["msa_e2e"] = {"tree_50": msa_e2e(50, 300, "global", "tree"),
+                                  "cli_default_50": msa_e2e(50, 300, "dummy", "ad_hoc"),
+                                  "larger_runs": "profiles/r02_msa_e2e_full.json (200 and 500 sequences, --full-msa)"}
+            if args.full_msa:
+                configs["msa_e2e"]["tree_200"] = msa_e2e(200, 300, "global", "tree", arms=("gpu", "cpun"))
+                configs["msa_e2e"]["tree_500"] = msa_e2e(500, 300, "global", "tree", arms=("gpu", "cpun"))
 
     if rank == 0:
         line = {"metric": "GCUPS all-vs-all affine DP", "value": gcups, "unit": "GCUPS", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None,
-                "dtype": "i16" if (eng.use_s16 and eng.fits_s16(S, gaps[0], gaps[1], batch.lens) is not None) else "f32",
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": "i16" if plan[5] else "f32",
                 "data": "synthetic",
-                "config": config_dict({"parallelism": "pairs sharded by DP cells over %d rank(s)%s"
-                                       % (world, ", NCCL all-gather of scores" if world > 1 else "")}, world),
+                "config": config_dict(C3, world),
+                "parallelism": "pairs sharded by DP cells over %d rank(s)%s"
+                               % (world, ", in-place NCCL all-gather of the score slices" if world > 1 else ""),
                 "clocks": clk_sum,
-                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                        "note": "host sequences -> pinned H2D -> plan (cached per lengths) -> kernel -> all-gather; every rank "
+                                "copies its slice into one pinned host vector shared by the ranks (bytes are sums over ranks)"},
+                "gpu_launches": int(launches), "parity_check": check["ok"], "parity": check,
+                "roofline": roof, "cpu_baseline": cpu, "configs": configs}
         emit(line)
+    ok = torch.tensor([1 if (rank != 0 or check["ok"]) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    host.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if int(ok.item()) == 0:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED: %s\n" % json.dumps(check))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

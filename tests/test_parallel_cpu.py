@@ -50,6 +50,23 @@ def _worker(rank, world, port, n, q):
             out[a:e] = truth[a:e]
     parallel.allgather_condensed(out, cuts)
     ok = bool(torch.equal(out, truth))
+    # the sliced layout the GPU path uses: every rank fills its slice through the shift the kernels get
+    # as a pointer offset, ONE in-place all-gather assembles it
+    sc = parallel.ShardedCondensed(cuts, torch.device("cpu"))
+    sc.buf.fill_(float("nan"))
+    sc.buf[lo + sc.shift[rank]:hi + sc.shift[rank]] = truth[lo:hi]
+    sc.allgather(rank)
+    ok = ok and bool(torch.equal(sc.condensed(), truth))
+    slots = np.arange(n_pairs)
+    ok = ok and bool(np.array_equal(sc.buf.numpy()[sc.where(slots)], truth.numpy()))
+    ok = ok and sc.width % 4 == 0 and sc.cuts == [int(c) for c in cuts]
+    # the node-shared pinned host vector of the end-to-end path (each rank writes its own slice)
+    hv = parallel.SharedHostVector(n_pairs, rank, world)
+    hv.tensor[lo:hi] = truth[lo:hi]
+    dist.barrier()
+    ok = ok and bool(torch.equal(hv.tensor, truth))
+    dist.barrier()
+    hv.close()
     d = parallel.scores_to_distance(out, n)
     ok = ok and bool(d[3, 5] == d[5, 3]) and bool(d.min() == 0)
     # preprofile stage: masters sharded by rank, count tables all-gathered
