@@ -482,32 +482,42 @@ def main():
                                 "identical_to_int16_vector": same32, "steps": 1, "warmup": 1}
     del sc32
     if not args.no_extras:
-        # the preprofile stage of configs[2]: every master against all other sequences, traced on the device into
-        # count tables (global master-slave alignments), masters sharded by rank, tables all-gathered
-        allm = np.arange(n)
-        mine, cuts = parallel.shard_masters(allm, lens, rank, world)
-        eng.preprofile_stage(batch, S, gaps, masters=mine[:40])          # warm-up
+        # the preprofile stage of configs[2]: every master against all other sequences (99,990,000 ordered pairs), traced
+        # on the device into count tables.  Symmetric path: every UNORDERED pair is filled once on the paired-resident
+        # traced kernel and walked in both orientations; the pair list is cut by DP cells over the ranks and the
+        # full-size tables are summed by one all-reduce.  Checked at full size against the per-master path (one fill
+        # per ordered pair, the round-1 path) on a sample of masters taken from every rank's part of the id range.
+        small = eng.batch(seqs[:64])
+        eng.preprofile_stage(small, S, gaps)                               # warm-up (both kernels, both streams)
+        del small
         sync()
         l0 = eng.launches
         t0 = time.perf_counter()
-        cnt_dev, where, cells_mine = eng.preprofile_stage(batch, S, gaps, masters=mine)
-        if world > 1:
-            sizes = [int(lens[allm[cuts[r]:cuts[r + 1]]].sum()) * S.shape[0] for r in range(world)]
-            cnt_all = parallel.allgather_counts(cnt_dev, sizes)
-        else:
-            cnt_all = cnt_dev
-        counts_sum = int(cnt_all.sum(dtype=torch.int64).item())
+        cnt_dev, where, cells_mine = eng.preprofile_stage(batch, S, gaps, shard=(rank, world))
+        cnt_all = parallel.allreduce_counts(cnt_dev)
         sync()
         pre_s = allmax(time.perf_counter() - t0)
+        counts_sum = int(cnt_all.sum(dtype=torch.int64).item())
+        sample = np.unique(np.concatenate([np.arange(r * n // world, r * n // world + 3) for r in range(world)] + [[n - 1]]))
+        ref_cnt, ref_where, _ = eng.preprofile_stage(batch, S, gaps, masters=sample, shard=None)
+        same = True
+        for mid in sample:
+            o1, l1 = where[int(mid)]
+            o2, l2 = ref_where[int(mid)]
+            same = same and l1 == l2 and bool(torch.equal(cnt_all[o1:o1 + l1 * S.shape[0]], ref_cnt[o2:o2 + l2 * S.shape[0]]))
         pre_cells = float(lens.sum()) ** 2 - float((lens ** 2).sum())
-        configs["c3_preprofile"] = {"stage": "preprofile stage of BASELINE configs[2]: 99,990,000 traced global master-slave "
-                                             "alignments -> count tables on the device (preprofile.py:127-154, util/align.py:187-232)",
+        configs["c3_preprofile"] = {"stage": "preprofile stage of BASELINE configs[2]: 99,990,000 global master-slave alignments "
+                                             "-> count tables on the device (preprofile.py:127-154, util/align.py:187-232); "
+                                             "one traced fill per unordered pair, two walks (symmetric S, constant gaps)",
                                     "wall_s": pre_s, "gcups": pre_cells / pre_s / 1e9, "cells": pre_cells,
+                                    "cells_filled": pre_cells / 2, "gcups_filled": pre_cells / 2 / pre_s / 1e9,
                                     "counts_sum": counts_sum, "counts_sum_expected": 39090321290,
                                     "identical_counts_sum": counts_sum == 39090321290,
+                                    "sample_masters_identical_to_per_master_path": bool(same),
+                                    "sample_masters": [int(m) for m in sample],
                                     "gpu_launches_rank0": int(eng.launches - l0), "n_gpus": world}
-        check["ok"] = bool(check["ok"] and counts_sum == 39090321290)
-        del cnt_dev, cnt_all
+        check["ok"] = bool(check["ok"] and counts_sum == 39090321290 and same)
+        del cnt_dev, cnt_all, ref_cnt
 
     # ---- roofline of the dominant kernel, timed live with CUDA events ---------------------------
     roof = None

@@ -151,6 +151,33 @@ int pgpu_align_tiles16_traced(int K, int transposed, const uint8_t* seqs_dev, co
                               int32_t* emit_t_dev, int64_t* pair_tb_dev, void* stream);
 
 /*
+ * Paired-resident traced fill: tiles as for pgpu_align_tiles16 with paired = 1 (residents (i, i+1) in the two
+ * register halves, one shared stream); every slot is an UNORDERED pair filled ONCE.  With a symmetric
+ * substitution matrix and constant gap penalties the DP values of (sequence_one = s, sequence_two = r) are
+ * the transpose of those of (r, s) (cext.c:155-200), so one nibble per cell serves the walks of both
+ * alignments (tb_fmt 2 of the walk: pgpu_traceback_dual).  The kernel records every slot's (resident,
+ * streamed) sequence ids.  Replaces the two PairwiseAligner executions per unordered pair of a global
+ * preprofile (component/preprofile.py:127-154, component/align.py:357-431, cext.c:99-306).  The caller
+ * checks the symmetry of S and the +-16000 value range. */
+int pgpu_align_tiles16_paired_traced(int K, const uint8_t* seqs_dev, const int64_t* offs_dev, const void* tiles_dev,
+                                     int n_tiles, const float* S_dev, int A, int gap_open, int gap_extend, int neg,
+                                     const float* topD_dev, int left0, int left1, int border_len, float* scores_dev,
+                                     uint32_t* tb_dev, const int64_t* tb_base_dev, int32_t* emit_t_dev,
+                                     int64_t* pair_tb_dev, int32_t* slot_res_dev, int32_t* slot_str_dev, void* stream);
+
+/*
+ * Both walks of every slot of pgpu_align_tiles16_paired_traced: walk 2k takes slot k with the resident as
+ * sequence one, walk 2k + 1 with the streamed sequence as sequence one (get_paths, util/align.py:144-185,
+ * tie order :161-174).  counts + seq_cnt_off (offset of every sequence's [L x A] table, < 0: not a master):
+ * preprofile mode as in pgpu_traceback_tiles; path_* are indexed by walk (2 * slot + orientation). */
+int pgpu_traceback_dual(int K, const int64_t* offs_dev, const int32_t* slot_res_dev, const int32_t* slot_str_dev,
+                        int64_t n_slots, const uint32_t* tb_dev, const int32_t* emit_t_dev, const int64_t* pair_tb_dev,
+                        int code00, int top_ramp, int left_ramp, const uint8_t* seqs_dev, int32_t* counts_dev,
+                        const int64_t* seq_cnt_off_dev, int A, const float* scores_dev, int use_thr, float thr,
+                        const int64_t* path_off_dev, int32_t* path_buf_dev, int32_t* path_start_dev,
+                        int32_t* path_len_dev, void* stream);
+
+/*
  * Traceback of an inter-task batch (K4).  Replaces get_paths (util/align.py:144-185), the
  * semiglobal end-cell scan (component/align.py:405-426) and extend_path_semiglobal
  * (util/align.py:268-297).  Paths are (y, x) rows in the reference orientation, written

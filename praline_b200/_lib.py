@@ -35,6 +35,12 @@ _SIGNATURES = {
     "pgpu_align_tiles16_traced": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                           c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),
+    "pgpu_align_tiles16_paired_traced": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                                 c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p]),
+    "pgpu_traceback_dual": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
     "pgpu_align_tiles_local": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int,
                                        c_float, c_float, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -144,6 +144,50 @@ int pgpu_traceback_tiles(int mode, int K, int transposed, const int64_t* offs, c
     return pg_launch_traceback(a, (cudaStream_t)stream);
 }
 
+// Paired-resident traced fill (gotoh_stream16r.cuh, TB): tiles as for pgpu_align_tiles16 with paired = 1; every
+// slot is an UNORDERED pair whose words serve both orientations (tb_fmt = 2, pgpu_traceback_dual).  The kernel
+// records the (resident, streamed) sequence ids of every slot.  Needs a symmetric S (the caller checks).
+int pgpu_align_tiles16_paired_traced(int K, const uint8_t* seqs, const int64_t* offs, const void* tiles, int n_tiles,
+                                     const float* S, int A, int gap_open, int gap_extend, int neg, const float* topD,
+                                     int left0, int left1, int border_len, float* scores, uint32_t* tb,
+                                     const int64_t* tb_base, int32_t* emit_t, int64_t* pair_tb, int32_t* slot_res,
+                                     int32_t* slot_str, void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    if (border_len < 32 * K + 1) { pg_set_error("border array too short for K=%d", K); return 1; }
+    if (neg > -1 || neg < -16000) { pg_set_error("sentinel %d outside the traced int16 working range", neg); return 1; }
+    if (!tb || !tb_base || !emit_t || !pair_tb || !slot_res || !slot_str) { pg_set_error("traced launch needs the traceback buffers"); return 1; }
+    StreamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seqs = seqs; a.offs = offs; a.stream_ids = nullptr; a.tiles = (const PgTile*)tiles;
+    a.S = S; a.A = A; a.transposed = 1; a.topD = topD; a.border_len = border_len; a.scores = scores;
+    a.go16 = gap_open; a.ge16 = gap_extend; a.neg16 = neg; a.left0_16 = left0; a.left1_16 = left1;
+    a.tb = tb; a.tb_base = tb_base; a.emit_t = emit_t; a.pair_tb = pair_tb; a.slot_res = slot_res; a.slot_str = slot_str;
+    return pg_launch_stream16rt(a, n_tiles, K, (cudaStream_t)stream);
+}
+
+// Both walks of every slot of a paired-resident traced fill: thread 2k = (sequence_one = resident), 2k + 1 =
+// (sequence_one = streamed).  counts + seq_cnt_off (offset of every sequence's table, < 0: not a master):
+// preprofile mode; path_* (indexed by 2 * slot + orientation): reference-format paths.
+int pgpu_traceback_dual(int K, const int64_t* offs, const int32_t* slot_res, const int32_t* slot_str, int64_t n_slots,
+                        const uint32_t* tb, const int32_t* emit_t, const int64_t* pair_tb, int code00, int top_ramp,
+                        int left_ramp, const uint8_t* seqs, int32_t* counts, const int64_t* seq_cnt_off, int A,
+                        const float* scores, int use_thr, float thr, const int64_t* path_off, int32_t* path_buf,
+                        int32_t* path_start, int32_t* path_len, void* stream)
+{
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tb_fmt = 2; a.dual = 1;
+    a.n_slots = n_slots; a.mode = PG_GLOBAL; a.K = K; a.offs = offs;
+    a.slot_resident = slot_res; a.slot_stream = slot_str; a.tb = tb; a.emit_t = emit_t; a.pair_tb = pair_tb;
+    a.code00 = code00; a.top_ramp = top_ramp; a.left_ramp = left_ramp;
+    a.path_off = path_off; a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
+    a.seqs = seqs; a.counts = counts; a.seq_cnt_off = seq_cnt_off; a.A = A; a.scores = scores; a.use_thr = use_thr; a.thr = thr;
+    if (counts && (!seqs || !seq_cnt_off || (use_thr && !scores))) { pg_set_error("preprofile mode needs seqs, seq_cnt_off and scores"); return 1; }
+    if (!counts && !path_buf) { pg_set_error("nothing to produce: neither paths nor counts requested"); return 1; }
+    return pg_launch_traceback(a, (cudaStream_t)stream);
+}
+
 // Local traced batch (K2 local instantiations) and its walk (K4 local mode): the inner loop of
 // LocalMasterSlaveAligner (preprofile.py:227-267), boxes = Waterman-Eggert masks per slot.
 int pgpu_align_tiles_local(int K, const uint8_t* seqs, const int64_t* offs, const int32_t* stream_ids,
@@ -307,6 +351,7 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
     a.lastrow = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L2 + 1));
     a.lastcol = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L1 + 1));
     a.best = (unsigned long long*)w;
+    a.err = (int*)(w + 16);
     a.score_out = score_out; a.cell_out = cell_out;
     a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
     return pg_launch_general(a, kg, (cudaStream_t)stream);

@@ -66,6 +66,8 @@ struct StreamArgs {
     const int4* boxes;           // local traced + masks: [slot][PG_NBOX] boxes
     const float* mwave;          // profile batches: match scores [row][32*K], rows in stream order
     const int64_t* mrow_base;    // first matrix row per (tile, warp); row 0 of a region is the dummy row
+    int32_t* slot_res;           // paired-resident traced launches: the kernel records (resident, streamed)
+    int32_t* slot_str;           //   sequence ids of every slot for the walk
 };
 
 // Arguments of the per-pair traceback walk (traceback.cu).
@@ -96,7 +98,10 @@ struct TraceArgs {
     const int32_t* boxes;           // local mode: [slot][PG_NBOX][4] masked boxes (may be NULL)
     int32_t* box_out;               // local mode: [slot][PG_NBOX][4], the walk writes the bounding box of its path
     int box_slot;                   //             into box number box_slot (may alias `boxes`)
-    int tb_fmt;                     // 0: f32 kernel's nibbles, 8 rows per word; 1: packed int16 kernel's words (4 rows x 2 halves)
+    int tb_fmt;                     // 0: f32 kernel's nibbles, 8 rows per word; 1: packed int16 kernel's words (4 rows x 2 halves);
+                                    // 2: paired-resident traced kernel (gotoh_stream16r.cuh): both orientations in one nibble
+    int dual;                       // tb_fmt 2: two walks per slot (thread 2s: resident = sequence one, 2s+1: streamed = sequence one)
+    const int64_t* seq_cnt_off;     // dual preprofile walks: offset of every sequence's count table, < 0 = not a master
 };
 
 // Arguments of the general single-alignment path (general.cu).
@@ -113,6 +118,7 @@ struct GenArgs {
     float* lastrow;                      // [3][L2+1]
     float* lastcol;                      // [3][L1+1]
     unsigned long long* best;            // local mode: (ordered value << 32 | ~linear index)
+    int* err;                            // device error word: a strip hand-off timed out (the fill is then invalid)
     int n_strips;
     int flag_fmt;                        // 0: the reference's seven flag bits, 1: compact sign bits, 2: lean words
     uint32_t* flagw;                     // lean kernel: [n_strips][L1+31][32] flag words (4 cells x 5 bits + mask bits)
@@ -162,6 +168,7 @@ int pg_launch_stream(const StreamArgs& a, int n_tiles, int K, int mode, bool tb,
 int pg_launch_stream_ms(const StreamArgs& a, int n_tiles, int K, int km, cudaStream_t st);
 int pg_launch_stream_local(const StreamArgs& a, int n_tiles, int K, bool masked, cudaStream_t st);
 int pg_launch_stream16(const StreamArgs& a, int n_tiles, int K, int paired, cudaStream_t st);
+int pg_launch_stream16rt(const StreamArgs& a, int n_tiles, int K, cudaStream_t st);
 int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,
                           int mode, int transposed, float* scores, cudaStream_t st);
 int pg_launch_traceback(const TraceArgs& a, cudaStream_t st);

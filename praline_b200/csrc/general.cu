@@ -79,6 +79,7 @@ __global__ void k_gen_init(const GenArgs a)
         a.progress[0] = L1;
         for (int s = 1; s <= a.n_strips; s++) a.progress[s] = 0;
         *a.best = 0ull;
+        *a.err = 0;
     }
 }
 
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(256) k_gen_fill(const GenArgs a)
                 if (lane == 0) {
                     // bounded spin: a protocol bug must fail a test, not hang the GPU
                     for (long long spins = 0; (avail = *pin) < need && spins < (1ll << 26); spins++) __nanosleep(32);
+                    if (avail < need) atomicOr(a.err, 1);     // timed out: flag it (k_gen_finalize -> NaN score)
                 }
                 avail = __shfl_sync(FULL, avail, 0);
                 __threadfence();
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(256) k_gen_fill_fast(const GenArgs a)
                         if (avail >= need) break;
                         __nanosleep(32);
                     }
+                    if (avail < need) atomicOr(a.err, 1);     // timed out: flag it (k_gen_finalize -> NaN score)
                 }
                 avail = __shfl_sync(FULL, avail, 0);
             }
@@ -501,21 +504,25 @@ __device__ __forceinline__ bool edge_ok(const float4& e0, const float4& e1, int 
 }
 // lane 0, record of row y not there yet: let the producer get a full ring ahead, then put the
 // records of rows y .. y+WV_R-1 (all requested already, possibly too early) into their slots
-__device__ __forceinline__ void wave_refill(const float* ein, float* ring_lane0, int slotp, int y, int t, int L1)
+__device__ __forceinline__ void wave_refill(const float* ein, float* ring_lane0, int slotp, int y, int t, int L1, int* err)
 {
     asm volatile("cp.async.wait_group 0;" ::: "memory");      // nothing in flight may land on top of the fix-up
     const int target = min(y + WV_R - 1, L1);
     float4 e0, e1;
-    for (long long spins = 0; spins < (1ll << 24); spins++) {  // bounded: fail a test, never hang
+    bool ok = false;
+    for (long long spins = 0; spins < (1ll << 24); spins++) {  // bounded: never hang ...
         ld_edge(ein + (size_t)target * 8, e0, e1);
-        if (edge_ok(e0, e1, target)) break;
+        if ((ok = edge_ok(e0, e1, target))) break;
         __nanosleep(64);
     }
+    if (!ok) atomicOr(err, 1);      // ... but never continue silently either: k_gen_finalize turns this into a NaN score
     for (int r = y; r <= target; r++) {
+        ok = false;
         for (int spins = 0; spins < (1 << 20); spins++) {
             ld_edge(ein + (size_t)r * 8, e0, e1);
-            if (edge_ok(e0, e1, r)) break;
+            if ((ok = edge_ok(e0, e1, r))) break;
         }
+        if (!ok) atomicOr(err, 1);
         float* s = ring_lane0 + ((t + (r - y)) & (WV_R - 1)) * 32 * slotp;
         *reinterpret_cast<float4*>(s + 4) = e0;
         *reinterpret_cast<float4*>(s + 8) = e1;
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
 #ifdef WAVE_DEBUG
                     atomicAdd(a.progress + strip, 1);
 #endif
-                    wave_refill(ein, ring, SLOTP, y, t, L1);
+                    wave_refill(ein, ring, SLOTP, y, t, L1, a.err);
                     asm volatile("" ::: "memory");
                     e0 = *reinterpret_cast<const float4*>(slot + 4);
                     e1 = *reinterpret_cast<const float4*>(slot + 8);
@@ -837,6 +844,7 @@ __global__ void __launch_bounds__(256) k_gen_finalize(const GenArgs a)
         if (rmax > cmax && from_row) { cy = L1; cx = (int)((br & 0xffffffffull) >> 2); ck = 3 - (int)(br & 3ull); score = rmax; }
         else { cy = (int)((bc & 0xffffffffull) >> 2); cx = L2; ck = 3 - (int)(bc & 3ull); score = cmax; }
     }
+    if (*a.err) score = __int_as_float(0x7fc00000);   // a strip hand-off timed out: the host raises on NaN
     *a.score_out = score;
     a.cell_out[0] = cy; a.cell_out[1] = cx; a.cell_out[2] = ck;
 }
@@ -1337,7 +1345,10 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
         auto kern = k_wave<LO, MA, VG>;                                                              \
         const size_t sm = (size_t)wpc * WV_R * 32 * (VG ? 16 : 12) * sizeof(float);                   \
         PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-        kern<<<ctas, wpc * 32, sm, st>>>(a);                                                         \
+        void* kargs[] = {(void*)&a};                                                                 \
+        /* strips spin on their left neighbours: every CTA must be resident, which a cooperative launch */ \
+        /* guarantees (it fails instead of deadlocking when the grid cannot be co-scheduled) */          \
+        PG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas), dim3(wpc * 32), kargs, sm, st)); \
     } while (0)
         const bool vg = a.var_gaps != 0;
         if (local) { if (mask) { if (vg) PG_WAVE(true, true, true); else PG_WAVE(true, true, false); }

@@ -286,286 +286,9 @@ __global__ void __launch_bounds__(NW * 32) k_stream16(const StreamArgs a)
     }
 }
 
-// ---- paired RESIDENTS: the all-vs-all shape -------------------------------------------------------
-// The low and high halves carry two RESIDENT sequences (tile.resident, tile.resident2) and ONE
-// stream runs through both: the substitution profile is stored pre-packed,
-//     prof2[a][x] = { S[a][resA[x]] , S[a][resB[x]] },
-// so a single shared-memory row feeds both halves without the per-column PRMT, there is one
-// ring, one set of row flags, and the border re-arm is a plain register reload.  In an
-// all-vs-all, residents i and i+1 share every streamed j > i+1; the pair (i, i+1) itself rides
-// along as the first stream element with its high half ignored (tile.b_skip).
-//
-// Step loop (round 2).  The DPX instructions (2 VIADDMNMX + 1 VIMNMX3 per column step) run on the
-// half-rate ALU pipe, which is the binding unit; everything else is kept OFF that pipe and out of
-// the issue slots:
-//  * 8-step blocks come in two forms.  The ring knows 32 steps ahead where sequences end, and a lane
-//    is l steps behind lane 0, so "some lane meets a LAST row in this block" is a warp-uniform
-//    function of two ballot masks.  Blocks without one (about 90 % at 400 rows per sequence) run
-//    straight-line code: no flag test, no border re-arm, no emit, no register shuffling at a join.
-//    The other blocks run the general step (k16r_step<true>) in a rolled loop.
-//  * the strip edge is TWO shuffles: the sender finishes the left-gap recurrence of the receiver's
-//    first column (l_out = max(L + ext, M + open) of its last column), so (l_out, D_last) is all that
-//    moves; the seed of the diagonal rides in Dleft_prev as before.
-//  * the column-0 substitution in lane 0 (M = L = -inf, D = the U border) is arithmetic on per-lane
-//    constants, x * c1 + c2 with c1 = (lane != 0), which ptxas keeps as IMADs on the FMA pipe instead of
-//    SELs on the ALU pipe; the border ramp is a packed add of a per-lane constant (0 off lane 0).
-//  * the eight ring words of a block arrive as two LDS.128: the ring is kept in four copies shifted by
-//    one word each, so that every lane's run of 8 slots is 16-byte aligned in the copy (lane & 3).
-//    Ring words are NEGATED row offsets: address = word * all_ones + lane base is one IMAD.
-struct K16rConst {
-    uint32_t go2, ge2, NEG2, c1, c2, left1z, lanebase, ones;
-};
+// ---- paired RESIDENTS (the all-vs-all shape): gotoh_stream16r.cuh ------------------------------------
+#include "gotoh_stream16r.cuh"
 
-// l_src / D_src: the edge values this lane's left neighbour produced for the row this lane works on now
-// (its previous step with a lane skew of 1, two steps back with a skew of 2).
-template <int K>
-__device__ __forceinline__ void k16r_step(uint32_t w, const K16rConst& c, uint32_t (&Mo)[K], uint32_t (&U)[K], uint32_t (&D)[K],
-                                          uint32_t l_src, uint32_t D_src, uint32_t& l_out, uint32_t& D_last,
-                                          uint32_t& Dleft_prev, uint32_t& bordz)
-{
-    constexpr int NCH = (K + 3) / 4;
-    const uint32_t pa = w * c.ones + c.lanebase;
-    uint32_t sc[NCH * 4];
-#pragma unroll
-    for (int j = 0; j < NCH; j++) {
-        if (4 * j + 1 >= K)         // a chunk that holds one column only
-            asm("ld.shared.u32 %0, [%1];" : "=r"(sc[4 * j]) : "r"(pa + (uint32_t)j * 512u));
-        else
-            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                : "=r"(sc[4 * j]), "=r"(sc[4 * j + 1]), "=r"(sc[4 * j + 2]), "=r"(sc[4 * j + 3])
-                : "r"(pa + (uint32_t)j * 512u));
-    }
-    uint32_t l = __shfl_up_sync(FULL, l_src, 1) * c.c1 + c.c2;       // lane 0: L(y, 1) of an empty left side
-    const uint32_t Dn = __shfl_up_sync(FULL, D_src, 1) * c.c1 + bordz;   // lane 0: the U border of this row
-    bordz = __vadd2(bordz, c.left1z);
-    uint32_t diag = Dleft_prev;
-    Dleft_prev = Dn;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const uint32_t m = __vadd2(diag, sc[k]);
-        const uint32_t u = __viaddmax_s16x2(U[k], c.ge2, Mo[k]);
-        diag = D[k];
-        const uint32_t d = __vimax3_s16x2(m, u, l);
-        const uint32_t mo = __vadd2(m, c.go2);
-        l = __viaddmax_s16x2(l, c.ge2, mo);       // L of the next column (the receiver's first one after k = K-1)
-        Mo[k] = mo;
-        U[k] = u;
-        D[k] = d;
-    }
-    l_out = l;
-    D_last = D[K - 1];
-}
-
-// CTAs per SM the register allocation aims at: 24 warps per SM (80 registers) up to 13 columns per lane --
-// measured 6.94 -> 7.21 TCUPS at K = 13 against 16 warps with 121 registers --, 16 warps up to K = 24, and
-// one CTA with the full register file for K = 32 (96 state registers).
-#ifndef K16R_MINB
-#define K16R_MINB(K) ((K) <= 13 ? 3 : ((K) <= 24 ? 2 : 1))
-#endif
-// Lane skew: lane l works on stream row t - SKEW * l at step t.  With a skew of 2 the edge a lane needs
-// was produced by its neighbour TWO steps earlier, so the left-gap chains of consecutive steps of a warp do
-// not depend on each other (the shuffle of step t+1 can be issued before step t ends): two chains in flight
-// per warp instead of one, at the price of a 62-step pipeline fill per warp and a longer ring.
-#ifndef K16R_SKEW
-#define K16R_SKEW 1
-#endif
-template <int K, int NW>
-__global__ void __launch_bounds__(NW * 32, K16R_MINB(K)) k_stream16r(const StreamArgs a)
-{
-    constexpr int NCH = (K + 3) / 4;        // 16-byte chunks of 4 packed columns per lane
-    constexpr int ROWB = NCH * 512;
-    constexpr int KP = (K + 3) & ~3;
-    constexpr int SKEW = K16R_SKEW;
-    constexpr int RN = 64 * SKEW;           // ring slots: a window of 32 new slots + 31 * SKEW slots of lookback
-    constexpr int RL = RN + 8;              // words per ring copy: the slots + the first 8 again
-    constexpr int RW = 4 * RL + RN;         // per warp: four shifted copies of the offsets + the flag ring
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* prof = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* top2 = reinterpret_cast<uint32_t*>(smem + (size_t)a.A * ROWB);            // [32][KP + 4]
-    uint32_t* ring = top2 + 32 * (KP + 4) + (threadIdx.x >> 5) * RW;
-    uint32_t* fring = ring + 4 * RL;
-
-    const PgTile tile = a.tiles[blockIdx.x];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t roffA = a.offs[tile.resident];
-    const int LrA = (int)(a.offs[tile.resident + 1] - roffA);
-    const bool hasB = tile.resident2 >= 0;
-    const int64_t roffB = hasB ? a.offs[tile.resident2] : 0;
-    const int LrB = hasB ? (int)(a.offs[tile.resident2 + 1] - roffB) : 1;
-
-    {
-        const int n = a.A * NCH * 128;
-        for (int idx = threadIdx.x; idx < n; idx += NW * 32) {
-            const int c = idx & 3, l = (idx >> 2) & 31, j = (idx >> 7) % NCH, sym = idx / (NCH * 128);
-            const int k = 4 * j + c, x = l * K + k;
-            int va = 0, vb = 0;
-            if (k < K && x < LrA) {
-                const int b = a.seqs[roffA + x];
-                va = (int)(a.transposed ? a.S[b * a.A + sym] : a.S[sym * a.A + b]);
-            }
-            if (hasB && k < K && x < LrB) {
-                const int b = a.seqs[roffB + x];
-                vb = (int)(a.transposed ? a.S[b * a.A + sym] : a.S[sym * a.A + b]);
-            }
-            prof[idx] = ((uint32_t)(va & 0xffff)) | ((uint32_t)vb << 16);
-        }
-        for (int idx = threadIdx.x; idx < 32 * (KP + 4); idx += NW * 32) {
-            const int l = idx / (KP + 4), k = idx % (KP + 4);
-            int v = 0;
-            if (k < K) v = (int)a.topD[l * K + k + 1];
-            else if (k == KP) v = (int)a.topD[l * K];
-            top2[idx] = pack2(v);
-        }
-    }
-    const uint32_t prof_s = (uint32_t)__cvta_generic_to_shared(smem);
-    for (int i = lane; i < RW; i += 32) ring[i] = 0u;
-    __syncthreads();
-    if (prof_s & 15u) __trap();
-
-    const int n_str = tile.stream_end - tile.stream_begin;
-    const int per = (n_str + NW - 1) / NW;
-    const int sb = tile.stream_begin + warp * per;
-    const int se = min(sb + per, tile.stream_end);
-    if (sb >= se) return;
-
-    auto seq_id = [&](int s) -> int { return a.stream_ids ? a.stream_ids[s] : s; };
-    auto seq_len = [&](int s) -> int {
-        if (s < sb) return 1;
-        const int id = seq_id(s);
-        return (int)(a.offs[id + 1] - a.offs[id]);
-    };
-    int total = 0;
-    for (int s = sb + lane; s < se; s += 32) total += seq_len(s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-    const int T = (total + 1 + 31 * SKEW + 31) & ~31;
-
-    const int lrA = (LrA - 1) / K, klA = (LrA - 1) % K, lrB = (LrB - 1) / K, klB = (LrB - 1) % K;
-    K16rConst c;
-    c.ones = (uint32_t)a.all_ones;                       // 0xffffffff, opaque to the compiler
-    c.go2 = pack2(a.go16);
-    c.ge2 = pack2(a.ge16);
-    c.NEG2 = pack2(a.neg16);
-    c.c1 = (lane != 0) ? (0u - c.ones) : 0u;             // 1 / 0
-    c.c2 = (lane != 0) ? 0u : __viaddmax_s16x2(c.NEG2, c.ge2, c.NEG2);
-    c.left1z = (lane != 0) ? 0u : pack2(a.left1_16);
-    c.lanebase = prof_s + ((uint32_t)lane << 4);
-    const uint32_t left0z = (lane != 0) ? 0u : pack2(a.left0_16);
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-    // slot (t - SKEW * lane) of an aligned block start t, in copy (SKEW * lane) & 3: position (t - (SKEW * lane & ~3)) & (RN - 1)
-    const int back = SKEW * lane;
-    const uint32_t ring_mine = ring_s + (uint32_t)(back & 3) * (RL * 4u);
-    const uint32_t* mytop = top2 + lane * (KP + 4);
-
-    uint32_t Mo[K], U[K], D[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) { Mo[k] = 0u; U[k] = 0u; D[k] = 0u; }
-    uint32_t l_out = 0u, D_last = 0u, Dleft_prev = 0u, bordz = 0u;
-    uint32_t l_out1 = 0u, D_last1 = 0u;      // SKEW 2: the edge of the step before the last one
-    int q = sb;
-    int ps = sb - 1, pp = 0;
-    uint32_t last_prev = 0u, last_prev2 = 0u;   // LAST slots of the previous 32-slot windows (bit j = slot t0 - 32 + j, t0 - 64 + j)
-
-    for (int t0 = 0; t0 < T; t0 += 32) {
-        uint32_t last_cur;
-        {
-            int s = ps, p = pp + lane;
-            int len = (s < se) ? seq_len(s) : 0;
-            while (s < se && p >= len) {
-                p -= len;
-                s++;
-                len = (s < se) ? seq_len(s) : 0;
-            }
-            uint32_t off = 0u, flags = 0u;
-            if (s < se) {
-                if (s < sb) {
-                    flags = FLAG_LAST;
-                } else {
-                    const int sym = a.seqs[a.offs[seq_id(s)] + p];
-                    off = (uint32_t)(sym * ROWB);
-                    flags = (p == len - 1) ? (FLAG_LAST | FLAG_EMIT) : 0u;
-                }
-            }
-            last_cur = __ballot_sync(FULL, flags != 0u);
-            __syncwarp();
-            const uint32_t word = 0u - off;
-#pragma unroll
-            for (int cpy = 0; cpy < 4; cpy++) {
-                const int pos = (t0 + lane + cpy) & (RN - 1);
-                ring[cpy * RL + pos] = word;
-                if (pos < 8) ring[cpy * RL + RN + pos] = word;
-            }
-            fring[(t0 + lane) & (RN - 1)] = flags;
-            __syncwarp();
-            int s31 = __shfl_sync(FULL, s, 31), p31 = __shfl_sync(FULL, p, 31) + 1;
-            const int len31 = __shfl_sync(FULL, len, 31);
-            if (s31 < se && p31 >= len31) { p31 = 0; s31++; }
-            ps = s31;
-            pp = p31;
-        }
-
-#pragma unroll 1
-        for (int g = 0; g < 32; g += 8) {
-            // a LAST slot s is met by lane l at step s + SKEW * l: the block [t0+g, t0+g+8) is free of them
-            // iff no LAST slot lies in [t0+g - 31*SKEW, t0+g+7]
-            const uint32_t busy = (last_cur & (0xffffffffu >> (24 - g))) |
-                                  (SKEW == 1 ? (last_prev >> (g + 1)) : (last_prev | (last_prev2 >> (g + 2))));
-            const uint32_t rp = ring_mine + ((uint32_t)((t0 + g - (back & ~3)) & (RN - 1)) << 2);
-            if (busy == 0u) {
-                uint32_t w[8];
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(rp) : "memory");
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(rp + 16u) : "memory");
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (SKEW == 1) {
-                        k16r_step<K>(w[i], c, Mo, U, D, l_out, D_last, l_out, D_last, Dleft_prev, bordz);
-                    } else {
-                        const uint32_t ls = l_out1, ds = D_last1;
-                        l_out1 = l_out;
-                        D_last1 = D_last;
-                        k16r_step<K>(w[i], c, Mo, U, D, ls, ds, l_out, D_last, Dleft_prev, bordz);
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (int i = 0; i < 8; i++) {
-                    uint32_t w;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)i * 4u) : "memory");
-                    const uint32_t f = fring[(t0 + g + i - back) & (RN - 1)];
-                    if (SKEW == 1) {
-                        k16r_step<K>(w, c, Mo, U, D, l_out, D_last, l_out, D_last, Dleft_prev, bordz);
-                    } else {
-                        const uint32_t ls = l_out1, ds = D_last1;
-                        l_out1 = l_out;
-                        D_last1 = D_last;
-                        k16r_step<K>(w, c, Mo, U, D, ls, ds, l_out, D_last, Dleft_prev, bordz);
-                    }
-                    if (f & FLAG_LAST) {
-                        if (f & FLAG_EMIT) {
-                            const int e = q - tile.stream_begin;
-                            if (lane == lrA) a.scores[tile.out_base + e] = (float)(int)(int16_t)(pick_u<K>(D, klA) & 0xffffu);
-                            if (hasB && lane == lrB && e >= tile.b_skip)
-                                a.scores[tile.out_base2 + (e - tile.b_skip)] = (float)(int)(int16_t)(pick_u<K>(D, klB) >> 16);
-                            q++;
-                        }
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            Mo[k] = c.NEG2;
-                            U[k] = c.NEG2;
-                            D[k] = mytop[k];
-                        }
-                        Dleft_prev = mytop[KP];
-                        bordz = left0z;
-                    }
-                }
-            }
-        }
-        last_prev2 = last_prev;
-        last_prev = last_cur;
-    }
-}
 
 // ---- launch ------------------------------------------------------------------------------------
 constexpr int kNW16 = 8;
@@ -577,7 +300,7 @@ static int launch16(const StreamArgs& a, int n_tiles, int paired, cudaStream_t s
     if (paired) {
         constexpr int NCH = (K + 3) / 4;
         const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16 * (4 * (64 * K16R_SKEW + 8) + 64 * K16R_SKEW) * sizeof(uint32_t);
-        auto kern = k_stream16r<K, kNW16>;
+        auto kern = k_stream16r<K, kNW16, false>;
         PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         StreamArgs b = a;
         b.all_ones = -1;

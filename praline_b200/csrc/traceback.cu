@@ -38,6 +38,15 @@
 // "first row per master index" rule, plus what extend_path_local's -1 padding does to
 // get_frequencies (util/align.py:205-211, :234-266): the step from -1 to x0 at master row y0 >= 1
 // counts slave[x0 - 1] (Python indexing: x0 = 0 is the LAST residue) against master position y0.
+//
+// Dual walks (tb_fmt 2, a.dual).  The paired-resident traced kernel (gotoh_stream16r.cuh) fills an unordered
+// pair (r, s) ONCE; with a symmetric substitution matrix and constant gaps the DP values of the alignment
+// (sequence_one = r, sequence_two = s) are the transpose of those of (s, r), so both master-slave alignments
+// of a global preprofile (preprofile.py:127-154) are walks over the same words: thread 2k takes slot k with
+// the resident as sequence one (transposed tie order), thread 2k + 1 with the streamed sequence as sequence
+// one.  Nibble: bit 0 = U (from above) is a maximum and M is not, bit 1 = the same for L (from the left),
+// bit 2 = U of this cell was opened, bit 3 = L of the NEXT column was opened (column 1 always opens: its
+// left neighbours are the -inf border).  Each orientation picks its first-priority gap state from bits 0-1.
 #include "common.cuh"
 
 __device__ __forceinline__ float tkey_value(unsigned long long k)
@@ -54,7 +63,8 @@ constexpr int NWIN = PG_TB_WINDOW;
 
 __global__ void k_traceback(const TraceArgs a)
 {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = a.dual ? (tid >> 1) : tid;
     if (slot >= a.n_slots) return;
     const bool local = a.mode == PG_LOCAL;
     const bool below = a.counts && a.use_thr && !(a.scores[slot] >= a.thr);
@@ -66,19 +76,28 @@ __global__ void k_traceback(const TraceArgs a)
     const int emit = a.emit_t[slot] & 0x3fffffff;
     const int half = (a.emit_t[slot] >> 30) & 1;            // packed kernel: register half that carried this pair
     const uint32_t* tbw = a.tb + a.pair_tb[slot];
-    const bool TR = a.transposed != 0;
+    const bool TR = a.dual ? ((tid & 1) == 0) : (a.transposed != 0);
     const int L1 = TR ? Lr : Ls, L2 = TR ? Ls : Lr;        // reference lengths
+    const int fmt = a.tb_fmt;
 
     // word holding the flags of interior cell (yk, xk), and the nibble inside it
     auto word_index = [&](int yk, int xk) -> int64_t {
         const int lane = (xk - 1) / K, k = (xk - 1) - lane * K;
         const int step = emit - (Ls - yk) - (lr - lane);
-        return (int64_t)(step >> (a.tb_fmt == 1 ? 2 : 3)) * (K * 32) + k * 32 + lane;
+        return (int64_t)(step >> (fmt != 0 ? 2 : 3)) * (K * 32) + k * 32 + lane;
     };
     auto nib_of = [&](uint32_t w, int yk, int xk) -> uint32_t {
         const int lane = (xk - 1) / K;
         const int step = emit - (Ls - yk) - (lr - lane);
-        if (a.tb_fmt == 1) {
+        if (fmt == 2) {
+            // paired-resident kernel: 4 rows x 4 bits per register half; -> the common nibble, except that bit 3
+            // of THIS cell's nibble speaks about the next column (the L branch of the walk reads it from x - 1)
+            const uint32_t n = (w >> (16 * half + 4 * (3 - (step & 3)))) & 15u;
+            const uint32_t gap = (n & 3u) ? 1u : 0u;
+            const uint32_t second = TR ? ((n & 2u) ? 0u : 1u) : ((n & 1u) ? 0u : 1u);
+            return gap | ((gap & second) << 1) | (((n >> 2) & 1u) ^ 1u) << 2 | (((n >> 3) & 1u) ^ 1u) << 3;
+        }
+        if (fmt == 1) {
             // packed kernel (gotoh_stream16.cu): 4 rows per word, row r at bits 2*(3-r) of every byte;
             // byte 2h+1 = (M is max, U opened), byte 2h = (first gap state is max, L opened); 1 = yes
             const int sh = 2 * (3 - (step & 3));
@@ -110,7 +129,7 @@ __global__ void k_traceback(const TraceArgs a)
         return nib_of(pw[0], yk, xk);
     };
     auto code_at = [&](int yk, int xk) -> int {
-        if (yk == 0 && xk == 0) return a.code00;
+        if (yk == 0 && xk == 0) return (a.dual && !TR && a.code00) ? 3 - a.code00 : a.code00;   // a.code00: resident = sequence one
         if (yk == 0) return 2;
         if (xk == 0) return 1;
         const uint32_t nb = nib_at(yk, xk);
@@ -147,7 +166,8 @@ __global__ void k_traceback(const TraceArgs a)
     int s = local ? 0 : code_at(yk, xk);
     const int end_y = yk, end_x = xk;
 
-    const int64_t base = a.path_buf ? a.path_off[slot] : 0;
+    const int64_t pidx = a.dual ? tid : slot;      // dual walks: two path regions per slot
+    const int64_t base = a.path_buf ? a.path_off[pidx] : 0;
     const int cap = Lr + Ls + 2;
     int w = cap;
     const bool want_path = a.path_buf != nullptr;
@@ -159,7 +179,16 @@ __global__ void k_traceback(const TraceArgs a)
         }
     };
     // preprofile mode: sequence one is the master, sequence two the slave
-    int* cnt = (a.counts && !below) ? a.counts + a.cnt_off[slot] : nullptr;
+    int* cnt = nullptr;
+    if (a.counts && !below) {
+        if (a.seq_cnt_off) {            // dual walks: the master is sequence one of this thread's orientation
+            const int64_t o = a.seq_cnt_off[TR ? rid : sid];
+            if (o < 0) return;          // not a master: nothing to add
+            cnt = a.counts + o;
+        } else {
+            cnt = a.counts + a.cnt_off[slot];
+        }
+    }
     const uint8_t* slave = a.seqs ? a.seqs + a.offs[TR ? sid : rid] : nullptr;
     int pend_y = -1, pend_x = 0;
     auto kept = [&](int yr, int xr) {   // (yr, xr) is the first path row with master index yr
@@ -194,9 +223,9 @@ __global__ void k_traceback(const TraceArgs a)
             ny--; nx--;
             s = code_at(ny, nx);
         } else {
-            const uint32_t nib = nib_at(yk, xk);
-            if (s == 1) { s = ((nib >> 2) & 1u) ? 1 : 0; ny--; }
-            else        { s = ((nib >> 3) & 1u) ? 2 : 0; nx--; }
+            if (s == 1) { s = ((nib_at(yk, xk) >> 2) & 1u) ? 1 : 0; ny--; }
+            else if (fmt == 2) { s = (xk >= 2 && ((nib_at(yk, xk - 1) >> 3) & 1u)) ? 2 : 0; nx--; }
+            else        { s = ((nib_at(yk, xk) >> 3) & 1u) ? 2 : 0; nx--; }
         }
         if (!moved) { kept(cy, cx); break; }              // row 0 of the path is always kept
         if ((TR ? nx : ny) == cy - 1) kept(cy, cx);       // the master index steps here
@@ -215,8 +244,8 @@ __global__ void k_traceback(const TraceArgs a)
         else if (x0 != 0) { for (int v = x0 - 1; v >= 0; v--) push(0, v); }
     }
     if (want_path) {
-        a.path_start[slot] = w;
-        a.path_len[slot] = cap - w;
+        a.path_start[pidx] = w;
+        a.path_len[pidx] = cap - w;
     }
 }
 
@@ -227,7 +256,12 @@ int pg_launch_traceback(const TraceArgs& a, cudaStream_t st)
         pg_set_error("local walks need the f32 kernel's layout in the reference orientation");
         return 1;
     }
-    k_traceback<<<(unsigned)((a.n_slots + 127) / 128), 128, 0, st>>>(a);
+    if (a.dual && (a.tb_fmt != 2 || a.mode != PG_GLOBAL)) {
+        pg_set_error("dual walks read the paired-resident kernel's words (global mode)");
+        return 1;
+    }
+    const int64_t n_threads = a.dual ? 2 * a.n_slots : a.n_slots;
+    k_traceback<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(a);
     PG_CUDA_OK(cudaGetLastError());
     return 0;
 }

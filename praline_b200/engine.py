@@ -628,19 +628,35 @@ class Engine(object):
         return cnt.cpu().numpy().astype(np.int64), {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, scores
 
     def preprofile_stage(self, batch, S, gap_series, threshold=None, masters=None, mode="global", iterations=2,
-                         chunk_pairs=1 << 20):
+                         chunk_pairs=1 << 20, shard=(0, 1)):
         """The whole preprofile stage of the workflow (workflow.py:139-161 + :211-224): every master
         against ALL other sequences of the batch, count tables on the device.  Masters are processed in
         chunks of about chunk_pairs pairs; nothing synchronises between chunks, so the host plans
         chunk c + 1 while the device traces chunk c.  mode: "global" (GlobalMasterSlaveAligner) or
         "local" (LocalMasterSlaveAligner with `iterations` Waterman-Eggert iterations).
 
+        Global mode with every sequence a master, a symmetric integer matrix and the packed range: the
+        symmetric path (allpairs_dual) fills every UNORDERED pair once and walks it in both orientations;
+        shard = (rank, world) then splits the pair list (tables must be summed over ranks), shard = None
+        forces the per-master path.
+
         Returns (count tables as ONE int32 device tensor, {master id: (offset, length)}, DP cells)."""
         S = np.ascontiguousarray(S, np.float32)
         A = S.shape[0]
         n = batch.n
+        all_masters = masters is None
         masters = np.arange(n, dtype=np.int64) if masters is None else np.unique(np.asarray(masters, np.int64))
         cnt, off, uniq, lens, slot_of = self._own_counts(batch, masters, A)
+        if mode == "global" and shard is not None and (all_masters or len(masters) == n) and n >= 2 and \
+                self.dual_traced_ok(S, gap_series, batch.lens) is not None:
+            # one fill per UNORDERED pair feeds both master-slave walks; shard = (rank, world) cuts the pair list by
+            # DP cells, every rank holds full-size tables and the caller sums them (parallel.allreduce_counts)
+            rank, world = shard
+            if rank != 0:
+                cnt.zero_()             # the masters' own residues are counted once, on rank 0
+            _, _, cells = self.allpairs_dual(batch, S, gap_series, counts=(cnt, self.dev(off[:-1].astype(np.int64)), threshold),
+                                             shard=shard)
+            return cnt, {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, 2 * cells
         per = max(1, int(chunk_pairs) // max(n - 1, 1))
         everyone = np.arange(n, dtype=np.int64)
         cells = 0
@@ -662,6 +678,238 @@ class Engine(object):
         if mode == "local":
             cells *= iterations
         return cnt, {int(u): (int(off[k]), int(lens[k])) for k, u in enumerate(uniq)}, cells
+
+    # -- symmetric traced all-vs-all: one fill per unordered pair, both master-slave walks -------------
+    def dual_traced_ok(self, S, gap_series, lens):
+        """One fill can serve the alignments (a, b) and (b, a) when the substitution matrix is symmetric
+        (constant gaps are what PairwiseAligner always builds, component/align.py:212-217) and the packed
+        traced range holds; returns the int16 sentinel or None."""
+        S = np.asarray(S, np.float32)
+        go, ge = _gaps(gap_series)
+        if not self.use_s16 or os.environ.get("PGPU_NO_DUAL", "") != "" or not np.array_equal(S, S.T):
+            return None
+        return self.fits_s16(S, go, ge, lens, limit=16000)
+
+    def _tb_words16r(self, tiles, K, cs):
+        """Traceback words per (tile, warp) of the paired-resident traced kernel: four steps per word,
+        T = the warp's stream rows + dummy row + pipeline drain, rounded to 32 (gotoh_stream16r.cuh)."""
+        nw = self.nw
+        tb_, te_ = tiles["stream_begin"].astype(np.int64), tiles["stream_end"].astype(np.int64)
+        per = (te_ - tb_ + nw - 1) // nw
+        w = np.arange(nw)[None, :]
+        sb = tb_[:, None] + w * per[:, None]
+        se = np.minimum(sb + per[:, None], te_[:, None])
+        sb = np.minimum(sb, se)
+        rows = cs[se] - cs[sb]
+        T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
+        return (T // 4) * (K * 32)
+
+    def _dual_state(self, n_streams):
+        """Streams and traceback buffers of the dual path live in the engine: allocating 2 x 16 GiB per call
+        costs more than a small stage takes."""
+        st = self.__dict__.setdefault("_dual", {"streams": [], "bufs": []})
+        while len(st["streams"]) < n_streams:
+            st["streams"].append(torch.cuda.Stream(self.device))
+            st["bufs"].append(None)
+        return st
+
+    def _dual_bufs(self, st, k, n_words, n_slots):
+        b = st["bufs"][k]
+        if b is None or b[0].numel() < n_words or b[1].numel() < n_slots:
+            if b is not None:
+                st["streams"][k].synchronize()
+            st["bufs"][k] = b = None
+            nw_, ns_ = max(n_words, 1 << 20), max(n_slots, 1 << 12)
+            with torch.cuda.stream(st["streams"][k]):
+                b = (torch.empty(nw_, dtype=torch.int32, device=self.device),       # traceback words
+                     torch.empty(ns_, dtype=torch.int32, device=self.device),       # emit_t
+                     torch.empty(ns_, dtype=torch.int64, device=self.device),       # pair_tb
+                     torch.empty(ns_, dtype=torch.int32, device=self.device),       # slot_res
+                     torch.empty(ns_, dtype=torch.int32, device=self.device),       # slot_str
+                     torch.empty(ns_, dtype=torch.float32, device=self.device))     # scores
+            st["bufs"][k] = b
+        return b
+
+    def allpairs_dual(self, batch, S, gap_series, counts=None, want_paths=False, shard=(0, 1), n_streams=None,
+                      tile=None):
+        """All unordered pairs (i < j) of the batch, global mode, traced ONCE per pair on the paired-resident
+        packed kernel; the walk then runs both orientations (sequence_one = i and sequence_one = j) over the
+        same traceback words (pgpu_traceback_dual).  counts = (count tables int32 on the device, offset of
+        every sequence's table as a device int64 tensor (< 0: not a master), threshold): preprofile mode --
+        what N x GlobalMasterSlaveAligner + ProfileBuilder produce (preprofile.py:127-154, profile.py:56).
+        want_paths: returns {(i, j): path, (j, i): path} in reference format (tests; small batches).
+        Waves alternate between n_streams streams with their own traceback buffers, so that the walk of one
+        wave and the tail of its fill overlap the fill of the next.
+
+        Returns (scores dict or None, paths dict or None, DP cells filled)."""
+        go, ge = _gaps(gap_series)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        neg16 = self.dual_traced_ok(S, gap_series, batch.lens)
+        if neg16 is None:
+            raise _lib.PralineGpuError("the dual traced path needs a symmetric integer matrix inside the packed range")
+        if batch.max_sym >= A:
+            raise ValueError("sequence symbol outside the score matrix")
+        lib = self.lib
+        n = batch.n
+        n_streams = n_streams or int(os.environ.get("PGPU_DUAL_STREAMS", "2"))
+        tile = tile or self._pick_tile_dual(n * (n - 1) // 2)
+        lens = batch.lens
+        cs = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=cs[1:])
+        kcls = self.k_classes(lens)
+        if (kcls < 0).any():
+            raise _lib.PralineGpuError("sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
+        # units = resident pairs (2p, 2p+1) with their stream j = 2p+1 .. n-1 (as Engine.allpairs_tiles, paired=True);
+        # the shard is a contiguous unit range of equal DP cells
+        rank, world = shard
+        ui = np.arange(0, n - 1, 2, dtype=np.int64)
+        uhb = ui + 1 <= n - 2
+        ucells = lens[ui] * (cs[n] - cs[ui + 1]) + np.where(uhb, lens[np.minimum(ui + 1, n - 1)] * (cs[n] - cs[np.minimum(ui + 2, n)]), 0)
+        ucum = np.concatenate([[0], np.cumsum(ucells)])
+        ucuts = np.searchsorted(ucum, ucum[-1] * np.arange(world + 1) / world, side="left")
+        ucuts[0], ucuts[-1] = 0, len(ui)
+        ucuts = np.maximum.accumulate(ucuts)
+        u_lo, u_hi = int(ucuts[rank]), int(ucuts[rank + 1])
+        cells = int(ucum[u_hi] - ucum[u_lo])
+        S_dev = self.dev(S)
+        maxlen_all = int(lens.max())
+        budget = max(1 << 20, self.tb_budget_words)
+
+        def unit_tiles(u0, u1):
+            """Tile records of units [u0, u1), grouped by columns-per-lane class."""
+            gi_u, hb_u = ui[u0:u1], uhb[u0:u1]
+            cnt = n - 1 - gi_u
+            ntile = (cnt + tile - 1) // tile
+            unit = np.repeat(np.arange(len(gi_u)), ntile)
+            first = np.cumsum(ntile) - ntile
+            gi = gi_u[unit]
+            tb_ = gi + 1 + (np.arange(int(ntile.sum())) - first[unit]) * tile
+            te_ = np.minimum(tb_ + tile, n)
+            hb = hb_u[unit]
+            t = np.zeros(len(tb_), TILE_DTYPE)
+            t["resident"] = gi
+            t["resident2"] = np.where(hb, gi + 1, -1)
+            t["stream_begin"] = tb_
+            t["stream_end"] = te_
+            t["b_skip"] = np.where(hb & (tb_ == gi + 1), 1, 0)
+            kk = np.maximum(kcls[gi], np.where(hb, kcls[np.minimum(gi + 1, n - 1)], 0))
+            return {int(K): t[kk == K] for K in np.unique(kk)}
+
+        def plan_waves():
+            """Waves of <= budget traceback words, planned a chunk of units at a time so that the host plans
+            chunk c + 1 while the device fills chunk c (393,000 tiles at BASELINE config 3: 0.5 s in one go)."""
+            pending = {}
+            chunk = max(1, int(os.environ.get("PGPU_DUAL_CHUNK", "24")))
+            for u0 in list(range(u_lo, u_hi, chunk)) + [None]:
+                if u0 is not None:
+                    for K, t in unit_tiles(u0, min(u0 + chunk, u_hi)).items():
+                        w = self._tb_words16r(t, K, cs)
+                        if K in pending:
+                            pending[K] = (np.concatenate([pending[K][0], t]), np.concatenate([pending[K][1], w]))
+                        else:
+                            pending[K] = (t, w)
+                for K in list(pending):
+                    tiles, words = pending[K]
+                    wcum = np.concatenate([[0], np.cumsum(words.sum(axis=1))])
+                    lo = 0
+                    while lo < len(tiles):
+                        hi = max(lo + 1, int(np.searchsorted(wcum, wcum[lo] + budget, side="right")) - 1)
+                        if hi >= len(tiles) and u0 is not None and wcum[-1] - wcum[lo] < budget:
+                            break                      # a partial wave: wait for the next chunk's tiles
+                        hi = min(hi, len(tiles))
+                        wt = tiles[lo:hi].copy()
+                        na = (wt["stream_end"] - wt["stream_begin"]).astype(np.int64)
+                        nb = np.where(wt["resident2"] >= 0, na - wt["b_skip"], 0)
+                        base = np.zeros(len(wt), np.int64)
+                        np.cumsum((na + nb)[:-1], out=base[1:])
+                        wt["out_base"] = base
+                        wt["out_base2"] = base + na
+                        wbase = np.zeros(words[lo:hi].size, np.int64)
+                        np.cumsum(words[lo:hi].ravel()[:-1], out=wbase[1:])
+                        yield K, wt, wbase, int((na + nb).sum()), int(wcum[hi] - wcum[lo]), na, nb
+                        lo = hi
+                    if lo >= len(tiles):
+                        del pending[K]
+                    else:
+                        pending[K] = (tiles[lo:], words[lo:])
+
+        cur = torch.cuda.current_stream(self.device)
+        state = self._dual_state(n_streams)
+        streams = state["streams"][:n_streams]
+        for st in streams:
+            st.wait_stream(cur)             # inputs and count tables were written on the caller's stream
+        # buffers sized once: a full wave (or everything, for small jobs)
+        # (a cell is half a byte of traceback = 1/8 word; _dual_bufs grows a buffer when a wave needs more)
+        est_words = int(min(budget + (1 << 22), (ucum[u_hi] - ucum[u_lo]) / 8 * 1.3 + (1 << 22)))
+        est_slots = int(est_words * 8 / max(float(lens.mean()) ** 2, 1.0) * 1.5) + (1 << 12)
+        sc_out, path_out = ({}, {}) if want_paths else (None, None)
+        cnt_dev, seq_off_dev, thr = counts if counts is not None else (None, None, None)
+        for wave_no, (K, wt, wbase, ns, n_words, na, nb) in enumerate(plan_waves()):
+            maxlen = max(32 * K, maxlen_all) + 2
+            bkey = (0, float(go), float(ge), maxlen, True)
+            if bkey not in self._borders:
+                B = borders(0, go, ge, maxlen, True)
+                with torch.cuda.stream(cur):
+                    self._borders[bkey] = (B, self.dev(B["topD"]), self.dev(B["leftD"]))
+                for st in streams:
+                    st.wait_stream(cur)
+            B, top_dev, _ = self._borders[bkey]
+            k = wave_no % n_streams
+            st = streams[k]
+            tb, emit_t, pair_tb, slot_res, slot_str, sc = self._dual_bufs(state, k, max(est_words, n_words), max(est_slots, ns))
+            with torch.cuda.stream(st):
+                tiles_dev, wbase_dev = self.dev(wt.view(np.uint8)), self.dev(wbase)
+                sptr = ctypes.c_void_p(st.cuda_stream)
+                _lib.check(lib.pgpu_align_tiles16_paired_traced(
+                    K, self.ptr(batch.flat_dev), self.ptr(batch.offs_dev), self.ptr(tiles_dev), len(wt),
+                    self.ptr(S_dev), A, int(go), int(ge), neg16, self.ptr(top_dev), int(B["left0"]), int(B["left1"]),
+                    maxlen + 1, self.ptr(sc), self.ptr(tb), self.ptr(wbase_dev), self.ptr(emit_t), self.ptr(pair_tb),
+                    self.ptr(slot_res), self.ptr(slot_str), sptr))
+                poff_dev = pbuf = pstart = plen = None
+                if want_paths:
+                    # host copy of what the kernel records per slot: (resident, streamed) ids
+                    res_h = np.concatenate([np.concatenate([np.full(a_, r1), np.full(b_, r2)]) for a_, b_, r1, r2 in
+                                            zip(na, nb, wt["resident"], wt["resident2"])]).astype(np.int64)
+                    str_h = np.concatenate([np.concatenate([np.arange(t0, t0 + a_), np.arange(t0 + sk, t0 + sk + b_)])
+                                            for a_, b_, t0, sk in zip(na, nb, wt["stream_begin"], wt["b_skip"])]).astype(np.int64)
+                    cap = np.repeat(batch.lens[res_h] + batch.lens[str_h] + 2, 2).astype(np.int64)
+                    poff = np.zeros(2 * ns, np.int64)
+                    np.cumsum(cap[:-1], out=poff[1:])
+                    poff_dev = self.dev(poff)
+                    pbuf = torch.empty((int(cap.sum()), 2), dtype=torch.int32, device=self.device)
+                    pstart = torch.empty(2 * ns, dtype=torch.int32, device=self.device)
+                    plen = torch.empty(2 * ns, dtype=torch.int32, device=self.device)
+                _lib.check(lib.pgpu_traceback_dual(
+                    K, self.ptr(batch.offs_dev), self.ptr(slot_res), self.ptr(slot_str), ns, self.ptr(tb),
+                    self.ptr(emit_t), self.ptr(pair_tb), B["code00"], B["top_ramp"], B["left_ramp"],
+                    self.ptr(batch.flat_dev), self.ptr(cnt_dev), self.ptr(seq_off_dev), A, self.ptr(sc),
+                    int(thr is not None), float(thr if thr is not None else 0.0), self.ptr(poff_dev), self.ptr(pbuf),
+                    self.ptr(pstart), self.ptr(plen), sptr))
+                # the records were allocated under this stream: the caching allocator hands their memory out again
+                # only to later work of the same stream, so dropping the references here is safe
+                del tiles_dev, wbase_dev
+                self.launches += 2
+                if want_paths:
+                    st.synchronize()
+                    assert np.array_equal(slot_res[:ns].cpu().numpy(), res_h) and np.array_equal(slot_str[:ns].cpu().numpy(), str_h)
+                    pb, ps_, pl, sch = pbuf.cpu().numpy(), pstart.cpu().numpy(), plen.cpu().numpy(), sc[:ns].cpu().numpy()
+                    for q in range(ns):
+                        i, j = int(res_h[q]), int(str_h[q])
+                        sc_out[(i, j)] = sch[q]
+                        o = poff[2 * q] + ps_[2 * q]
+                        path_out[(i, j)] = pb[o:o + pl[2 * q]].copy()
+                        o = poff[2 * q + 1] + ps_[2 * q + 1]
+                        path_out[(j, i)] = pb[o:o + pl[2 * q + 1]].copy()
+        for st in streams:
+            cur.wait_stream(st)
+        return sc_out, path_out, cells
+
+    def _pick_tile_dual(self, n_pairs):
+        # traced waves hold a few hundred tiles only: shorter streams per warp keep the last round of CTAs full
+        if os.environ.get("PGPU_TILE_DUAL"):
+            return int(os.environ["PGPU_TILE_DUAL"])
+        return self.nw * 8 if n_pairs >= 148 * 6 * self.nw * 8 else self._pick_tile(n_pairs)
 
     NBOX = 3    # PGPU_NBOX: boxes per pair -> up to NBOX + 1 Waterman-Eggert iterations on the device
 
@@ -1116,6 +1364,8 @@ class Engine(object):
         self.launches += 3 + int(want_path)
         h = outb.cpu().numpy()          # the single device -> host read of this alignment
         score = float(h[:1].view(np.float32)[0])
+        if score != score:      # k_gen_finalize: a strip hand-off timed out (GPU shared / preempted); the fill is invalid
+            raise _lib.PralineGpuError("wavefront kernel: a strip-to-strip hand-off timed out; no result was produced")
         res = dict(score=score, cell=tuple(int(v) for v in h[1:4]))
         if want_path:
             st, ln = int(h[4]), int(h[5])

@@ -117,6 +117,16 @@ def allgather_counts(local_counts, sizes, group=None):
     return torch.cat([recv[r * width:r * width + sizes[r]] for r in range(world)])
 
 
+def allreduce_counts(counts, group=None):
+    """Symmetric preprofile stage (Engine.preprofile_stage with shard=(rank, world)): the UNORDERED pair list
+    is cut by DP cells, a rank's walks add into full-size count tables of every master (both orientations of
+    a pair land in different masters' tables), and one sum all-reduce -- exact, the tables are int32 --
+    hands every rank the complete tables (430 MB at BASELINE config 3: milliseconds on NVLink).  In place."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
 class SharedHostVector(object):
     """One pinned host vector shared by the ranks of a node (POSIX shared memory registered with
     the CUDA driver in every process): each rank copies ITS slice of the condensed vector device ->

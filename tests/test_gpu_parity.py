@@ -735,6 +735,81 @@ def test_preprofile_stage_chunks_equal_one_batch(eng, mode):
     assert cells == int((lens.sum() ** 2 - (lens ** 2).sum())) * (2 if mode == "local" else 1)
 
 
+@pytest.mark.parametrize("gaps", [[-11.0, -1.0], [-2.0], [-4.0, -2.0], [0.0, 0.0]])
+def test_dual_traced_fill_serves_both_orientations(eng, gaps):
+    """Paired-resident traced kernel + dual walk (gotoh_stream16r.cuh, tb_fmt 2): ONE fill of an unordered
+    pair must give the reference's path for (i, j) AND for (j, i) -- tie order included (util/align.py:161-174)
+    -- on tie-heavy inputs (three-letter sequences, linear and zero gaps), ragged lengths over several
+    columns-per-lane classes, odd sequence counts, several waves and both streams."""
+    S = matrices.blosum62()
+    assert np.array_equal(S, S.T)
+    rng = np.random.default_rng(int(-gaps[0]) + 5)
+    seqs = synth.family(77, 9, 90)
+    seqs += [rng.integers(0, 3, int(rng.integers(1, 140))).astype(np.int32) for _ in range(10)]       # tie-heavy
+    seqs += [rng.integers(0, 20, L).astype(np.int32) for L in (1, 2, 33, 64, 65, 129, 193, 260)]
+    batch = eng.batch(seqs)
+    flat, offs = synth.pack(seqs)
+    n = len(seqs)
+    budget = eng.tb_budget_words
+    eng.tb_budget_words = 1 << 20            # force several waves
+    try:
+        scores, paths, cells = eng.allpairs_dual(batch, S, gaps, want_paths=True, tile=16)
+    finally:
+        eng.tb_budget_words = budget
+    pi, pj = synth.all_pairs(n)
+    assert cells == int((batch.lens[pi] * batch.lens[pj]).sum())
+    both_i = np.concatenate([pi, pj])
+    both_j = np.concatenate([pj, pi])
+    want, want_paths = oracle.align_batch("global", flat, offs, both_i, both_j, S, gaps, want_paths=True)
+    assert len(paths) == 2 * len(pi)
+    differ = 0
+    for k, (i, j) in enumerate(zip(both_i, both_j)):
+        i, j = int(i), int(j)
+        assert scores[(min(i, j), max(i, j))] == want[k], (i, j)
+        assert np.array_equal(paths[(i, j)], want_paths[k]), (gaps, i, j)
+    for i, j in zip(pi, pj):
+        differ += not np.array_equal(paths[(int(i), int(j))][:, ::-1], paths[(int(j), int(i))])
+    assert differ > 0          # the two orientations really break ties differently on these inputs
+
+
+def test_dual_traced_long_residents(eng):
+    """The same on the K classes of BASELINE config 3 and beyond (400-aa residents: K = 13; up to K = 20 -- the
+    traced packed range, +-16000, ends near 660 residues with BLOSUM62 and [-11, -1])."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(5)
+    seqs = synth.family(3, 7, 400) + [rng.integers(0, 20, L).astype(np.int32) for L in (417, 448, 512, 640)]
+    batch = eng.batch(seqs)
+    flat, offs = synth.pack(seqs)
+    assert eng.dual_traced_ok(S, [-11.0, -1.0], batch.lens) is not None
+    scores, paths, _ = eng.allpairs_dual(batch, S, [-11.0, -1.0], want_paths=True, tile=16)
+    pi, pj = synth.all_pairs(len(seqs))
+    both_i, both_j = np.concatenate([pi, pj]), np.concatenate([pj, pi])
+    want, want_paths = oracle.align_batch("global", flat, offs, both_i, both_j, S, [-11.0, -1.0], want_paths=True)
+    for k, (i, j) in enumerate(zip(both_i, both_j)):
+        assert scores[(int(min(i, j)), int(max(i, j)))] == want[k]
+        assert np.array_equal(paths[(int(i), int(j))], want_paths[k]), (i, j)
+
+
+def test_preprofile_stage_symmetric_path_equals_per_master_path(eng):
+    """Engine.preprofile_stage: the symmetric path (one fill per unordered pair, two walks) and the per-master
+    path (one fill per ordered pair) give identical count tables; sharded over two ranks the tables add up."""
+    S = matrices.blosum62()
+    rng = np.random.default_rng(12)
+    seqs = synth.family(31, 37, 120) + [rng.integers(0, 4, int(rng.integers(5, 90))).astype(np.int32) for _ in range(6)]
+    batch = eng.batch(seqs)
+    for thr in (None, 40.0):
+        want, where, cells = eng.preprofile_stage(batch, S, [-11.0, -1.0], threshold=thr, shard=None)
+        got, where2, cells2 = eng.preprofile_stage(batch, S, [-11.0, -1.0], threshold=thr)
+        assert where == where2 and cells == cells2
+        assert np.array_equal(got.cpu().numpy(), want.cpu().numpy()), thr
+        parts = [eng.preprofile_stage(batch, S, [-11.0, -1.0], threshold=thr, shard=(r, 2))[0].cpu().numpy() for r in range(2)]
+        assert np.array_equal(parts[0] + parts[1], want.cpu().numpy()), thr
+    asym = S.copy()
+    asym[0, 1] += 1.0
+    assert eng.dual_traced_ok(asym, [-11.0, -1.0], batch.lens) is None          # not symmetric: per-master path
+    assert eng.dual_traced_ok(S, [-11.0, -1.0], batch.lens) is not None
+
+
 @pytest.mark.parametrize("resident", ["one", "two"])
 @pytest.mark.parametrize("mode", ["global", "local"])
 def test_tensor_core_score_rows(eng, resident, mode):

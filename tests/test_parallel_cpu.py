@@ -77,6 +77,14 @@ def _worker(rank, world, port, n, q):
     allc = parallel.allgather_counts(local, sizes)
     want = torch.cat([torch.full((int(b.lens[m]) * A,), float(m)) for m in range(n)])
     ok = ok and bool(torch.equal(allc, want)) and cuts[0] == 0 and cuts[-1] == n
+    # symmetric preprofile stage: pairs sharded, every rank adds into full-size tables, one sum all-reduce
+    part = torch.zeros(int(b.lens.sum()) * A, dtype=torch.int32)
+    part[rank::world] = rank + 1
+    total = parallel.allreduce_counts(part.clone())
+    want_sum = torch.zeros_like(part)
+    for r in range(world):
+        want_sum[r::world] = r + 1
+    ok = ok and bool(torch.equal(total, want_sum))
     q.put((rank, ok, cells))
     dist.barrier()
     dist.destroy_process_group()
