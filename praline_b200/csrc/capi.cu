@@ -315,7 +315,7 @@ int64_t pgpu_general_workspace_bytes(int L1, int L2)
     const int ns = (nsa > nsb ? nsa : nsb) > nsl ? (nsa > nsb ? nsa : nsb) : nsl;
     const size_t fp = up256((size_t)L2 + 1);
     size_t b = 0;
-    b += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 31));    // lean kernel's flag words
+    b += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 128));   // lean kernels' flag words (row-blocked: 4 * (ceil(L1 / 4) + 31) rows)
     b += up256((size_t)(L1 + 1) * fp);                              // flags
     b += up256(sizeof(float) * 8 * (size_t)(ns + 1) * (L1 + 1));    // edge (16-byte records; 32-byte tagged ones in the lean kernel)
     b += up256(sizeof(int) * (size_t)(ns + 1));                     // progress
@@ -342,7 +342,7 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
     a.z = z; a.z_pitch = z_pitch; a.o_full = o_full; a.t_full = t_full;
     unsigned char* w = (unsigned char*)workspace;
     const size_t fp = up256((size_t)L2 + 1);
-    a.flagw = (uint32_t*)w; w += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 31));
+    a.flagw = (uint32_t*)w; w += up256(sizeof(uint32_t) * 32 * (size_t)nsl * (L1 + 128));
     a.var_gaps = var_gaps;
     a.flags = w; a.f_pitch = (int)fp; w += up256((size_t)(L1 + 1) * fp);
     a.edge = (float*)w; w += up256(sizeof(float) * 8 * (size_t)(ns + 1) * (L1 + 1));

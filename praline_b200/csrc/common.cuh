@@ -123,6 +123,7 @@ struct GenArgs {
     int flag_fmt;                        // 0: the reference's seven flag bits, 1: compact sign bits, 2: lean words
     uint32_t* flagw;                     // lean kernel: [n_strips][L1+31][32] flag words (4 cells x 5 bits + mask bits)
     int var_gaps;                        // gap arrays vary per position (else g1[0..1], g2[0..1] are THE gap pairs)
+    int flag_skew, flag_rows;            // lean kernels: word row of (y, lane) = y - 1 + flag_skew * lane; rows per strip
     // finalize / traceback outputs
     float* score_out;                    // [1]
     int32_t* cell_out;                   // [3] y, x, state

@@ -698,6 +698,256 @@ __global__ void __launch_bounds__(256) k_wave(const GenArgs a)
     }
 }
 
+// ---- K3, row-blocked form: 4 rows x 4 columns per lane and step ----------------------------------------
+// k_wave advances ONE row per step: three shuffles, a cp.async wait, a tag check and a vote sit between every
+// two rows of a strip, and a 20k x 20k matrix is 20,000 + 32 * 157 such steps of ~600 ns (one warp per
+// scheduler, IPC 0.2: a dependent chain, profiles/r01_kwave_v3_*).  Here a lane owns a 4 x 4 block per step:
+// lane l works on rows 4(t - l) + 1 .. + 4 of its four columns at step t, the twelve edge values of a block
+// cross to lane l + 1 by shuffles issued back to back, lane 0 reads four tagged records of the left strip, and
+// the sixteen cells of a block hold an anti-diagonal of independent work (critical path 7 cells of 16).  Steps
+// per strip: L1 / 4 + 31; the critical path of the whole matrix L1 / 4 + 32 * strips steps.  Same arithmetic as
+// k_wave (three separate sums, sign-bit flags, cext.c:155-290), same tagged 32-byte records, same flag words
+// (one per row and lane, row y of lane l at word row y - 1 + 4 l).  Global and semiglobal modes, constant gap
+// pairs, no mask; everything else runs k_wave.
+#define W4_R 4                         // ring depth in steps: scores and records are requested 3 steps ahead
+#define W4_SLOTF (32 * 16 + 32)        // floats per ring slot: scores [row][lane][4] + four records [8]
+__global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
+{
+    extern __shared__ __align__(16) float wsm[];
+    const int L1 = a.L1, L2 = a.L2, W = L2 + 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const float NINF = -INFINITY;
+    float* ring = wsm + (size_t)wib * (W4_R * W4_SLOTF);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const int NB = (L1 + 3) >> 2;            // row blocks
+    const int TT = NB + 31;                  // steps per strip
+    const float g1o = a.g1[0], g1e = a.g1[1], g2o = a.g2[0], g2e = a.g2[1];
+
+    for (int strip = gw; strip < a.n_strips; strip += nw) {
+        const int x0 = strip * 128 + lane * 4 + 1;
+        const float* ein = a.edge + (size_t)strip * (L1 + 1) * 8;
+        float* eout = a.edge + (size_t)(strip + 1) * (L1 + 1) * 8;
+        const bool last_strip = strip == a.n_strips - 1;
+        const bool lane_on = x0 <= L2;
+        uint32_t* fout = a.flagw + (size_t)strip * (TT * 4) * 32 + lane;
+        const int lcol = (L2 - 1 - strip * 128) >> 2, kcol = (L2 - 1) & 3;   // lane / cell of column L2 (last strip)
+
+        float Mp[4], Up[4], Lp[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = x0 + k;
+            const bool v = x <= L2;
+            Mp[k] = v ? a.top[x] : NINF;
+            Up[k] = v ? a.top[W + x] : NINF;
+            Lp[k] = v ? a.top[2 * W + x] : NINF;
+        }
+        // the left neighbour's last column in the row above the block (row 0: the top border)
+        float e0M = NINF, e0U = NINF, e0L = NINF;
+        if (lane_on) { e0M = a.top[x0 - 1]; e0U = a.top[W + x0 - 1]; e0L = a.top[2 * W + x0 - 1]; }
+        float rM[4], rU[4], rL[4];              // my last column, rows of the block just finished
+#pragma unroll
+        for (int r = 0; r < 4; r++) { rM[r] = 0.f; rU[r] = 0.f; rL[r] = 0.f; }
+
+        // block bb -> ring slot of the step that consumes it.  Branch-free: rows are clamped into the matrix (blocks
+        // outside it load a row nobody uses; the padded pitch covers every lane's columns), lane 0's two record
+        // copies per row are predicated instructions.
+        const float* mcol = a.m + (x0 - 1);
+        const int is0 = (lane == 0);
+        auto request = [&](int bb, int use_step) {
+            const uint32_t dst = ring_s + (uint32_t)((use_step & (W4_R - 1)) * W4_SLOTF) * 4u;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int yy = min(max(4 * bb + 1 + r, 1), L1);
+                cp_async16(dst + (uint32_t)(r * 128 + lane * 4) * 4u, mcol + (size_t)(yy - 1) * a.m_pitch);
+                const float* rec = ein + (size_t)yy * 8;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+                             "@p cp.async.cg.shared.global [%0], [%2], 16;\n\t"
+                             "@p cp.async.cg.shared.global [%1], [%2+16], 16;\n\t}"
+                             :: "r"(dst + (uint32_t)(512 + r * 8) * 4u), "r"(dst + (uint32_t)(512 + r * 8 + 4) * 4u), "l"(rec), "r"(is0)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        __syncwarp();
+#pragma unroll 1
+        for (int d = 0; d < W4_R - 1; d++) request(d - lane, d);
+
+        for (int t = 0; t < TT; t++) {
+            __syncwarp();
+            const int b = t - lane;
+            request(b + W4_R - 1, t + W4_R - 1);
+            float nM[4], nU[4], nL[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                nM[r] = __shfl_up_sync(FULL, rM[r], 1);
+                nU[r] = __shfl_up_sync(FULL, rU[r], 1);
+                nL[r] = __shfl_up_sync(FULL, rL[r], 1);
+            }
+            asm volatile("cp.async.wait_group %0;" ::"n"(W4_R - 1) : "memory");
+            float* slot = ring + (t & (W4_R - 1)) * W4_SLOTF;
+            // lane 0: the left strip's four records of this block.  Every lane loads them (one broadcast each)
+            // and the miss path is entered by the whole warp through a vote, so that lane 0 never runs the step
+            // loop as a warp of its own (independent thread scheduling keeps a lane that took a long private
+            // branch apart from the others: the first version of this kernel ran every step twice).
+            const int nrow = min(4, L1 - 4 * t);      // valid rows of lane 0's block (b = t there)
+            float4 e0[4], e1[4];
+            bool miss = false;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                e0[r] = *reinterpret_cast<const float4*>(slot + 512 + r * 8);
+                e1[r] = *reinterpret_cast<const float4*>(slot + 512 + r * 8 + 4);
+                miss |= (lane == 0) && (r < nrow) && !edge_ok(e0[r], e1[r], 4 * t + 1 + r);
+            }
+            if (__any_sync(FULL, miss)) {
+                // The records were requested before the left strip had written them.  Fetch the four of THIS block
+                // directly (all loads in flight together), as often as it takes; records requested for later steps
+                // are checked at their own steps.  While a strip runs in this mode its steps carry an L2 round trip
+                // more than its producer's, so the producer pulls ahead until the prefetches hit again: no waiting
+                // for a full ring (the first version did, and every strip started 60-80 steps behind its neighbour
+                // instead of 35).
+                if (lane == 0) {
+                    bool ok = false;
+                    for (int spins = 0; spins < (1 << 22) && !ok; spins++) {     // bounded: never hang ...
+                        ok = true;
+#pragma unroll
+                        for (int r = 0; r < 4; r++) ld_edge(ein + (size_t)min(4 * t + 1 + r, L1) * 8, e0[r], e1[r]);
+#pragma unroll
+                        for (int r = 0; r < 4; r++) ok = ok && (r >= nrow || edge_ok(e0[r], e1[r], 4 * t + 1 + r));
+                    }
+                    if (!ok) atomicOr(a.err, 1);        // ... and never continue silently: k_gen_finalize -> NaN score
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) { nM[r] = e0[r].x; nU[r] = e0[r].z; nL[r] = e1[r].x; }
+            }
+            __syncwarp();
+            if (t < NB - 1) {
+                // ---- interior steps: every active lane holds a full block that is not its last one.  Straight-line
+                // code, cells in ANTI-DIAGONAL order (the issue order is the program order: a row-major block runs as
+                // four dependent chains one after the other), nothing conditional between the cells.
+                if (b >= 0 && lane_on) {
+                    float sc[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const float4 sv = *reinterpret_cast<const float4*>(slot + r * 128 + lane * 4);
+                        sc[r][0] = sv.x; sc[r][1] = sv.y; sc[r][2] = sv.z; sc[r][3] = sv.w;
+                    }
+                    float Mc[4][4], Uc[4][4], Lc[4][4];
+                    uint32_t fw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int d = 0; d < 7; d++) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const int k = d - r;
+                            if (k < 0 || k > 3) continue;
+                            // neighbours: above (r-1, k), left (r, k-1), diagonal (r-1, k-1)
+                            const float aM = r ? Mc[r - 1][k] : Mp[k], aU = r ? Uc[r - 1][k] : Up[k];
+                            const float lM = k ? Mc[r][k - 1] : nM[r], lL = k ? Lc[r][k - 1] : nL[r];
+                            float dM_, dU_, dL_;
+                            if (r && k) { dM_ = Mc[r - 1][k - 1]; dU_ = Uc[r - 1][k - 1]; dL_ = Lc[r - 1][k - 1]; }
+                            else if (r) { dM_ = nM[r - 1]; dU_ = nU[r - 1]; dL_ = nL[r - 1]; }
+                            else if (k) { dM_ = Mp[k - 1]; dU_ = Up[k - 1]; dL_ = Lp[k - 1]; }
+                            else { dM_ = e0M; dU_ = e0U; dL_ = e0L; }
+                            const float s_ = sc[r][k];
+                            const float mm = dM_ + s_, mu = dU_ + s_, ml = dL_ + s_;
+                            const float M = fmaxf(fmaxf(mm, mu), ml);
+                            const float uo = aM + g1o, ue = aU + g1e;
+                            const float lo = lM + g2o, le = lL + g2e;
+                            const float U = fmaxf(uo, ue), L = fmaxf(lo, le);
+                            uint32_t f = 0;
+                            f = __funnelshift_l(__float_as_uint(lo - L), f, 1);
+                            f = __funnelshift_l(__float_as_uint(uo - U), f, 1);
+                            f = __funnelshift_l(__float_as_uint(mu - M), f, 1);
+                            f = __funnelshift_l(__float_as_uint(mm - M), f, 1);
+                            fw[r] |= f << (5 * k);
+                            Mc[r][k] = M; Uc[r][k] = U; Lc[r][k] = L;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        fout[(size_t)(4 * t + r) * 32] = fw[r];
+                        rM[r] = Mc[r][3]; rU[r] = Uc[r][3]; rL[r] = Lc[r][3];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { Mp[k] = Mc[3][k]; Up[k] = Uc[3][k]; Lp[k] = Lc[3][k]; }
+                    e0M = nM[3]; e0U = nU[3]; e0L = nL[3];
+                    if (last_strip) {
+                        if (lane == lcol) {
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                float m_ = Mc[r][0], u_ = Uc[r][0], l_ = Lc[r][0];
+#pragma unroll
+                                for (int k = 1; k < 4; k++) if (kcol == k) { m_ = Mc[r][k]; u_ = Uc[r][k]; l_ = Lc[r][k]; }
+                                const int y = 4 * b + 1 + r;
+                                a.lastcol[y] = m_; a.lastcol[(L1 + 1) + y] = u_; a.lastcol[2 * (L1 + 1) + y] = l_;
+                            }
+                        }
+                    } else if (lane == 31) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) st_edge(eout + (size_t)(4 * b + 1 + r) * 8, rM[r], rU[r], rL[r], 4 * b + 1 + r);
+                    }
+                }
+            } else
+            if (b >= 0 && b < NB && lane_on) {
+                float dM = e0M, dU = e0U, dL = e0L;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int y = 4 * b + 1 + r;
+                    const float4 sv = *reinterpret_cast<const float4*>(slot + r * 128 + lane * 4);
+                    const float sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                    float cMl = nM[r], cLl = nL[r];
+                    float Md = dM, Ud = dU, Ld = dL;
+                    uint32_t fw = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float mm = Md + sc[k], mu = Ud + sc[k], ml = Ld + sc[k];
+                        const float M = fmaxf(fmaxf(mm, mu), ml);
+                        const float uo = Mp[k] + g1o, ue = Up[k] + g1e;
+                        const float lo = cMl + g2o, le = cLl + g2e;
+                        const float U = fmaxf(uo, ue), L = fmaxf(lo, le);
+                        uint32_t f = 0;
+                        f = __funnelshift_l(__float_as_uint(lo - L), f, 1);
+                        f = __funnelshift_l(__float_as_uint(uo - U), f, 1);
+                        f = __funnelshift_l(__float_as_uint(mu - M), f, 1);
+                        f = __funnelshift_l(__float_as_uint(mm - M), f, 1);
+                        fw |= f << (5 * k);
+                        Md = Mp[k]; Ud = Up[k]; Ld = Lp[k];
+                        Mp[k] = M; Up[k] = U; Lp[k] = L;
+                        cMl = M; cLl = L;
+                    }
+                    dM = nM[r]; dU = nU[r]; dL = nL[r];        // the diagonal of the next row's first cell
+                    fout[(size_t)(4 * t + r) * 32] = fw;
+                    rM[r] = Mp[3]; rU[r] = Up[3]; rL[r] = Lp[3];
+                    if (y == L1) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (x0 + k <= L2) { a.lastrow[x0 + k] = Mp[k]; a.lastrow[W + x0 + k] = Up[k]; a.lastrow[2 * W + x0 + k] = Lp[k]; }
+                    }
+                    if (y <= L1) {
+                        if (last_strip) {
+                            if (lane == lcol) {
+                                float m_ = Mp[0], u_ = Up[0], l_ = Lp[0];
+#pragma unroll
+                                for (int k = 1; k < 4; k++) if (kcol == k) { m_ = Mp[k]; u_ = Up[k]; l_ = Lp[k]; }
+                                a.lastcol[y] = m_; a.lastcol[(L1 + 1) + y] = u_; a.lastcol[2 * (L1 + 1) + y] = l_;
+                            }
+                        } else if (lane == 31) {
+                            st_edge(eout + (size_t)y * 8, Mp[3], Up[3], Lp[3], y);
+                        }
+                    }
+                }
+                e0M = nM[3]; e0U = nU[3]; e0L = nL[3];
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+}
+
 // Traceback over the lean kernel's flag words: one warp stages WT_WIN steps x 32 lanes of the
 // current strip (16 KB, every row a coalesced 128-byte line, all requests in flight at once) and
 // lane 0 walks inside that window -- one memory round trip per ~100 path cells.
@@ -706,7 +956,7 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
 {
     __shared__ uint32_t tile[WT_WIN][32];
     const int lane = threadIdx.x;
-    const int L1 = a.L1, L2 = a.L2, TT = L1 + 31;
+    const int L1 = a.L1, L2 = a.L2, TT = a.flag_rows, SK = a.flag_skew;   // word row of (y, lane) = y - 1 + SK * lane
     const bool u_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_ONE);
     const bool l_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_TWO);
     int y = a.cell_out[0], x = a.cell_out[1], k = a.cell_out[2];
@@ -725,7 +975,7 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
         int strip = 0, tlo = 0;
         if (y >= 1 && x >= 1) {
             strip = (x - 1) >> 7;
-            const int tcur = y - 1 + (((x - 1) & 127) >> 2);
+            const int tcur = y - 1 + SK * (((x - 1) & 127) >> 2);
             tlo = max(0, tcur - (WT_WIN - 1));
             const uint32_t* src = a.flagw + ((size_t)strip * TT + tlo) * 32 + lane;
             const int nrow = min(WT_WIN, TT - tlo);
@@ -742,7 +992,7 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
                 bool stop = false;
                 if (y >= 1 && x >= 1) {
                     const int ln = ((x - 1) & 127) >> 2, kk = (x - 1) & 3;
-                    const uint32_t word = tile[y - 1 + ln - tlo][ln];
+                    const uint32_t word = tile[y - 1 + SK * ln - tlo][ln];
                     const uint32_t c = (word >> (5 * kk)) & 31u;
                     if ((word >> (24 + kk)) & 1u) stop = true;              // masked cell: no flags
                     else if (k == 0) {
@@ -756,7 +1006,7 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
                 if (stop) { done = 1; break; }
                 y = ny; x = nx; k = nk;
                 if (y >= 1 && x >= 1) {   // still inside the staged window of this strip?
-                    const int tn = y - 1 + (((x - 1) & 127) >> 2);
+                    const int tn = y - 1 + SK * (((x - 1) & 127) >> 2);
                     if (((x - 1) >> 7) != strip || tn < tlo) break;
                 }
             }
@@ -1019,6 +1269,149 @@ __global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int 
             const int x = x0 + c * 32 + tx, y = y0 + r * 8 + ty;
             if (x < L2 && y < L1) m[(size_t)y * m_pitch + x] = score[r][c];
         }
+}
+
+// ---- K1 for LARGE single matrices (BASELINE config 5: 20 kb x 20 kb) --------------------------------
+// k_build_scores stages and compacts (8*RG + 32*CG) profile rows per 1024 cells and runs two nested
+// data-dependent loops per cell whose trip counts differ from lane to lane: 5.7 ms for 4e8 cells of
+// depth-8 DNA profiles, 12 % of its own instruction bound.  Here a block owns 128 COLUMNS (one per
+// thread) x BC_ROWS rows:
+//  * the first rounded product of a term, fl(P2[x][j] * S[i][j]) (cext.c:89, evaluation order in the
+//    header above), depends on the column and the symbol pair only: every thread tabulates it once per
+//    block for its own column, T[i][q][x][4] = four consecutive nonzero entries j of column x (ascending,
+//    zero padded), so that a thread's quad is one conflict-free LDS.128;
+//  * the block's rows of P1 are compacted once (value, table offset of symbol i; ascending i) and every
+//    thread walks the SAME row at the same time: the outer trip count is uniform, the inner one is the
+//    block's maximum quad count (a padded entry adds fl(0 * p1) = 0 and leaves every partial sum as it is);
+//  * a cell costs nnz1 x nq x {LDS.128, 4 FMUL, 4 FADD} + one broadcast LDS.64 per nnz1, in the
+//    reference's order with its two roundings per term; the row of 128 results is one coalesced store.
+// Blocks whose columns need more quads than the table has room for take the direct path (no table).
+#define BC_ROWS 128
+__global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, int L1, int L2, float* __restrict__ m, int m_pitch, int nq_cap)
+{
+    extern __shared__ __align__(16) float csm[];
+    const int A = st.A;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * BC_ROWS;
+    const int nrows = min(BC_ROWS, L1 - y0), ncols = min(128, L2 - x0);
+    float* T = csm;                                              // [A][nq_cap][128][4]
+    float* sS = T + (size_t)A * nq_cap * 512;                    // [A][A]
+    float2* rows = reinterpret_cast<float2*>(sS + ((A * A + 1) & ~1));     // [BC_ROWS][A] (value, byte offset of T[i])
+    float* raw = reinterpret_cast<float*>(rows + BC_ROWS * A);   // [128][A] staged profile rows (P2, then P1)
+    float* cval = raw + 128 * A;                                 // [A][128] compacted column entries: value
+    int* cidx = reinterpret_cast<int*>(cval + A * 128);          // [A][128]                           symbol j
+    __shared__ int rcnt[BC_ROWS];
+    __shared__ int nqmax;
+    if (tid == 0) nqmax = 0;
+    for (int i = tid; i < A * A; i += 128) sS[i] = st.S[i];
+    {
+        const float* s2 = st.P2 + (size_t)x0 * A;
+        for (int i = tid; i < ncols * A; i += 128) raw[i] = s2[i];
+    }
+    __syncthreads();
+    int n2 = 0;
+    if (tid < ncols) {
+        for (int j = 0; j < A; j++) {
+            const float p = raw[tid * A + j];
+            if (p != 0.f) { cval[n2 * 128 + tid] = p; cidx[n2 * 128 + tid] = j; n2++; }
+        }
+        atomicMax(&nqmax, (n2 + 3) >> 2);
+    }
+    __syncthreads();
+    const int nq = nqmax;
+    const bool table = nq <= nq_cap;
+    if (table && tid < 128) {
+        for (int i = 0; i < A; i++)
+            for (int q = 0; q < nq; q++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int b = 4 * q + e;
+                    if (tid < ncols && b < n2) pv[e] = __fmul_rn(cval[b * 128 + tid], sS[i * A + cidx[b * 128 + tid]]);
+                }
+                *reinterpret_cast<float4*>(T + ((size_t)(i * nq + q) * 128 + tid) * 4) = v;
+            }
+    }
+    __syncthreads();            // raw is free again
+    {
+        const float* s1 = st.P1 + (size_t)y0 * A;
+        for (int i = tid; i < nrows * A; i += 128) raw[i] = s1[i];
+    }
+    __syncthreads();
+    if (tid < nrows) {
+        int c = 0;
+        for (int i = 0; i < A; i++) {
+            const float p = raw[tid * A + i];
+            if (p != 0.f) { rows[tid * A + c] = make_float2(p, __int_as_float(table ? i * nq * 2048 : i * A)); c++; }
+        }
+        rcnt[tid] = c;
+    }
+    __syncthreads();
+    if (tid >= ncols) return;
+    float* out = m + (size_t)y0 * m_pitch + x0 + tid;
+    if (table) {
+        // explicit shared-space addresses: through generic pointers every load paid an address-space
+        // conversion (S2UR CgaCtaId ...) and the loop ran 42 instructions per entry instead of 13
+        const uint32_t Ts = (uint32_t)__cvta_generic_to_shared(T) + (uint32_t)tid * 16u;
+        const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+        auto lds2 = [](uint32_t addr, float& x, uint32_t& y) {
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(x), "=r"(y) : "r"(addr));
+        };
+        auto lds4 = [](uint32_t addr) -> float4 {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            return v;
+        };
+        if (nq == 1) {
+            for (int r = 0; r < nrows; r++) {
+                const int n1 = rcnt[r];
+                uint32_t ra = rows_s + (uint32_t)(r * A) * 8u;
+                float acc = 0.f;
+                for (int a = 0; a < n1; a++, ra += 8u) {
+                    float p1; uint32_t off;
+                    lds2(ra, p1, off);
+                    const float4 t4 = lds4(Ts + off);
+                    acc = __fadd_rn(acc, __fmul_rn(t4.x, p1));
+                    acc = __fadd_rn(acc, __fmul_rn(t4.y, p1));
+                    acc = __fadd_rn(acc, __fmul_rn(t4.z, p1));
+                    acc = __fadd_rn(acc, __fmul_rn(t4.w, p1));
+                }
+                out[(size_t)r * m_pitch] = __fadd_rn(0.f, acc);
+            }
+        } else {
+            for (int r = 0; r < nrows; r++) {
+                const int n1 = rcnt[r];
+                uint32_t ra = rows_s + (uint32_t)(r * A) * 8u;
+                float acc = 0.f;
+                for (int a = 0; a < n1; a++, ra += 8u) {
+                    float p1; uint32_t off;
+                    lds2(ra, p1, off);
+                    for (int q = 0; q < nq; q++) {
+                        const float4 t4 = lds4(Ts + off + (uint32_t)q * 2048u);
+                        acc = __fadd_rn(acc, __fmul_rn(t4.x, p1));
+                        acc = __fadd_rn(acc, __fmul_rn(t4.y, p1));
+                        acc = __fadd_rn(acc, __fmul_rn(t4.z, p1));
+                        acc = __fadd_rn(acc, __fmul_rn(t4.w, p1));
+                    }
+                }
+                out[(size_t)r * m_pitch] = __fadd_rn(0.f, acc);
+            }
+        }
+    } else {
+        for (int r = 0; r < nrows; r++) {
+            const int n1 = rcnt[r];
+            const float2* rr = rows + r * A;
+            float acc = 0.f;
+            for (int a = 0; a < n1; a++) {
+                const float2 e = rr[a];
+                const float* srow = sS + __float_as_int(e.y);
+                for (int b = 0; b < n2; b++)
+                    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(cval[b * 128 + tid], srow[cidx[b * 128 + tid]]), e.x));
+            }
+            out[(size_t)r * m_pitch] = __fadd_rn(0.f, acc);
+        }
+    }
 }
 
 // Batched form for the matrix-fed streaming kernel: one matrix row per stream position of a
@@ -1351,6 +1744,17 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
         PG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas), dim3(wpc * 32), kargs, sm, st)); \
     } while (0)
         const bool vg = a.var_gaps != 0;
+        a.flag_skew = 1;
+        a.flag_rows = a.L1 + 31;
+        if (!local && !mask && !vg && getenv("PGPU_NO_WAVE4") == nullptr) {
+            a.flag_skew = 4;
+            a.flag_rows = (((a.L1 + 3) >> 2) + 31) * 4;
+            auto kern = k_wave4;
+            const size_t sm = (size_t)wpc * W4_R * W4_SLOTF * sizeof(float);
+            PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            void* kargs[] = {(void*)&a};
+            PG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas), dim3(wpc * 32), kargs, sm, st));
+        } else
         if (local) { if (mask) { if (vg) PG_WAVE(true, true, true); else PG_WAVE(true, true, false); }
                      else { if (vg) PG_WAVE(true, false, true); else PG_WAVE(true, false, false); } }
         else { if (mask) { if (vg) PG_WAVE(false, true, true); else PG_WAVE(false, true, false); }
@@ -1414,6 +1818,20 @@ int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int 
     for (int i = 0; i < sets.n; i++) {
         if (sets.s[i].A > BS_MAXA) { pg_set_error("alphabet size %d above %d", sets.s[i].A, BS_MAXA); return 1; }
         if (sets.s[i].A > amax) amax = sets.s[i].A;
+    }
+    if (sets.n == 1 && (size_t)L1 * L2 >= (size_t)1 << 21 && getenv("PGPU_K1_COLS_OFF") == nullptr) {
+        // large single matrix: column-per-thread kernel with tabulated first products
+        const int A = sets.s[0].A;
+        int nq_cap = (32 * 1024) / (A * 2048);     // 30 KB of tables at A = 15: three blocks per SM
+        if (nq_cap < 1) nq_cap = 1;
+        if (nq_cap > (A + 3) / 4) nq_cap = (A + 3) / 4;
+        const size_t smc = sizeof(float) * ((size_t)A * nq_cap * 512 + ((A * A + 1) & ~1) + 2 * (size_t)BC_ROWS * A + 128 * A + 2 * A * 128) + 64;
+        auto kern = k_build_scores_cols;
+        PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+        dim3 g((L2 + 127) / 128, (L1 + BC_ROWS - 1) / BC_ROWS);
+        kern<<<g, 128, smc, st>>>(sets.s[0], L1, L2, m, m_pitch, nq_cap);
+        PG_CUDA_OK(cudaGetLastError());
+        return 0;
     }
     const char* ev = getenv("PGPU_K1_BIG");
     const bool big = ev ? atoi(ev) != 0 : (size_t)L1 * L2 >= (size_t)1 << 21;   // measured: 7.7 -> 5.7 ms at 20k x 20k

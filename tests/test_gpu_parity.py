@@ -427,6 +427,38 @@ def test_long_profile_alignment_vs_oracle(eng):
             assert np.array_equal(r["path"], wp), (mode, gaps)
 
 
+def test_large_score_matrix_kernel_edge_shapes(eng):
+    """k_build_scores_cols (column-per-thread K1 for matrices of 2M cells and more) is bit-identical to the
+    oracle's evaluation order (cext.c:63-95, :388-421) on ragged shapes, sparse DNA profiles (table path) and dense
+    amino-acid profiles whose columns need more quads than the table holds (direct path)."""
+    for seed, (L1, L2, depth, nsym, A, S) in enumerate([(1500, 1411, 8, 4, 15, matrices.nucleotide()),
+                                                       (129, 16400, 3, 4, 15, matrices.nucleotide()),
+                                                       (1900, 1153, 40, 20, 27, matrices.blosum62())]):
+        p1 = synth.profile_from_counts(synth.count_profile(50 + seed, L1, depth, nsym, A))
+        p2 = synth.profile_from_counts(synth.count_profile(60 + seed, L2, depth, nsym, A))
+        m = eng.build_scores([p1], [p2], [S])
+        assert np.array_equal(m.cpu().numpy(), oracle.build_scores([p1], [p2], [S])), (L1, L2, A)
+
+
+@pytest.mark.parametrize("mode", ["global", "semiglobal_both", "semiglobal_one", "semiglobal_two"])
+def test_row_blocked_wavefront_vs_oracle(eng, mode):
+    """k_wave4 (4 rows x 4 columns per lane and step) against the oracle: row counts around the block size,
+    several strips, a last strip with idle lanes, tie-heavy integer scores and f32 profile scores."""
+    rng = np.random.default_rng(3)
+    S = matrices.nucleotide()
+    for L1, L2 in [(1, 1), (2, 5), (3, 129), (4, 128), (5, 127), (7, 300), (257, 515), (1001, 777)]:
+        a_, b_ = rng.integers(0, 4, L1), rng.integers(0, 4, L2)
+        m = np.ascontiguousarray(S[a_][:, b_])
+        if L1 > 200:
+            m = m + rng.integers(-2, 3, m.shape).astype(np.float32) * 0.25       # non-integer, still tie-prone
+        for gaps in ([-11.0, -1.0], [-2.0], [-0.5, -0.5]):
+            g1, g2 = oracle.gap_arrays(L1, L2, gaps)
+            r = eng.align_general(mode, m, g1, g2)
+            ws, wp = oracle.align_raw(mode, m, g1, g2)
+            assert r["score"] == ws, (mode, L1, L2, gaps)
+            assert np.array_equal(r["path"], wp), (mode, L1, L2, gaps)
+
+
 def test_config5_full_size_properties(eng):
     """20,000 x 20,000 (BASELINE config 5): too large for the oracle in a test, so size-independent
     properties: the traced path is monotone, spans the matrix and re-scores to the reported score;
