@@ -540,36 +540,52 @@ def main():
         # the kernel's cell rate.  ncu's sm__inst_executed_pipe_alu of the same kernel adds the few non-DPX ALU
         # instructions (profiles/r02_kstream16r_*).
         alu_peak = mb["viaddmnmx_s16x2"] * 32.0 * sms * 1e9
-        alu_ach = rate * 1.5
         mix_peak = mb["cell_mix16"] * 32.0 * sms * 1e9      # bare 5-instruction recurrence of two cells
         issue_peak = mb["fadd"] * 32.0 * sms * 1e9          # full-rate issue (FADD)
+        # ALU-pipe lane-instructions per cell of the shipped kernel, from the committed ncu capture of the same build
+        # (tools/roofline_counters.py -> profiles/r02_roofline_counters.json): 1.5 DPX + the kernel's other ALU-pipe
+        # instructions.  frac = that x the cell rate timed HERE / the ALU-pipe rate measured HERE: it reproduces ncu's
+        # sm__inst_executed_pipe_alu percentage of the capture when the cell rates agree.
+        cnt = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_roofline_counters.json")) as f:
+                cnt = json.load(f).get("k_stream16r_13", {})
+        except Exception:
+            pass
+        alu_per_cell = float(cnt.get("alu_lane_instr_per_cell", 1.5))
+        alu_ach = rate * alu_per_cell
         roof = {"bound": "cuda_core_alu_pipe", "achieved": alu_ach / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s",
                 "frac": alu_ach / alu_peak,
-                "frac_note": "of measured: DPX lane-instructions per second of this kernel (1.5 per cell: 2 VIADDMNMX.S16x2 + "
-                             "1 VIMNMX3.S16x2 per two cells) / the VIADDMNMX.S16x2 rate of this box (pgpu_microbench, %.2f "
-                             "warp-instr/ns/SM) -- the share of the binding ALU pipe the recurrence itself uses; ncu's "
-                             "pipe_alu utilisation of the same launch is this plus the kernel's other ALU instructions"
-                             % mb["viaddmnmx_s16x2"],
+                "frac_note": "of measured: utilisation of the binding unit, the half-rate ALU pipe that executes the DPX "
+                             "instructions = ALU-pipe lane-instructions per cell of this kernel (%.3f: 1.5 DPX -- 2 VIADDMNMX.S16x2 "
+                             "+ 1 VIMNMX3.S16x2 per two cells -- plus its other ALU-pipe instructions, from the committed ncu "
+                             "capture) x the cell rate timed in this run / the VIADDMNMX.S16x2 rate of this box (pgpu_microbench, "
+                             "%.2f warp-instr/ns/SM); ncu's sm__inst_executed_pipe_alu of the capture: %.1f %%"
+                             % (alu_per_cell, mb["viaddmnmx_s16x2"], float(cnt.get("alu_pipe_pct", float("nan")))),
+                "frac_recurrence_only": rate * 1.5 / alu_peak,
                 "frac_of_bare_recurrence_mix": rate * 2.5 / mix_peak,
-                "frac_of_issue": rate * 2.5 / issue_peak,
-                "frac_notes": "bare mix: 2.5 lane-instructions per cell against the bare 5-instruction packed recurrence "
-                              "(no loads, shuffles or loop) measured on this box; issue: the same against the full FADD issue rate",
+                "frac_of_issue": rate * float(cnt.get("lane_instr_per_cell", 2.5)) / issue_peak,
+                "frac_of_issue_recurrence_only": rate * 2.5 / issue_peak,
+                "frac_notes": "recurrence_only: the 1.5 DPX lane-instructions per cell alone on the ALU pipe; bare mix: 2.5 "
+                              "lane-instructions per cell against the bare 5-instruction packed recurrence (no loads, shuffles or "
+                              "loop) measured on this box; issue: all issued lane-instructions per cell (ncu capture) against the "
+                              "full FADD issue rate = ncu's issue-slot utilisation; issue_recurrence_only: the 2.5 recurrence "
+                              "instructions alone",
+                "ncu_capture": {k: cnt.get(k) for k in ("capture", "workload", "ncu_duration_ms", "plain_run_kernel_ms",
+                                                        "gcups_under_ncu", "alu_pipe_pct", "fma_pipe_pct", "fmaheavy_cycles_pct",
+                                                        "issue_active_pct", "lane_instr_per_cell", "alu_lane_instr_per_cell",
+                                                        "recurrence_share_of_issued", "dpx_share_of_alu_pipe")},
                 # SURVEY 8d's W = 11 f32 add/max per cell against the measured f32 add issue rate: a note only -- above 1
                 # for the packed kernel because one DPX instruction does two cells and fuses add+max
                 "survey_w11_note": {"w_ops_per_cell": W_FLOPS_PER_CELL, "achieved": rate * W_FLOPS_PER_CELL / 1e12,
                                     "peak": issue_peak / 1e12, "frac": rate * W_FLOPS_PER_CELL / issue_peak},
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                # (profiles/r02_kstream16r_k13_*): algorithmic bytes per launch = sequences + tiles in, 4 B per pair out
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the ncu --set full capture, scaled by
+                # cells to this launch; algorithmic bytes per launch = sequences + tiles in, 4 B per pair out
+                "traffic": (float(cnt["dram_bytes"]) * my_cells / float(cnt["cells"])) if cnt.get("dram_bytes") else None,
                 "algorithmic_bytes": int(batch.h2d_bytes + sum(t.nbytes for t in plan[0].values()) + 4 * (plan[1][1] - plan[1][0])),
                 "kernel": "k_stream16r<13> (packed s16x2 DPX, paired residents)", "kernel_ms": kms,
                 "gcups_kernel": rate / 1e9, "pipe_rates": mb,
                 "note": "HBM is not the bound (4 B per pair out, 8e4 cells per pair); tensor cores have nothing to contract"}
-        try:
-            with open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")) as f:
-                roof["traffic"] = json.load(f).get("k_stream16r_13_dram_bytes")
-        except Exception:
-            pass
 
     if rank == 0 and not args.no_extras and world == 1:
         # BASELINE configs[1]: 1,000 x 300 aa on one B200, packed int16 and f32 kernels
@@ -649,6 +665,15 @@ def main():
                              "exact_profile_scores": _tool("run_c4.py", [2000, 400, 40], timeout=900)[-1],
                              "tolerance_profile_scores": _tool("run_c4.py", [2000, 400, 0], timeout=900,
                                                                env={"PGPU_FAST_PROFILES": "1"})[-1]}
+            c4 = configs["c4"]
+            # does the tolerance mode (profile scores within 1e-5, north_star) change the guide tree or any column?
+            c4["tolerance_mode_alignment_identical_to_exact"] = bool(
+                c4["exact_profile_scores"].get("fasta_md5") is not None and
+                c4["exact_profile_scores"].get("fasta_md5") == c4["tolerance_profile_scores"].get("fasta_md5"))
+            c4["bound_note"] = ("exact mode is bound by the reference's evaluation order of the profile score rows in the "
+                                "guide-tree stage: 2.0e6 dense profile pairs x 1.6e5 cells x ~400 individually rounded "
+                                "mul+add terms (cext.c:63-95) = 2.6e14 flops >= 7 s at the FP32 pipe peak of one B200; the merges "
+                                "themselves are a small part (DESIGN.md)")
             # BASELINE configs[0] / second half of the metric: MSA wall time next to the host-CPU reference
             configs["msa_e2e"] = {"tree_50": msa_e2e(50, 300, "global", "tree"),
                                   "cli_default_50": msa_e2e(50, 300, "dummy", "ad_hoc"),

@@ -951,7 +951,7 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
 // Traceback over the lean kernel's flag words: one warp stages WT_WIN steps x 32 lanes of the
 // current strip (16 KB, every row a coalesced 128-byte line, all requests in flight at once) and
 // lane 0 walks inside that window -- one memory round trip per ~100 path cells.
-#define WT_WIN 128
+#define WT_WIN 256      // word rows staged per window (32 KB): a diagonal path crosses 1 + flag_skew / 4 word rows per step
 __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
 {
     __shared__ uint32_t tile[WT_WIN][32];
@@ -986,7 +986,32 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
         }
         __syncwarp();
         if (lane == 0) {
+            // interior cells first, as a select chain without data-dependent branches (the walk is one dependent
+            // chain: every resolved branch costs more than the arithmetic it skips); borders, masked cells and
+            // the local stop code leave this loop and take the general step below
+            const int xlo = strip * 128;
             for (;;) {
+                bool handled = false;
+                while (y >= 1 && x > xlo) {
+                    const int ln = ((x - 1) & 127) >> 2, kk = (x - 1) & 3;
+                    const int tn = y - 1 + SK * ln;
+                    if (tn < tlo) break;
+                    const uint32_t word = tile[tn - tlo][ln];
+                    const uint32_t c = (word >> (5 * kk)) & 31u;
+                    if (((word >> (24 + kk)) & 1u) | ((k == 0) & ((c & 19u) == 19u))) break;   // masked / local stop: general step
+                    push(y, x);
+                    const int nk0 = !(c & 1u) ? 0 : (!(c & 2u) ? 1 : 2);
+                    const int nk1 = (c & 4u) ? 1 : 0, nk2 = (c & 8u) ? 2 : 0;
+                    y -= (k != 2);
+                    x -= (k != 1);
+                    k = (k == 0) ? nk0 : ((k == 1) ? nk1 : nk2);
+                    handled = true;
+                }
+                if (handled && y >= 1 && x >= 1) {
+                    // left the window or the strip: stage again (unless the stop conditions above broke the loop)
+                    const int tn = y - 1 + SK * (((x - 1) & 127) >> 2);
+                    if (((x - 1) >> 7) != strip || tn < tlo) break;
+                }
                 push(y, x);
                 int ny = y, nx = x, nk = k;
                 bool stop = false;

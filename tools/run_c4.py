@@ -38,7 +38,9 @@ t0 = time.perf_counter()
 got = R.workflow_fasta(mgr, mk(n), sm, "global", "tree", extra=extra)
 res["gpu_s"] = time.perf_counter() - t0
 res["gpu_launches"] = eng.launches - l0
+import hashlib
 res["alignment_columns"] = len(got.split("\n")[1]) if got else 0
+res["fasta_md5"] = hashlib.md5(got.encode()).hexdigest() if got else None
 if sub > 1:
     mgr2 = plugin.GpuBatchManager(R.reference_index())
     t0 = time.perf_counter()
