@@ -299,6 +299,20 @@ int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const floa
                           int L2, float* m_dev, int m_pitch, void* stream);
 
 /*
+ * Progressive-merge glue on device-resident count tables (the loop of
+ * TreeMultipleSequenceAligner, component/msa.py:124-237).
+ * pgpu_counts_to_profile: ProfileTrack.profile (container/sequence.py:191-203) -- f32 totals, float64 division,
+ * f32 result -- for n_rows positions of [n_rows][A] int32 counts.
+ * pgpu_merge_counts: ProfileTrack.merge (container/sequence.py:205-239) along the path that pgpu_align_general
+ * left on the device: align_out_dev is that call's contiguous int32 output block laid out as
+ * [score, cell y, x, state, path_start, path_len, 0, 0, path rows (y, x) ...]; merged_dev receives path_len - 1 rows
+ * (at most max_rows) of A counts.
+ */
+int pgpu_counts_to_profile(const int32_t* counts_dev, int64_t n_rows, int A, float* prof_dev, void* stream);
+int pgpu_merge_counts(const int32_t* counts_one_dev, const int32_t* counts_two_dev, int A, const int32_t* align_out_dev,
+                      int32_t* merged_dev, int max_rows, void* stream);
+
+/*
  * General single alignment (K3 wavefront + traceback).  Replaces RawPairwiseAligner.execute
  * (component/align.py:302-447): arbitrary match scores m [L1][m_pitch], per-position gap
  * arrays g1 [L1][2], g2 [L2][2] (var_gaps = 0 promises that every row of g1 equals g1[0] and

@@ -395,6 +395,21 @@ int pgpu_fill_debug(int mode, const float* m, const float* g1, const float* g2, 
     return rc;
 }
 
+// Progressive-merge glue on device-resident count tables (merge.cu).
+int pgpu_counts_to_profile(const int32_t* counts_dev, int64_t n_rows, int A, float* prof_dev, void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    return pg_launch_counts_to_profile(counts_dev, n_rows, A, prof_dev, (cudaStream_t)stream);
+}
+
+int pgpu_merge_counts(const int32_t* counts_one_dev, const int32_t* counts_two_dev, int A, const int32_t* align_out_dev,
+                      int32_t* merged_dev, int max_rows, void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    if (!counts_one_dev || !counts_two_dev || !align_out_dev || !merged_dev) { pg_set_error("merge_counts: null buffer"); return 1; }
+    return pg_launch_merge_counts(counts_one_dev, counts_two_dev, A, align_out_dev, merged_dev, max_rows, (cudaStream_t)stream);
+}
+
 // Guide-tree clustering (cluster.cu): the merge order of praline/util/cluster.py:27-57.
 int64_t pgpu_cluster_workspace_bytes(int n) { return n < 1 ? 0 : (int64_t)pg_cluster_workspace_bytes(n); }
 

@@ -173,6 +173,9 @@ int pg_launch_stream16rt(const StreamArgs& a, int n_tiles, int K, cudaStream_t s
 int pg_launch_semi_scores(int64_t n, const unsigned long long* rowkey, const unsigned long long* colkey,
                           int mode, int transposed, float* scores, cudaStream_t st);
 int pg_launch_traceback(const TraceArgs& a, cudaStream_t st);
+int pg_launch_counts_to_profile(const int32_t* counts, int64_t n_rows, int A, float* prof, cudaStream_t st);
+int pg_launch_merge_counts(const int32_t* c1, const int32_t* c2, int A, const int32_t* hdr, int32_t* out, int max_rows,
+                           cudaStream_t st);
 
 #define PG_CUDA_OK(expr)                                                                  \
     do {                                                                                  \

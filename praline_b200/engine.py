@@ -546,6 +546,9 @@ class Engine(object):
             raise ValueError("sequence symbol outside the score matrix")
         if n == 0:
             return np.zeros(0, np.float32), ([] if want_paths else None)
+        if md == 1 and not (go <= ge <= 0):
+            raise _lib.PralineGpuError("batched local scores need open <= extend <= 0 (the border cell open - extend takes "
+                                       "part in the reference's argmax): use align_general")
         if want_paths:
             if md == 1:
                 raise _lib.PralineGpuError("batched local traceback is served by the general kernel")
@@ -918,7 +921,9 @@ class Engine(object):
         residents within the K classes, streamed sequences below 2^20 rows (end-cell key)."""
         go, ge = _gaps(gap_series)
         lens = np.asarray(lens, np.int64)
-        return bool(go <= 0 and ge <= 0 and len(lens) and lens.min() >= 1 and lens.max() < (1 << 20)
+        # go <= ge: the border cell o[0,0,1] = open - extend takes part in the reference's argmax (align.py:371, :401-403)
+        # and must not be positive, since the batched reduction looks at interior cells only
+        return bool(go <= ge <= 0 and len(lens) and lens.min() >= 1 and lens.max() < (1 << 20)
                     and self.k_for(int(lens.max())) is not None
                     and self.integer_exact(S, go, ge, int(lens.max())))
 
@@ -1372,6 +1377,102 @@ class Engine(object):
             res["path"] = h[8:].reshape(-1, 2)[st:st + ln].copy()
         if want_matrices:
             res["o"], res["t"] = o.cpu().numpy(), t.cpu().numpy()
+        return res
+
+    # -- progressive merge: count tables stay on the device, one guide-tree level per call -----------
+    def merge_level(self, jobs, S, gap_series, mode, n_streams=8):
+        """The independent merges of ONE guide-tree level (TreeMultipleSequenceAligner, component/msa.py:124-237):
+        jobs = [(counts_one, rows_one, counts_two, rows_two)] with int32 [rows x A] count tables on the device.
+        Per job, on one of n_streams streams: probability profiles from the counts (pgpu_counts_to_profile =
+        ProfileTrack.profile), K1 score matrix in the reference's evaluation order, K3 wavefront fill + walk, and the
+        merged count table gathered along the path on the device (pgpu_merge_counts = ProfileTrack.merge).  One
+        synchronisation and ONE device -> host read per level bring back the paths (Alignment.merge is host
+        bookkeeping the output needs anyway).  Returns [(merged counts tensor, rows, path int32 [rows + 1, 2], score)]."""
+        md = MODES[mode]
+        go, ge = _gaps(gap_series)
+        S = np.ascontiguousarray(S, np.float32)
+        A = S.shape[0]
+        if not jobs:
+            return []
+        lib = self.lib
+        cur = torch.cuda.current_stream(self.device)
+        state = self._dual_state(n_streams)
+        streams = state["streams"][:n_streams]
+        for st in streams:
+            st.wait_stream(cur)
+        S_dev = self.dev(S)
+        maxlen = max(max(j[1], j[3]) for j in jobs)
+        gkey = ("gapconst", float(go), float(ge))
+        cache = self.__dict__.setdefault("_gap_cache", {})
+        if gkey not in cache or cache[gkey].shape[0] < maxlen:
+            g = np.empty((max(maxlen, 1024) * 2, 2), np.float32)
+            g[:] = (go, ge)
+            cache[gkey] = self.dev(g)
+        g_dev = cache[gkey]
+        for st in streams:
+            st.wait_stream(cur)
+        # one int32 block per job: [score | cell y x k | path start | path len | pad 2] + path rows; all in one tensor.
+        # Every buffer of the level is ONE allocation carved by offsets (six torch.empty per merge, most of them a
+        # cudaMalloc on a fresh stream pool, cost more than the kernels of a 400 x 400 merge).
+        nj = len(jobs)
+        offs = np.zeros(nj + 1, np.int64)
+        p_off = np.zeros(nj + 1, np.int64)      # profile rows (both operands)
+        m_off = np.zeros(nj + 1, np.int64)      # match-score floats
+        w_off = np.zeros(nj + 1, np.int64)      # workspace bytes
+        o_off = np.zeros(nj + 1, np.int64)      # merged count rows
+        pitch = [0] * nj
+        for k, (c1, r1, c2, r2) in enumerate(jobs):
+            offs[k + 1] = offs[k] + 8 + 2 * (r1 + r2 + 2)
+            p_off[k + 1] = p_off[k] + r1 + r2
+            pitch[k] = (r2 + 127) // 128 * 128
+            m_off[k + 1] = m_off[k] + r1 * pitch[k]
+            w_off[k + 1] = w_off[k] + (int(lib.pgpu_general_workspace_bytes(r1, r2)) + 255) // 256 * 256
+            o_off[k + 1] = o_off[k] + r1 + r2 + 1
+        outs = torch.zeros(int(offs[-1]), dtype=torch.int32, device=self.device)
+        prof = torch.empty((int(p_off[-1]), A), dtype=torch.float32, device=self.device)
+        mbuf = torch.empty(int(m_off[-1]), dtype=torch.float32, device=self.device)
+        wbuf = torch.empty(int(w_off[-1]), dtype=torch.uint8, device=self.device)
+        obuf = torch.empty((int(o_off[-1]), A), dtype=torch.int32, device=self.device)
+        for st in streams:
+            st.wait_stream(cur)
+        merged = []
+        arr1 = ctypes.c_void_p * 1
+        cA = (ctypes.c_int * 1)(A)
+        for k, (c1, r1, c2, r2) in enumerate(jobs):
+            st = streams[k % n_streams]
+            sptr = ctypes.c_void_p(st.cuda_stream)
+            p1 = prof.data_ptr() + 4 * A * int(p_off[k])
+            p2 = p1 + 4 * A * r1
+            mp = mbuf.data_ptr() + 4 * int(m_off[k])
+            _lib.check(lib.pgpu_counts_to_profile(self.ptr(c1), r1, A, ctypes.c_void_p(p1), sptr))
+            _lib.check(lib.pgpu_counts_to_profile(self.ptr(c2), r2, A, ctypes.c_void_p(p2), sptr))
+            _lib.check(lib.pgpu_build_scores(1, arr1(p1), arr1(p2), arr1(S_dev.data_ptr()), cA, r1, r2, ctypes.c_void_p(mp),
+                                             pitch[k], sptr))
+            base = outs.data_ptr() + 4 * int(offs[k])
+            _lib.check(lib.pgpu_align_general(md, r1, r2, ctypes.c_void_p(mp), pitch[k], self.ptr(g_dev), self.ptr(g_dev),
+                                              0, None, r2 + 1, ctypes.c_void_p(wbuf.data_ptr() + int(w_off[k])),
+                                              ctypes.c_void_p(base), ctypes.c_void_p(base + 4),
+                                              ctypes.c_void_p(base + 32), ctypes.c_void_p(base + 16),
+                                              ctypes.c_void_p(base + 20), None, None, sptr))
+            out = obuf[int(o_off[k]):int(o_off[k + 1])]
+            _lib.check(lib.pgpu_merge_counts(self.ptr(c1), self.ptr(c2), A, ctypes.c_void_p(base), self.ptr(out),
+                                             r1 + r2 + 1, sptr))
+            merged.append(out)
+            self.launches += 7
+        keep = (prof, mbuf, wbuf)
+        for st in streams:
+            cur.wait_stream(st)
+        h = outs.cpu().numpy()          # the single device -> host read of the level
+        del keep
+        res = []
+        for k, (c1, r1, c2, r2) in enumerate(jobs):
+            b = h[offs[k]:offs[k + 1]]
+            score = float(b[:1].view(np.float32)[0])
+            if score != score:
+                raise _lib.PralineGpuError("wavefront kernel: a strip-to-strip hand-off timed out; no result was produced")
+            st_, ln = int(b[4]), int(b[5])
+            path = b[8:].reshape(-1, 2)[st_:st_ + ln].copy()
+            res.append((merged[k][:ln - 1], ln - 1, path, score))
         return res
 
     def build_scores_seq(self, batch, i, j, S_dev, A):

@@ -325,6 +325,11 @@ def _batchable(sets, gaps, zero_idxs, mode, engine):
     longest = max(len(a), len(b))
     if engine.k_for(longest) is None or not engine.integer_exact(S, gaps[0], gaps[1], longest):
         return None
+    if mode == "local" and not (gaps[0] <= gaps[1] <= 0):
+        # the reference takes argmax over the WHOLE o array, border cell o[0,0,1] = open - extend included
+        # (component/align.py:371, :401-403); the batched local reduction covers interior cells only, which is the
+        # same thing only while that border value is <= 0: anything else runs the general kernel
+        return None
     return a, b, S
 
 
@@ -346,6 +351,20 @@ class GpuPairwiseAligner(Component):
                 score_matrices):
         gap_series = self.environment['gap_series']
         debug = self.environment['debug']
+        log = None
+        if debug > 0:       # the component's own log bundle, component/align.py:93-112
+            log = LogBundle()
+            log.message(ROOT_LOG_NAME, "Entering component '{0}'".format(self.tid))
+            log.message(ROOT_LOG_NAME, "Alignment mode: '{0}'".format(mode))
+            log.message(ROOT_LOG_NAME, "Gap scores: {0}".format(gap_series))
+            msg = "Sequence one: '{0}', sequence two: '{1}'"
+            log.message(ROOT_LOG_NAME, msg.format(sequence_one.name, sequence_two.name))
+            log.message(ROOT_LOG_NAME, "Track id sets for sequence one:")
+            for track_id_set in track_id_sets_one:
+                log.message(ROOT_LOG_NAME, "\t{0}".format(", ".join(track_id_set)))
+            log.message(ROOT_LOG_NAME, "Track id sets for sequence two:")
+            for track_id_set in track_id_sets_two:
+                log.message(ROOT_LOG_NAME, "\t{0}".format(", ".join(track_id_set)))
         sets, gaps = _prepare(sequence_one, sequence_two, track_id_sets_one, track_id_sets_two, score_matrices,
                               gap_series)
         _check_mode(mode)
@@ -357,6 +376,10 @@ class GpuPairwiseAligner(Component):
             scores, paths = eng.align_pairs(batch, [0], [1], S, gaps, mode=mode, want_paths=True, resident="two")
             score, path = float(scores[0]), paths[0]
             alignment = Alignment([sequence_one, sequence_two], _path_container(mode, path))
+            # the message sequence of the reference: the nested RawPairwiseAligner task begins and completes under
+            # this component's tag (component/align.py:225-237; bulk data stripped as Execution.run does)
+            for msg in _nested_raw_messages(self.tag):
+                yield msg
             yield CompleteMessage(outputs={'alignment': alignment, 'score': score})
             return
         # general path: score models on the device, then the raw aligner (component/align.py:200-237)
@@ -376,7 +399,26 @@ class GpuPairwiseAligner(Component):
                     gap_score_model_two=GapScoreModel(sequence_two, g2), zero_idxs=zero_idxs)
         for msg in execution.run():
             yield msg
-        yield CompleteMessage(outputs=execution.outputs[0])
+        outputs = execution.outputs[0]
+        if log is not None:     # component/align.py:239-249
+            log.message(ROOT_LOG_NAME, "Alignment score: {0}".format(outputs["score"]))
+            log.message(ROOT_LOG_NAME, "Done!")
+            archive_path = log.archive()
+            log.delete()
+            yield LogMessage(path_to_url(archive_path))
+        yield CompleteMessage(outputs=outputs)
+
+
+def _nested_raw_messages(parent_tag):
+    """Begin + Complete of a RawPairwiseAligner task as a parent component sees them (core/manager.py:212-214,
+    core/execution.py:176-186: tag = class name # uuid, outputs stripped on the way up)."""
+    from uuid import uuid4
+    tag = "{0}#{1}".format(RAW_TID.split(".")[-1], uuid4().hex)
+    begin = BeginMessage(parent_tag)
+    begin.tag = tag
+    done = CompleteMessage(outputs=None)
+    done.tag = tag
+    return [begin, done]
 
 
 class DeviceMatchScoreModel(MatchScoreModel):
@@ -581,6 +623,9 @@ class GpuTreeMultipleSequenceAligner(Component):
                 'aligner_env': Environment({}), 'merge_mode': 'semiglobal',
                 'debug': 0, 'log_track_ids': [TRACK_ID_INPUT]}
 
+    def _device_merge_plan(self, sequences, track_id_sets, score_matrices, merge_mode, track_ids):
+        return _tree_device_merge_ok(self, sequences, track_id_sets, score_matrices, merge_mode, track_ids)
+
     def execute(self, sequences, guide_tree, track_id_sets, score_matrices):
         merge_mode = self.environment['merge_mode']
         if self.environment['debug'] > 0:
@@ -602,6 +647,39 @@ class GpuTreeMultipleSequenceAligner(Component):
         members = {i: [seq] for i, seq in enumerate(sequences)}
         index = self.manager.index
         total = len(guide_tree.merge_orders)
+        device = self._device_merge_plan(sequences, track_id_sets, score_matrices, merge_mode, track_ids)
+        if device is not None and total > 0:
+            # Count tables stay on the device between merges and the independent merges of one guide-tree level run
+            # together (Engine.merge_level): level(merge) = 1 + the deeper of its two clusters.  The alignment-path
+            # bookkeeping (Alignment.merge) stays on the host -- it is the output.
+            S, gaps, mode = device
+            eng = get_engine()
+            track_id = track_ids[0]
+            A = S.shape[0]
+            tables = {}
+            for i in clusters:
+                c = np.ascontiguousarray(clusters[i].get_track(track_id).counts, dtype=np.int32)
+                tables[i] = (eng.dev(c), c.shape[0])
+            depth = {i: 0 for i in clusters}
+            levels = {}
+            for (i, j) in guide_tree.merge_orders:
+                d = max(depth[i], depth[j]) + 1
+                depth[i] = d
+                levels.setdefault(d, []).append((i, j))
+            done = 0
+            for d in sorted(levels):
+                jobs = [(tables[i][0], tables[i][1], tables[j][0], tables[j][1]) for (i, j) in levels[d]]
+                for (i, j), (merged, rows, path, _score) in zip(levels[d], eng.merge_level(jobs, S, gaps, mode)):
+                    tables[i] = (merged, rows)
+                    del tables[j]
+                    paths[i] = merge_alignment_paths(paths[i], paths[j], path)
+                    members[i] = members[i] + members[j]
+                    del paths[j], members[j]
+                    done += 1
+                    yield ProgressMessage(progress=done / total)
+            first = next(iter(paths))
+            yield CompleteMessage(outputs={'alignment': Alignment(members[first], paths[first])})
+            return
         for step, (i, j) in enumerate(guide_tree.merge_orders):
             one, two = clusters[i], clusters[j]
             if merge_mode == "semiglobal":
@@ -633,6 +711,35 @@ class GpuTreeMultipleSequenceAligner(Component):
             yield ProgressMessage(progress=(step + 1) / total)
         first = next(iter(paths))
         yield CompleteMessage(outputs={'alignment': Alignment(members[first], paths[first])})
+
+
+def _tree_device_merge_ok(component, sequences, track_id_sets, score_matrices, merge_mode, track_ids):
+    """The device-resident merge path of GpuTreeMultipleSequenceAligner serves one track set with one track, the
+    GPU PairwiseAligner with constant gap penalties and merge_mode global / semiglobal; -> (S, gaps, mode) or None."""
+    import os as _os
+    env = component.environment
+    if _os.environ.get("PGPU_NO_DEVICE_MERGE", "") != "" or merge_mode not in ("global", "semiglobal"):
+        return None
+    if len(track_id_sets) != 1 or len(track_id_sets[0]) != 1 or len(track_ids) != 1 or len(sequences) < 2:
+        return None
+    if env['aligner'] != PAIRWISE_TID or component.manager.index.resolve(PAIRWISE_TID) is not GpuPairwiseAligner:
+        return None
+    sub_env = Environment(keys=env['aligner_env'].keys, component=GpuPairwiseAligner, parent=env)
+    if sub_env['debug'] != 0:
+        return None
+    try:    # the per-pair checks of PairwiseAligner.execute are per-sequence properties
+        gaps = S = None
+        for seq in sequences:
+            sets, gaps = _prepare(seq, seq, track_id_sets, track_id_sets, score_matrices, sub_env['gap_series'])
+            if len(sets) != 1:
+                return None
+            S = sets[0][2].matrix.astype(np.float32)
+    except (ComponentError, DataError):
+        return None
+    track_id = track_id_sets[0][0]
+    if min(len(seq.get_track(track_id)) for seq in sequences) < 1:
+        return None
+    return S, list(gaps), ("semiglobal_both" if merge_mode == "semiglobal" else "global")
 
 
 def _cluster_tracks(sequences, track_ids):
@@ -1036,6 +1143,8 @@ class GpuBatchManager(Manager):
             begin = BeginMessage(parent_tag)
             begin.tag = tag
             yield begin
+            for msg in _nested_raw_messages(tag):       # the reference's nested RawPairwiseAligner task
+                yield msg
             alignment = LazyAlignment([inputs['sequence_one'], inputs['sequence_two']], g.path, k)
             done = CompleteMessage(outputs={'alignment': alignment, 'score': float(g.scores[k])})
             done.tag = tag

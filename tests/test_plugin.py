@@ -402,6 +402,133 @@ def test_tree_msa_component_matches_reference(merge_mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("merge_mode", ["global", "semiglobal"])
+def test_tree_msa_device_resident_levels_equal_per_merge_path(merge_mode, monkeypatch):
+    """The device-resident, level-batched merge path (Engine.merge_level: count tables never leave the device,
+    one launch group per guide-tree level) gives the alignment of the per-merge path (every merge through the
+    manager as a PairwiseAligner task) on preprofile tracks of 36 sequences and a guide tree with levels of
+    several independent merges; a 12-sequence subset is also checked against the reference's own component."""
+    from praline.container import SequenceTree, ProfileTrack, ALPHABET_AA
+    sm = _blosum()
+    rng = np.random.default_rng(5)
+    fam = synth.family(71, 36, 70)
+
+    def mk(k):
+        seqs = []
+        for i, s in enumerate(fam[:k]):
+            q = _seq("s%d" % i, s)
+            counts = np.zeros((len(s), 27), np.int64)          # a preprofile-like count track: own residue + noise
+            counts[np.arange(len(s)), s] = 6
+            counts[np.arange(len(s)), rng.integers(0, 20, len(s))] += rng.integers(0, 4, len(s))
+            q.add_track("prof", ProfileTrack(counts, ALPHABET_AA))
+            seqs.append(q)
+        return seqs
+
+    def orders(k):          # pairs first (one wide level), then a chain over the survivors
+        o = [(i, i + 1) for i in range(0, k - 1, 2)]
+        alive = list(range(0, k, 2))
+        while len(alive) > 1:
+            nxt = []
+            for a in range(0, len(alive) - 1, 2):
+                o.append((alive[a], alive[a + 1]))
+                nxt.append(alive[a])
+            if len(alive) % 2:
+                nxt.append(alive[-1])
+            alive = nxt
+        return o
+
+    def run(mgr, k, track):
+        seqs = mk(k)
+        env = {'gap_series': [-11.0, -1.0], 'merge_mode': merge_mode, 'aligner': pc.PairwiseAligner.tid}
+        out, _ = R.run_task(mgr, pc.TreeMultipleSequenceAligner, env, sequences=seqs,
+                            guide_tree=SequenceTree(seqs, orders(k)), track_id_sets=[[track]], score_matrices=[sm])
+        return [s.name for s in out['alignment'].items], np.asarray(out['alignment'].path)
+
+    for track in ("prof", TRACK_ID_INPUT):
+        rng = np.random.default_rng(5)
+        fast = run(plugin.GpuBatchManager(R.reference_index()), 36, track)
+        monkeypatch.setenv("PGPU_NO_DEVICE_MERGE", "1")
+        rng = np.random.default_rng(5)
+        slow = run(plugin.GpuBatchManager(R.reference_index()), 36, track)
+        monkeypatch.delenv("PGPU_NO_DEVICE_MERGE")
+        assert fast[0] == slow[0] and np.array_equal(fast[1], slow[1]), track
+    rng = np.random.default_rng(5)
+    got = run(plugin.GpuBatchManager(R.reference_index()), 12, "prof")
+    rng = np.random.default_rng(5)
+    want = run(Manager(R.reference_index()), 12, "prof")
+    assert got[0] == want[0] and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.gpu
+def test_pairwise_aligner_message_sequence_matches_reference():
+    """SURVEY 4 message sequence: a PairwiseAligner task yields Begin(self), Begin(RawPairwiseAligner),
+    [Log(Raw)], Complete(Raw), [Log(self)], Complete(self) -- the same kinds, tag classes and parent links from the
+    GPU components on the single-request fast path, the general path with debug = 1 (both log bundles) and the
+    batched execute_many path."""
+    from praline.core import Execution, Environment
+    sm = _blosum()
+    fam = synth.family(13, 4, 40)
+
+    def shape(msgs):
+        out = []
+        tags = {}
+        for m in msgs:
+            cls = m.tag.split("#")[0]
+            tags.setdefault(m.tag, len(tags))
+            parent = getattr(m, "parent_tag", None)
+            out.append((m.kind, cls, tags[m.tag], tags.get(parent) if parent in tags else (parent.split("#")[0] if parent else None)))
+        return out
+
+    for debug in (0, 1):
+        got = []
+        for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+            seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+            env = {'gap_series': [-11.0, -1.0], 'debug': debug}
+            _, msgs = R.run_task(mgr, pc.PairwiseAligner, env, mode="global", sequence_one=seqs[0], sequence_two=seqs[1],
+                                 track_id_sets_one=[[TRACK_ID_INPUT]], track_id_sets_two=[[TRACK_ID_INPUT]],
+                                 score_matrices=[sm])
+            got.append(shape(msgs))
+        assert got[0] == got[1], debug
+    got = []
+    for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):     # three tasks: batched
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(fam)]
+        ex = Execution(mgr, R.ROOT_TAG)
+        for a, b in ((0, 1), (0, 2), (1, 3)):
+            t = ex.add_task(pc.PairwiseAligner)
+            t.environment(Environment(keys={'gap_series': [-11.0, -1.0], 'debug': 0}))
+            t.inputs(mode="global", sequence_one=seqs[a], sequence_two=seqs[b], track_id_sets_one=[[TRACK_ID_INPUT]],
+                     track_id_sets_two=[[TRACK_ID_INPUT]], score_matrices=[sm])
+        got.append(shape([m for m in ex.run()]))
+    assert got[0] == got[1]
+
+
+@pytest.mark.gpu
+def test_local_with_open_weaker_than_extend_matches_reference():
+    """gap_series [-1, -5]: the border cell o[0,0,1] = open - extend = 4 is positive and takes part in the reference's
+    argmax over the whole o array (component/align.py:371, :401-403).  Such requests must not ride the batched local
+    reduction (interior cells only); single requests and execute_many batches both have to give the reference's
+    score and path -- including pairs where nothing in the interior beats the border."""
+    from praline.core import Execution, Environment
+    sm = _blosum()
+    G, W = 7, 17            # glycine / tryptophan: S[G][W] = -2, no positive cell
+    rng = np.random.default_rng(4)
+    seqs_idx = [np.full(6, G), np.full(5, W), rng.integers(0, 20, 30), rng.integers(0, 20, 28)]
+    outs = []
+    for mgr in (Manager(R.reference_index()), plugin.GpuBatchManager(R.reference_index())):
+        seqs = [_seq("s%d" % i, s) for i, s in enumerate(seqs_idx)]
+        ex = Execution(mgr, R.ROOT_TAG)
+        for a, b in ((0, 1), (2, 3), (0, 2), (1, 3)):
+            t = ex.add_task(pc.PairwiseAligner)
+            t.environment(Environment(keys={'gap_series': [-1.0, -5.0], 'debug': 0}))
+            t.inputs(mode="local", sequence_one=seqs[a], sequence_two=seqs[b], track_id_sets_one=[[TRACK_ID_INPUT]],
+                     track_id_sets_two=[[TRACK_ID_INPUT]], score_matrices=[sm])
+        for _ in ex.run():
+            pass
+        outs.append([(o['score'], [tuple(p) for p in o['alignment'].path]) for o in ex.outputs])
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 2, 3])
 def test_gpu_guide_tree_tiny_inputs(n):
     """One, two and three sequences through the GPU GuideTreeBuilder and the tree MSA."""
