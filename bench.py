@@ -541,7 +541,8 @@ def main():
         # instructions (profiles/r02_kstream16r_*).
         alu_peak = mb["viaddmnmx_s16x2"] * 32.0 * sms * 1e9
         mix_peak = mb["cell_mix16"] * 32.0 * sms * 1e9      # bare 5-instruction recurrence of two cells
-        issue_peak = mb["fadd"] * 32.0 * sms * 1e9          # full-rate issue (FADD)
+        issue_peak = mb["fadd"] * 32.0 * sms * 1e9          # full-rate FP32 pipe (FADD), measured: ~3.6 warp-instr/clk/SM
+        slots_peak = 4.0 * mb["sm_mhz"] * 1e6 * 32.0 * sms  # issue slots: 4 warp-instructions per clock and SM at the measured clock
         # ALU-pipe lane-instructions per cell of the shipped kernel, from the committed ncu capture of the same build
         # (tools/roofline_counters.py -> profiles/r02_roofline_counters.json): 1.5 DPX + the kernel's other ALU-pipe
         # instructions.  frac = that x the cell rate timed HERE / the ALU-pipe rate measured HERE: it reproduces ncu's
@@ -564,13 +565,13 @@ def main():
                              % (alu_per_cell, mb["viaddmnmx_s16x2"], float(cnt.get("alu_pipe_pct", float("nan")))),
                 "frac_recurrence_only": rate * 1.5 / alu_peak,
                 "frac_of_bare_recurrence_mix": rate * 2.5 / mix_peak,
-                "frac_of_issue": rate * float(cnt.get("lane_instr_per_cell", 2.5)) / issue_peak,
-                "frac_of_issue_recurrence_only": rate * 2.5 / issue_peak,
+                "frac_of_issue": rate * float(cnt.get("lane_instr_per_cell", 2.5)) / slots_peak,
+                "frac_of_issue_recurrence_only": rate * 2.5 / slots_peak,
                 "frac_notes": "recurrence_only: the 1.5 DPX lane-instructions per cell alone on the ALU pipe; bare mix: 2.5 "
                               "lane-instructions per cell against the bare 5-instruction packed recurrence (no loads, shuffles or "
-                              "loop) measured on this box; issue: all issued lane-instructions per cell (ncu capture) against the "
-                              "full FADD issue rate = ncu's issue-slot utilisation; issue_recurrence_only: the 2.5 recurrence "
-                              "instructions alone",
+                              "loop) measured on this box; issue: all issued lane-instructions per cell (ncu capture) against 4 "
+                              "issue slots per clock and SM at the clock pgpu_microbench measured = ncu's issue-slot utilisation; "
+                              "issue_recurrence_only: the 2.5 recurrence instructions alone",
                 "ncu_capture": {k: cnt.get(k) for k in ("capture", "workload", "ncu_duration_ms", "plain_run_kernel_ms",
                                                         "gcups_under_ncu", "alu_pipe_pct", "fma_pipe_pct", "fmaheavy_cycles_pct",
                                                         "issue_active_pct", "lane_instr_per_cell", "alu_lane_instr_per_cell",

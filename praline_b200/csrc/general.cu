@@ -1389,7 +1389,47 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
             return v;
         };
         if (nq == 1) {
-            for (int r = 0; r < nrows; r++) {
+            // two rows per pass: the cell's dependent FADD chain (4 per entry) is what a thread waits on, and two
+            // independent chains per thread hide it at 12 warps per SM
+            int r = 0;
+            for (; r + 1 < nrows; r += 2) {
+                const int n1a = rcnt[r], n1b = rcnt[r + 1];
+                uint32_t ra = rows_s + (uint32_t)(r * A) * 8u, rb = ra + (uint32_t)A * 8u;
+                float acca = 0.f, accb = 0.f;
+                const int nmin = min(n1a, n1b);
+                int a = 0;
+                for (; a < nmin; a++, ra += 8u, rb += 8u) {
+                    float pa, pb; uint32_t oa, ob;
+                    lds2(ra, pa, oa);
+                    lds2(rb, pb, ob);
+                    const float4 ta = lds4(Ts + oa), tb = lds4(Ts + ob);
+                    acca = __fadd_rn(acca, __fmul_rn(ta.x, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.x, pb));
+                    acca = __fadd_rn(acca, __fmul_rn(ta.y, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.y, pb));
+                    acca = __fadd_rn(acca, __fmul_rn(ta.z, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.z, pb));
+                    acca = __fadd_rn(acca, __fmul_rn(ta.w, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.w, pb));
+                }
+                for (int a2 = a; a2 < n1a; a2++, ra += 8u) {
+                    float p1; uint32_t off;
+                    lds2(ra, p1, off);
+                    const float4 t4 = lds4(Ts + off);
+                    acca = __fadd_rn(acca, __fmul_rn(t4.x, p1));
+                    acca = __fadd_rn(acca, __fmul_rn(t4.y, p1));
+                    acca = __fadd_rn(acca, __fmul_rn(t4.z, p1));
+                    acca = __fadd_rn(acca, __fmul_rn(t4.w, p1));
+                }
+                for (int a2 = a; a2 < n1b; a2++, rb += 8u) {
+                    float p1; uint32_t off;
+                    lds2(rb, p1, off);
+                    const float4 t4 = lds4(Ts + off);
+                    accb = __fadd_rn(accb, __fmul_rn(t4.x, p1));
+                    accb = __fadd_rn(accb, __fmul_rn(t4.y, p1));
+                    accb = __fadd_rn(accb, __fmul_rn(t4.z, p1));
+                    accb = __fadd_rn(accb, __fmul_rn(t4.w, p1));
+                }
+                out[(size_t)r * m_pitch] = __fadd_rn(0.f, acca);
+                out[(size_t)(r + 1) * m_pitch] = __fadd_rn(0.f, accb);
+            }
+            for (; r < nrows; r++) {
                 const int n1 = rcnt[r];
                 uint32_t ra = rows_s + (uint32_t)(r * A) * 8u;
                 float acc = 0.f;

@@ -1090,6 +1090,9 @@ class Engine(object):
         fast=True factors the contraction through W = P . S^T (A fused multiply-adds per cell instead
         of nnz1 x nnz2 terms): scores within 1e-5 relative of the reference, not bit-identical."""
         md = MODES[mode]
+        if md == 1 and not (_gaps(gap_series)[0] <= _gaps(gap_series)[1] <= 0):
+            raise _lib.PralineGpuError("batched local scores need open <= extend <= 0 (the border cell open - extend takes "
+                                       "part in the reference's argmax): use align_general")
         go, ge = _gaps(gap_series)
         pi = np.asarray(pi, np.int64)
         pj = np.asarray(pj, np.int64)

@@ -1108,6 +1108,8 @@ class GpuBatchManager(Manager):
             # profile x profile, one track set: matrix-fed batch (scores), exact general path (paths)
             if len(sets) != 1:
                 return None
+            if mode == "local" and not (gaps[0] <= gaps[1] <= 0):
+                return None     # a positive border cell open - extend takes part in the reference's argmax: general kernel
             t1, t2, sm = sets[0]
             if eng.k_for(max(len(t1), len(t2))) is None:
                 return None
