@@ -29,7 +29,8 @@ struct PgTile {
     int64_t out_base;       // output slot of the first streamed sequence; slots are consecutive
     int64_t out_base2;      // paired-resident launches: first slot of the second resident
     int32_t b_skip;         // leading stream elements that have no pair with resident2
-    int32_t _pad;
+    int32_t slot_stride;    // output slot of stream element e: out_base + e * slot_stride (0 = 1); the traced paired kernel
+                            // interleaves the slots of its two residents (stride 2) so that their walkers sit side by side
 };
 
 struct PgBorder {

@@ -141,7 +141,7 @@ __device__ __forceinline__ void k16r_step(uint32_t w, const K16rConst& c, uint32
 #define K16R_SKEW 1
 #endif
 template <int K, int NW, bool TB>
-__global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_stream16r(const StreamArgs a)
+__device__ __forceinline__ void k16r_body(const StreamArgs& a)
 {
     constexpr int NCH = (K + 3) / 4;        // 16-byte chunks of 4 packed columns per lane
     constexpr int ROWB = NCH * 512;
@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_
     uint32_t* top2 = reinterpret_cast<uint32_t*>(smem + (size_t)a.A * ROWB);            // [32][KP + 4]
     uint32_t* ring = top2 + 32 * (KP + 4) + (threadIdx.x >> 5) * RW;
     uint32_t* fring = ring + 4 * RL;
+    // traced: per-warp staging block of one traceback word row, [lane][KS] (KS odd: conflict-free both ways)
+    constexpr int KS = K | 1;
+    uint32_t* tstage = top2 + 32 * (KP + 4) + NW * RW + (threadIdx.x >> 5) * (32 * KS);
 
     const PgTile tile = a.tiles[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_
             const uint32_t busy = (last_cur & (0xffffffffu >> (32 - BLK - g))) |
                                   (SKEW == 1 ? (last_prev >> (g + 1)) : (last_prev | (last_prev2 >> (g + 2))));
             const uint32_t rp = ring_mine + ((uint32_t)((t0 + g - (back & ~3)) & (RN - 1)) << 2);
-            uint32_t* tbdst = TB ? a.tb + tbw0 + (int64_t)((t0 + g) >> 2) * (K * 32) + lane : nullptr;
+            uint32_t* tbdst = TB ? a.tb + tbw0 + (int64_t)((t0 + g) >> 2) * (KS * 32) + lane : nullptr;
             if (busy == 0u) {
                 uint32_t w[8];
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -314,8 +317,17 @@ __global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_
                         k16r_step<K, TB>(w[i], c, Mo, U, D, ls, ds, l_out, D_last, Dleft_prev, bordz, acc, (i & 3) == 0);
                     }
                     if (TB && (i & 3) == 3) {
+                        // The walk moves along diagonals: (y - 1, x - 1) is the NEXT COLUMN of the same lane.  Words are
+                        // therefore stored [step / 4][lane][k] -- neighbouring columns in one 32-byte sector -- instead
+                        // of [k][lane] (a new 128-byte line per walker step: the walk ran at the random-access limit of
+                        // HBM and slowed the concurrent fill down).  The warp transposes the word row through its
+                        // staging block: K conflict-free STS, then KS coalesced 128-byte lines.
+                        __syncwarp();
 #pragma unroll
-                        for (int k = 0; k < K; k++) tbdst[(i >> 2) * (K * 32) + k * 32] = acc[k];
+                        for (int k = 0; k < K; k++) tstage[lane * KS + k] = acc[k];
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < KS; j++) tbdst[(i >> 2) * (KS * 32) + j * 32] = tstage[j * 32 + lane];
                     }
                 }
             } else {
@@ -333,14 +345,24 @@ __global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_
                         k16r_step<K, TB>(w, c, Mo, U, D, ls, ds, l_out, D_last, Dleft_prev, bordz, acc, (i & 3) == 0);
                     }
                     if (TB && (i & 3) == 3) {
+                        // The walk moves along diagonals: (y - 1, x - 1) is the NEXT COLUMN of the same lane.  Words are
+                        // therefore stored [step / 4][lane][k] -- neighbouring columns in one 32-byte sector -- instead
+                        // of [k][lane] (a new 128-byte line per walker step: the walk ran at the random-access limit of
+                        // HBM and slowed the concurrent fill down).  The warp transposes the word row through its
+                        // staging block: K conflict-free STS, then KS coalesced 128-byte lines.
+                        __syncwarp();
 #pragma unroll
-                        for (int k = 0; k < K; k++) tbdst[(i >> 2) * (K * 32) + k * 32] = acc[k];
+                        for (int k = 0; k < K; k++) tstage[lane * KS + k] = acc[k];
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < KS; j++) tbdst[(i >> 2) * (KS * 32) + j * 32] = tstage[j * 32 + lane];
                     }
                     if (f & FLAG_LAST) {
                         if (f & FLAG_EMIT) {
                             const int e = q - tile.stream_begin;
+                            const int sstr = tile.slot_stride ? tile.slot_stride : 1;      // 2: the slots of A and B interleave
                             if (lane == lrA) {
-                                const int64_t slot = tile.out_base + e;
+                                const int64_t slot = tile.out_base + (int64_t)e * sstr;
                                 a.scores[slot] = (float)(int)(int16_t)(pick_ur<K>(D, klA) & 0xffffu);
                                 if (TB) {
                                     a.emit_t[slot] = t0 + g + i;
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_
                                 }
                             }
                             if (hasB && lane == lrB && e >= tile.b_skip) {
-                                const int64_t slot = tile.out_base2 + (e - tile.b_skip);
+                                const int64_t slot = tile.out_base2 + (int64_t)(e - tile.b_skip) * sstr;
                                 a.scores[slot] = (float)(int)(int16_t)(pick_ur<K>(D, klB) >> 16);
                                 if (TB) {
                                     a.emit_t[slot] = (t0 + g + i) | (1 << 30);      // bit 30: the high register half
@@ -376,4 +398,24 @@ __global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_
         last_prev2 = last_prev;
         last_prev = last_cur;
     }
+}
+
+// Score-only kernel: launch bounds as measured in round 2.
+template <int K, int NW, bool TB>
+__global__ void __launch_bounds__(NW * 32, TB ? K16RT_MINB(K) : K16R_MINB(K)) k_stream16r(const StreamArgs a)
+{
+    k16r_body<K, NW, TB>(a);
+}
+
+// Traced kernel: capped at 112 registers up to K = 13 (no spills), so that two CTAs leave 8,192 registers of an SM
+// free -- exactly one 128-thread block of the walk (k_traceback, 64 registers): the walk of wave w then runs in the
+// leftover slots WHILE wave w + 1 fills, instead of taking turns with it (a __launch_bounds__ kernel and
+// __maxnreg__ cannot be combined, hence the second entry point).
+#ifndef K16RT_MAXREG
+#define K16RT_MAXREG(K) ((K) <= 13 ? 112 : ((K) <= 14 ? 128 : 255))
+#endif
+template <int K, int NW>
+__global__ void __maxnreg__(K16RT_MAXREG(K)) k_stream16rt(const StreamArgs a)
+{
+    k16r_body<K, NW, true>(a);
 }

@@ -11,8 +11,9 @@ static int launch16rt(const StreamArgs& a, int n_tiles, cudaStream_t st)
 {
     constexpr int KP = (K + 3) & ~3;
     constexpr int NCH = (K + 3) / 4;
-    const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16t * (4 * (64 + 8) + 64) * sizeof(uint32_t);
-    auto kern = k_stream16r<K, kNW16t, true>;
+    const size_t smem = (size_t)a.A * NCH * 512 + 32 * (KP + 4) * 4 + kNW16t * (4 * (64 + 8) + 64) * sizeof(uint32_t) +
+                        (size_t)kNW16t * 32 * (K | 1) * sizeof(uint32_t);      // + the per-warp traceback staging blocks
+    auto kern = k_stream16rt<K, kNW16t>;
     PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StreamArgs b = a;
     b.all_ones = -1;

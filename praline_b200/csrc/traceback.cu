@@ -61,7 +61,8 @@ __device__ __forceinline__ float tkey_value(unsigned long long k)
 #endif
 constexpr int NWIN = PG_TB_WINDOW;
 
-__global__ void k_traceback(const TraceArgs a)
+// 64 registers: a 128-thread block of walkers fits the 8,192 registers two CTAs of the traced fill leave free on an SM
+__global__ void __maxnreg__(64) k_traceback(const TraceArgs a)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t slot = a.dual ? (tid >> 1) : tid;
@@ -69,6 +70,7 @@ __global__ void k_traceback(const TraceArgs a)
     const bool local = a.mode == PG_LOCAL;
     const bool below = a.counts && a.use_thr && !(a.scores[slot] >= a.thr);
     if (below && !(local && a.box_out)) return;   // a Waterman-Eggert box is due even below the threshold
+    if (a.dual && a.emit_t[slot] < 0) return;          // a hole of the interleaved slot numbering (no pair there)
     const int rid = a.slot_resident[slot], sid = a.slot_stream[slot];
     const int Lr = (int)(a.offs[rid + 1] - a.offs[rid]);   // kernel columns
     const int Ls = (int)(a.offs[sid + 1] - a.offs[sid]);   // kernel rows
@@ -84,6 +86,8 @@ __global__ void k_traceback(const TraceArgs a)
     auto word_index = [&](int yk, int xk) -> int64_t {
         const int lane = (xk - 1) / K, k = (xk - 1) - lane * K;
         const int step = emit - (Ls - yk) - (lr - lane);
+        if (fmt == 2)       // paired-resident kernel: [step / 4][lane][k], k padded to odd -- a diagonal step is the next word
+            return (int64_t)(step >> 2) * ((K | 1) * 32) + lane * (K | 1) + k;
         return (int64_t)(step >> (fmt != 0 ? 2 : 3)) * (K * 32) + k * 32 + lane;
     };
     auto nib_of = [&](uint32_t w, int yk, int xk) -> uint32_t {

@@ -705,7 +705,7 @@ class Engine(object):
         sb = np.minimum(sb, se)
         rows = cs[se] - cs[sb]
         T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
-        return (T // 4) * (K * 32)
+        return (T // 4) * ((K | 1) * 32)        # word rows of [lane][k], k padded to odd
 
     def _dual_state(self, n_streams):
         """Streams and traceback buffers of the dual path live in the engine: allocating 2 x 16 GiB per call
@@ -824,13 +824,17 @@ class Engine(object):
                         wt = tiles[lo:hi].copy()
                         na = (wt["stream_end"] - wt["stream_begin"]).astype(np.int64)
                         nb = np.where(wt["resident2"] >= 0, na - wt["b_skip"], 0)
+                        # slots of the two residents interleave (A of element e at base + 2 e, B at base + 2 e + 1): the
+                        # four walkers of a stream element (2 residents x 2 orientations) are neighbouring threads and
+                        # share the sectors they read; elements without a B pair leave a hole (emit_t = -1)
                         base = np.zeros(len(wt), np.int64)
-                        np.cumsum((na + nb)[:-1], out=base[1:])
+                        np.cumsum((2 * na)[:-1], out=base[1:])
                         wt["out_base"] = base
-                        wt["out_base2"] = base + na
+                        wt["out_base2"] = base + 1 + 2 * wt["b_skip"]
+                        wt["reserved"] = 2
                         wbase = np.zeros(words[lo:hi].size, np.int64)
                         np.cumsum(words[lo:hi].ravel()[:-1], out=wbase[1:])
-                        yield K, wt, wbase, int((na + nb).sum()), int(wcum[hi] - wcum[lo]), na, nb
+                        yield K, wt, wbase, int(2 * na.sum()), int(wcum[hi] - wcum[lo]), na, nb
                         lo = hi
                     if lo >= len(tiles):
                         del pending[K]
@@ -848,6 +852,7 @@ class Engine(object):
         est_slots = int(est_words * 8 / max(float(lens.mean()) ** 2, 1.0) * 1.5) + (1 << 12)
         sc_out, path_out = ({}, {}) if want_paths else (None, None)
         cnt_dev, seq_off_dev, thr = counts if counts is not None else (None, None, None)
+        trace = [] if os.environ.get("PGPU_DUAL_TRACE", "") != "" else None
         for wave_no, (K, wt, wbase, ns, n_words, na, nb) in enumerate(plan_waves()):
             maxlen = max(32 * K, maxlen_all) + 2
             bkey = (0, float(go), float(ge), maxlen, True)
@@ -864,6 +869,11 @@ class Engine(object):
             with torch.cuda.stream(st):
                 tiles_dev, wbase_dev = self.dev(wt.view(np.uint8)), self.dev(wbase)
                 sptr = ctypes.c_void_p(st.cuda_stream)
+                emit_t[:ns].fill_(-1)           # holes of the interleaved numbering stay -1: the walk skips them
+                tr = None
+                if trace is not None:       # PGPU_DUAL_TRACE: device timeline of the waves (fill / walk per stream)
+                    tr = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    tr[0].record(st)
                 _lib.check(lib.pgpu_align_tiles16_paired_traced(
                     K, self.ptr(batch.flat_dev), self.ptr(batch.offs_dev), self.ptr(tiles_dev), len(wt),
                     self.ptr(S_dev), A, int(go), int(ge), neg16, self.ptr(top_dev), int(B["left0"]), int(B["left1"]),
@@ -872,32 +882,46 @@ class Engine(object):
                 poff_dev = pbuf = pstart = plen = None
                 if want_paths:
                     # host copy of what the kernel records per slot: (resident, streamed) ids
-                    res_h = np.concatenate([np.concatenate([np.full(a_, r1), np.full(b_, r2)]) for a_, b_, r1, r2 in
-                                            zip(na, nb, wt["resident"], wt["resident2"])]).astype(np.int64)
-                    str_h = np.concatenate([np.concatenate([np.arange(t0, t0 + a_), np.arange(t0 + sk, t0 + sk + b_)])
-                                            for a_, b_, t0, sk in zip(na, nb, wt["stream_begin"], wt["b_skip"])]).astype(np.int64)
-                    cap = np.repeat(batch.lens[res_h] + batch.lens[str_h] + 2, 2).astype(np.int64)
+                    res_h = np.full(ns, -1, np.int64)
+                    str_h = np.full(ns, -1, np.int64)
+                    for a_, b_, r1, r2, t0, sk, ob in zip(na, nb, wt["resident"], wt["resident2"], wt["stream_begin"],
+                                                          wt["b_skip"], wt["out_base"]):
+                        res_h[ob:ob + 2 * a_:2] = r1
+                        str_h[ob:ob + 2 * a_:2] = np.arange(t0, t0 + a_)
+                        if b_ > 0:
+                            res_h[ob + 1 + 2 * sk:ob + 2 * a_:2] = r2
+                            str_h[ob + 1 + 2 * sk:ob + 2 * a_:2] = np.arange(t0 + sk, t0 + a_)
+                    live = res_h >= 0
+                    cap = np.repeat(np.where(live, batch.lens[np.maximum(res_h, 0)] + batch.lens[np.maximum(str_h, 0)] + 2, 0), 2).astype(np.int64)
                     poff = np.zeros(2 * ns, np.int64)
                     np.cumsum(cap[:-1], out=poff[1:])
                     poff_dev = self.dev(poff)
                     pbuf = torch.empty((int(cap.sum()), 2), dtype=torch.int32, device=self.device)
                     pstart = torch.empty(2 * ns, dtype=torch.int32, device=self.device)
                     plen = torch.empty(2 * ns, dtype=torch.int32, device=self.device)
-                _lib.check(lib.pgpu_traceback_dual(
+                if tr is not None:
+                    tr[1].record(st)
+                if os.environ.get("PGPU_DUAL_SKIP_WALK", "") == "":     # (timing experiments only: fill without the walk)
+                  _lib.check(lib.pgpu_traceback_dual(
                     K, self.ptr(batch.offs_dev), self.ptr(slot_res), self.ptr(slot_str), ns, self.ptr(tb),
                     self.ptr(emit_t), self.ptr(pair_tb), B["code00"], B["top_ramp"], B["left_ramp"],
                     self.ptr(batch.flat_dev), self.ptr(cnt_dev), self.ptr(seq_off_dev), A, self.ptr(sc),
                     int(thr is not None), float(thr if thr is not None else 0.0), self.ptr(poff_dev), self.ptr(pbuf),
                     self.ptr(pstart), self.ptr(plen), sptr))
+                if tr is not None:
+                    tr[2].record(st)
+                    trace.append((k, tr))
                 # the records were allocated under this stream: the caching allocator hands their memory out again
                 # only to later work of the same stream, so dropping the references here is safe
                 del tiles_dev, wbase_dev
                 self.launches += 2
                 if want_paths:
                     st.synchronize()
-                    assert np.array_equal(slot_res[:ns].cpu().numpy(), res_h) and np.array_equal(slot_str[:ns].cpu().numpy(), str_h)
+                    assert np.array_equal(slot_res[:ns].cpu().numpy()[live], res_h[live])
+                    assert np.array_equal(slot_str[:ns].cpu().numpy()[live], str_h[live])
+                    assert np.array_equal(emit_t[:ns].cpu().numpy() >= 0, live)
                     pb, ps_, pl, sch = pbuf.cpu().numpy(), pstart.cpu().numpy(), plen.cpu().numpy(), sc[:ns].cpu().numpy()
-                    for q in range(ns):
+                    for q in np.flatnonzero(live):
                         i, j = int(res_h[q]), int(str_h[q])
                         sc_out[(i, j)] = sch[q]
                         o = poff[2 * q] + ps_[2 * q]
@@ -906,6 +930,10 @@ class Engine(object):
                         path_out[(j, i)] = pb[o:o + pl[2 * q + 1]].copy()
         for st in streams:
             cur.wait_stream(st)
+        if trace:
+            torch.cuda.synchronize(self.device)
+            t0 = trace[0][1][0]
+            self.dual_trace = [(k, t0.elapsed_time(e[0]), t0.elapsed_time(e[1]), t0.elapsed_time(e[2])) for k, e in trace]
         return sc_out, path_out, cells
 
     def _pick_tile_dual(self, n_pairs):

@@ -48,4 +48,6 @@ if check:
         o2, l2 = rwhere[int(m)]
         same = same and bool(torch.equal(cnt[o1:o1 + l1 * 27], ref[o2:o2 + l2 * 27]))
     res["sample_identical"] = same
+if getattr(eng, "dual_trace", None):
+    res["trace_ms_stream_fill0_fill1_walk1"] = [[k, round(a, 2), round(b, 2), round(c, 2)] for k, a, b, c in eng.dual_trace[:14]]
 print(json.dumps(res))
