@@ -751,33 +751,30 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
         for (int r = 0; r < 4; r++) { rM[r] = 0.f; rU[r] = 0.f; rL[r] = 0.f; }
 
         // block bb -> ring slot of the step that consumes it.  Branch-free: rows are clamped into the matrix (blocks
-        // outside it load a row nobody uses; the padded pitch covers every lane's columns), lane 0's two record
-        // copies per row are predicated instructions.
+        // outside it load a row nobody uses; the padded pitch covers every lane's columns).  The four 32-byte records
+        // lane 0 will need (block bb0 of the left strip's edge) are eight 16-byte pieces: lane p & 7 copies piece p --
+        // one cp.async instruction for the warp (lanes 8..31 repeat the pieces of lanes 0..7: same bytes, same place).
         const float* mcol = a.m + (x0 - 1);
-        const int is0 = (lane == 0);
-        auto request = [&](int bb, int use_step) {
+        const int pc = lane & 7;                  // my piece: row pc >> 1 of the block, half pc & 1 of its record
+        auto request = [&](int bb, int bb0, int use_step) {
             const uint32_t dst = ring_s + (uint32_t)((use_step & (W4_R - 1)) * W4_SLOTF) * 4u;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int yy = min(max(4 * bb + 1 + r, 1), L1);
                 cp_async16(dst + (uint32_t)(r * 128 + lane * 4) * 4u, mcol + (size_t)(yy - 1) * a.m_pitch);
-                const float* rec = ein + (size_t)yy * 8;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
-                             "@p cp.async.cg.shared.global [%0], [%2], 16;\n\t"
-                             "@p cp.async.cg.shared.global [%1], [%2+16], 16;\n\t}"
-                             :: "r"(dst + (uint32_t)(512 + r * 8) * 4u), "r"(dst + (uint32_t)(512 + r * 8 + 4) * 4u), "l"(rec), "r"(is0)
-                             : "memory");
             }
+            const int yr = min(max(4 * bb0 + 1 + (pc >> 1), 1), L1);
+            cp_async16(dst + (uint32_t)(512 + pc * 4) * 4u, ein + (size_t)yr * 8 + (pc & 1) * 4);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         __syncwarp();
 #pragma unroll 1
-        for (int d = 0; d < W4_R - 1; d++) request(d - lane, d);
+        for (int d = 0; d < W4_R - 1; d++) request(d - lane, d, d);
 
         for (int t = 0; t < TT; t++) {
             __syncwarp();
             const int b = t - lane;
-            request(b + W4_R - 1, t + W4_R - 1);
+            request(b + W4_R - 1, t + W4_R - 1, t + W4_R - 1);
             float nM[4], nU[4], nL[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) {
@@ -792,13 +789,21 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
             // loop as a warp of its own (independent thread scheduling keeps a lane that took a long private
             // branch apart from the others: the first version of this kernel ran every step twice).
             const int nrow = min(4, L1 - 4 * t);      // valid rows of lane 0's block (b = t there)
+            // validity: lane p < 8 tests the tags of ITS piece (first half of a record: the M and U tags, second half:
+            // the L tag); the values go to lane 0 (every lane loads them: broadcasts, no divergence)
+            bool miss;
+            {
+                const float4 pv = *reinterpret_cast<const float4*>(slot + 512 + pc * 4);
+                const uint32_t tg = (uint32_t)(4 * t + 1 + (pc >> 1));
+                const bool okp = (pc & 1) ? (__float_as_uint(pv.y) == tg)
+                                          : (__float_as_uint(pv.y) == tg && __float_as_uint(pv.w) == tg);
+                miss = (lane < 8) && ((pc >> 1) < nrow) && !okp;
+            }
             float4 e0[4], e1[4];
-            bool miss = false;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 e0[r] = *reinterpret_cast<const float4*>(slot + 512 + r * 8);
                 e1[r] = *reinterpret_cast<const float4*>(slot + 512 + r * 8 + 4);
-                miss |= (lane == 0) && (r < nrow) && !edge_ok(e0[r], e1[r], 4 * t + 1 + r);
             }
             if (__any_sync(FULL, miss)) {
                 // The records were requested before the left strip had written them.  Fetch the four of THIS block

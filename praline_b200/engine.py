@@ -131,7 +131,7 @@ def row_block_quads(blocks, offs=None, padoff=None):
     """128-row tiles of the tensor-core score-row kernel (pgpu_quad): groups of <= 4 consecutive row
     blocks with one resident, each with the resident's first profile row and length.  Without `offs`
     returns just int32 [n_quads x 2] = (first block, number of blocks)."""
-    res = np.asarray(blocks["res"])
+    res = np.ascontiguousarray(blocks["res"])
     n = len(res)
     if n == 0:
         return np.zeros((0, 2), np.int32) if offs is None else np.zeros(0, QUAD_DTYPE)
@@ -142,29 +142,31 @@ def row_block_quads(blocks, offs=None, padoff=None):
     count = np.diff(np.append(first, n))
     if offs is None:
         return np.stack([first, count], axis=1).astype(np.int32)
+    # field views of a structured array are strided: gather from contiguous copies, build every quad field as a
+    # plain 2-D array and assign each field once (this runs per wave of a profile batch, on the host)
     q = np.zeros(len(first), QUAD_DTYPE)
     r = res[first]
     q["q0"] = offs[r]
     q["Lr"] = offs[r + 1] - offs[r]
-    q["can0"] = -1
+    q["nblk"] = count
+    idx = np.minimum(first[:, None] + np.arange(4)[None, :], n - 1)
+    ok = np.arange(4)[None, :] < count[:, None]
+    src0 = np.ascontiguousarray(blocks["src0"], np.int64)
+    dummy = np.ascontiguousarray(blocks["dummy"])
+    q["row0"] = np.where(ok, np.ascontiguousarray(blocks["row0"])[idx], 0)
+    q["src0"] = np.where(ok, src0[idx], 0)
+    q["rows"] = np.where(ok, np.ascontiguousarray(blocks["rows"])[idx], 0)
+    q["dummy"] = np.where(ok, dummy[idx], 0)
     if padoff is not None:
         q["bcan"] = padoff[r]
         # streamed side: a block whose first profile row sits on an 8-row group of its sequence's pre-split
         # rows (every block but the ones that carry a region's dummy row in front) can be fetched by TMA
-        src0 = np.asarray(blocks["src0"], np.int64)
         seq = np.clip(np.searchsorted(offs, src0, side="right") - 1, 0, len(offs) - 2)
         rel = src0 - offs[seq]
-        can = np.where((np.asarray(blocks["dummy"]) == 0) & (rel >= 0) & (rel % 8 == 0), padoff[seq] + rel, -1)
-    q["nblk"] = count
-    for j in range(4):
-        idx = np.minimum(first + j, n - 1)
-        ok = j < count
-        q["row0"][:, j] = np.where(ok, blocks["row0"][idx], 0)
-        q["src0"][:, j] = np.where(ok, blocks["src0"][idx], 0)
-        q["rows"][:, j] = np.where(ok, blocks["rows"][idx], 0)
-        q["dummy"][:, j] = np.where(ok, blocks["dummy"][idx], 0)
-        if padoff is not None:
-            q["can0"][:, j] = np.where(ok, can[idx], -1)
+        can = np.where((dummy == 0) & (rel >= 0) & (rel % 8 == 0), padoff[seq] + rel, -1)
+        q["can0"] = np.where(ok, can[idx], -1)
+    else:
+        q["can0"] = -1
     return q
 
 
@@ -220,6 +222,109 @@ class GrowingProfileBatch(ProfileBatch):
         self.offs_dev = self._engine.dev(self.offs)
         self.n += 1
         return self.n - 1
+
+
+def tb_words16r(tiles, K, cs, nw):
+    """Traceback words per (tile, warp) of the paired-resident traced kernel: four steps per word row of
+    32 x (K | 1) words, T = the warp's stream rows + dummy row + pipeline drain, rounded to 32
+    (gotoh_stream16r.cuh)."""
+    tb_, te_ = tiles["stream_begin"].astype(np.int64), tiles["stream_end"].astype(np.int64)
+    per = (te_ - tb_ + nw - 1) // nw
+    w = np.arange(nw)[None, :]
+    sb = tb_[:, None] + w * per[:, None]
+    se = np.minimum(sb + per[:, None], te_[:, None])
+    sb = np.minimum(sb, se)
+    rows = cs[se] - cs[sb]
+    T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
+    return (T // 4) * ((K | 1) * 32)
+
+
+class DualWavePlan(object):
+    """Host plan of the symmetric traced all-vs-all (Engine.allpairs_dual), pure numpy (tested on the CPU).
+
+    Units = resident pairs (2p, 2p+1) with their stream j = 2p+1 .. n-1, as Engine.allpairs_tiles(paired=True); the
+    shard (rank, world) is a contiguous unit range of equal DP cells.  waves() yields launches of at most `budget`
+    traceback words, one columns-per-lane class each, planned `chunk` units at a time so that the host plans the next
+    chunk while the device fills this one (393,000 tiles at BASELINE config 3 take 0.5 s in one go).  Slots are
+    wave-local and the two residents of a tile interleave: A of stream element e at out_base + 2 e, B at
+    out_base + 2 e + 1 -- the four walkers of a stream element (2 residents x 2 orientations) are neighbouring threads
+    and share the sectors they read; an element without a B pair leaves a hole (emit_t stays -1)."""
+
+    def __init__(self, lens, kcls, nw, tile, budget, shard=(0, 1), chunk=24):
+        self.lens = lens = np.asarray(lens, np.int64)
+        self.kcls, self.nw, self.tile, self.budget, self.chunk = np.asarray(kcls), int(nw), int(tile), int(budget), max(1, int(chunk))
+        n = self.n = len(lens)
+        cs = self.cs = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=cs[1:])
+        rank, world = shard
+        ui = self.ui = np.arange(0, n - 1, 2, dtype=np.int64)
+        uhb = self.uhb = ui + 1 <= n - 2
+        ucells = lens[ui] * (cs[n] - cs[ui + 1]) + np.where(uhb, lens[np.minimum(ui + 1, n - 1)] * (cs[n] - cs[np.minimum(ui + 2, n)]), 0)
+        ucum = self.ucum = np.concatenate([[0], np.cumsum(ucells)])
+        ucuts = np.searchsorted(ucum, ucum[-1] * np.arange(world + 1) / world, side="left")
+        ucuts[0], ucuts[-1] = 0, len(ui)
+        ucuts = np.maximum.accumulate(ucuts)
+        self.u_lo, self.u_hi = int(ucuts[rank]), int(ucuts[rank + 1])
+        self.cells = int(ucum[self.u_hi] - ucum[self.u_lo])
+
+    def unit_tiles(self, u0, u1):
+        """Tile records of units [u0, u1), grouped by columns-per-lane class."""
+        n, tile, kcls = self.n, self.tile, self.kcls
+        gi_u, hb_u = self.ui[u0:u1], self.uhb[u0:u1]
+        cnt = n - 1 - gi_u
+        ntile = (cnt + tile - 1) // tile
+        unit = np.repeat(np.arange(len(gi_u)), ntile)
+        first = np.cumsum(ntile) - ntile
+        gi = gi_u[unit]
+        tb_ = gi + 1 + (np.arange(int(ntile.sum())) - first[unit]) * tile
+        te_ = np.minimum(tb_ + tile, n)
+        hb = hb_u[unit]
+        t = np.zeros(len(tb_), TILE_DTYPE)
+        t["resident"] = gi
+        t["resident2"] = np.where(hb, gi + 1, -1)
+        t["stream_begin"] = tb_
+        t["stream_end"] = te_
+        t["b_skip"] = np.where(hb & (tb_ == gi + 1), 1, 0)
+        kk = np.maximum(kcls[gi], np.where(hb, kcls[np.minimum(gi + 1, n - 1)], 0))
+        return {int(K): t[kk == K] for K in np.unique(kk)}
+
+    def waves(self):
+        """-> (K, tile records, word offset per (tile, warp), slots, words, stream elements per tile for A, for B)."""
+        pending = {}
+        budget = self.budget
+        for u0 in list(range(self.u_lo, self.u_hi, self.chunk)) + [None]:
+            if u0 is not None:
+                for K, t in self.unit_tiles(u0, min(u0 + self.chunk, self.u_hi)).items():
+                    w = tb_words16r(t, K, self.cs, self.nw)
+                    if K in pending:
+                        pending[K] = (np.concatenate([pending[K][0], t]), np.concatenate([pending[K][1], w]))
+                    else:
+                        pending[K] = (t, w)
+            for K in list(pending):
+                tiles, words = pending[K]
+                wcum = np.concatenate([[0], np.cumsum(words.sum(axis=1))])
+                lo = 0
+                while lo < len(tiles):
+                    hi = max(lo + 1, int(np.searchsorted(wcum, wcum[lo] + budget, side="right")) - 1)
+                    if hi >= len(tiles) and u0 is not None and wcum[-1] - wcum[lo] < budget:
+                        break                      # a partial wave: wait for the next chunk's tiles
+                    hi = min(hi, len(tiles))
+                    wt = tiles[lo:hi].copy()
+                    na = (wt["stream_end"] - wt["stream_begin"]).astype(np.int64)
+                    nb = np.where(wt["resident2"] >= 0, na - wt["b_skip"], 0)
+                    base = np.zeros(len(wt), np.int64)
+                    np.cumsum((2 * na)[:-1], out=base[1:])
+                    wt["out_base"] = base
+                    wt["out_base2"] = base + 1 + 2 * wt["b_skip"]
+                    wt["reserved"] = 2                      # PgTile.slot_stride
+                    wbase = np.zeros(words[lo:hi].size, np.int64)
+                    np.cumsum(words[lo:hi].ravel()[:-1], out=wbase[1:])
+                    yield K, wt, wbase, int(2 * na.sum()), int(wcum[hi] - wcum[lo]), na, nb
+                    lo = hi
+                if lo >= len(tiles):
+                    del pending[K]
+                else:
+                    pending[K] = (tiles[lo:], words[lo:])
 
 
 class Engine(object):
@@ -694,18 +799,7 @@ class Engine(object):
         return self.fits_s16(S, go, ge, lens, limit=16000)
 
     def _tb_words16r(self, tiles, K, cs):
-        """Traceback words per (tile, warp) of the paired-resident traced kernel: four steps per word,
-        T = the warp's stream rows + dummy row + pipeline drain, rounded to 32 (gotoh_stream16r.cuh)."""
-        nw = self.nw
-        tb_, te_ = tiles["stream_begin"].astype(np.int64), tiles["stream_end"].astype(np.int64)
-        per = (te_ - tb_ + nw - 1) // nw
-        w = np.arange(nw)[None, :]
-        sb = tb_[:, None] + w * per[:, None]
-        se = np.minimum(sb + per[:, None], te_[:, None])
-        sb = np.minimum(sb, se)
-        rows = cs[se] - cs[sb]
-        T = np.where(se > sb, (rows + 1 + 31 + 31) // 32 * 32, 0)
-        return (T // 4) * ((K | 1) * 32)        # word rows of [lane][k], k padded to odd
+        return tb_words16r(tiles, K, cs, self.nw)
 
     def _dual_state(self, n_streams):
         """Streams and traceback buffers of the dual path live in the engine: allocating 2 x 16 GiB per call
@@ -763,83 +857,13 @@ class Engine(object):
         kcls = self.k_classes(lens)
         if (kcls < 0).any():
             raise _lib.PralineGpuError("sequence longer than %d: use the general kernel" % (32 * self.k_set[-1]))
-        # units = resident pairs (2p, 2p+1) with their stream j = 2p+1 .. n-1 (as Engine.allpairs_tiles, paired=True);
-        # the shard is a contiguous unit range of equal DP cells
-        rank, world = shard
-        ui = np.arange(0, n - 1, 2, dtype=np.int64)
-        uhb = ui + 1 <= n - 2
-        ucells = lens[ui] * (cs[n] - cs[ui + 1]) + np.where(uhb, lens[np.minimum(ui + 1, n - 1)] * (cs[n] - cs[np.minimum(ui + 2, n)]), 0)
-        ucum = np.concatenate([[0], np.cumsum(ucells)])
-        ucuts = np.searchsorted(ucum, ucum[-1] * np.arange(world + 1) / world, side="left")
-        ucuts[0], ucuts[-1] = 0, len(ui)
-        ucuts = np.maximum.accumulate(ucuts)
-        u_lo, u_hi = int(ucuts[rank]), int(ucuts[rank + 1])
-        cells = int(ucum[u_hi] - ucum[u_lo])
+        budget = max(1 << 20, self.tb_budget_words)
+        plan = DualWavePlan(lens, kcls, self.nw, tile, budget, shard, chunk=int(os.environ.get("PGPU_DUAL_CHUNK", "24")))
+        cells = plan.cells
+        ucum, u_lo, u_hi = plan.ucum, plan.u_lo, plan.u_hi
+        plan_waves = plan.waves
         S_dev = self.dev(S)
         maxlen_all = int(lens.max())
-        budget = max(1 << 20, self.tb_budget_words)
-
-        def unit_tiles(u0, u1):
-            """Tile records of units [u0, u1), grouped by columns-per-lane class."""
-            gi_u, hb_u = ui[u0:u1], uhb[u0:u1]
-            cnt = n - 1 - gi_u
-            ntile = (cnt + tile - 1) // tile
-            unit = np.repeat(np.arange(len(gi_u)), ntile)
-            first = np.cumsum(ntile) - ntile
-            gi = gi_u[unit]
-            tb_ = gi + 1 + (np.arange(int(ntile.sum())) - first[unit]) * tile
-            te_ = np.minimum(tb_ + tile, n)
-            hb = hb_u[unit]
-            t = np.zeros(len(tb_), TILE_DTYPE)
-            t["resident"] = gi
-            t["resident2"] = np.where(hb, gi + 1, -1)
-            t["stream_begin"] = tb_
-            t["stream_end"] = te_
-            t["b_skip"] = np.where(hb & (tb_ == gi + 1), 1, 0)
-            kk = np.maximum(kcls[gi], np.where(hb, kcls[np.minimum(gi + 1, n - 1)], 0))
-            return {int(K): t[kk == K] for K in np.unique(kk)}
-
-        def plan_waves():
-            """Waves of <= budget traceback words, planned a chunk of units at a time so that the host plans
-            chunk c + 1 while the device fills chunk c (393,000 tiles at BASELINE config 3: 0.5 s in one go)."""
-            pending = {}
-            chunk = max(1, int(os.environ.get("PGPU_DUAL_CHUNK", "24")))
-            for u0 in list(range(u_lo, u_hi, chunk)) + [None]:
-                if u0 is not None:
-                    for K, t in unit_tiles(u0, min(u0 + chunk, u_hi)).items():
-                        w = self._tb_words16r(t, K, cs)
-                        if K in pending:
-                            pending[K] = (np.concatenate([pending[K][0], t]), np.concatenate([pending[K][1], w]))
-                        else:
-                            pending[K] = (t, w)
-                for K in list(pending):
-                    tiles, words = pending[K]
-                    wcum = np.concatenate([[0], np.cumsum(words.sum(axis=1))])
-                    lo = 0
-                    while lo < len(tiles):
-                        hi = max(lo + 1, int(np.searchsorted(wcum, wcum[lo] + budget, side="right")) - 1)
-                        if hi >= len(tiles) and u0 is not None and wcum[-1] - wcum[lo] < budget:
-                            break                      # a partial wave: wait for the next chunk's tiles
-                        hi = min(hi, len(tiles))
-                        wt = tiles[lo:hi].copy()
-                        na = (wt["stream_end"] - wt["stream_begin"]).astype(np.int64)
-                        nb = np.where(wt["resident2"] >= 0, na - wt["b_skip"], 0)
-                        # slots of the two residents interleave (A of element e at base + 2 e, B at base + 2 e + 1): the
-                        # four walkers of a stream element (2 residents x 2 orientations) are neighbouring threads and
-                        # share the sectors they read; elements without a B pair leave a hole (emit_t = -1)
-                        base = np.zeros(len(wt), np.int64)
-                        np.cumsum((2 * na)[:-1], out=base[1:])
-                        wt["out_base"] = base
-                        wt["out_base2"] = base + 1 + 2 * wt["b_skip"]
-                        wt["reserved"] = 2
-                        wbase = np.zeros(words[lo:hi].size, np.int64)
-                        np.cumsum(words[lo:hi].ravel()[:-1], out=wbase[1:])
-                        yield K, wt, wbase, int(2 * na.sum()), int(wcum[hi] - wcum[lo]), na, nb
-                        lo = hi
-                    if lo >= len(tiles):
-                        del pending[K]
-                    else:
-                        pending[K] = (tiles[lo:], words[lo:])
 
         cur = torch.cuda.current_stream(self.device)
         state = self._dual_state(n_streams)

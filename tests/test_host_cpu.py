@@ -309,3 +309,42 @@ def test_tf32_split_accuracy_model():
     assert (np.abs(got - exact) <= 2e-6 * scale).all()
     one_term = (Ph.astype(np.float64) @ Wh.astype(np.float64).T)
     assert (np.abs(one_term - exact) > 1e-5 * scale).any()       # plain tf32 would NOT meet the bound
+
+
+def test_dual_wave_plan_covers_every_pair_once():
+    """Host plan of the symmetric traced all-vs-all (engine.DualWavePlan, pure numpy): over all waves and both
+    ranks of a 2-way shard every unordered pair appears exactly once, slots of the two residents interleave without
+    collisions, word regions of (tile, warp) do not overlap, no wave exceeds the traceback budget (beyond one tile),
+    a wave holds one columns-per-lane class, and the cell count matches."""
+    from praline_b200 import engine as E
+    rng = np.random.default_rng(11)
+    for n, tile, budget, chunk in ((2, 16, 1 << 12, 3), (3, 16, 1 << 12, 1), (37, 16, 1 << 14, 2), (64, 8, 1 << 13, 5)):
+        lens = rng.integers(1, 140, n).astype(np.int64)
+        lens[rng.integers(0, n)] = 300           # a second K class
+        ks = np.array([1, 2, 3, 4, 6, 8, 10, 12, 13, 14, 16, 20, 24, 32])
+        kcls = ks[np.searchsorted(32 * ks, lens, side="left")]
+        seen = set()
+        cells = 0
+        for rank in range(2):
+            plan = E.DualWavePlan(lens, kcls, 8, tile, budget, (rank, 2), chunk=chunk)
+            cells += plan.cells
+            for K, wt, wbase, ns, n_words, na, nb in plan.waves():
+                words = E.tb_words16r(wt, K, plan.cs, 8)
+                assert n_words == int(words.sum()) and np.array_equal(wbase, np.concatenate([[0], np.cumsum(words.ravel())[:-1]]))
+                assert n_words <= budget or len(wt) == 1
+                slots = set()
+                for t in wt:
+                    r1, r2, b0, b1, sk, st = int(t["resident"]), int(t["resident2"]), int(t["stream_begin"]), int(t["stream_end"]), int(t["b_skip"]), int(t["reserved"])
+                    assert st == 2 and K == max(kcls[r1], kcls[r2] if r2 >= 0 else 0)
+                    for e in range(b1 - b0):
+                        j = b0 + e
+                        sa = int(t["out_base"]) + e * st
+                        assert r1 < j and (r1, j) not in seen and sa not in slots and sa < ns
+                        seen.add((r1, j)); slots.add(sa)
+                        if r2 >= 0 and e >= sk:
+                            sb_ = int(t["out_base2"]) + (e - sk) * st
+                            assert r2 < j and (r2, j) not in seen and sb_ not in slots and sb_ < ns
+                            seen.add((r2, j)); slots.add(sb_)
+        assert seen == {(i, j) for i in range(n) for j in range(i + 1, n)}
+        ii, jj = np.triu_indices(n, 1)
+        assert cells == int((lens[ii] * lens[jj]).sum())
