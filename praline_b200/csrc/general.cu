@@ -1610,6 +1610,37 @@ __device__ __forceinline__ float rows_t_cell(uint32_t tr_s, uint32_t ent_s, int 
     return acc;
 }
 
+// two streamed rows at once for one resident row: the entry loads and the loop are shared and the two cells'
+// FADD chains are independent (a cell is one dependent chain of nnz1 x 4 N4 adds: a lone chain per thread leaves the
+// FP32 pipe a third busy).  N4 covers the longer of the two rows; the shorter one's table is zero padded.
+template <int N4>
+__device__ __forceinline__ void rows_t_cell2(uint32_t tra_s, uint32_t trb_s, uint32_t ent_s, int nres, float& ra, float& rb)
+{
+    float acca = 0.f, accb = 0.f;
+    for (int a = 0; a < nres; a++) {
+        float p1;
+        uint32_t off;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(p1), "=r"(off) : "r"(ent_s + (uint32_t)a * 1024u));
+        float4 ta[N4], tb[N4];
+#pragma unroll
+        for (int b = 0; b < N4; b++) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(ta[b].x), "=f"(ta[b].y), "=f"(ta[b].z), "=f"(ta[b].w) : "r"(tra_s + off + (uint32_t)b * 16u));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(tb[b].x), "=f"(tb[b].y), "=f"(tb[b].z), "=f"(tb[b].w) : "r"(trb_s + off + (uint32_t)b * 16u));
+        }
+#pragma unroll
+        for (int b = 0; b < N4; b++) {
+            acca = __fadd_rn(acca, __fmul_rn(ta[b].x, p1)); accb = __fadd_rn(accb, __fmul_rn(tb[b].x, p1));
+            acca = __fadd_rn(acca, __fmul_rn(ta[b].y, p1)); accb = __fadd_rn(accb, __fmul_rn(tb[b].y, p1));
+            acca = __fadd_rn(acca, __fmul_rn(ta[b].z, p1)); accb = __fadd_rn(accb, __fmul_rn(tb[b].z, p1));
+            acca = __fadd_rn(acca, __fmul_rn(ta[b].w, p1)); accb = __fadd_rn(accb, __fmul_rn(tb[b].w, p1));
+        }
+    }
+    ra = acca;
+    rb = accb;
+}
+
 template <int RB>
 __global__ void __launch_bounds__(128) k_build_rows_t(const float* __restrict__ prof, const int64_t* __restrict__ rowoff,
                                                       int A, int ST, const float* __restrict__ S,
@@ -1673,7 +1704,30 @@ __global__ void __launch_bounds__(128) k_build_rows_t(const float* __restrict__ 
         }
         __syncthreads();
         if (x < width) {
-            for (int r = 0; r < nr; r++) {
+            int r = 0;
+            if (mine) {
+                // pairs of streamed rows with the common quad counts (the dummy row and odd tails go one by one below)
+                const int rfirst = (blk.dummy && r0 == 0) ? 1 : 0;
+                if (rfirst) mwave[(size_t)(blk.row0 + r0) * width + x] = 0.f;
+                for (r = rfirst; r + 1 < nr; r += 2) {
+                    const int n4 = (max(scnt[r], scnt[r + 1]) + 3) >> 2;
+                    if (n4 < 1 || n4 > 7 || 4 * n4 > ST) break;
+                    const uint32_t tra = T_s + (uint32_t)(r * A * ST) * 4u, trb = tra + (uint32_t)(A * ST) * 4u;
+                    float va, vb;
+                    switch (n4) {
+                        case 1: rows_t_cell2<1>(tra, trb, ent_s, nres, va, vb); break;
+                        case 2: rows_t_cell2<2>(tra, trb, ent_s, nres, va, vb); break;
+                        case 3: rows_t_cell2<3>(tra, trb, ent_s, nres, va, vb); break;
+                        case 4: rows_t_cell2<4>(tra, trb, ent_s, nres, va, vb); break;
+                        case 5: rows_t_cell2<5>(tra, trb, ent_s, nres, va, vb); break;
+                        case 6: rows_t_cell2<6>(tra, trb, ent_s, nres, va, vb); break;
+                        default: rows_t_cell2<7>(tra, trb, ent_s, nres, va, vb); break;
+                    }
+                    mwave[(size_t)(blk.row0 + r0 + r) * width + x] = __fadd_rn(0.f, va);
+                    mwave[(size_t)(blk.row0 + r0 + r + 1) * width + x] = __fadd_rn(0.f, vb);
+                }
+            }
+            for (; r < nr; r++) {
                 float v = padv;
                 if (blk.dummy && r0 + r == 0) v = 0.f;
                 else if (mine) {

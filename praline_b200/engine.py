@@ -1128,10 +1128,15 @@ class Engine(object):
         slot_of = np.full(batch.n, -1, np.int64)
         slot_of[uniq] = np.arange(len(uniq))
         cnt = torch.zeros(int(off[-1]), dtype=torch.int32, device=self.device)
-        rows = np.concatenate([np.arange(l) for l in lens]) if len(lens) else np.zeros(0, np.int64)
-        base = np.repeat(off[:-1], lens)
-        syms = np.concatenate([batch.flat_host.numpy()[batch.offs[u]:batch.offs[u + 1]] for u in uniq]).astype(np.int64)
-        cnt[self.dev(base + rows * A + syms)] = 1
+        if len(lens):
+            # position of every master residue in the concatenated tables, without a Python loop over the masters
+            starts = np.zeros(len(lens), np.int64)
+            np.cumsum(lens[:-1], out=starts[1:])
+            rows = np.arange(int(lens.sum()), dtype=np.int64) - np.repeat(starts, lens)
+            base = np.repeat(off[:-1], lens)
+            src = np.repeat(np.asarray(batch.offs, np.int64)[uniq], lens) + rows
+            syms = batch.flat_host.numpy()[src].astype(np.int64)
+            cnt[self.dev(base + rows * A + syms)] = 1
         return cnt, off, uniq, lens, slot_of
 
     def align_profile_pairs(self, pbatch, pi, pj, S, gap_series, mode="global", resident=None, fast=False):
