@@ -863,12 +863,12 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
                             const float uo = aM + g1o, ue = aU + g1e;
                             const float lo = lM + g2o, le = lL + g2e;
                             const float U = fmaxf(uo, ue), L = fmaxf(lo, le);
-                            uint32_t f = 0;
-                            f = __funnelshift_l(__float_as_uint(lo - L), f, 1);
-                            f = __funnelshift_l(__float_as_uint(uo - U), f, 1);
-                            f = __funnelshift_l(__float_as_uint(mu - M), f, 1);
-                            f = __funnelshift_l(__float_as_uint(mm - M), f, 1);
-                            fw[r] |= f << (5 * k);
+                            // four sign bits per cell pushed straight into the row's word (cells of a row are issued in
+                            // column order): cell k ends up in bits 4 (3 - k) .. + 3, no shift / OR per cell
+                            fw[r] = __funnelshift_l(__float_as_uint(lo - L), fw[r], 1);
+                            fw[r] = __funnelshift_l(__float_as_uint(uo - U), fw[r], 1);
+                            fw[r] = __funnelshift_l(__float_as_uint(mu - M), fw[r], 1);
+                            fw[r] = __funnelshift_l(__float_as_uint(mm - M), fw[r], 1);
                             Mc[r][k] = M; Uc[r][k] = U; Lc[r][k] = L;
                         }
                     }
@@ -914,12 +914,10 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
                         const float uo = Mp[k] + g1o, ue = Up[k] + g1e;
                         const float lo = cMl + g2o, le = cLl + g2e;
                         const float U = fmaxf(uo, ue), L = fmaxf(lo, le);
-                        uint32_t f = 0;
-                        f = __funnelshift_l(__float_as_uint(lo - L), f, 1);
-                        f = __funnelshift_l(__float_as_uint(uo - U), f, 1);
-                        f = __funnelshift_l(__float_as_uint(mu - M), f, 1);
-                        f = __funnelshift_l(__float_as_uint(mm - M), f, 1);
-                        fw |= f << (5 * k);
+                        fw = __funnelshift_l(__float_as_uint(lo - L), fw, 1);
+                        fw = __funnelshift_l(__float_as_uint(uo - U), fw, 1);
+                        fw = __funnelshift_l(__float_as_uint(mu - M), fw, 1);
+                        fw = __funnelshift_l(__float_as_uint(mm - M), fw, 1);
                         Md = Mp[k]; Ud = Up[k]; Ld = Lp[k];
                         Mp[k] = M; Up[k] = U; Lp[k] = L;
                         cMl = M; cLl = L;
@@ -962,6 +960,7 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
     __shared__ uint32_t tile[WT_WIN][32];
     const int lane = threadIdx.x;
     const int L1 = a.L1, L2 = a.L2, TT = a.flag_rows, SK = a.flag_skew;   // word row of (y, lane) = y - 1 + SK * lane
+    const bool nib4 = SK == 4;      // k_wave4's words: four bits per cell, cell 0 in the highest nibble; k_wave's: 5 bits, cell 0 lowest
     const bool u_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_ONE);
     const bool l_ramp = !(a.mode == PG_SG_BOTH || a.mode == PG_SG_TWO);
     int y = a.cell_out[0], x = a.cell_out[1], k = a.cell_out[2];
@@ -1002,8 +1001,8 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
                     const int tn = y - 1 + SK * ln;
                     if (tn < tlo) break;
                     const uint32_t word = tile[tn - tlo][ln];
-                    const uint32_t c = (word >> (5 * kk)) & 31u;
-                    if (((word >> (24 + kk)) & 1u) | ((k == 0) & ((c & 19u) == 19u))) break;   // masked / local stop: general step
+                    const uint32_t c = nib4 ? ((word >> (4 * (3 - kk))) & 15u) : ((word >> (5 * kk)) & 31u);
+                    if ((!nib4 & ((word >> (24 + kk)) & 1u)) | ((k == 0) & ((c & 19u) == 19u))) break;   // masked / local stop: general step
                     push(y, x);
                     const int nk0 = !(c & 1u) ? 0 : (!(c & 2u) ? 1 : 2);
                     const int nk1 = (c & 4u) ? 1 : 0, nk2 = (c & 8u) ? 2 : 0;
@@ -1023,8 +1022,8 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
                 if (y >= 1 && x >= 1) {
                     const int ln = ((x - 1) & 127) >> 2, kk = (x - 1) & 3;
                     const uint32_t word = tile[y - 1 + SK * ln - tlo][ln];
-                    const uint32_t c = (word >> (5 * kk)) & 31u;
-                    if ((word >> (24 + kk)) & 1u) stop = true;              // masked cell: no flags
+                    const uint32_t c = nib4 ? ((word >> (4 * (3 - kk))) & 15u) : ((word >> (5 * kk)) & 31u);
+                    if (!nib4 && ((word >> (24 + kk)) & 1u)) stop = true;   // masked cell: no flags
                     else if (k == 0) {
                         ny = y - 1; nx = x - 1;
                         if (!(c & 1)) nk = 0; else if (!(c & 2)) nk = 1; else if (c & 16) stop = true; else nk = 2;
