@@ -253,10 +253,13 @@ typedef struct pgpu_row_block {
  * Match scores of a wave of profile x profile pairs in stream order (feeds pgpu_align_tiles).
  * Same evaluation order as cext_build_scores (cext.c:63-95) for ONE track set.  prof [rows][A]
  * holds all profiles, rowoff [n_seqs+1] their row offsets; the wave is described by row blocks.
+ * dense_syms: 0, or -- for batches of DENSE profiles with sequence one resident (transposed = 1) -- the number of
+ * alphabet symbols that have a nonzero entry anywhere in prof: selects the packed f32x2 kernel (score_rows_x2.cu;
+ * same bits, the symbol count sizes its tables; a count that is too small gives NaN rows, not wrong numbers).
  */
 int pgpu_build_rows(const float* prof_dev, const int64_t* rowoff_dev, int A, const float* S_dev,
                     const void* blocks_dev, int n_blocks, int width, int transposed, int local_mode,
-                    float* mwave_dev, void* stream);
+                    int dense_syms, float* mwave_dev, void* stream);
 /*
  * Tolerance-mode (<= 1e-5 relative, not the reference's evaluation order) variant for score-only
  * profile batches: W = P . S^T (transposed = 0) or P . S (transposed = 1) per profile row from

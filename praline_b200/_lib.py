@@ -50,8 +50,8 @@ _SIGNATURES = {
                                            c_void_p]),
     "pgpu_build_scores": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                   c_void_p]),
-    "pgpu_build_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                c_void_p]),
+    "pgpu_build_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p]),
     "pgpu_profile_times_matrix": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "pgpu_build_rows_fast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                      c_void_p]),

@@ -252,11 +252,11 @@ int pgpu_build_scores(int n_sets, const float* const* P1, const float* const* P2
 }
 
 int pgpu_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const void* blocks, int n_blocks,
-                    int width, int transposed, int local_mode, float* mwave, void* stream)
+                    int width, int transposed, int local_mode, int dense_syms, float* mwave, void* stream)
 {
     if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
     return pg_launch_build_rows(prof, rowoff, A, S, (const PgRowBlock*)blocks, n_blocks, width, transposed,
-                                local_mode ? -INFINITY : 0.f, mwave, (cudaStream_t)stream);
+                                local_mode ? -INFINITY : 0.f, dense_syms, mwave, (cudaStream_t)stream);
 }
 
 int pgpu_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const void* blocks,

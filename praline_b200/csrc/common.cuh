@@ -149,7 +149,9 @@ struct PgRowBlock {
     int32_t _pad;
 };
 int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const PgRowBlock* blocks,
-                         int n_blocks, int width, int transposed, float padv, float* mwave, cudaStream_t st);
+                         int n_blocks, int width, int transposed, float padv, int dense_syms, float* mwave, cudaStream_t st);
+int pg_launch_build_rows_x2(const float* prof, const int64_t* rowoff, int A, const float* S, const PgRowBlock* blocks,
+                            int n_blocks, int width, float padv, int ucap, float* mwave, cudaStream_t st);
 int pg_launch_build_rows_fast(const float* prof, const float* wres, const int64_t* rowoff, int A, const PgRowBlock* blocks,
                               int n_blocks, int width, float padv, float* mwave, cudaStream_t st);
 int pg_launch_build_rows_tc(const float* prof, const float* wres, int A, const void* quads, int n_quads, int width,

@@ -1972,9 +1972,12 @@ int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int 
     return 0;
 }
 int pg_launch_build_rows(const float* prof, const int64_t* rowoff, int A, const float* S, const PgRowBlock* blocks,
-                         int n_blocks, int width, int transposed, float padv, float* mwave, cudaStream_t st)
+                         int n_blocks, int width, int transposed, float padv, int dense_syms, float* mwave, cudaStream_t st)
 {
     if (n_blocks <= 0) return 0;
+    // dense profiles (the caller counted the symbols in use): packed f32x2 rows, two resident columns per thread
+    if (transposed && dense_syms > 0 && A <= 32 && getenv("PGPU_NO_ROWS_X2") == nullptr)
+        return pg_launch_build_rows_x2(prof, rowoff, A, S, blocks, n_blocks, width, padv, dense_syms, mwave, st);
     const int64_t nb = (int64_t)n_blocks * ((width + 127) / 128);
     if (nb > 0x7fffffffll) { pg_set_error("wave too large for one launch (%lld blocks)", (long long)nb); return 1; }
     if (transposed && getenv("PGPU_NO_ROWS_T") == nullptr) {

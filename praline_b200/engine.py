@@ -185,10 +185,25 @@ class ProfileBatch(object):
         self.n = len(profiles)
         self.offs = np.zeros(self.n + 1, np.int64)
         np.cumsum(self.lens, out=self.offs[1:])
-        self.prof_dev = engine.dev(np.concatenate(profiles, axis=0))
+        flat = np.concatenate(profiles, axis=0)
+        self.prof_dev = engine.dev(flat)
         self.offs_dev = engine.dev(self.offs)
         self.flat_dev = None
         self.max_sym = self.A - 1
+        # symbols in use and entries per row: dense batches get the packed f32x2 score rows (score_rows_x2.cu)
+        nzm = flat != 0
+        self.sym_used = nzm.any(axis=0)
+        self.nnz_total = int(nzm.sum())
+
+    def dense_syms(self):
+        """Number of symbols with a nonzero entry anywhere in the batch when its rows are dense enough for the
+        union-of-symbols kernel to pay (its work per cell is symbols_in_use x entries of the streamed row, against
+        entries x entries of the compacted walk), else 0."""
+        u = int(self.sym_used.sum())
+        rows = int(self.offs[-1])
+        if self.A > 32 or u < 1 or rows < 1:
+            return 0
+        return u if self.nnz_total >= 0.55 * u * rows else 0
 
 
 class GrowingProfileBatch(ProfileBatch):
@@ -217,6 +232,9 @@ class GrowingProfileBatch(ProfileBatch):
             self._store = bigger
         self._store[r0:r1].copy_(torch.from_numpy(p), non_blocking=False)
         self.prof_dev = self._store[:r1]
+        nzm = p != 0
+        self.sym_used = self.sym_used | nzm.any(axis=0)
+        self.nnz_total += int(nzm.sum())
         self.lens = np.append(self.lens, p.shape[0])
         self.offs = np.append(self.offs, r1)
         self.offs_dev = self._engine.dev(self.offs)
@@ -350,6 +368,7 @@ class Engine(object):
         self.keep_mwave = False
         self.tc_tma = os.environ.get("PGPU_TC_TMA", "1") not in ("", "0")      # B tiles by TMA bulk copy
         self.fast_tc = os.environ.get("PGPU_FAST_TC", "1") not in ("", "0")   # tolerance-mode score rows on tcgen05
+        self.rows_x2 = os.environ.get("PGPU_ROWS_X2", "1") not in ("", "0")   # exact score rows of dense batches: packed f32x2
 
     # -- helpers -------------------------------------------------------------------------------
     def _trace_event(self, name, chain=None):
@@ -1244,7 +1263,9 @@ class Engine(object):
                 else:
                     _lib.check(self.lib.pgpu_build_rows(self.ptr(pbatch.prof_dev), self.ptr(pbatch.offs_dev), A,
                                                         self.ptr(S_dev), self.ptr(blocks_dev), len(blocks), width,
-                                                        int(transposed), int(md == 1), self.ptr(mwave), self.stream()))
+                                                        int(transposed), int(md == 1),
+                                                        pbatch.dense_syms() if self.rows_x2 else 0,
+                                                        self.ptr(mwave), self.stream()))
                 self.launches += 1
                 self._trace_event("matrix-fed stream", ev)
                 if self.keep_mwave:      # tests compare the score rows of the three builders element by element

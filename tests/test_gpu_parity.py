@@ -874,3 +874,41 @@ def test_tensor_core_score_rows(eng, resident, mode):
     assert np.abs(m_tc[fin] - m_exact[fin]).max() <= 4e-6 * scale
     assert np.abs(m_tc[fin] - m_fma[fin]).max() <= 4e-6 * scale
     assert np.allclose(s_tc, s_exact, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["global", "local"])
+def test_dense_profile_rows_packed_f32x2(eng, mode):
+    """k_build_rows_x2 (packed f32x2, union of the resident's symbols, two streamed rows per register) gives the
+    bits of k_build_rows_t over a whole wave of DENSE profiles -- and both the oracle's scores (cext.c:63-95 order):
+    ragged lengths over several K classes (one above 512 columns: two column blocks), a sparse profile and a rare
+    symbol in the batch (zero-padded union entries), odd row counts per block, an asymmetric matrix."""
+    S = matrices.blosum62().copy()
+    S[3, 7] += 2.0
+    S[20:24, :20] = np.arange(-4, 0, dtype=np.float32)[:, None]
+    lens = [5, 31, 64, 65, 150, 301, 410, 520, 97, 33]
+    profs = [synth.profile_from_counts(synth.count_profile(160 + k, L, 150 + 300 * k, 20, 27)) for k, L in enumerate(lens)]
+    profs[8] = synth.profile_from_counts(synth.count_profile(99, 97, 3, 20, 27))            # a sparse one
+    c = synth.count_profile(98, 33, 400, 20, 27)
+    c[7, 22] = 5                                                                              # a rare symbol
+    profs[9] = synth.profile_from_counts(c)
+    pb = eng.profile_batch(profs)
+    assert pb.dense_syms() == 21
+    pi, pj = synth.all_pairs(len(profs))
+    pi, pj = np.concatenate([pi, pj[:12]]), np.concatenate([pj, pi[:12]])
+    rows = {}
+    try:
+        eng.keep_mwave = True
+        for x2 in (True, False):
+            eng.rows_x2 = x2
+            l0 = eng.launches
+            sc = eng.align_profile_pairs(pb, pi, pj, S, [-11.0, -1.0], mode=mode, resident="one")
+            rows[x2] = (eng.last_mwave.cpu().numpy().copy(), sc)
+    finally:
+        eng.keep_mwave, eng.rows_x2 = False, True
+    assert np.array_equal(rows[True][0].view(np.uint32), rows[False][0].view(np.uint32))      # the last wave, bit for bit
+    assert np.array_equal(rows[True][1].view(np.uint32), rows[False][1].view(np.uint32))
+    for k in range(0, len(pi), 3):
+        p1, p2 = profs[pi[k]], profs[pj[k]]
+        g1, g2 = oracle.gap_arrays(p1.shape[0], p2.shape[0], [-11.0, -1.0])
+        want, _ = oracle.align_raw(mode, oracle.build_scores([p1], [p2], [S]), g1, g2)
+        assert float(rows[True][1][k]) == want, k
