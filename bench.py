@@ -654,6 +654,39 @@ def main():
                                      "profile_batch_gcups_device": pcells / ((tc_ms + sum(fed)) * 1e-3) / 1e9 if tc_ms else None}
         except Exception as e:   # the headline numbers stand on their own
             roof["score_rows_tc"] = {"error": str(e)[:200]}
+        # the exact-order score rows (what bounds BASELINE configs[3] in exact mode): FP32-pipe utilisation of
+        # k_build_rows_x2 on 120 dense depth-2000 preprofiles of length 400.  Algorithmic work = 2 individually rounded
+        # f32 operations (one multiply, one add; cext.c:89) per (nonzero of row y) x (nonzero of row x) per cell;
+        # peak = the FADD rate of this box (pgpu_microbench) x 32 lanes.
+        try:
+            profs = [synth.profile_from_counts(synth.count_profile(3000 + k, 400, 2000, 20, 27)) for k in range(120)]
+            pbat = eng.profile_batch(profs)
+            ppi, ppj = synth.all_pairs(len(profs))
+            eng.align_profile_pairs(pbat, ppi, ppj, S, gaps, mode=mode, fast=False)
+            eng.take_trace()
+            eng.trace_on = True
+            eng.align_profile_pairs(pbat, ppi, ppj, S, gaps, mode=mode, fast=False)
+            eng.trace_on = False
+            tr = eng.take_trace()
+            ex_ms = sum(ms for nm, ms in tr if nm.startswith("score rows exact"))
+            fed_ms = sum(ms for nm, ms in tr if nm == "matrix-fed stream")
+            nnz = [(p_ != 0).sum(axis=1).astype(np.float64) for p_ in profs]
+            tot = np.array([v.sum() for v in nnz])
+            lane_ops = 2.0 * float((tot[ppi] * tot[ppj]).sum())
+            pcells = float((pbat.lens[ppi] * pbat.lens[ppj]).sum())
+            fp_peak = mb["fadd"] * 1e9 * 32 * sms / 1e12 if mb.get("fadd") else None
+            roof["score_rows_exact"] = {"kernel": "k_build_rows_x2 (packed f32x2: FFMA2 with a -0 addend + FADD2, reference evaluation order)",
+                                        "bound": "cuda_core_fp32_pipe", "kernel_ms": ex_ms,
+                                        "achieved": lane_ops / (ex_ms * 1e-3) / 1e12 if ex_ms else None,
+                                        "peak": fp_peak, "unit": "Tlane-op/s",
+                                        "frac": (lane_ops / (ex_ms * 1e-3) / 1e12 / fp_peak) if ex_ms and fp_peak else None,
+                                        "frac_note": "useful individually rounded f32 operations per second / measured FADD lane rate; "
+                                                     "the kernel's own pipe time also covers the 416-column padding of 400-column "
+                                                     "residents (ncu capture profiles/r02_kbuildrows_x2_*: fmaheavy pipe 82.8 % busy)",
+                                        "dense_syms": pbat.dense_syms(), "matrix_fed_stream_ms": fed_ms,
+                                        "profile_batch_gcups_device": pcells / ((ex_ms + fed_ms) * 1e-3) / 1e9 if ex_ms else None}
+        except Exception as e:
+            roof["score_rows_exact"] = {"error": str(e)[:200]}
         # BASELINE configs[4]: 20 kb x 20 kb DNA profiles on the intra-task wavefront path (own process)
         c5 = _tool("run_c5.py", [20000, 3], timeout=600)
         configs["c5"] = {"workload": "long nucleotide profile x profile alignment, 20 kb x 20 kb, depth-8 count profiles (BASELINE configs[4])",
@@ -673,8 +706,9 @@ def main():
                 c4["exact_profile_scores"].get("fasta_md5") == c4["tolerance_profile_scores"].get("fasta_md5"))
             c4["bound_note"] = ("exact mode is bound by the reference's evaluation order of the profile score rows in the "
                                 "guide-tree stage: 2.0e6 dense profile pairs x 1.6e5 cells x ~400 individually rounded "
-                                "mul+add terms (cext.c:63-95) = 2.6e14 flops >= 7 s at the FP32 pipe peak of one B200; the merges "
-                                "themselves are a small part (DESIGN.md)")
+                                "mul+add terms (cext.c:63-95) = 2.6e14 f32 operations >= 6.9 s at the FP32 pipe peak of one B200 "
+                                "on top of the ~4 s the rest of the workflow takes; roofline.score_rows_exact gives the pipe "
+                                "fraction the packed f32x2 kernel reaches (DESIGN.md)")
             # BASELINE configs[0] / second half of the metric: MSA wall time next to the host-CPU reference
             configs["msa_e2e"] = {"tree_50": msa_e2e(50, 300, "global", "tree"),
                                   "cli_default_50": msa_e2e(50, 300, "dummy", "ad_hoc"),
