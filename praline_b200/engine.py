@@ -170,6 +170,16 @@ def row_block_quads(blocks, offs=None, padoff=None):
     return q
 
 
+def dense_symbol_count(sym_used, nnz_total, rows, A):
+    """Number of symbols with a nonzero entry anywhere in a profile batch when its rows are dense enough for the
+    symbols-in-use kernel (score_rows_x2.cu) to pay -- its work per cell is symbols_in_use x entries of the streamed
+    row, against entries x entries of the compacted walk of k_build_rows_t --, else 0."""
+    u = int(np.count_nonzero(sym_used))
+    if A > 32 or u < 1 or rows < 1:
+        return 0
+    return u if nnz_total >= 0.55 * u * rows else 0
+
+
 class ProfileBatch(object):
     """A set of f32 profiles [L x A] resident on the device: one [rows x A] array plus int64 row
     offsets (the analogue of SeqBatch for ProfileTrack inputs, component/align.py:171-172)."""
@@ -196,14 +206,8 @@ class ProfileBatch(object):
         self.nnz_total = int(nzm.sum())
 
     def dense_syms(self):
-        """Number of symbols with a nonzero entry anywhere in the batch when its rows are dense enough for the
-        union-of-symbols kernel to pay (its work per cell is symbols_in_use x entries of the streamed row, against
-        entries x entries of the compacted walk), else 0."""
-        u = int(self.sym_used.sum())
-        rows = int(self.offs[-1])
-        if self.A > 32 or u < 1 or rows < 1:
-            return 0
-        return u if self.nnz_total >= 0.55 * u * rows else 0
+        """Number of symbols in use when the batch is dense enough for the packed f32x2 score rows, else 0."""
+        return dense_symbol_count(self.sym_used, self.nnz_total, int(self.offs[-1]), self.A)
 
 
 class GrowingProfileBatch(ProfileBatch):

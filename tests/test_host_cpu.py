@@ -348,3 +348,16 @@ def test_dual_wave_plan_covers_every_pair_once():
         assert seen == {(i, j) for i in range(n) for j in range(i + 1, n)}
         ii, jj = np.triu_indices(n, 1)
         assert cells == int((lens[ii] * lens[jj]).sum())
+
+
+def test_dense_symbol_count():
+    """Host side of the packed f32x2 score rows (Engine.align_profile_pairs -> pgpu_build_rows): the number of symbols
+    in use is passed only for dense batches; sparse ones and large alphabets stay on k_build_rows_t."""
+    from praline_b200.engine import dense_symbol_count
+    used = np.zeros(27, bool)
+    used[:20] = True
+    used[22] = True
+    assert dense_symbol_count(used, int(0.9 * 21 * 1000), 1000, 27) == 21
+    assert dense_symbol_count(used, int(0.3 * 21 * 1000), 1000, 27) == 0
+    assert dense_symbol_count(np.ones(40, bool), 10 ** 6, 100, 40) == 0
+    assert dense_symbol_count(np.zeros(27, bool), 0, 100, 27) == 0
