@@ -298,6 +298,21 @@ int pgpu_build_rows_tc(const float* prof_dev, const float* wres_dev, int A, cons
  * whi_dev / wlo_dev: padoff[n_seqs] * 128 bytes each. */
 int pgpu_split_residents(const float* wres_dev, const int64_t* rowoff_dev, const int64_t* padoff_dev, int n_seqs, int A,
                          void* whi_dev, void* wlo_dev, void* stream);
+/*
+ * HOST-side planner of one wave of a profile batch (no device work; what Engine.align_profile_pairs feeds the
+ * score-row kernels above).  Tiles [tile_begin, tile_end) are runs of stream elements, contiguous in stream order;
+ * each is split over nw warps; every (tile, warp) region holds one dummy row followed by the profile rows of its
+ * streamed sequences.  cs: prefix sums of the streamed lengths lens_s; str_s / res_s: streamed / resident sequence
+ * per element; offs: profile row offsets per sequence.  Writes the first matrix row per region (mrow_base
+ * [n_tiles * nw]), the row blocks of <= rows_per_block rows, the number of matrix rows and -- want_quads -- the
+ * 128-row quads of pgpu_build_rows_tc (padoff: NULL, or the pre-split row offsets of pgpu_split_residents).
+ * Returns the number of row blocks, -1 on error (capacity too small: pgpu_last_error).
+ */
+long long pgpu_plan_profile_wave(int n_tiles, const int64_t* tile_begin, const int64_t* tile_end, int nw,
+                                 const int64_t* cs, const int64_t* lens_s, const int64_t* str_s, const int64_t* res_s,
+                                 const int64_t* offs, int rows_per_block, int64_t* mrow_base, pgpu_row_block* blocks,
+                                 long long blocks_cap, int64_t* n_rows_out, int want_quads, const int64_t* padoff,
+                                 struct pgpu_quad* quads, long long quads_cap, long long* n_quads_out);
 int pgpu_build_scores_seq(const uint8_t* a_dev, const uint8_t* b_dev, const float* S_dev, int A, int L1,
                           int L2, float* m_dev, int m_pitch, void* stream);
 

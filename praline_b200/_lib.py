@@ -71,6 +71,9 @@ _SIGNATURES = {
     "pgpu_cluster_workspace_bytes": (c_int64, [c_int]),
     "pgpu_cluster_merge_order": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgpu_tree_distance": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgpu_plan_profile_wave": (ctypes.c_longlong, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_int, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int,
+                                                   c_void_p, c_void_p, ctypes.c_longlong, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -180,6 +180,35 @@ def dense_symbol_count(sym_used, nnz_total, rows, A):
     return u if nnz_total >= 0.55 * u * rows else 0
 
 
+def plan_profile_wave_native(wt, nw, cs, lens_s, str_s, res_s, offs, want_quads=False, padoff=None, rows_per_block=32):
+    """plan_profile_wave (+ row_block_quads) in one pass of the library's host planner (csrc/host_plan.cu,
+    pgpu_plan_profile_wave): the same (first row per region, row blocks, number of rows[, quads]) -- the numpy
+    functions above are its specification (tests/test_host_cpu.py compares them)."""
+    lib = _lib.load()
+    tb = np.ascontiguousarray(wt["stream_begin"], np.int64)
+    te = np.ascontiguousarray(wt["stream_end"], np.int64)
+    arrs = [np.ascontiguousarray(a, np.int64) for a in (cs, lens_s, str_s, res_s, offs)]
+    n_el = int(te[-1] - tb[0])
+    rows = int(arrs[0][te[-1]] - arrs[0][tb[0]])
+    cap = n_el + (rows + n_el) // rows_per_block + 1
+    blocks = np.empty(cap, ROWBLOCK_DTYPE)
+    quads = np.empty(cap if want_quads else 0, QUAD_DTYPE)
+    mrow_base = np.empty(len(tb) * nw, np.int64)
+    n_rows = ctypes.c_int64(0)
+    n_quads = ctypes.c_longlong(0)
+    pad = np.ascontiguousarray(padoff, np.int64) if padoff is not None else None
+    nb = lib.pgpu_plan_profile_wave(len(tb), tb.ctypes.data, te.ctypes.data, int(nw), arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                    arrs[2].ctypes.data, arrs[3].ctypes.data, arrs[4].ctypes.data, int(rows_per_block),
+                                    mrow_base.ctypes.data, blocks.ctypes.data, cap, ctypes.byref(n_rows), int(want_quads),
+                                    pad.ctypes.data if pad is not None else None, quads.ctypes.data if want_quads else None,
+                                    cap, ctypes.byref(n_quads))
+    if nb < 0:
+        raise _lib.PralineGpuError("libpraline_b200: %s" % lib.pgpu_last_error().decode())
+    if want_quads:
+        return mrow_base, blocks[:nb], int(n_rows.value), quads[:n_quads.value]
+    return mrow_base, blocks[:nb], int(n_rows.value)
+
+
 class ProfileBatch(object):
     """A set of f32 profiles [L x A] resident on the device: one [rows x A] array plus int64 row
     offsets (the analogue of SeqBatch for ProfileTrack inputs, component/align.py:171-172)."""
@@ -1236,22 +1265,26 @@ class Engine(object):
             for f in ("stream_begin", "stream_end", "out_base"):
                 tiles[f] += a
             rows_per_tile = (cs[tiles["stream_end"]] - cs[tiles["stream_begin"]]) + nw
+            cum_floats = np.cumsum(rows_per_tile) * width
             lo = 0
             while lo < len(tiles):   # waves bounded by the matrix budget
-                acc = np.cumsum(rows_per_tile[lo:]) * width
-                hi = lo + max(1, int(np.searchsorted(acc, self.m_budget_floats, side="right")))
+                done = int(cum_floats[lo - 1]) if lo else 0
+                hi = max(lo + 1, int(np.searchsorted(cum_floats, done + self.m_budget_floats, side="right")))
                 wt = tiles[lo:hi]
-                mrow_base, blocks, n_rows = plan_profile_wave(wt, nw, cs, lens_s, str_s, res_s, pbatch.offs)
+                use_tc = fast and self.fast_tc and A <= 32
+                if use_tc:
+                    mrow_base, blocks, n_rows, quads = plan_profile_wave_native(wt, nw, cs, lens_s, str_s, res_s, pbatch.offs,
+                                                                                want_quads=True, padoff=padoff)
+                else:
+                    mrow_base, blocks, n_rows = plan_profile_wave_native(wt, nw, cs, lens_s, str_s, res_s, pbatch.offs)
                 # + 4 floats: the matrix-fed kernel reads whole aligned float4s around a lane's K scores
                 mwave = torch.empty(n_rows * width + 4, dtype=torch.float32, device=self.device)[:n_rows * width]
                 # keep every device temporary referenced until the launches that read it are queued:
                 # a tensor freed right after data_ptr() is handed to the next allocation
                 blocks_dev = self.dev(blocks.view(np.uint8))
-                use_tc = fast and self.fast_tc and A <= 32
                 if use_tc:
                     # tensor-core score rows (tcgen05 tf32 with a hi/lo split): 128-row tiles = quads of
                     # consecutive row blocks that share a resident
-                    quads = row_block_quads(blocks, pbatch.offs, padoff)
                     quads_dev = self.dev(quads.view(np.uint8))
                 ev = self._trace_event("score rows %s (%d B)" % ("tc" if use_tc else "fma" if fast else "exact",
                                                                n_rows * width * 4))

@@ -361,3 +361,37 @@ def test_dense_symbol_count():
     assert dense_symbol_count(used, int(0.3 * 21 * 1000), 1000, 27) == 0
     assert dense_symbol_count(np.ones(40, bool), 10 ** 6, 100, 40) == 0
     assert dense_symbol_count(np.zeros(27, bool), 0, 100, 27) == 0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_native_profile_wave_planner_equals_numpy(seed):
+    """pgpu_plan_profile_wave (csrc/host_plan.cu, host code of the library) against its numpy specification
+    plan_profile_wave + row_block_quads: region rows, row blocks and quads field by field, with and without the
+    pre-split row offsets, ragged lengths incl. multiples of 32 and single rows, empty warp regions."""
+    rng = np.random.default_rng(seed)
+    nseq = 11
+    lens = rng.choice([1, 2, 31, 32, 33, 64, 65, 100, 7], nseq).astype(np.int64)
+    offs = np.r_[0, np.cumsum(lens)].astype(np.int64)
+    padoff = np.r_[0, np.cumsum((lens + 31) // 32 * 32)].astype(np.int64)
+    n = int(rng.integers(3, 70))
+    res_s = np.sort(rng.integers(0, nseq, n)).astype(np.int64)
+    str_s = rng.integers(0, nseq, n).astype(np.int64)
+    eng = _FakeEngine()
+    tiles = eng._make_tiles(res_s, n, int(rng.integers(2, 20)))
+    lens_s = lens[str_s]
+    cs = np.r_[0, np.cumsum(lens_s)].astype(np.int64)
+    for nw in (8, 3):
+        mb, blocks, nr = E.plan_profile_wave(tiles, nw, cs, lens_s, str_s, res_s, offs)
+        mb2, blocks2, nr2 = E.plan_profile_wave_native(tiles, nw, cs, lens_s, str_s, res_s, offs)
+        assert nr == nr2 and np.array_equal(mb, mb2)
+        assert blocks2.dtype == blocks.dtype and len(blocks) == len(blocks2)
+        for f in ("row0", "src0", "rows", "res", "dummy"):
+            assert np.array_equal(blocks[f], blocks2[f]), f
+        for pad in (None, padoff):
+            want = E.row_block_quads(blocks, offs, pad)
+            mb3, blocks3, nr3, quads = E.plan_profile_wave_native(tiles, nw, cs, lens_s, str_s, res_s, offs,
+                                                                  want_quads=True, padoff=pad)
+            assert nr3 == nr and np.array_equal(mb3, mb) and np.array_equal(blocks3["row0"], blocks["row0"])
+            assert len(quads) == len(want)
+            for f in ("q0", "Lr", "nblk", "row0", "src0", "rows", "dummy", "bcan", "can0"):
+                assert np.array_equal(quads[f], want[f]), (f, pad is None)
