@@ -348,6 +348,19 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m_dev, int m_pitch
                        float* score_out_dev, int32_t* cell_out_dev, int32_t* path_buf_dev,
                        int32_t* path_start_dev, int32_t* path_len_dev, float* o_full_dev,
                        uint8_t* t_full_dev, void* stream);
+/*
+ * One LONG profile x profile alignment in one call (BASELINE config 5: 20 kb x 20 kb): cext_build_scores for one
+ * track set (cext.c:308-455) into m_dev [L1][m_pitch] + pgpu_align_general on it (no mask, no debug arrays).  When
+ * the row-blocked wavefront serves the fill (global / semiglobal modes, var_gaps = 0, padded pitch) and the matrix
+ * has 2^21 cells or more, the score matrix is built BESIDE the fill: K1 publishes a flag per finished 128 x 128
+ * block, the fill (on a high-priority stream inside the library, joined to `stream` before the call returns to
+ * stream order) acquires a block's flag before it reads rows of it.  Same results as the two calls in sequence;
+ * workspace_dev as for pgpu_align_general.  PGPU_NO_K1_OVERLAP=1 runs the two in sequence.
+ */
+int pgpu_align_profile_long(int mode, const float* P1_dev, const float* P2_dev, const float* S_dev, int A, int L1, int L2,
+                            float* m_dev, int m_pitch, const float* g1_dev, const float* g2_dev, int var_gaps,
+                            void* workspace_dev, float* score_out_dev, int32_t* cell_out_dev, int32_t* path_buf_dev,
+                            int32_t* path_start_dev, int32_t* path_len_dev, void* stream);
 
 /*
  * Parity shim with the exact shape of the reference's cext_align_<mode>(m, g1, g2, o, t, z)

@@ -321,22 +321,22 @@ int64_t pgpu_general_workspace_bytes(int L1, int L2)
     b += up256(sizeof(int) * (size_t)(ns + 1));                     // progress
     b += 2 * up256(sizeof(float) * 3 * (size_t)(L2 + 1));           // top, lastrow
     b += up256(sizeof(float) * 3 * (size_t)(L1 + 1));               // lastcol
-    b += 256;                                                       // best
+    b += 256;                                                       // best, err
+    b += up256(sizeof(int) * (size_t)((L1 + 127) / 128) * ((L2 + 127) / 128));   // K1 block flags (pgpu_align_profile_long)
     return (int64_t)b;
 }
 
-int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, const float* g1,
-                       const float* g2, int var_gaps, const uint8_t* z, int z_pitch, void* workspace, float* score_out,
-                       int32_t* cell_out, int32_t* path_buf, int32_t* path_start, int32_t* path_len,
-                       float* o_full, uint8_t* t_full, void* stream)
+static int general_args(GenArgs& a, int& kg, int mode, int L1, int L2, const float* m, int m_pitch, const float* g1,
+                        const float* g2, int var_gaps, const uint8_t* z, int z_pitch, void* workspace, float* score_out,
+                        int32_t* cell_out, int32_t* path_buf, int32_t* path_start, int32_t* path_len,
+                        float* o_full, uint8_t* t_full, int** ready_out)
 {
     if (mode < 0 || mode > 4) { pg_set_error("unknown alignment mode %d", mode); return 1; }
     if (L1 < 1 || L2 < 1) { pg_set_error("empty sequence (L1=%d, L2=%d)", L1, L2); return 1; }
-    const int kg = general_kg(L2, o_full != nullptr);
+    kg = general_kg(L2, o_full != nullptr);
     const int nsa = general_strips(L2, general_kg(L2, false)), nsb = general_strips(L2, general_kg(L2, true));
     const int nsl = (L2 + 127) / 128;
     const int ns = (nsa > nsb ? nsa : nsb) > nsl ? (nsa > nsb ? nsa : nsb) : nsl;   // workspace fits every layout
-    GenArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = mode; a.L1 = L1; a.L2 = L2; a.m = m; a.m_pitch = m_pitch; a.g1 = g1; a.g2 = g2;
     a.z = z; a.z_pitch = z_pitch; a.o_full = o_full; a.t_full = t_full;
@@ -352,9 +352,82 @@ int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, co
     a.lastcol = (float*)w; w += up256(sizeof(float) * 3 * (size_t)(L1 + 1));
     a.best = (unsigned long long*)w;
     a.err = (int*)(w + 16);
+    w += 256;
+    if (ready_out) *ready_out = (int*)w;        // [ceil(L1 / 128)][ceil(L2 / 128)] block flags of K1 (pgpu_align_profile_long)
     a.score_out = score_out; a.cell_out = cell_out;
     a.path_buf = path_buf; a.path_start = path_start; a.path_len = path_len;
+    return 0;
+}
+
+int pgpu_align_general(int mode, int L1, int L2, const float* m, int m_pitch, const float* g1,
+                       const float* g2, int var_gaps, const uint8_t* z, int z_pitch, void* workspace, float* score_out,
+                       int32_t* cell_out, int32_t* path_buf, int32_t* path_start, int32_t* path_len,
+                       float* o_full, uint8_t* t_full, void* stream)
+{
+    GenArgs a;
+    int kg = 0;
+    const int rc = general_args(a, kg, mode, L1, L2, m, m_pitch, g1, g2, var_gaps, z, z_pitch, workspace, score_out, cell_out,
+                                path_buf, path_start, path_len, o_full, t_full, nullptr);
+    if (rc) return rc;
     return pg_launch_general(a, kg, (cudaStream_t)stream);
+}
+
+// One long profile x profile alignment, K1 and K3 in one call (BASELINE config 5): cext_build_scores for one track set +
+// RawPairwiseAligner (cext.c:308-455, component/align.py:302-447).  When the row-blocked wavefront serves the fill
+// (global / semiglobal, constant gaps) and the column kernel builds m, the two run SIDE BY SIDE: K1 on the caller's
+// stream publishes a flag per finished 128 x 128 block of m, the fill -- on a high-priority stream of its own, so that
+// its few CTAs are placed as soon as K1's first blocks retire -- acquires the flag of a block before it requests rows
+// of it.  The fill is a latency-bound wavefront on 79 SMs x 2 warps and K1 needs a fifth of its time: K1 disappears
+// behind it.  Launch order K1 first: under a serialising tool (ncu, CUDA_LAUNCH_BLOCKING) the fill simply finds every
+// flag set.  Anything else runs K1, then the fill, on the caller's stream.
+int pgpu_align_profile_long(int mode, const float* P1, const float* P2, const float* S, int A, int L1, int L2, float* m,
+                            int m_pitch, const float* g1, const float* g2, int var_gaps, void* workspace, float* score_out,
+                            int32_t* cell_out, int32_t* path_buf, int32_t* path_start, int32_t* path_len, void* stream)
+{
+    if (A < 1 || A > 64) { pg_set_error("alphabet size %d outside 1..64", A); return 1; }
+    GenArgs a;
+    int kg = 0;
+    int* ready = nullptr;
+    int rc = general_args(a, kg, mode, L1, L2, m, m_pitch, g1, g2, var_gaps, nullptr, 0, workspace, score_out, cell_out,
+                          path_buf, path_start, path_len, nullptr, nullptr, &ready);
+    if (rc) return rc;
+    ScoreSets h;
+    h.n = 1;
+    h.s[0].P1 = P1; h.s[0].P2 = P2; h.s[0].S = S; h.s[0].A = A;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool side_by_side = pg_general_uses_wave4(a) && pg_build_scores_flags_blocks(1, L1, L2) &&
+                              getenv("PGPU_NO_K1_OVERLAP") == nullptr;
+    if (!side_by_side) {
+        rc = pg_launch_build_scores(h, L1, L2, m, m_pitch, st);
+        return rc ? rc : pg_launch_general(a, kg, st);
+    }
+    // one high-priority stream and two events per device, made on first use
+    static cudaStream_t hp[16] = {};
+    static cudaEvent_t ev[16][2] = {};
+    int dev = 0;
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { pg_set_error("device ordinal %d outside 0..15", dev); return 1; }
+    if (hp[dev] == nullptr) {
+        int lo = 0, hi = 0;
+        PG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PG_CUDA_OK(cudaStreamCreateWithPriority(&hp[dev], cudaStreamNonBlocking, hi));
+        PG_CUDA_OK(cudaEventCreateWithFlags(&ev[dev][0], cudaEventDisableTiming));
+        PG_CUDA_OK(cudaEventCreateWithFlags(&ev[dev][1], cudaEventDisableTiming));
+    }
+    const int nx = (L2 + 127) / 128, ny = (L1 + 127) / 128;
+    PG_CUDA_OK(cudaMemsetAsync(ready, 0, sizeof(int) * (size_t)nx * ny, st));
+    PG_CUDA_OK(cudaEventRecord(ev[dev][0], st));            // the caller's uploads and the cleared flags
+    PG_CUDA_OK(cudaStreamWaitEvent(hp[dev], ev[dev][0], 0));
+    rc = pg_launch_build_scores(h, L1, L2, m, m_pitch, st, ready);
+    if (rc) return rc;
+    a.m_ready = ready;
+    a.m_ready_nx = nx;
+    rc = pg_launch_general(a, kg, hp[dev]);
+    // the caller's stream continues when both are done (success or not: nothing may outlive the call's buffers)
+    if (cudaEventRecord(ev[dev][1], hp[dev]) != cudaSuccess || cudaStreamWaitEvent(st, ev[dev][1], 0) != cudaSuccess) {
+        if (!rc) { pg_set_error("joining the fill's stream failed"); rc = 2; }
+    }
+    return rc;
 }
 
 // B3 parity shim: the reference's cext_align_<mode>(m, g1, g2, o, t, z) with host buffers

@@ -125,6 +125,8 @@ struct GenArgs {
     uint32_t* flagw;                     // lean kernel: [n_strips][L1+31][32] flag words (4 cells x 5 bits + mask bits)
     int var_gaps;                        // gap arrays vary per position (else g1[0..1], g2[0..1] are THE gap pairs)
     int flag_skew, flag_rows;            // lean kernels: word row of (y, lane) = y - 1 + flag_skew * lane; rows per strip
+    const int* m_ready;                  // k_wave4 only: [ceil(L1 / 128)][m_ready_nx] flags set by k_build_scores_cols as it
+    int m_ready_nx;                      //   finishes a 128 x 128 block of m (K1 running beside the fill); NULL: m is complete
     // finalize / traceback outputs
     float* score_out;                    // [1]
     int32_t* cell_out;                   // [3] y, x, state
@@ -138,7 +140,9 @@ struct ScoreSets { ScoreSet s[8]; int n; };   // passed by value as a kernel arg
 
 void pg_set_error(const char* fmt, ...);
 int pg_launch_general(GenArgs a, int kg, cudaStream_t st);
-int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st);
+int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st, int* ready = nullptr);
+bool pg_build_scores_flags_blocks(int n_sets, int L1, int L2);     // the launch above publishes per-block ready flags
+bool pg_general_uses_wave4(const GenArgs& a);                      // pg_launch_general will run k_wave4 (which can poll them)
 // <= 32 consecutive matrix rows of one streamed sequence in a wave of a profile batch
 struct PgRowBlock {
     int64_t row0;     // first matrix row

@@ -767,13 +767,34 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
             cp_async16(dst + (uint32_t)(512 + pc * 4) * 4u, ein + (size_t)yr * 8 + (pc & 1) * 4);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // K1 beside the fill (GenArgs.m_ready): the 128 x 128 block of m that holds the rows lane 0 is about to request --
+        // the furthest of the warp -- must be complete.  One acquire load per 32 steps once K1 is ahead, which it is after
+        // the first blocks (it needs a fifth of the fill's time for the whole matrix).
+        const int* mrd = a.m_ready ? a.m_ready + strip : nullptr;
+        int yb_ok = -1;
+        auto wait_rows = [&](int bb) {
+            const int ybn = min(max(bb, 0), NB - 1) >> 5;
+            if (mrd == nullptr || ybn <= yb_ok) return;
+            const int* f = mrd + (size_t)ybn * a.m_ready_nx;
+            int v = 0;
+            for (int spins = 0; spins < (1 << 22); spins++) {       // bounded: never hang ...
+                asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v) break;
+                __nanosleep(200);
+            }
+            if (!v && lane == 0) atomicOr(a.err, 1);                // ... and never continue silently
+            yb_ok = ybn;
+            __syncwarp();
+        };
         __syncwarp();
+        wait_rows(W4_R - 2);
 #pragma unroll 1
         for (int d = 0; d < W4_R - 1; d++) request(d - lane, d, d);
 
         for (int t = 0; t < TT; t++) {
             __syncwarp();
             const int b = t - lane;
+            wait_rows(t + W4_R - 1);
             request(b + W4_R - 1, t + W4_R - 1, t + W4_R - 1);
             float nM[4], nU[4], nL[4];
 #pragma unroll
@@ -1316,7 +1337,8 @@ __global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int 
 //    reference's order with its two roundings per term; the row of 128 results is one coalesced store.
 // Blocks whose columns need more quads than the table has room for take the direct path (no table).
 #define BC_ROWS 128
-__global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, int L1, int L2, float* __restrict__ m, int m_pitch, int nq_cap)
+__global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, int L1, int L2, float* __restrict__ m, int m_pitch, int nq_cap,
+                                                           int* __restrict__ ready)
 {
     extern __shared__ __align__(16) float csm[];
     const int A = st.A;
@@ -1377,7 +1399,7 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
         rcnt[tid] = c;
     }
     __syncthreads();
-    if (tid >= ncols) return;
+    if (tid < ncols) {
     float* out = m + (size_t)y0 * m_pitch + x0 + tid;
     if (table) {
         // explicit shared-space addresses: through generic pointers every load paid an address-space
@@ -1479,6 +1501,16 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
                     acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(cval[b * 128 + tid], srow[cidx[b * 128 + tid]]), e.x));
             }
             out[(size_t)r * m_pitch] = __fadd_rn(0.f, acc);
+        }
+    }
+    }
+    if (ready != nullptr) {
+        // K1 beside the fill (pgpu_align_profile_long): this 128 x 128 block of m is complete.  Every thread's stores,
+        // then a device-scope release by one thread; k_wave4 acquires the flag before it requests rows of the block.
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(ready + (size_t)blockIdx.y * gridDim.x + blockIdx.x), "r"(1) : "memory");
         }
     }
 }
@@ -1828,6 +1860,19 @@ __global__ void k_build_scores_seq(const uint8_t* a, const uint8_t* b, const flo
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// the lean kernels need the padded matrix pitch the engine allocates; anything else (and the debug dumps) runs the
+// general-layout kernels
+static bool general_lean(const GenArgs& a)
+{
+    const int lean_strips = (a.L2 + 127) / 128;
+    return !a.o_full && a.flagw && a.m_pitch % 4 == 0 && a.m_pitch >= lean_strips * 128 &&
+           ((reinterpret_cast<uintptr_t>(a.m) & 15) == 0) && getenv("PGPU_NO_LEAN") == nullptr;
+}
+bool pg_general_uses_wave4(const GenArgs& a)
+{
+    return general_lean(a) && a.mode != PG_LOCAL && a.z == nullptr && a.var_gaps == 0 && a.L1 > 0 && a.L2 > 0 &&
+           getenv("PGPU_NO_WAVE4") == nullptr;
+}
 int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
 {
     int dev = 0, sms = 148;
@@ -1836,8 +1881,7 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
     // the lean kernel needs the padded matrix pitch the engine allocates; anything else (and the
     // debug dumps) runs the general-layout kernels
     const int lean_strips = (a.L2 + 127) / 128;
-    const bool lean = !a.o_full && a.flagw && a.m_pitch % 4 == 0 && a.m_pitch >= lean_strips * 128 &&
-                      ((reinterpret_cast<uintptr_t>(a.m) & 15) == 0) && getenv("PGPU_NO_LEAN") == nullptr;
+    const bool lean = general_lean(a);
     a.n_strips = lean ? lean_strips : (a.L2 + 32 * kg - 1) / (32 * kg);
     if (a.n_strips < 1) a.n_strips = 1;
     if (lean) {
@@ -1869,7 +1913,7 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
         const bool vg = a.var_gaps != 0;
         a.flag_skew = 1;
         a.flag_rows = a.L1 + 31;
-        if (!local && !mask && !vg && getenv("PGPU_NO_WAVE4") == nullptr) {
+        if (pg_general_uses_wave4(a)) {
             a.flag_skew = 4;
             a.flag_rows = (((a.L1 + 3) >> 2) + 31) * 4;
             auto kern = k_wave4;
@@ -1934,7 +1978,11 @@ int pg_launch_general(GenArgs a, int kg, cudaStream_t st)
     return 0;
 }
 
-int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st)
+bool pg_build_scores_flags_blocks(int n_sets, int L1, int L2)
+{
+    return n_sets == 1 && (size_t)L1 * L2 >= (size_t)1 << 21 && getenv("PGPU_K1_COLS_OFF") == nullptr;
+}
+int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int m_pitch, cudaStream_t st, int* ready)
 {
     if (L1 <= 0 || L2 <= 0) return 0;
     int amax = 1;
@@ -1952,10 +2000,13 @@ int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int 
         auto kern = k_build_scores_cols;
         PG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
         dim3 g((L2 + 127) / 128, (L1 + BC_ROWS - 1) / BC_ROWS);
-        kern<<<g, 128, smc, st>>>(sets.s[0], L1, L2, m, m_pitch, nq_cap);
+        // (beside the fill, `ready`: fewer resident blocks per SM only starve the wavefront -- measured 11.5 ms with the
+        // usual occupancy, 13.5 ms with two blocks per SM, 15.3 ms with one)
+        kern<<<g, 128, smc, st>>>(sets.s[0], L1, L2, m, m_pitch, nq_cap, ready);
         PG_CUDA_OK(cudaGetLastError());
         return 0;
     }
+    if (ready != nullptr) { pg_set_error("build_scores: ready flags need the column kernel"); return 1; }
     const char* ev = getenv("PGPU_K1_BIG");
     const bool big = ev ? atoi(ev) != 0 : (size_t)L1 * L2 >= (size_t)1 << 21;   // measured: 7.7 -> 5.7 ms at 20k x 20k
     const int nr = big ? 16 : 8, nc = big ? 64 : 32;

@@ -1497,6 +1497,44 @@ class Engine(object):
             res["o"], res["t"] = o.cpu().numpy(), t.cpu().numpy()
         return res
 
+    def align_profile_pair(self, mode, p1, p2, S, g1, g2, want_path=True):
+        """One profile x profile alignment of ONE track set, K1 + K3 in one library call (pgpu_align_profile_long):
+        the same result as build_scores + align_general; long global / semiglobal alignments with constant gap
+        pairs (BASELINE config 5) have the score matrix built beside the wavefront fill."""
+        md = MODES[mode]
+        d1, d2 = self.dev(np.asarray(p1, np.float32)), self.dev(np.asarray(p2, np.float32))
+        S_dev = self.dev(np.asarray(S, np.float32))
+        L1, L2, A = int(d1.shape[0]), int(d2.shape[0]), int(d1.shape[1])
+        if L1 < 1 or L2 < 1:
+            raise ValueError("empty sequences cannot be aligned")
+        if int(d2.shape[1]) != A or tuple(S_dev.shape) != (A, A):
+            raise ValueError("profile alphabets do not match the score matrix")
+        g1h = np.asarray(g1, np.float32).reshape(L1, 2)
+        g2h = np.asarray(g2, np.float32).reshape(L2, 2)
+        var_gaps = int(not ((g1h == g1h[0]).all() and (g2h == g2h[0]).all()))
+        g1_dev, g2_dev = self.dev(g1h), self.dev(g2h)
+        m = self.padded_matrix(L1, L2)
+        ws = torch.empty(int(self.lib.pgpu_general_workspace_bytes(L1, L2)), dtype=torch.uint8, device=self.device)
+        nrows = (L1 + L2 + 2) if want_path else 0
+        outb = torch.zeros(8 + 2 * nrows, dtype=torch.int32, device=self.device)
+        base = outb.data_ptr()
+        _lib.check(self.lib.pgpu_align_profile_long(md, self.ptr(d1), self.ptr(d2), self.ptr(S_dev), A, L1, L2, self.ptr(m),
+                                                    int(m.stride(0)), self.ptr(g1_dev), self.ptr(g2_dev), var_gaps, self.ptr(ws),
+                                                    ctypes.c_void_p(base), ctypes.c_void_p(base + 4),
+                                                    ctypes.c_void_p(base + 32) if want_path else None,
+                                                    ctypes.c_void_p(base + 16) if want_path else None,
+                                                    ctypes.c_void_p(base + 20) if want_path else None, self.stream()))
+        self.launches += 4 + int(want_path)
+        h = outb.cpu().numpy()          # the single device -> host read of this alignment
+        score = float(h[:1].view(np.float32)[0])
+        if score != score:
+            raise _lib.PralineGpuError("wavefront kernel: a hand-off timed out; no result was produced")
+        res = dict(score=score, cell=tuple(int(v) for v in h[1:4]))
+        if want_path:
+            st, ln = int(h[4]), int(h[5])
+            res["path"] = h[8:].reshape(-1, 2)[st:st + ln].copy()
+        return res
+
     # -- progressive merge: count tables stay on the device, one guide-tree level per call -----------
     def merge_level(self, jobs, S, gap_series, mode, n_streams=8):
         """The independent merges of ONE guide-tree level (TreeMultipleSequenceAligner, component/msa.py:124-237):

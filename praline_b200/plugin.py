@@ -383,9 +383,14 @@ class GpuPairwiseAligner(Component):
             yield CompleteMessage(outputs={'alignment': alignment, 'score': score})
             return
         # general path: score models on the device, then the raw aligner (component/align.py:200-237)
-        m = eng.build_scores([_profile_of(t1) for t1, _, _ in sets], [_profile_of(t2) for _, t2, _ in sets],
-                             [sm.matrix.astype(np.float32) for _, _, sm in sets])
-        L1, L2 = int(m.shape[0]), int(m.shape[1])
+        p1s, p2s = [_profile_of(t1) for t1, _, _ in sets], [_profile_of(t2) for _, t2, _ in sets]
+        mats = [sm.matrix.astype(np.float32) for _, _, sm in sets]
+        L1, L2 = int(p1s[0].shape[0]), int(p2s[0].shape[0])
+        if len(sets) == 1 and L1 * L2 >= (1 << 21):
+            # one long profile pair: the raw aligner builds the scores beside its fill (pgpu_align_profile_long)
+            m = (p1s[0], p2s[0], mats[0])
+        else:
+            m = eng.build_scores(p1s, p2s, mats)
         g1 = np.empty((L1, 2), dtype=np.float32)
         g2 = np.empty((L2, 2), dtype=np.float32)
         g1[:] = gaps
@@ -427,15 +432,25 @@ class DeviceMatchScoreModel(MatchScoreModel):
     tid = MatchScoreModel.tid
 
     def __init__(self, sequence_one, sequence_two, scores_dev):
-        if len(sequence_one) != scores_dev.shape[0]:
+        # scores_dev: the device matrix, or the operands (P1, P2, S) of ONE track set it is still to be built from
+        self.operands = scores_dev if isinstance(scores_dev, tuple) else None
+        shape = (self.operands[0].shape[0], self.operands[1].shape[0]) if self.operands is not None else scores_dev.shape
+        if len(sequence_one) != shape[0]:
             s = "sequence length {0} does not correspond to array shape {1}"
-            raise DataError(s.format(len(sequence_one), scores_dev.shape[0]))
-        if len(sequence_two) != scores_dev.shape[1]:
+            raise DataError(s.format(len(sequence_one), shape[0]))
+        if len(sequence_two) != shape[1]:
             s = "sequence length {0} does not correspond to array shape {1}"
-            raise DataError(s.format(len(sequence_two), scores_dev.shape[1]))
+            raise DataError(s.format(len(sequence_two), shape[1]))
         self.sequence_one = sequence_one
         self.sequence_two = sequence_two
-        self.scores_dev = scores_dev
+        self._scores_dev = None if self.operands is not None else scores_dev
+
+    @property
+    def scores_dev(self):
+        if self._scores_dev is None:
+            p1, p2, S = self.operands
+            self._scores_dev = get_engine().build_scores([p1], [p2], [S])
+        return self._scores_dev
 
     @property
     def scores(self):
@@ -467,11 +482,17 @@ class GpuRawPairwiseAligner(Component):
             log.message(ROOT_LOG_NAME, msg.format(sequence_one.name, sequence_two.name))
         _check_mode(mode)
         eng = get_engine()
-        m = getattr(match_score_model, "scores_dev", None)
-        if m is None:
-            m = np.ascontiguousarray(match_score_model.scores, dtype=np.float32)
-        r = eng.align_general(mode, m, gap_score_model_one.scores, gap_score_model_two.scores,
-                              zero_idxs=zero_idxs, want_matrices=debug > 1)
+        operands = getattr(match_score_model, "operands", None)
+        if operands is not None and not zero_idxs and debug <= 1:
+            # a long profile pair straight from GpuPairwiseAligner: K1 beside the fill, one library call
+            r = eng.align_profile_pair(mode, operands[0], operands[1], operands[2], gap_score_model_one.scores,
+                                       gap_score_model_two.scores)
+        else:
+            m = getattr(match_score_model, "scores_dev", None)
+            if m is None:
+                m = np.ascontiguousarray(match_score_model.scores, dtype=np.float32)
+            r = eng.align_general(mode, m, gap_score_model_one.scores, gap_score_model_two.scores,
+                                  zero_idxs=zero_idxs, want_matrices=debug > 1)
         if debug > 1:   # component/align.py:390-399
             log.message(ROOT_LOG_NAME, "Dumping DP & traceback matrices...")
             for k in range(3):

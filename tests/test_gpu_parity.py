@@ -427,6 +427,43 @@ def test_long_profile_alignment_vs_oracle(eng):
             assert np.array_equal(r["path"], wp), (mode, gaps)
 
 
+def test_profile_pair_in_one_call_vs_oracle(eng, monkeypatch):
+    """pgpu_align_profile_long (Engine.align_profile_pair): K1 beside the wavefront fill -- per-block ready flags
+    instead of a finished matrix -- gives the oracle's score and path on the config 5 shape (2600 x 3100: 21 x 25
+    blocks of m, the last ones ragged), the sequential path the same, and small or non-eligible inputs (local mode,
+    varying gaps, matrices below 2^21 cells) take the sequential path inside the same call."""
+    S = matrices.nucleotide()
+    p1 = synth.profile_from_counts(synth.count_profile(5, 2600, 8, 4, 15))
+    p2 = synth.profile_from_counts(synth.count_profile(6, 3100, 8, 4, 15))
+    want_m = oracle.build_scores([p1], [p2], [S])
+    for mode in ("global", "semiglobal_both"):
+        for gaps in ([-11.0, -1.0], [-2.0]):
+            g1, g2 = oracle.gap_arrays(2600, 3100, gaps)
+            ws, wp = oracle.align_raw(mode, want_m, g1, g2)
+            for rep in range(2):                    # the flags are cleared per call
+                r = eng.align_profile_pair(mode, p1, p2, S, g1, g2)
+                assert r["score"] == ws and np.array_equal(r["path"], wp), (mode, gaps, rep)
+            monkeypatch.setenv("PGPU_NO_K1_OVERLAP", "1")
+            r = eng.align_profile_pair(mode, p1, p2, S, g1, g2)
+            monkeypatch.delenv("PGPU_NO_K1_OVERLAP")
+            assert r["score"] == ws and np.array_equal(r["path"], wp), (mode, gaps)
+    rng = np.random.default_rng(2)
+    g1, g2 = oracle.gap_arrays(2600, 3100, [-11.0, -1.0])
+    g1v = g1.copy()
+    g1v[7] = (-3.0, -0.5)                           # per-position gaps: k_wave, K1 first
+    for mode, ga in (("local", g1), ("global", g1v)):
+        r = eng.align_profile_pair(mode, p1, p2, S, ga, g2)
+        ws, wp = oracle.align_raw(mode, want_m, ga, g2)
+        assert r["score"] == ws and np.array_equal(r["path"], wp), mode
+    q1 = synth.profile_from_counts(synth.count_profile(15, int(rng.integers(40, 90)), 5, 20, 27))
+    q2 = synth.profile_from_counts(synth.count_profile(16, int(rng.integers(40, 90)), 5, 20, 27))
+    B = matrices.blosum62()
+    h1, h2 = oracle.gap_arrays(q1.shape[0], q2.shape[0], [-11.0, -1.0])
+    r = eng.align_profile_pair("semiglobal_both", q1, q2, B, h1, h2)
+    ws, wp = oracle.align_raw("semiglobal_both", oracle.build_scores([q1], [q2], [B]), h1, h2)
+    assert r["score"] == ws and np.array_equal(r["path"], wp)
+
+
 def test_large_score_matrix_kernel_edge_shapes(eng):
     """k_build_scores_cols (column-per-thread K1 for matrices of 2M cells and more) is bit-identical to the
     oracle's evaluation order (cext.c:63-95, :388-421) on ragged shapes, sparse DNA profiles (table path) and dense

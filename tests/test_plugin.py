@@ -132,6 +132,26 @@ def test_profile_component_matches_reference():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["global", "semiglobal_both", "local"])
+def test_long_profile_pair_through_the_component_matches_reference(mode):
+    """A profile pair of 2^21 cells and more goes from GpuPairwiseAligner to GpuRawPairwiseAligner as OPERANDS and
+    is aligned by one library call (pgpu_align_profile_long: score matrix beside the wavefront fill in the global and
+    semiglobal modes, in sequence for local); same alignment and score as the reference's two components."""
+    sm = _blosum()
+    ref_mgr, gpu_mgr = Manager(R.reference_index()), Manager(plugin.register(R.reference_index()))
+    c1 = synth.count_profile(140, 1500, 4, 20, 27)
+    c2 = synth.count_profile(141, 1450, 3, 20, 27)
+    a = Sequence("p1", [(TRACK_ID_PREPROFILE, ProfileTrack(c1, ALPHABET_AA))])
+    b = Sequence("p2", [(TRACK_ID_PREPROFILE, ProfileTrack(c2, ALPHABET_AA))])
+    kw = dict(mode=mode, sequence_one=a, sequence_two=b, track_id_sets_one=[[TRACK_ID_PREPROFILE]],
+              track_id_sets_two=[[TRACK_ID_PREPROFILE]], score_matrices=[sm])
+    want, _ = R.run_task(ref_mgr, pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
+    got, _ = R.run_task(gpu_mgr, pc.PairwiseAligner, {'gap_series': [-11.0, -1.0]}, **kw)
+    assert got['score'] == want['score']
+    _same_alignment(got, want)
+
+
+@pytest.mark.gpu
 def test_raw_component_matches_reference():
     rng = np.random.default_rng(4)
     ref_mgr, gpu_mgr = Manager(R.reference_index()), Manager(plugin.register(R.reference_index()))
