@@ -1397,6 +1397,9 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
             if (p != 0.f) { rows[tid * A + c] = make_float2(p, __int_as_float(table ? i * nq * 2048 : i * A)); c++; }
         }
         rcnt[tid] = c;
+        // (0, first table row) behind the entries: rows walked together run to the longest count, and
+        // fl(t * 0) = 0 leaves a partial sum as it is
+        for (int k = c; k < A; k++) rows[tid * A + k] = make_float2(0.f, __int_as_float(0));
     }
     __syncthreads();
     if (tid < ncols) {
@@ -1415,45 +1418,35 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
             return v;
         };
         if (nq == 1) {
-            // two rows per pass: the cell's dependent FADD chain (4 per entry) is what a thread waits on, and two
-            // independent chains per thread hide it at 12 warps per SM
+            // four rows per pass: the cell's dependent FADD chain (4 per entry) is what a thread waits on; four
+            // independent chains per thread hide it at 12 warps per SM (two: 2.4 ms at 20k x 20k).  The rows run to
+            // the longest of their counts over zero padded entries.
             int r = 0;
-            for (; r + 1 < nrows; r += 2) {
-                const int n1a = rcnt[r], n1b = rcnt[r + 1];
-                uint32_t ra = rows_s + (uint32_t)(r * A) * 8u, rb = ra + (uint32_t)A * 8u;
-                float acca = 0.f, accb = 0.f;
-                const int nmin = min(n1a, n1b);
-                int a = 0;
-                for (; a < nmin; a++, ra += 8u, rb += 8u) {
-                    float pa, pb; uint32_t oa, ob;
-                    lds2(ra, pa, oa);
-                    lds2(rb, pb, ob);
-                    const float4 ta = lds4(Ts + oa), tb = lds4(Ts + ob);
-                    acca = __fadd_rn(acca, __fmul_rn(ta.x, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.x, pb));
-                    acca = __fadd_rn(acca, __fmul_rn(ta.y, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.y, pb));
-                    acca = __fadd_rn(acca, __fmul_rn(ta.z, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.z, pb));
-                    acca = __fadd_rn(acca, __fmul_rn(ta.w, pa)); accb = __fadd_rn(accb, __fmul_rn(tb.w, pb));
+            for (; r + 3 < nrows; r += 4) {
+                const int nmax = max(max(rcnt[r], rcnt[r + 1]), max(rcnt[r + 2], rcnt[r + 3]));
+                uint32_t ra = rows_s + (uint32_t)(r * A) * 8u;
+                const uint32_t rstep = (uint32_t)A * 8u;
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                for (int a = 0; a < nmax; a++, ra += 8u) {
+                    float p0, p1, p2, p3; uint32_t o0, o1, o2, o3;
+                    lds2(ra, p0, o0);
+                    lds2(ra + rstep, p1, o1);
+                    lds2(ra + 2u * rstep, p2, o2);
+                    lds2(ra + 3u * rstep, p3, o3);
+                    const float4 t0 = lds4(Ts + o0), t1 = lds4(Ts + o1), t2 = lds4(Ts + o2), t3 = lds4(Ts + o3);
+                    acc0 = __fadd_rn(acc0, __fmul_rn(t0.x, p0)); acc1 = __fadd_rn(acc1, __fmul_rn(t1.x, p1));
+                    acc2 = __fadd_rn(acc2, __fmul_rn(t2.x, p2)); acc3 = __fadd_rn(acc3, __fmul_rn(t3.x, p3));
+                    acc0 = __fadd_rn(acc0, __fmul_rn(t0.y, p0)); acc1 = __fadd_rn(acc1, __fmul_rn(t1.y, p1));
+                    acc2 = __fadd_rn(acc2, __fmul_rn(t2.y, p2)); acc3 = __fadd_rn(acc3, __fmul_rn(t3.y, p3));
+                    acc0 = __fadd_rn(acc0, __fmul_rn(t0.z, p0)); acc1 = __fadd_rn(acc1, __fmul_rn(t1.z, p1));
+                    acc2 = __fadd_rn(acc2, __fmul_rn(t2.z, p2)); acc3 = __fadd_rn(acc3, __fmul_rn(t3.z, p3));
+                    acc0 = __fadd_rn(acc0, __fmul_rn(t0.w, p0)); acc1 = __fadd_rn(acc1, __fmul_rn(t1.w, p1));
+                    acc2 = __fadd_rn(acc2, __fmul_rn(t2.w, p2)); acc3 = __fadd_rn(acc3, __fmul_rn(t3.w, p3));
                 }
-                for (int a2 = a; a2 < n1a; a2++, ra += 8u) {
-                    float p1; uint32_t off;
-                    lds2(ra, p1, off);
-                    const float4 t4 = lds4(Ts + off);
-                    acca = __fadd_rn(acca, __fmul_rn(t4.x, p1));
-                    acca = __fadd_rn(acca, __fmul_rn(t4.y, p1));
-                    acca = __fadd_rn(acca, __fmul_rn(t4.z, p1));
-                    acca = __fadd_rn(acca, __fmul_rn(t4.w, p1));
-                }
-                for (int a2 = a; a2 < n1b; a2++, rb += 8u) {
-                    float p1; uint32_t off;
-                    lds2(rb, p1, off);
-                    const float4 t4 = lds4(Ts + off);
-                    accb = __fadd_rn(accb, __fmul_rn(t4.x, p1));
-                    accb = __fadd_rn(accb, __fmul_rn(t4.y, p1));
-                    accb = __fadd_rn(accb, __fmul_rn(t4.z, p1));
-                    accb = __fadd_rn(accb, __fmul_rn(t4.w, p1));
-                }
-                out[(size_t)r * m_pitch] = __fadd_rn(0.f, acca);
-                out[(size_t)(r + 1) * m_pitch] = __fadd_rn(0.f, accb);
+                out[(size_t)r * m_pitch] = __fadd_rn(0.f, acc0);
+                out[(size_t)(r + 1) * m_pitch] = __fadd_rn(0.f, acc1);
+                out[(size_t)(r + 2) * m_pitch] = __fadd_rn(0.f, acc2);
+                out[(size_t)(r + 3) * m_pitch] = __fadd_rn(0.f, acc3);
             }
             for (; r < nrows; r++) {
                 const int n1 = rcnt[r];
