@@ -1002,10 +1002,13 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
             strip = (x - 1) >> 7;
             const int tcur = y - 1 + SK * (((x - 1) & 127) >> 2);
             tlo = max(0, tcur - (WT_WIN - 1));
-            const uint32_t* src = a.flagw + ((size_t)strip * TT + tlo) * 32 + lane;
+            // 16-byte copies: lane l moves piece l & 7 of row 4 i + (l >> 3), four whole 128-byte rows per instruction
+            // (64 instructions per window instead of 256 four-byte ones)
+            const uint32_t* src = a.flagw + ((size_t)strip * TT + tlo) * 32 + (lane & 7) * 4;
             const int nrow = min(WT_WIN, TT - tlo);
 #pragma unroll 8
-            for (int r = 0; r < nrow; r++) cp_async4(tile_s + (uint32_t)(r * 32 + lane) * 4u, src + (size_t)r * 32);
+            for (int r = lane >> 3; r < nrow; r += 4)
+                cp_async16(tile_s + (uint32_t)(r * 32 + (lane & 7) * 4) * 4u, src + (size_t)r * 32);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
