@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(256) k_build_scores(const ScoreSets sets, int 
 // Blocks whose columns need more quads than the table has room for take the direct path (no table).
 #define BC_ROWS 128
 __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, int L1, int L2, float* __restrict__ m, int m_pitch, int nq_cap,
-                                                           int* __restrict__ ready)
+                                                           int* __restrict__ ready, uint64_t nz)
 {
     extern __shared__ __align__(16) float csm[];
     const int A = st.A;
@@ -1356,7 +1356,18 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
     int* cidx = reinterpret_cast<int*>(cval + A * 128);          // [A][128]                           symbol j
     __shared__ int rcnt[BC_ROWS];
     __shared__ int nqmax;
-    if (tid == 0) nqmax = 0;
+    __shared__ unsigned umask;                                   // symbols the block's rows of P1 use (A <= 32)
+    if (tid == 0) { nqmax = 0; umask = 0u; }
+    __syncthreads();
+    if (A <= 32) {
+        unsigned mk = 0u;
+        if (tid < nrows) {
+            const float* r1 = st.P1 + (size_t)(y0 + tid) * A;
+            for (int i = 0; i < A; i++) if (r1[i] != 0.f) mk |= 1u << i;
+        }
+        mk = __reduce_or_sync(0xffffffffu, mk);
+        if ((tid & 31) == 0 && mk) atomicOr(&umask, mk);
+    }
     for (int i = tid; i < A * A; i += 128) sS[i] = st.S[i];
     {
         const float* s2 = st.P2 + (size_t)x0 * A;
@@ -1373,7 +1384,11 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
     }
     __syncthreads();
     const int nq = nqmax;
-    const bool table = nq <= nq_cap;
+    // SMALL symbol sets (config 5: DNA profiles): at most four symbols in the block's rows and four entries per column --
+    // the column's whole table lives in registers, see the register path below
+    const unsigned um = umask;
+    const bool regp = A <= 32 && nq <= 1 && __popc(um) <= 4 && nz != 0ull;
+    const bool table = !regp && nq <= nq_cap;
     if (table && tid < 128) {
         for (int i = 0; i < A; i++)
             for (int q = 0; q < nq; q++) {
@@ -1405,6 +1420,62 @@ __global__ void __launch_bounds__(128) k_build_scores_cols(const ScoreSet st, in
         for (int k = c; k < A; k++) rows[tid * A + k] = make_float2(0.f, __int_as_float(0));
     }
     __syncthreads();
+    if (regp) {
+        // ---- register path.  T[u][b] = fl(P2[x][j_b] * S[i_u][j_b]) for the block's (at most four) symbols i_u and the
+        // column's (at most four) entries: 16 values per thread.  The rows become dense over the four symbols (p1 = 0
+        // where a row lacks one: fl(t * 0) = 0 leaves a partial sum as it is) and two rows share every instruction in the
+        // packed f32x2 forms (score_rows_x2.cu: FFMA2 with the -0 addend nz = the rounded product, FADD2); the p1 pairs of
+        // four rows arrive as four broadcast LDS.128.  Per two cells 16 FFMA2 + 16 FADD2, in the reference's order.
+        int us[4];
+        {
+            unsigned r = um;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { us[u] = r ? __ffs(r) - 1 : 0; r &= r - 1; }
+        }
+        const int U = __popc(um);
+        float* pdn = T;                                          // [64 row pairs][4 symbols][2 rows]
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            pdn[((tid >> 1) * 4 + u) * 2 + (tid & 1)] = (tid < nrows && u < U) ? raw[tid * A + us[u]] : 0.f;
+        float Tr[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                Tr[u][b] = (tid < ncols && u < U && b < n2) ? __fmul_rn(cval[b * 128 + tid], sS[us[u] * A + cidx[b * 128 + tid]]) : 0.f;
+        __syncthreads();
+        if (tid < ncols) {
+            float* out = m + (size_t)y0 * m_pitch + x0 + tid;
+            const uint32_t pdn_s = (uint32_t)__cvta_generic_to_shared(pdn);
+            for (int r = 0; r < nrows; r += 4) {
+                uint64_t pa[4], pb[4];                           // (row r, r + 1) and (row r + 2, r + 3) per symbol
+                const uint32_t ad = pdn_s + (uint32_t)(r >> 1) * 32u;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(pa[0]), "=l"(pa[1]) : "r"(ad));
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(pa[2]), "=l"(pa[3]) : "r"(ad + 16u));
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(pb[0]), "=l"(pb[1]) : "r"(ad + 32u));
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(pb[2]), "=l"(pb[3]) : "r"(ad + 48u));
+                uint64_t acca = 0ull, accb = 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        uint64_t tt, pr;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(Tr[u][b]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pr) : "l"(pa[u]), "l"(tt), "l"(nz));
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acca) : "l"(acca), "l"(pr));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pr) : "l"(pb[u]), "l"(tt), "l"(nz));
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(accb) : "l"(accb), "l"(pr));
+                    }
+                float v0, v1, v2, v3;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(acca));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(v2), "=f"(v3) : "l"(accb));
+                out[(size_t)r * m_pitch] = __fadd_rn(0.f, v0);
+                if (r + 1 < nrows) out[(size_t)(r + 1) * m_pitch] = __fadd_rn(0.f, v1);
+                if (r + 2 < nrows) out[(size_t)(r + 2) * m_pitch] = __fadd_rn(0.f, v2);
+                if (r + 3 < nrows) out[(size_t)(r + 3) * m_pitch] = __fadd_rn(0.f, v3);
+            }
+        }
+    } else
     if (tid < ncols) {
     float* out = m + (size_t)y0 * m_pitch + x0 + tid;
     if (table) {
@@ -1998,7 +2069,8 @@ int pg_launch_build_scores(const ScoreSets& sets, int L1, int L2, float* m, int 
         dim3 g((L2 + 127) / 128, (L1 + BC_ROWS - 1) / BC_ROWS);
         // (beside the fill, `ready`: fewer resident blocks per SM only starve the wavefront -- measured 11.5 ms with the
         // usual occupancy, 13.5 ms with two blocks per SM, 15.3 ms with one)
-        kern<<<g, 128, smc, st>>>(sets.s[0], L1, L2, m, m_pitch, nq_cap, ready);
+        kern<<<g, 128, smc, st>>>(sets.s[0], L1, L2, m, m_pitch, nq_cap, ready,
+                                  getenv("PGPU_K1_REG_OFF") ? 0ull : 0x8000000080000000ull);
         PG_CUDA_OK(cudaGetLastError());
         return 0;
     }
