@@ -2,6 +2,7 @@
 // Plain pointers and sizes only; every entry returns 0 on success or a non-zero code with the
 // text available from pgpu_last_error().  Nothing here throws across the boundary.
 #include "common.cuh"
+#include <mutex>
 #include "../../include/praline_b200.h"
 
 #include <stdarg.h>
@@ -407,6 +408,9 @@ int pgpu_align_profile_long(int mode, const float* P1, const float* P2, const fl
     int dev = 0;
     PG_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16) { pg_set_error("device ordinal %d outside 0..15", dev); return 1; }
+    static std::mutex once;
+    std::lock_guard<std::mutex> guard(once);                 // creation, and one overlapped alignment per process at a time:
+                                                             // the events are shared
     if (hp[dev] == nullptr) {
         int lo = 0, hi = 0;
         PG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
