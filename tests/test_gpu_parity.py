@@ -949,3 +949,15 @@ def test_dense_profile_rows_packed_f32x2(eng, mode):
         g1, g2 = oracle.gap_arrays(p1.shape[0], p2.shape[0], [-11.0, -1.0])
         want, _ = oracle.align_raw(mode, oracle.build_scores([p1], [p2], [S]), g1, g2)
         assert float(rows[True][1][k]) == want, k
+    # a small alphabet in use (dense DNA profiles: 4 of 15 symbols, two-entry table rows)
+    Sn = matrices.nucleotide()
+    dna = [synth.profile_from_counts(synth.count_profile(260 + k, L, 60, 4, 15)) for k, L in enumerate([40, 129, 64, 7])]
+    pbn = eng.profile_batch(dna)
+    assert pbn.dense_syms() == 4
+    qi, qj = synth.all_pairs(len(dna))
+    got = eng.align_profile_pairs(pbn, qi, qj, Sn, [-11.0, -1.0], mode=mode, resident="one")
+    for k in range(len(qi)):
+        p1, p2 = dna[qi[k]], dna[qj[k]]
+        g1, g2 = oracle.gap_arrays(p1.shape[0], p2.shape[0], [-11.0, -1.0])
+        want, _ = oracle.align_raw(mode, oracle.build_scores([p1], [p2], [Sn]), g1, g2)
+        assert float(got[k]) == want, ("dna", k)
