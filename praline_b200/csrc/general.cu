@@ -777,6 +777,7 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
             if (mrd == nullptr || ybn <= yb_ok) return;
             const int* f = mrd + (size_t)ybn * a.m_ready_nx;
             int v = 0;
+#pragma unroll 1
             for (int spins = 0; spins < (1 << 22); spins++) {       // bounded: never hang ...
                 asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
                 if (v) break;
