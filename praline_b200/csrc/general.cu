@@ -1021,19 +1021,33 @@ __global__ void __launch_bounds__(32) k_wave_traceback(const GenArgs a)
             const int xlo = strip * 128;
             for (;;) {
                 bool handled = false;
-                while (y >= 1 && x > xlo) {
-                    const int ln = ((x - 1) & 127) >> 2, kk = (x - 1) & 3;
-                    const int tn = y - 1 + SK * ln;
-                    if (tn < tlo) break;
-                    const uint32_t word = tile[tn - tlo][ln];
+                // The move out of a cell depends on the STATE alone (diagonal, up, left), the cell's flags only choose the
+                // next state: the word of the NEXT cell is requested before the current one is decoded, so that the
+                // shared-memory latency runs beside the decode instead of in front of it (the walk is one dependent chain).
+                bool ok = y >= 1 && x > xlo;
+                int kk = (x - 1) & 3;
+                uint32_t word = 0u;
+                if (ok) {
+                    const int ln = ((x - 1) & 127) >> 2, tn = y - 1 + SK * ln;
+                    ok = tn >= tlo;
+                    if (ok) word = tile[tn - tlo][ln];
+                }
+                while (ok) {
+                    const int y2 = y - (k != 2), x2 = x - (k != 1);
+                    const int ln2 = ((x2 - 1) & 127) >> 2, kk2 = (x2 - 1) & 3, tn2 = y2 - 1 + SK * ln2;
+                    const bool ok2 = (y2 >= 1) & (x2 > xlo) & (tn2 >= tlo);
+                    const uint32_t word2 = tile[min(max(tn2 - tlo, 0), WT_WIN - 1)][ln2];   // clamped into the tile; used only when ok2
                     const uint32_t c = nib4 ? ((word >> (4 * (3 - kk))) & 15u) : ((word >> (5 * kk)) & 31u);
                     if ((!nib4 & ((word >> (24 + kk)) & 1u)) | ((k == 0) & ((c & 19u) == 19u))) break;   // masked / local stop: general step
                     push(y, x);
                     const int nk0 = !(c & 1u) ? 0 : (!(c & 2u) ? 1 : 2);
                     const int nk1 = (c & 4u) ? 1 : 0, nk2 = (c & 8u) ? 2 : 0;
-                    y -= (k != 2);
-                    x -= (k != 1);
                     k = (k == 0) ? nk0 : ((k == 1) ? nk1 : nk2);
+                    y = y2;
+                    x = x2;
+                    kk = kk2;
+                    word = word2;
+                    ok = ok2;
                     handled = true;
                 }
                 if (handled && y >= 1 && x >= 1) {
