@@ -59,17 +59,18 @@ class SeqBatch(object):
     """A set of index sequences resident on the device (uint8 symbols + int64 offsets)."""
 
     def __init__(self, engine, seqs):
-        self.lens = np.fromiter((len(s) for s in seqs), np.int64, len(seqs))
+        self.lens = np.fromiter(map(len, seqs), np.int64, len(seqs))
         if len(seqs) == 0 or (self.lens <= 0).any():
             raise ValueError("empty sequences cannot be aligned")
-        flat = np.concatenate([np.asarray(s) for s in seqs])
+        # (the packing is part of every end-to-end step of bench.py: one concatenate over the caller's arrays)
+        flat = np.concatenate(seqs if all(type(s) is np.ndarray for s in seqs) else [np.asarray(s) for s in seqs])
         if flat.min() < 0 or flat.max() > 63:
             raise ValueError("symbol indices must lie in 0..63")
         self.n = len(seqs)
         self.offs = np.zeros(self.n + 1, np.int64)
         np.cumsum(self.lens, out=self.offs[1:])
-        self.flat_host = torch.from_numpy(flat.astype(np.uint8)).pin_memory() if engine.pin else \
-            torch.from_numpy(flat.astype(np.uint8))
+        flat8 = flat if flat.dtype == np.uint8 else flat.astype(np.uint8)
+        self.flat_host = torch.from_numpy(flat8).pin_memory() if engine.pin else torch.from_numpy(flat8)
         self.offs_host = torch.from_numpy(self.offs)
         self.flat_dev = self.flat_host.to(engine.device, non_blocking=True)
         self.offs_dev = self.offs_host.to(engine.device, non_blocking=True)
