@@ -132,6 +132,43 @@ def test_align_profiles_entry_point(lib, mode):
     assert np.array_equal(path.cpu().numpy()[L1 + L2 + 2 - n:], want_path)
 
 
+@pytest.mark.parametrize("mode", ["global", "semiglobal_both", "local"])
+def test_align_profile_long_entry_point(lib, mode):
+    """pgpu_align_profile_long straight through ctypes on caller-allocated buffers (padded score matrix, workspace of
+    pgpu_general_workspace_bytes): score matrix beside the fill for the global / semiglobal modes (2^21 cells and
+    more), in sequence for local; a non-default stream; score, end cell and path against the oracle; errors."""
+    import torch
+    S = matrices.nucleotide()
+    L1, L2 = 1600, 1377
+    p1 = synth.profile_from_counts(synth.count_profile(31, L1, 8, 4, 15))
+    p2 = synth.profile_from_counts(synth.count_profile(32, L2, 8, 4, 15))
+    g1, g2 = oracle.gap_arrays(L1, L2, [-11.0, -1.0])
+    want_s, want_p = oracle.align_raw(mode, oracle.build_scores([p1], [p2], [S]), g1, g2)
+    pitch = (L2 + 127) // 128 * 128
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d1, d2, dS, dg1, dg2 = _dev(p1), _dev(p2), _dev(S.astype(np.float32)), _dev(g1), _dev(g2)
+        m = torch.empty((L1, pitch), dtype=torch.float32, device="cuda")
+        ws = torch.empty(int(lib.pgpu_general_workspace_bytes(L1, L2)), dtype=torch.uint8, device="cuda")
+        out = torch.zeros(8 + 2 * (L1 + L2 + 2), dtype=torch.int32, device="cuda")
+        base = out.data_ptr()
+        for rep in range(2):
+            _lib.check(lib.pgpu_align_profile_long(MODE_ID[mode], _ptr(d1), _ptr(d2), _ptr(dS), 15, L1, L2, _ptr(m), pitch,
+                                                   _ptr(dg1), _ptr(dg2), 0, _ptr(ws), ctypes.c_void_p(base),
+                                                   ctypes.c_void_p(base + 4), ctypes.c_void_p(base + 32),
+                                                   ctypes.c_void_p(base + 16), ctypes.c_void_p(base + 20),
+                                                   ctypes.c_void_p(st.cuda_stream)))
+            st.synchronize()
+            h = out.cpu().numpy()
+            assert float(h[:1].view(np.float32)[0]) == want_s, (mode, rep)
+            got = h[8:].reshape(-1, 2)[int(h[4]):int(h[4]) + int(h[5])]
+            assert np.array_equal(got, want_p), (mode, rep)
+        assert np.array_equal(m[:, :L2].cpu().numpy(), oracle.build_scores([p1], [p2], [S]))     # the matrix it built
+    assert lib.pgpu_align_profile_long(MODE_ID[mode], _ptr(d1), _ptr(d2), _ptr(dS), 15, 0, L2, _ptr(m), pitch, _ptr(dg1),
+                                       _ptr(dg2), 0, _ptr(ws), None, None, None, None, None, None) != 0
+    assert b"empty" in lib.pgpu_last_error()
+
+
 def test_plain_c_program(lib, tmp_path):
     """examples/capi_demo.c: the library driven from plain C (cudart only, no Python in the data path).
     Built with gcc here, run as a subprocess; every printed score and path equals the oracle's."""
