@@ -1302,7 +1302,7 @@ class Engine(object):
                     _lib.check(self.lib.pgpu_build_rows(self.ptr(pbatch.prof_dev), self.ptr(pbatch.offs_dev), A,
                                                         self.ptr(S_dev), self.ptr(blocks_dev), len(blocks), width,
                                                         int(transposed), int(md == 1),
-                                                        pbatch.dense_syms() if self.rows_x2 else 0,
+                                                        getattr(pbatch, "dense_syms", lambda: 0)() if self.rows_x2 else 0,
                                                         self.ptr(mwave), self.stream()))
                 self.launches += 1
                 self._trace_event("matrix-fed stream", ev)
