@@ -754,17 +754,24 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
         // outside it load a row nobody uses; the padded pitch covers every lane's columns).  The four 32-byte records
         // lane 0 will need (block bb0 of the left strip's edge) are eight 16-byte pieces: lane p & 7 copies piece p --
         // one cp.async instruction for the warp (lanes 8..31 repeat the pieces of lanes 0..7: same bytes, same place).
-        const float* mcol = a.m + (x0 - 1);
         const int pc = lane & 7;                  // my piece: row pc >> 1 of the block, half pc & 1 of its record
+        // byte pointers and byte strides: one IMAD.WIDE per address (a float index costs a multiply-add plus a two-instruction
+        // scale-and-add)
+        const char* mcolb = reinterpret_cast<const char*>(a.m + (x0 - 1));
+        const char* einb = reinterpret_cast<const char*>(ein) + (pc & 1) * 16;
+        const int pitchb = a.m_pitch * 4;
+        const uint32_t dst_lane = ring_s + (uint32_t)(lane * 16);
         auto request = [&](int bb, int bb0, int use_step) {
-            const uint32_t dst = ring_s + (uint32_t)((use_step & (W4_R - 1)) * W4_SLOTF) * 4u;
+            const uint32_t slot_b = (uint32_t)((use_step & (W4_R - 1)) * (W4_SLOTF * 4));
+            const uint32_t dst = dst_lane + slot_b;
+            const int yb = 4 * bb;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const int yy = min(max(4 * bb + 1 + r, 1), L1);
-                cp_async16(dst + (uint32_t)(r * 128 + lane * 4) * 4u, mcol + (size_t)(yy - 1) * a.m_pitch);
+                const int y0 = min(max(yb + r, 0), L1 - 1);
+                cp_async16(dst + (uint32_t)(r * 512), mcolb + (int64_t)y0 * pitchb);
             }
             const int yr = min(max(4 * bb0 + 1 + (pc >> 1), 1), L1);
-            cp_async16(dst + (uint32_t)(512 + pc * 4) * 4u, ein + (size_t)yr * 8 + (pc & 1) * 4);
+            cp_async16(ring_s + slot_b + (uint32_t)(2048 + pc * 16), einb + (int64_t)yr * 32);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         // K1 beside the fill (GenArgs.m_ready): the 128 x 128 block of m that holds the rows lane 0 is about to request --
@@ -795,7 +802,7 @@ __global__ void __launch_bounds__(256, 1) k_wave4(const GenArgs a)
         for (int t = 0; t < TT; t++) {
             __syncwarp();
             const int b = t - lane;
-            wait_rows(t + W4_R - 1);
+            if (mrd != nullptr && ((t + W4_R - 1) & 31) == 0) wait_rows(t + W4_R - 1);     // a new 128-row block of m
             request(b + W4_R - 1, t + W4_R - 1, t + W4_R - 1);
             float nM[4], nU[4], nL[4];
 #pragma unroll
